@@ -1,0 +1,169 @@
+"""Seeded synthetic inputs restating the reference's data generators.
+
+These are host-side fixtures for tests and bench.py (the data is then made
+resident on the device by the shim); nothing here is on the hot path.
+
+* horns      -- gensimple_horns.py:15-39  (x: 200 channels, one narrow line, noise 0.01)
+* nothing    -- gennothing.py:7-12        (pure noise)
+* realistic  -- gen_realistic.py:16-50    (1000 channels, broad+narrow line); the
+                reference always simulates 10 000 spectra and truncates
+                (gen_realistic.py:18,52-53); here N is a parameter.
+* muse       -- a cube of the reference shape: nspec=3600 (musefuse.py:35),
+                ndata=4223 (pres/massivens4.lyx:2229), variance bands inflated by
+                1e10 as at musefuse.py:128-132.
+
+`legacy=True` reproduces the reference's numpy.random (RandomState) stream
+bit-for-bit for the same N; `legacy=False` uses the faster PCG64 generator for
+the 1e6-data-set measurement inputs.  Matrices are returned channel-major
+(y[nx, ndata], C-contiguous, data-set index fastest) exactly as sample.py:31
+hands them to the native code.
+"""
+import numpy
+
+NOISE_LEVEL = 0.01            # sample.py:45, gensimple_horns.py:28
+
+
+def _gauss(x, A, mu, sig):
+    # gensimple_horns.py:8-13 -- rows = data sets, columns = channels
+    return A.reshape((-1, 1)) * numpy.exp(
+        -0.5 * ((mu.reshape((-1, 1)) - x.reshape((1, -1))) / sig.reshape((-1, 1))) ** 2)
+
+
+def horns(N, nx=200, legacy=True, seed=None):
+    """gensimple_horns.py: returns x[nx], y[nx, N], truth dict."""
+    x = numpy.linspace(400, 800, nx)
+    seed = N if seed is None else seed
+    if legacy:
+        rs = numpy.random.RandomState(seed)
+        z = numpy.arctan(rs.uniform(-numpy.pi, numpy.pi, size=N)) * 0.1
+        height = 0.02 / rs.power(3, size=N)
+        # gensimple_horns.py:37-38 draws len(x) normals per data set, in data-set order;
+        # one (N, nx) draw consumes the RandomState stream identically (nx even).
+        noise = rs.normal(0, NOISE_LEVEL, size=(N, nx))
+    else:
+        rg = numpy.random.default_rng(seed)
+        z = numpy.arctan(rg.uniform(-numpy.pi, numpy.pi, size=N)) * 0.1
+        height = 0.02 / rg.power(3, size=N)
+        noise = rg.standard_normal(size=(N, nx))
+        noise *= NOISE_LEVEL
+    mean = 656 * (1 + z)
+    width = 5.0 * numpy.ones(N)
+    step = 65536
+    y = numpy.empty((nx, N))
+    for lo in range(0, N, step):      # chunked to bound temporaries at N = 1e6
+        hi = min(N, lo + step)
+        ym = _gauss(x, height[lo:hi], mean[lo:hi], width[lo:hi])
+        ym += noise[lo:hi]
+        y[:, lo:hi] = ym.T
+    return x, y, dict(z=z, mean_narrow=mean, width_narrow=width, height_narrow=height)
+
+
+def nothing(N, nx=200, legacy=True, seed=None):
+    """gennothing.py:7-12."""
+    x = numpy.linspace(400, 800, nx)
+    seed = N if seed is None else seed
+    if legacy:
+        y = numpy.random.RandomState(seed).normal(0, NOISE_LEVEL, size=(nx, N))
+    else:
+        y = numpy.random.default_rng(seed).standard_normal(size=(nx, N))
+        y *= NOISE_LEVEL
+    return x, y
+
+
+def realistic(N, nx=1000, seed=1):
+    """gen_realistic.py:16-50 with the 10 000 cap lifted (same distributions)."""
+    x = numpy.linspace(400, 800, nx)
+    rs = numpy.random.RandomState(seed)
+    z = rs.beta(2, 30, size=N) * 2
+    rest_wave = 440
+    width_broad = 10 ** rs.normal(3, 0.2, size=N) * rest_wave / 300000
+    width_narrow = 10 ** rs.normal(1, 0.2, size=N) * rest_wave / 300000
+    signal_level = 1. / (rs.power(1, size=N) * 100 + 2)
+    is_type1 = rs.uniform(size=N) < 0.5
+    height_broad = numpy.where(is_type1, 10 ** rs.normal(0, 0.2, size=N),
+                               10 ** rs.normal(-2, 0.2, size=N)) * signal_level
+    height_narrow = signal_level
+    mu = rest_wave * numpy.ones(N)
+    y = numpy.empty((nx, N))
+    step = 16384
+    rg = numpy.random.default_rng(seed)
+    for lo in range(0, N, step):
+        hi = min(N, lo + step)
+        xz = x.reshape((1, -1)) / (1. + z[lo:hi].reshape((-1, 1)))
+        ym = height_broad[lo:hi, None] * numpy.exp(
+            -0.5 * ((mu[lo:hi, None] - xz) / width_broad[lo:hi, None]) ** 2)
+        ym += height_narrow[lo:hi, None] * numpy.exp(
+            -0.5 * ((mu[lo:hi, None] - xz) / width_narrow[lo:hi, None]) ** 2)
+        ym += rg.standard_normal(size=ym.shape) * NOISE_LEVEL
+        y[:, lo:hi] = ym.T
+    return x, y, dict(z=z)
+
+
+MUSE_NSPEC = 3600
+MUSE_NDATA = 4223
+MUSE_BANDS = ((1600, 1670), (1730, 1780), (1950, 2000), (2250, 2700), (2800, 3000))
+
+
+def muse_template(nspec=MUSE_NSPEC, phase=0.0):
+    """Non-negative smooth model spectrum of the cube's length (stand-in for
+    musefuse.py:222-284, which needs external BC03 grids)."""
+    t = numpy.linspace(0, 1, nspec)
+    return (1.0 + 0.5 * numpy.sin(7 * t + phase) + 0.3 * numpy.exp(-0.5 * ((t - 0.4) / 0.01) ** 2)
+            + 0.8 * t)
+
+
+def muse(ndata=MUSE_NDATA, nspec=MUSE_NSPEC, seed=3):
+    """MUSE-shaped cube: y[nspec, ndata], variance v[nspec, ndata] (>0, bands += 1e10)."""
+    rg = numpy.random.default_rng(seed)
+    v = rg.uniform(0.5, 2.0, size=(nspec, ndata))
+    template = muse_template(nspec)
+    scale = rg.uniform(0.5, 20.0, size=ndata)
+    y = template.reshape((-1, 1)) * scale.reshape((1, -1))
+    y += rg.standard_normal(size=y.shape) * numpy.sqrt(v)
+    for lo, hi in MUSE_BANDS:
+        if lo < nspec:
+            v[lo:min(hi, nspec), :] += 1e10
+    return y, v, template
+
+
+def priortransform(cube):
+    """sample.py:52-58 -- unit cube -> (A, mu, log_sig)."""
+    cube = numpy.array(cube, dtype=float, copy=True)
+    cube[..., 0] = 10 ** (cube[..., 0] * 2 - 2)
+    cube[..., 1] = cube[..., 1] * 400 + 400
+    cube[..., 2] = cube[..., 2] * 2
+    return cube
+
+
+def parameter_points(K, seed=7):
+    """K prior draws -> rows (A, mu, sig) with sig = 10**log_sig (sample.py:102-103)."""
+    u = numpy.random.RandomState(seed).uniform(size=(K, 3))
+    p = priortransform(u)
+    p[:, 2] = 10 ** p[:, 2]
+    return p
+
+
+def masks(N, seed=11):
+    """The mask shapes the sampler produces (multi_nested_sampler.py:373-388,148-162)."""
+    rs = numpy.random.RandomState(seed)
+    return {
+        'all': numpy.ones(N, dtype=bool),
+        'half': rs.uniform(size=N) < 0.5,
+        'sparse': rs.uniform(size=N) < 0.01,
+        'prefix': numpy.arange(N) < max(1, N // 3),
+        'none': numpy.zeros(N, dtype=bool),
+    }
+
+
+def members_and_candidates(n, m, ndim, seed=5):
+    """Live-point union in a unit box and uniform candidates (radfriendsregion.py:139)."""
+    rs = numpy.random.RandomState(seed)
+    return rs.uniform(size=(n, ndim)), rs.uniform(size=(m, ndim))
+
+
+def bootstrap_chosen(n, nbootstraps, rs=numpy.random):
+    """The 0/1 float64 matrix drawn at clustering/neighbors.py:172-174."""
+    chosen = numpy.zeros((n, nbootstraps))
+    for b in range(nbootstraps):
+        chosen[rs.choice(numpy.arange(n), size=n, replace=True), b] = 1.
+    return chosen

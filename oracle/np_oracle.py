@@ -1,0 +1,76 @@
+"""numpy/scipy restatement of the hot-path formulas (test infrastructure).
+
+Not bit-identical to the C (different summation order); agrees to ~1e-15
+relative for the likelihoods and exactly for the neighbour counts except at
+floating-point ties of the distance threshold.
+"""
+import numpy
+import scipy.spatial
+
+
+def line_model(x, A, mu, sig):
+    """clike.c:65 / sample.py:68 -- Gaussian line on the wavelength grid."""
+    return A * numpy.exp(-0.5 * ((mu - x) / sig) ** 2)
+
+
+def clike(x, y, A, mu, sig, noise, data_mask):
+    """sample.py:64-71 without the -0.5 (what clike.c accumulates in Lout)."""
+    ypred = line_model(x, A, mu, sig)
+    return (((ypred.reshape((-1, 1)) - y[:, data_mask]) / noise) ** 2).sum(axis=0)
+
+
+def clike_spectrum(ypred, y, noise, data_mask):
+    return (((ypred.reshape((-1, 1)) - y[:, data_mask]) / noise) ** 2).sum(axis=0)
+
+
+def cmuselike(y, v, ypred, data_mask):
+    """musefuse.py:474-480 (vectorised twin of cmuselike.c:48-64), without the
+    random jitter term; returns the full-length vector with NaN outside the mask."""
+    yd = y[:, data_mask]
+    vd = v[:, data_mask]
+    yp = ypred.reshape((-1, 1))
+    s = numpy.sum(yd * yp / vd, axis=0) / (numpy.sum(yp ** 2 / vd, axis=0) + 1e-10)
+    chi2 = numpy.sum((yd - s.reshape((1, -1)) * yp) ** 2 / vd, axis=0)
+    out = numpy.full(y.shape[1], numpy.nan)
+    out[data_mask] = -0.5 * chi2
+    return out
+
+
+def count_within_distance_of(members, maxdistance, us):
+    """clustering/neighbors.py:79-81."""
+    dists = scipy.spatial.distance.cdist(members, us, metric='euclidean')
+    return (dists < maxdistance).sum(axis=0)
+
+
+def any_within_distance_of(members, maxdistance, us):
+    """clustering/neighbors.py:83-85."""
+    dists = scipy.spatial.distance.cdist(members, us, metric='euclidean')
+    return (dists < maxdistance).any(axis=0)
+
+
+def most_distant_nearest_neighbor(u):
+    """clustering/neighbors.py:188-193 (scipy branch of nearest_rdistance_guess)."""
+    distances = scipy.spatial.distance.cdist(u, u, metric='euclidean')
+    numpy.fill_diagonal(distances, 1e300)
+    return numpy.max(numpy.min(distances, axis=1))
+
+
+def bootstrapped_maxdistance(u, chosen):
+    """Textbook restatement of cneighbors.c:140-176 with the i>=1 quirk (:162)."""
+    n, nboot = chosen.shape
+    d = scipy.spatial.distance.cdist(u, u, metric='sqeuclidean')
+    best = None
+    for b in range(nboot):
+        sel = chosen[:, b] != 0
+        unsel = ~sel
+        unsel[0] = False
+        if unsel.any():
+            if sel.any():
+                nearest = d[numpy.ix_(unsel, sel)].min(axis=1)
+            else:
+                nearest = numpy.full(unsel.sum(), 1e300)
+            furthest = numpy.sqrt(nearest).max()
+        else:
+            furthest = 0.0
+        best = furthest if best is None or furthest > best else best
+    return best
