@@ -1,0 +1,186 @@
+/*
+ * mdns_b200.h -- C ABI of libmdns_b200.so, the B200-native (sm_100a) hot path of
+ * massivedatans.  Plain C types only (pointers, sizes, doubles); loaded with
+ * ctypes exactly like the reference's clike.so / cmuselike.so / cneighbors.so.
+ *
+ * Each entry point names the reference interface it replaces; paths are
+ * relative to the upstream JohannesBuchner/massivedatans tree.
+ *
+ * Conventions
+ *   - every function returning int returns 0 (MDNS_OK) on success and a
+ *     negative MDNS_E* code on failure; mdns_last_error() then holds a message
+ *     (thread-local).  The reference C always returns 0 and its callers ignore
+ *     the value (sample.py:106, neighbors.py:141); here failures are loud.
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with MDNS_ECUDA.
+ *   - host matrices use the reference layout: channel-major, data-set index
+ *     fastest, element (channel j, data set i) at m[i + j*ndata]
+ *     (clike.c:72, cmuselike.c:53).  Masks are 1-byte C bool / numpy.bool_
+ *     arrays (sample.py:94); any non-zero byte means "active".
+ *   - all arithmetic is IEEE FP64.
+ */
+#ifndef MDNS_B200_H
+#define MDNS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDNS_OK        0
+#define MDNS_EINVAL   -1   /* bad argument                                  */
+#define MDNS_ECUDA    -2   /* CUDA runtime / launch failure, or no device   */
+#define MDNS_ENOMEM   -3   /* host or device allocation failed              */
+#define MDNS_ESTATE   -4   /* call sequence error (e.g. launch before stage)*/
+
+/* ---- process-wide ---------------------------------------------------- */
+const char *mdns_last_error(void);
+int         mdns_version(void);          /* 100*major + minor */
+int         mdns_device_count(void);     /* CUDA devices visible; 0 if none */
+/* Kernels launched by this library since load (bench.py's "gpu_launches"). */
+int64_t     mdns_launch_count(void);
+/* Host helper of the neighbour path: the smallest double T such that
+ * sqrt(T) >= r in IEEE arithmetic, so that  sqrt(d) < r  <=>  d < T  exactly
+ * (the compare at cneighbors.c:88,109 without a sqrt in the device loop). */
+double      mdns_sqrt_threshold(double r);
+/* Pinned host memory for result vectors (D2H lands without a bounce copy). */
+void       *mdns_host_alloc(int64_t bytes);
+int         mdns_host_free(void *p);
+
+/* ---- resident data sets ---------------------------------------------- */
+typedef struct mdns_dataset mdns_dataset;
+
+/*
+ * Upload the data once and keep it resident in HBM (replaces passing x, yy
+ * [and vv] host pointers on every call: sample.py:106, musefuse.py:534).
+ *   x   [nx]          wavelength grid, may be NULL when only *_spectra calls are used
+ *   yy  [nx*ndata]    data, reference layout
+ *   vv  [nx*ndata]    per-element variance (cmuselike.c:36) or NULL for the
+ *                     scalar-noise likelihood of clike.c
+ *   devices/ndevices  CUDA ordinals to shard the data sets over, contiguous
+ *                     ranges of the data-set index; NULL/0 = current device 0.
+ * The host arrays are copied; they may be freed after the call returns.
+ */
+int mdns_dataset_create(const double *x, const double *yy, const double *vv,
+                        int ndata, int nx, const int *devices, int ndevices,
+                        mdns_dataset **out);
+int mdns_dataset_destroy(mdns_dataset *ds);
+int mdns_dataset_info(const mdns_dataset *ds, int *ndata, int *nx, int *nshards,
+                      int64_t *resident_bytes);
+
+/*
+ * One-call evaluation with HOST inputs and outputs (the drop-in path).
+ *
+ * mdns_clike_eval_params: K parameter points params[k] = (A, mu, sig); the
+ * line model A*exp(-0.5*((mu-x_j)/sig)^2) (clike.c:65) is generated on the
+ * device, then for every active data set i (rank r among the active ones,
+ * clike.c:67-74):
+ *     Lout[k*n_act + r] = scale * sum_j ((ypred_kj - y_ij)/noise)^2
+ * scale = 1 gives what clike.c leaves in Lout, scale = -0.5 folds in
+ * sample.py:108.  mask == NULL means all data sets.  Lout must hold
+ * lout_capacity >= K*n_act doubles; *n_act_out (may be NULL) receives n_act.
+ * Replaces `like` of clike.c:34-40 called K times.
+ */
+int mdns_clike_eval_params(mdns_dataset *ds, const double *params, int K,
+                           double noise, double scale, const uint8_t *mask,
+                           double *Lout, int64_t lout_capacity, int *n_act_out);
+/* Same with K caller-provided model spectra ypred[K][nx] (the model() of
+ * musefuse.py:222-284 stays on the host). */
+int mdns_clike_eval_spectra(mdns_dataset *ds, const double *ypred, int K,
+                            double noise, double scale, const uint8_t *mask,
+                            double *Lout, int64_t lout_capacity, int *n_act_out);
+/*
+ * MUSE scaled chi-square (cmuselike.c:48-64): for every active data set i
+ *     Lout[k*ndata + i] = -0.5 * sum_j (y_ij - s*m_kj)^2 / v_ij ,
+ *     s = (sum_j y m / v) / (1e-10 + sum_j m^2 / v)
+ * un-compacted; entries of inactive data sets are left untouched
+ * (cmuselike.c:49,62).  Needs a data set created with vv.
+ * Replaces `like` of cmuselike.c:34-38 called K times.
+ */
+int mdns_muse_eval_spectra(mdns_dataset *ds, const double *ypred, int K,
+                           const uint8_t *mask, double *Lout);
+
+/*
+ * Staged interface (inputs resident in HBM; used for device-side timing and
+ * by callers that keep the mask across many candidates, e.g. one
+ * draw_constrained call, hiermetriclearn.py:173-211).
+ *   set_mask     upload + compact the mask (NULL = all); returns n_act
+ *   stage_params upload K (A,mu,sig) triples          (clike-type)
+ *   stage_spectra upload K model spectra [K][nx]      (either type)
+ *   launch       enqueue the kernels only (asynchronous, no copies)
+ *   fetch        D2H of the last launch's result + synchronise; layout as in
+ *                the one-call functions (compacted for clike, full for muse)
+ *   sync         wait for all enqueued work
+ */
+int mdns_set_mask(mdns_dataset *ds, const uint8_t *mask, int *n_act_out);
+int mdns_stage_params(mdns_dataset *ds, const double *params, int K);
+int mdns_stage_spectra(mdns_dataset *ds, const double *ypred, int K);
+int mdns_clike_launch(mdns_dataset *ds, double noise, double scale);
+int mdns_muse_launch(mdns_dataset *ds);
+int mdns_fetch(mdns_dataset *ds, double *Lout, int64_t lout_capacity);
+int mdns_sync(mdns_dataset *ds);
+/* CUDA-event stopwatch on the data set's own streams (max over shards). */
+int mdns_timer_start(mdns_dataset *ds);
+int mdns_timer_stop(mdns_dataset *ds, float *elapsed_ms);
+/* Kernel-variant override for experiments: lanes per data set (0 = auto),
+ * fragments in flight per lane (0 = auto), candidates per pass (0 = auto). */
+int mdns_set_tuning(mdns_dataset *ds, int lanes, int unroll, int ktile);
+
+/* ---- RadFriends neighbour tests --------------------------------------- */
+typedef struct mdns_region mdns_region;
+
+/* A region owns the resident member set (live-point union, metric space). */
+int mdns_region_create(int device, mdns_region **out);
+int mdns_region_destroy(mdns_region *rg);
+/* xx[n][ndim] row-major (neighbors.py:100 argtype); upload once per region
+ * (radfriendsregion.py:59-70 builds one region from `members`). */
+int mdns_region_set_members(mdns_region *rg, const double *xx, int n, int ndim);
+/* cneighbors.c:95-119: out[j] (caller-initialised, normally zeros) gains one
+ * per member within maxdistance of candidate yy[j]; with countmax > 0 the
+ * scan of candidate j stops once out[j] >= countmax.  Bit-exact. */
+int mdns_region_count_within(mdns_region *rg, double maxdistance,
+                             const double *yy, int m, double *out, int countmax);
+/* cneighbors.c:77-92: *result = 1 if any member is within maxdistance of y. */
+int mdns_region_is_within(mdns_region *rg, double maxdistance, const double *y,
+                          int *result);
+/* cneighbors.c:125-179: chosen[n][nboot] float64 0/1 (round index fastest). */
+int mdns_region_bootstrapped_maxdistance(mdns_region *rg, const double *chosen,
+                                         int nboot, double *result);
+/* cneighbors.c:32-75. */
+int mdns_region_most_distant_nearest_neighbor(mdns_region *rg, double *result);
+
+/*
+ * One-shot forms with the reference's exact C signatures (cneighbors.c:32-34,
+ * 77-79, 95-98, 125-130).  They run on a process-wide region on device 0 and
+ * skip the member upload when xx is byte-identical to the previous call's.
+ * On failure they print mdns_last_error() to stderr and return NaN / -1.
+ */
+double mdns_most_distant_nearest_neighbor(const void *xx, int nsamples, int ndim);
+int    mdns_is_within_distance_of(const void *xx, int nsamples, int ndim,
+                                  double maxdistance, const void *y);
+int    mdns_count_within_distance_of(const void *xx, int nsamples, int ndim,
+                                     double maxdistance, const void *yy,
+                                     int nothers, void *out, int countmax);
+double mdns_bootstrapped_maxdistance(const void *xx, int nsamples, int ndim,
+                                     const void *chosen, int nbootstraps);
+
+/*
+ * One-shot likelihoods with the reference's exact C signatures (clike.c:34-40,
+ * cmuselike.c:34-38).  The data matrix is made resident on first sight of
+ * (pointer, shape) and re-used afterwards; a strided content fingerprint is
+ * re-checked on every call and a changed matrix is uploaded again.
+ * mdns_clike_like accumulates into Lout as clike.c:72 does.
+ */
+int mdns_clike_like(const void *x, const void *yy, int ndata, int nx, double A,
+                    double mu, double sig, double noise_level,
+                    const void *data_mask, void *Lout);
+int mdns_cmuselike_like(const void *yy, const void *vv, const void *ypred,
+                        const void *data_mask, int ndata, int nx, void *Lout);
+/* Drop every data set cached by the two functions above. */
+int mdns_legacy_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDNS_B200_H */

@@ -1,0 +1,1111 @@
+// capi.cu -- the C ABI of libmdns_b200.so (see include/mdns_b200.h): resident data sets,
+// regions, host-side orchestration.  One host thread issues all work; every shard owns a
+// stream on its device; calls are synchronous at the boundary (the caller needs the result
+// immediately: hiermetriclearn.py:193 `numpy.any(L > Lmins)`).
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "hostutil.h"
+#include "kernels.cuh"
+
+namespace mdns {
+
+static thread_local std::string g_error;
+std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	g_error = buf;
+}
+
+static int sm_count_of(int device, int *out)
+{
+	int v = 0;
+	MDNS_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+	*out = v;
+	return MDNS_OK;
+}
+
+template <typename T>
+static int grow(T **p, size_t *cap, size_t want, bool zero)
+{
+	if (want <= *cap) return MDNS_OK;
+	if (*p) MDNS_CUDA(cudaFree(*p));
+	*p = nullptr;
+	*cap = 0;
+	size_t n = want + want / 4;
+	MDNS_CUDA(cudaMalloc((void **)p, n * sizeof(T)));
+	if (zero) MDNS_CUDA(cudaMemset(*p, 0, n * sizeof(T)));
+	*cap = n;
+	return MDNS_OK;
+}
+
+struct Shard {
+	int device = 0;
+	int i0 = 0, n = 0;            // data-set range [i0, i0+n) of the full problem
+	int sm_count = 148;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	double *Y = nullptr, *W = nullptr, *x = nullptr;
+	uint8_t *d_mask = nullptr;
+	int *d_active = nullptr, *d_scratch = nullptr, *d_nact = nullptr;
+	double *d_in = nullptr;
+	size_t in_cap = 0;
+	double *d_model = nullptr;
+	size_t model_cap = 0;
+	double *d_out = nullptr;
+	size_t out_cap = 0;
+	double *h_stage = nullptr;    // pinned
+	size_t stage_cap = 0;
+	int n_act = 0;
+	bool all_active = true;
+};
+
+}  // namespace mdns
+
+using namespace mdns;
+
+struct mdns_dataset {
+	int ndata = 0, nx = 0;
+	size_t pitch = 0;             // doubles per resident row
+	bool has_var = false, has_x = false;
+	std::vector<Shard> shards;
+	int K = 0;
+	int staged = 0;               // 0 nothing, 1 params, 2 spectra
+	int launched = 0;             // 0 nothing, 1 clike, 2 muse
+	int n_act_total = 0;
+	std::vector<uint8_t> host_mask;   // copy of the last mask (muse scatter); empty = all
+	Tuning tuning;
+	int64_t resident_bytes = 0;
+};
+
+static void shard_free(Shard &s)
+{
+	cudaSetDevice(s.device);
+	if (s.stream) cudaStreamSynchronize(s.stream);
+	cudaFree(s.Y);
+	cudaFree(s.W);
+	cudaFree(s.x);
+	cudaFree(s.d_mask);
+	cudaFree(s.d_active);
+	cudaFree(s.d_scratch);
+	cudaFree(s.d_nact);
+	cudaFree(s.d_in);
+	cudaFree(s.d_model);
+	cudaFree(s.d_out);
+	if (s.h_stage) cudaFreeHost(s.h_stage);
+	if (s.ev0) cudaEventDestroy(s.ev0);
+	if (s.ev1) cudaEventDestroy(s.ev1);
+	if (s.stream) cudaStreamDestroy(s.stream);
+	s = Shard();
+}
+
+// Upload columns [i0, i0+n) of a channel-major host matrix as data-set-major rows.
+static int upload_rows(Shard &s, const double *host, int ndata, int nx, size_t pitch, int recip,
+                       double **rows_out)
+{
+	double *rows = nullptr;
+	const size_t row_bytes = (size_t)s.n * pitch * sizeof(double);
+	MDNS_CUDA(cudaMalloc((void **)&rows, row_bytes));
+	MDNS_CUDA(cudaMemsetAsync(rows, 0, row_bytes, s.stream));
+	// staging chunk: at most ~256 MB, a multiple of 32 data sets
+	size_t nb = (size_t)(256u << 20) / ((size_t)nx * sizeof(double));
+	nb = nb / 32 * 32;
+	if (nb < 32) nb = 32;
+	if (nb > (size_t)s.n) nb = round_up(s.n, 32);
+	double *staging = nullptr;
+	MDNS_CUDA(cudaMalloc((void **)&staging, nb * (size_t)nx * sizeof(double)));
+	int rc = MDNS_OK;
+	for (size_t c0 = 0; c0 < (size_t)s.n && rc == MDNS_OK; c0 += nb) {
+		const size_t cb = std::min(nb, (size_t)s.n - c0);
+		cudaError_t e = cudaMemcpy2DAsync(staging, nb * sizeof(double), host + s.i0 + c0,
+		                                  (size_t)ndata * sizeof(double), cb * sizeof(double), nx,
+		                                  cudaMemcpyHostToDevice, s.stream);
+		if (e != cudaSuccess) {
+			set_error("upload of data sets [%zu,%zu) failed: %s", s.i0 + c0, s.i0 + c0 + cb,
+			          cudaGetErrorString(e));
+			rc = MDNS_ECUDA;
+			break;
+		}
+		rc = launch_transpose_rows(staging, nb, nx, (int)cb, rows + c0 * pitch, pitch, recip,
+		                           s.stream);
+	}
+	cudaError_t e = cudaStreamSynchronize(s.stream);
+	cudaFree(staging);
+	if (rc == MDNS_OK && e != cudaSuccess) {
+		set_error("upload failed: %s", cudaGetErrorString(e));
+		rc = MDNS_ECUDA;
+	}
+	if (rc != MDNS_OK) {
+		cudaFree(rows);
+		return rc;
+	}
+	*rows_out = rows;
+	return MDNS_OK;
+}
+
+extern "C" {
+
+const char *mdns_last_error(void) { return g_error.c_str(); }
+int mdns_version(void) { return 100; }
+int64_t mdns_launch_count(void) { return g_launches.load(); }
+double mdns_sqrt_threshold(double r) { return sqrt_threshold(r); }
+
+int mdns_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+void *mdns_host_alloc(int64_t bytes)
+{
+	void *p = nullptr;
+	if (bytes <= 0) bytes = 1;
+	cudaError_t e = cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable);
+	if (e != cudaSuccess) {
+		set_error("cudaHostAlloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e));
+		return nullptr;
+	}
+	return p;
+}
+
+int mdns_host_free(void *p)
+{
+	if (!p) return MDNS_OK;
+	MDNS_CUDA(cudaFreeHost(p));
+	return MDNS_OK;
+}
+
+int mdns_dataset_create(const double *x, const double *yy, const double *vv, int ndata, int nx,
+                        const int *devices, int ndevices, mdns_dataset **out)
+{
+	if (!yy || !out || ndata <= 0 || nx <= 0) {
+		set_error("mdns_dataset_create: need yy, out, ndata > 0, nx > 0");
+		return MDNS_EINVAL;
+	}
+	const int avail = mdns_device_count();
+	if (avail <= 0) {
+		set_error("no CUDA device available (libmdns_b200 has no CPU fallback)");
+		return MDNS_ECUDA;
+	}
+	int dflt = 0;
+	if (!devices || ndevices <= 0) {
+		devices = &dflt;
+		ndevices = 1;
+	}
+	if (ndevices > ndata) ndevices = ndata;
+	for (int d = 0; d < ndevices; ++d)
+		if (devices[d] < 0 || devices[d] >= avail) {
+			set_error("device ordinal %d out of range (%d visible)", devices[d], avail);
+			return MDNS_EINVAL;
+		}
+	mdns_dataset *ds = new mdns_dataset();
+	ds->ndata = ndata;
+	ds->nx = nx;
+	ds->pitch = round_up(nx, ROW_ALIGN);
+	ds->has_var = vv != nullptr;
+	ds->has_x = x != nullptr;
+	ds->shards.resize(ndevices);
+	int rc = MDNS_OK;
+	auto fail = [&](int code) {
+		for (auto &s : ds->shards) shard_free(s);
+		delete ds;
+		return code;
+	};
+	// contiguous ranges of the data-set index, remainder spread over the first shards
+	const int base = ndata / ndevices, extra = ndata % ndevices;
+	int i0 = 0;
+	for (int d = 0; d < ndevices; ++d) {
+		Shard &s = ds->shards[d];
+		s.device = devices[d];
+		s.i0 = i0;
+		s.n = base + (d < extra ? 1 : 0);
+		i0 += s.n;
+		cudaError_t e = cudaSetDevice(s.device);
+		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+		if (e == cudaSuccess) e = cudaEventCreate(&s.ev0);
+		if (e == cudaSuccess) e = cudaEventCreate(&s.ev1);
+		if (e != cudaSuccess) {
+			set_error("device %d setup failed: %s", s.device, cudaGetErrorString(e));
+			return fail(MDNS_ECUDA);
+		}
+		if ((rc = sm_count_of(s.device, &s.sm_count)) != MDNS_OK) return fail(rc);
+		if ((rc = upload_rows(s, yy, ndata, nx, ds->pitch, 0, &s.Y)) != MDNS_OK) return fail(rc);
+		if (vv && (rc = upload_rows(s, vv, ndata, nx, ds->pitch, 1, &s.W)) != MDNS_OK)
+			return fail(rc);
+		ds->resident_bytes += (int64_t)s.n * ds->pitch * 8 * (vv ? 2 : 1);
+		const size_t mask_bytes = round_up(s.n, 16) + 16;
+		e = cudaMalloc((void **)&s.d_mask, mask_bytes);
+		if (e == cudaSuccess) e = cudaMemset(s.d_mask, 0, mask_bytes);
+		if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_active, (size_t)s.n * sizeof(int));
+		if (e == cudaSuccess)
+			e = cudaMalloc((void **)&s.d_scratch, ((size_t)ceil_div(s.n, 4096) + 1) * sizeof(int));
+		if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_nact, sizeof(int));
+		if (e == cudaSuccess && x) {
+			e = cudaMalloc((void **)&s.x, (size_t)nx * sizeof(double));
+			if (e == cudaSuccess)
+				e = cudaMemcpy(s.x, x, (size_t)nx * sizeof(double), cudaMemcpyHostToDevice);
+		}
+		if (e != cudaSuccess) {
+			set_error("device %d allocation failed: %s", s.device, cudaGetErrorString(e));
+			return fail(e == cudaErrorMemoryAllocation ? MDNS_ENOMEM : MDNS_ECUDA);
+		}
+		s.n_act = s.n;
+		s.all_active = true;
+	}
+	ds->n_act_total = ndata;
+	*out = ds;
+	return MDNS_OK;
+}
+
+int mdns_dataset_destroy(mdns_dataset *ds)
+{
+	if (!ds) return MDNS_OK;
+	for (auto &s : ds->shards) shard_free(s);
+	delete ds;
+	return MDNS_OK;
+}
+
+int mdns_dataset_info(const mdns_dataset *ds, int *ndata, int *nx, int *nshards,
+                      int64_t *resident_bytes)
+{
+	if (!ds) {
+		set_error("null data set");
+		return MDNS_EINVAL;
+	}
+	if (ndata) *ndata = ds->ndata;
+	if (nx) *nx = ds->nx;
+	if (nshards) *nshards = (int)ds->shards.size();
+	if (resident_bytes) *resident_bytes = ds->resident_bytes;
+	return MDNS_OK;
+}
+
+int mdns_set_tuning(mdns_dataset *ds, int lanes, int unroll, int ktile)
+{
+	if (!ds) {
+		set_error("null data set");
+		return MDNS_EINVAL;
+	}
+	ds->tuning.lanes = lanes;
+	ds->tuning.unroll = unroll;
+	ds->tuning.ktile = ktile;
+	return MDNS_OK;
+}
+
+int mdns_set_mask(mdns_dataset *ds, const uint8_t *mask, int *n_act_out)
+{
+	if (!ds) {
+		set_error("null data set");
+		return MDNS_EINVAL;
+	}
+	int total = 0;
+	bool all = true;
+	for (auto &s : ds->shards) {
+		if (!mask) {
+			s.all_active = true;
+			s.n_act = s.n;
+		} else {
+			const long long cnt = count_nonzero_bytes(mask + s.i0, s.n);
+			s.n_act = (int)cnt;
+			s.all_active = cnt == s.n;
+			if (!s.all_active && cnt > 0) {
+				MDNS_CUDA(cudaSetDevice(s.device));
+				MDNS_CUDA(cudaMemcpyAsync(s.d_mask, mask + s.i0, s.n, cudaMemcpyHostToDevice,
+				                          s.stream));
+				int rc = launch_compact_mask(s.d_mask, s.n, s.d_scratch, s.d_active, s.d_nact,
+				                             s.stream);
+				if (rc != MDNS_OK) return rc;
+			}
+		}
+		all = all && s.all_active;
+		total += s.n_act;
+	}
+	if (mask && !all)
+		ds->host_mask.assign(mask, mask + ds->ndata);
+	else
+		ds->host_mask.clear();
+	ds->n_act_total = total;
+	ds->launched = 0;
+	if (n_act_out) *n_act_out = total;
+	return MDNS_OK;
+}
+
+static int ensure_batch(mdns_dataset *ds, Shard &s, int K)
+{
+	const int Kpad = (int)round_up(K, KT_MAX);
+	int rc;
+	if ((rc = grow(&s.d_model, &s.model_cap, (size_t)Kpad * ds->pitch, true)) != MDNS_OK) return rc;
+	return grow(&s.d_out, &s.out_cap, (size_t)K * s.n, false);
+}
+
+int mdns_stage_params(mdns_dataset *ds, const double *params, int K)
+{
+	if (!ds || !params || K <= 0) {
+		set_error("mdns_stage_params: need ds, params, K > 0");
+		return MDNS_EINVAL;
+	}
+	if (!ds->has_x || ds->has_var) {
+		set_error("parameter points need a scalar-noise data set created with the x grid");
+		return MDNS_ESTATE;
+	}
+	for (auto &s : ds->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		int rc = ensure_batch(ds, s, K);
+		if (rc == MDNS_OK) rc = grow(&s.d_in, &s.in_cap, (size_t)K * 3, false);
+		if (rc != MDNS_OK) return rc;
+		MDNS_CUDA(cudaMemcpyAsync(s.d_in, params, (size_t)K * 3 * sizeof(double),
+		                          cudaMemcpyHostToDevice, s.stream));
+	}
+	ds->K = K;
+	ds->staged = 1;
+	ds->launched = 0;
+	return MDNS_OK;
+}
+
+int mdns_stage_spectra(mdns_dataset *ds, const double *ypred, int K)
+{
+	if (!ds || !ypred || K <= 0) {
+		set_error("mdns_stage_spectra: need ds, ypred, K > 0");
+		return MDNS_EINVAL;
+	}
+	for (auto &s : ds->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		int rc = ensure_batch(ds, s, K);
+		if (rc != MDNS_OK) return rc;
+		// rows of nx doubles land in the zero-padded [Kpad][pitch] model buffer
+		MDNS_CUDA(cudaMemcpy2DAsync(s.d_model, ds->pitch * sizeof(double), ypred,
+		                            (size_t)ds->nx * sizeof(double), (size_t)ds->nx * sizeof(double),
+		                            K, cudaMemcpyHostToDevice, s.stream));
+	}
+	ds->K = K;
+	ds->staged = 2;
+	ds->launched = 0;
+	return MDNS_OK;
+}
+
+static void fill_args(const mdns_dataset *ds, const Shard &s, LikeArgs &a)
+{
+	a.Y = s.Y;
+	a.W = s.W;
+	a.pitch = (long long)ds->pitch;
+	a.nx = ds->nx;
+	a.active = s.all_active ? nullptr : s.d_active;
+	a.n_rows = s.n_act;
+	a.model = s.d_model;
+	a.mpitch = (int)ds->pitch;
+	a.K = ds->K;
+	a.out = s.d_out;
+}
+
+int mdns_clike_launch(mdns_dataset *ds, double noise, double scale)
+{
+	if (!ds || ds->staged == 0) {
+		set_error("mdns_clike_launch: stage parameter points or spectra first");
+		return MDNS_ESTATE;
+	}
+	if (ds->has_var) {
+		set_error("data set carries per-element variances: use mdns_muse_launch");
+		return MDNS_ESTATE;
+	}
+	for (auto &s : ds->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		int rc = MDNS_OK;
+		if (ds->staged == 1) {
+			const int Kpad = (int)round_up(ds->K, KT_MAX);
+			rc = launch_line_model(s.x, ds->nx, s.d_in, ds->K, Kpad, s.d_model, (int)ds->pitch,
+			                       s.stream);
+			if (rc != MDNS_OK) return rc;
+		}
+		LikeArgs a;
+		fill_args(ds, s, a);
+		a.noise2 = noise * noise;
+		a.scale = scale;
+		a.out_stride = s.n_act;
+		if ((rc = launch_clike(a, ds->tuning, s.sm_count, s.stream)) != MDNS_OK) return rc;
+	}
+	ds->launched = 1;
+	return MDNS_OK;
+}
+
+int mdns_muse_launch(mdns_dataset *ds)
+{
+	if (!ds || ds->staged != 2) {
+		set_error("mdns_muse_launch: stage model spectra first");
+		return MDNS_ESTATE;
+	}
+	if (!ds->has_var) {
+		set_error("data set has no variances: create it with vv");
+		return MDNS_ESTATE;
+	}
+	for (auto &s : ds->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		LikeArgs a;
+		fill_args(ds, s, a);
+		a.noise2 = 1.0;
+		a.scale = 1.0;
+		a.out_stride = s.n;
+		int rc = launch_muse(a, ds->tuning, s.sm_count, s.stream);
+		if (rc != MDNS_OK) return rc;
+	}
+	ds->launched = 2;
+	return MDNS_OK;
+}
+
+int mdns_sync(mdns_dataset *ds)
+{
+	if (!ds) {
+		set_error("null data set");
+		return MDNS_EINVAL;
+	}
+	for (auto &s : ds->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		MDNS_CUDA(cudaStreamSynchronize(s.stream));
+	}
+	return MDNS_OK;
+}
+
+int mdns_fetch(mdns_dataset *ds, double *Lout, int64_t lout_capacity)
+{
+	if (!ds || !Lout) {
+		set_error("mdns_fetch: need ds and Lout");
+		return MDNS_EINVAL;
+	}
+	if (ds->launched == 0) {
+		set_error("mdns_fetch: nothing launched since the last stage/set_mask");
+		return MDNS_ESTATE;
+	}
+	const int K = ds->K;
+	const bool single = ds->shards.size() == 1;
+	if (ds->launched == 1) {
+		const long long need = (long long)K * ds->n_act_total;
+		if (lout_capacity < need) {
+			set_error("Lout holds %lld doubles, %lld needed (K=%d, n_act=%d)",
+			          (long long)lout_capacity, need, K, ds->n_act_total);
+			return MDNS_EINVAL;
+		}
+		long long off = 0;
+		for (auto &s : ds->shards) {
+			MDNS_CUDA(cudaSetDevice(s.device));
+			if (s.n_act > 0) {
+				if (single)
+					MDNS_CUDA(cudaMemcpyAsync(Lout, s.d_out, (size_t)K * s.n_act * sizeof(double),
+					                          cudaMemcpyDeviceToHost, s.stream));
+				else
+					MDNS_CUDA(cudaMemcpy2DAsync(Lout + off, (size_t)ds->n_act_total * sizeof(double),
+					                            s.d_out, (size_t)s.n_act * sizeof(double),
+					                            (size_t)s.n_act * sizeof(double), K,
+					                            cudaMemcpyDeviceToHost, s.stream));
+			}
+			off += s.n_act;
+		}
+		return mdns_sync(ds);
+	}
+	// muse: un-compacted [K][ndata]; only active entries are written (cmuselike.c:49,62)
+	const long long need = (long long)K * ds->ndata;
+	if (lout_capacity < need) {
+		set_error("Lout holds %lld doubles, %lld needed (K=%d, ndata=%d)", (long long)lout_capacity,
+		          need, K, ds->ndata);
+		return MDNS_EINVAL;
+	}
+	for (auto &s : ds->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		if (s.n_act == 0) continue;
+		if (s.all_active) {
+			MDNS_CUDA(cudaMemcpy2DAsync(Lout + s.i0, (size_t)ds->ndata * sizeof(double), s.d_out,
+			                            (size_t)s.n * sizeof(double), (size_t)s.n * sizeof(double), K,
+			                            cudaMemcpyDeviceToHost, s.stream));
+		} else {
+			const size_t want = (size_t)K * s.n;
+			if (want > s.stage_cap) {
+				if (s.h_stage) MDNS_CUDA(cudaFreeHost(s.h_stage));
+				s.h_stage = nullptr;
+				s.stage_cap = 0;
+				MDNS_CUDA(cudaHostAlloc((void **)&s.h_stage, want * sizeof(double),
+				                        cudaHostAllocPortable));
+				s.stage_cap = want;
+			}
+			MDNS_CUDA(cudaMemcpyAsync(s.h_stage, s.d_out, want * sizeof(double),
+			                          cudaMemcpyDeviceToHost, s.stream));
+		}
+	}
+	int rc = mdns_sync(ds);
+	if (rc != MDNS_OK) return rc;
+	for (auto &s : ds->shards) {
+		if (s.all_active || s.n_act == 0) continue;
+		const uint8_t *m = ds->host_mask.data() + s.i0;
+		for (int k = 0; k < K; ++k) {
+			const double *src = s.h_stage + (size_t)k * s.n;
+			double *dst = Lout + (size_t)k * ds->ndata + s.i0;
+			for (int i = 0; i < s.n; ++i)
+				if (m[i]) dst[i] = src[i];
+		}
+	}
+	return MDNS_OK;
+}
+
+int mdns_timer_start(mdns_dataset *ds)
+{
+	if (!ds) {
+		set_error("null data set");
+		return MDNS_EINVAL;
+	}
+	for (auto &s : ds->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		MDNS_CUDA(cudaEventRecord(s.ev0, s.stream));
+	}
+	return MDNS_OK;
+}
+
+int mdns_timer_stop(mdns_dataset *ds, float *elapsed_ms)
+{
+	if (!ds || !elapsed_ms) {
+		set_error("mdns_timer_stop: need ds and elapsed_ms");
+		return MDNS_EINVAL;
+	}
+	for (auto &s : ds->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		MDNS_CUDA(cudaEventRecord(s.ev1, s.stream));
+	}
+	float worst = 0.f;
+	for (auto &s : ds->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		MDNS_CUDA(cudaEventSynchronize(s.ev1));
+		float ms = 0.f;
+		MDNS_CUDA(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+		worst = ms > worst ? ms : worst;
+	}
+	*elapsed_ms = worst;
+	return MDNS_OK;
+}
+
+static int eval_common(mdns_dataset *ds, int K, const uint8_t *mask, int *n_act_out,
+                       int64_t lout_capacity, bool compacted)
+{
+	int n_act = 0;
+	int rc = mdns_set_mask(ds, mask, &n_act);
+	if (rc != MDNS_OK) return rc;
+	if (n_act_out) *n_act_out = n_act;
+	const long long need = compacted ? (long long)K * n_act : (long long)K * ds->ndata;
+	if (lout_capacity < need) {
+		set_error("Lout holds %lld doubles, %lld needed", (long long)lout_capacity, need);
+		return MDNS_EINVAL;
+	}
+	return MDNS_OK;
+}
+
+int mdns_clike_eval_params(mdns_dataset *ds, const double *params, int K, double noise,
+                           double scale, const uint8_t *mask, double *Lout, int64_t lout_capacity,
+                           int *n_act_out)
+{
+	if (!ds || !Lout) {
+		set_error("mdns_clike_eval_params: need ds and Lout");
+		return MDNS_EINVAL;
+	}
+	int rc = mdns_stage_params(ds, params, K);
+	if (rc == MDNS_OK) rc = eval_common(ds, K, mask, n_act_out, lout_capacity, true);
+	if (rc == MDNS_OK) rc = mdns_clike_launch(ds, noise, scale);
+	if (rc == MDNS_OK) rc = mdns_fetch(ds, Lout, lout_capacity);
+	return rc;
+}
+
+int mdns_clike_eval_spectra(mdns_dataset *ds, const double *ypred, int K, double noise,
+                            double scale, const uint8_t *mask, double *Lout, int64_t lout_capacity,
+                            int *n_act_out)
+{
+	if (!ds || !Lout) {
+		set_error("mdns_clike_eval_spectra: need ds and Lout");
+		return MDNS_EINVAL;
+	}
+	int rc = mdns_stage_spectra(ds, ypred, K);
+	if (rc == MDNS_OK) rc = eval_common(ds, K, mask, n_act_out, lout_capacity, true);
+	if (rc == MDNS_OK) rc = mdns_clike_launch(ds, noise, scale);
+	if (rc == MDNS_OK) rc = mdns_fetch(ds, Lout, lout_capacity);
+	return rc;
+}
+
+int mdns_muse_eval_spectra(mdns_dataset *ds, const double *ypred, int K, const uint8_t *mask,
+                           double *Lout)
+{
+	if (!ds || !Lout) {
+		set_error("mdns_muse_eval_spectra: need ds and Lout");
+		return MDNS_EINVAL;
+	}
+	int rc = mdns_stage_spectra(ds, ypred, K);
+	if (rc == MDNS_OK) rc = mdns_set_mask(ds, mask, nullptr);
+	if (rc == MDNS_OK) rc = mdns_muse_launch(ds);
+	if (rc == MDNS_OK) rc = mdns_fetch(ds, Lout, (int64_t)K * ds->ndata);
+	return rc;
+}
+
+}  // extern "C"
+
+// ============================================================== regions ====
+struct mdns_region {
+	int device = 0;
+	int sm_count = 148;
+	cudaStream_t stream = nullptr;
+	int n = 0, ndim = 0, npad = 0;
+	double *d_xs = nullptr;
+	size_t xs_cap = 0;
+	std::vector<double> host_xx;      // last uploaded members (row-major), for change detection
+	std::vector<double> soa;
+	double *d_yy = nullptr;
+	size_t yy_cap = 0;
+	int *d_counts = nullptr;
+	size_t counts_cap = 0;
+	int *h_counts = nullptr;          // pinned
+	size_t h_counts_cap = 0;
+	double *d_chosen = nullptr;
+	size_t chosen_cap = 0;
+	int *d_qidx = nullptr, *d_ridx = nullptr;
+	size_t q_cap = 0, r_cap = 0;
+	unsigned long long *d_nearest = nullptr;
+	size_t nearest_cap = 0;
+	int *d_rcounts = nullptr;
+	size_t rcounts_cap = 0;
+	double *d_result = nullptr;       // 1 double
+	int *d_flag = nullptr;            // 1 int
+};
+
+extern "C" {
+
+int mdns_region_create(int device, mdns_region **out)
+{
+	if (!out) {
+		set_error("mdns_region_create: out is null");
+		return MDNS_EINVAL;
+	}
+	const int avail = mdns_device_count();
+	if (avail <= 0) {
+		set_error("no CUDA device available (libmdns_b200 has no CPU fallback)");
+		return MDNS_ECUDA;
+	}
+	if (device < 0 || device >= avail) {
+		set_error("device ordinal %d out of range (%d visible)", device, avail);
+		return MDNS_EINVAL;
+	}
+	mdns_region *rg = new mdns_region();
+	rg->device = device;
+	cudaError_t e = cudaSetDevice(device);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&rg->stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaMalloc((void **)&rg->d_result, sizeof(double));
+	if (e == cudaSuccess) e = cudaMalloc((void **)&rg->d_flag, sizeof(int));
+	if (e != cudaSuccess) {
+		set_error("region setup on device %d failed: %s", device, cudaGetErrorString(e));
+		mdns_region_destroy(rg);
+		return MDNS_ECUDA;
+	}
+	int rc = sm_count_of(device, &rg->sm_count);
+	if (rc != MDNS_OK) {
+		mdns_region_destroy(rg);
+		return rc;
+	}
+	*out = rg;
+	return MDNS_OK;
+}
+
+int mdns_region_destroy(mdns_region *rg)
+{
+	if (!rg) return MDNS_OK;
+	cudaSetDevice(rg->device);
+	if (rg->stream) cudaStreamSynchronize(rg->stream);
+	cudaFree(rg->d_xs);
+	cudaFree(rg->d_yy);
+	cudaFree(rg->d_counts);
+	if (rg->h_counts) cudaFreeHost(rg->h_counts);
+	cudaFree(rg->d_chosen);
+	cudaFree(rg->d_qidx);
+	cudaFree(rg->d_ridx);
+	cudaFree(rg->d_nearest);
+	cudaFree(rg->d_rcounts);
+	cudaFree(rg->d_result);
+	cudaFree(rg->d_flag);
+	if (rg->stream) cudaStreamDestroy(rg->stream);
+	delete rg;
+	return MDNS_OK;
+}
+
+int mdns_region_set_members(mdns_region *rg, const double *xx, int n, int ndim)
+{
+	if (!rg || !xx || n < 0 || ndim <= 0) {
+		set_error("mdns_region_set_members: need rg, xx, n >= 0, ndim > 0");
+		return MDNS_EINVAL;
+	}
+	MDNS_CUDA(cudaSetDevice(rg->device));
+	const int npad = (int)round_up(n > 0 ? n : 1, 32);
+	rg->soa.assign((size_t)ndim * npad, 0.0);
+	for (int i = 0; i < n; ++i)
+		for (int k = 0; k < ndim; ++k) rg->soa[(size_t)k * npad + i] = xx[(size_t)i * ndim + k];
+	int rc = grow(&rg->d_xs, &rg->xs_cap, rg->soa.size(), false);
+	if (rc != MDNS_OK) return rc;
+	MDNS_CUDA(cudaMemcpyAsync(rg->d_xs, rg->soa.data(), rg->soa.size() * sizeof(double),
+	                          cudaMemcpyHostToDevice, rg->stream));
+	MDNS_CUDA(cudaStreamSynchronize(rg->stream));   // soa may be rewritten by the next call
+	rg->n = n;
+	rg->ndim = ndim;
+	rg->npad = npad;
+	rg->host_xx.assign(xx, xx + (size_t)n * ndim);
+	return MDNS_OK;
+}
+
+int mdns_region_count_within(mdns_region *rg, double maxdistance, const double *yy, int m,
+                             double *out, int countmax)
+{
+	if (!rg || !yy || !out || m < 0) {
+		set_error("mdns_region_count_within: need rg, yy, out, m >= 0");
+		return MDNS_EINVAL;
+	}
+	if (rg->ndim == 0) {
+		set_error("region has no members: call mdns_region_set_members first");
+		return MDNS_ESTATE;
+	}
+	if (m == 0 || rg->n == 0) return MDNS_OK;
+	MDNS_CUDA(cudaSetDevice(rg->device));
+	int rc = grow(&rg->d_yy, &rg->yy_cap, (size_t)m * rg->ndim, false);
+	if (rc == MDNS_OK) rc = grow(&rg->d_counts, &rg->counts_cap, (size_t)m, false);
+	if (rc != MDNS_OK) return rc;
+	if ((size_t)m > rg->h_counts_cap) {
+		if (rg->h_counts) MDNS_CUDA(cudaFreeHost(rg->h_counts));
+		rg->h_counts = nullptr;
+		rg->h_counts_cap = 0;
+		const size_t cap = (size_t)m + m / 4;
+		MDNS_CUDA(cudaHostAlloc((void **)&rg->h_counts, cap * sizeof(int), cudaHostAllocPortable));
+		rg->h_counts_cap = cap;
+	}
+	// The device may stop scanning a candidate once `countmax` hits are seen only if every
+	// out[j] starts at zero (then out[j] >= countmax <=> hits >= countmax, cneighbors.c:112).
+	bool zero_start = true;
+	for (int j = 0; j < m && zero_start; ++j) zero_start = out[j] == 0.0;
+	const int stop_at = (countmax > 0 && zero_start) ? countmax : 0;
+	MDNS_CUDA(cudaMemcpyAsync(rg->d_yy, yy, (size_t)m * rg->ndim * sizeof(double),
+	                          cudaMemcpyHostToDevice, rg->stream));
+	rc = launch_count_within(rg->d_xs, rg->n, rg->npad, rg->ndim, rg->d_yy, m,
+	                         sqrt_threshold(maxdistance), stop_at, rg->d_counts, rg->sm_count,
+	                         rg->stream);
+	if (rc != MDNS_OK) return rc;
+	MDNS_CUDA(cudaMemcpyAsync(rg->h_counts, rg->d_counts, (size_t)m * sizeof(int),
+	                          cudaMemcpyDeviceToHost, rg->stream));
+	MDNS_CUDA(cudaStreamSynchronize(rg->stream));
+	// replay the reference's per-hit update of out[j] (cneighbors.c:110-114)
+	for (int j = 0; j < m; ++j) {
+		const int hits = rg->h_counts[j];
+		if (zero_start) {
+			out[j] = (double)((countmax > 0 && hits > countmax) ? countmax : hits);
+		} else {
+			for (int h = 0; h < hits; ++h) {
+				out[j] += 1.0;
+				if (countmax > 0 && out[j] >= countmax) break;
+			}
+		}
+	}
+	return MDNS_OK;
+}
+
+int mdns_region_is_within(mdns_region *rg, double maxdistance, const double *y, int *result)
+{
+	if (!rg || !y || !result) {
+		set_error("mdns_region_is_within: need rg, y, result");
+		return MDNS_EINVAL;
+	}
+	if (rg->ndim == 0) {
+		set_error("region has no members: call mdns_region_set_members first");
+		return MDNS_ESTATE;
+	}
+	*result = 0;
+	if (rg->n == 0) return MDNS_OK;
+	MDNS_CUDA(cudaSetDevice(rg->device));
+	int rc = grow(&rg->d_yy, &rg->yy_cap, (size_t)rg->ndim, false);
+	if (rc != MDNS_OK) return rc;
+	MDNS_CUDA(cudaMemcpyAsync(rg->d_yy, y, (size_t)rg->ndim * sizeof(double),
+	                          cudaMemcpyHostToDevice, rg->stream));
+	MDNS_CUDA(cudaMemsetAsync(rg->d_flag, 0, sizeof(int), rg->stream));
+	rc = launch_within_single(rg->d_xs, rg->n, rg->npad, rg->ndim, rg->d_yy,
+	                          sqrt_threshold(maxdistance), rg->d_flag, rg->stream);
+	if (rc != MDNS_OK) return rc;
+	int flag = 0;
+	MDNS_CUDA(cudaMemcpyAsync(&flag, rg->d_flag, sizeof(int), cudaMemcpyDeviceToHost, rg->stream));
+	MDNS_CUDA(cudaStreamSynchronize(rg->stream));
+	*result = flag ? 1 : 0;
+	return MDNS_OK;
+}
+
+static int nn_buffers(mdns_region *rg, int nrounds)
+{
+	const size_t cells = (size_t)nrounds * (rg->n > 0 ? rg->n : 1);
+	int rc = grow(&rg->d_qidx, &rg->q_cap, cells, false);
+	if (rc == MDNS_OK) rc = grow(&rg->d_ridx, &rg->r_cap, cells, false);
+	if (rc == MDNS_OK) rc = grow(&rg->d_nearest, &rg->nearest_cap, cells, false);
+	if (rc == MDNS_OK) rc = grow(&rg->d_rcounts, &rg->rcounts_cap, (size_t)2 * nrounds, false);
+	return rc;
+}
+
+static int nn_result(mdns_region *rg, int nrounds, int exclude_self, int skip_first, double *result)
+{
+	int rc = launch_nn_min(rg->d_xs, rg->n, rg->npad, rg->ndim, rg->d_qidx, rg->d_ridx,
+	                       rg->d_rcounts, nrounds, exclude_self, rg->d_nearest, rg->sm_count,
+	                       rg->stream);
+	if (rc == MDNS_OK)
+		rc = launch_nn_finalize(rg->d_qidx, rg->d_rcounts, rg->n, nrounds, skip_first,
+		                        rg->d_nearest, rg->d_result, rg->stream);
+	if (rc != MDNS_OK) return rc;
+	double maxd = 0.0;
+	MDNS_CUDA(cudaMemcpyAsync(&maxd, rg->d_result, sizeof(double), cudaMemcpyDeviceToHost,
+	                          rg->stream));
+	MDNS_CUDA(cudaStreamSynchronize(rg->stream));
+	// max_i sqrt(nearest_i) == sqrt(max_i nearest_i): sqrt is monotone and correctly rounded
+	*result = std::sqrt(maxd);
+	return MDNS_OK;
+}
+
+int mdns_region_bootstrapped_maxdistance(mdns_region *rg, const double *chosen, int nboot,
+                                         double *result)
+{
+	if (!rg || !chosen || !result || nboot <= 0) {
+		set_error("mdns_region_bootstrapped_maxdistance: need rg, chosen, result, nboot > 0");
+		return MDNS_EINVAL;
+	}
+	if (rg->ndim == 0) {
+		set_error("region has no members: call mdns_region_set_members first");
+		return MDNS_ESTATE;
+	}
+	if (rg->n == 0) {
+		*result = 0.0;   // cneighbors.c:142,172: every round yields 0
+		return MDNS_OK;
+	}
+	MDNS_CUDA(cudaSetDevice(rg->device));
+	int rc = nn_buffers(rg, nboot);
+	if (rc == MDNS_OK) rc = grow(&rg->d_chosen, &rg->chosen_cap, (size_t)rg->n * nboot, false);
+	if (rc != MDNS_OK) return rc;
+	MDNS_CUDA(cudaMemcpyAsync(rg->d_chosen, chosen, (size_t)rg->n * nboot * sizeof(double),
+	                          cudaMemcpyHostToDevice, rg->stream));
+	rc = launch_bootstrap_lists(rg->d_chosen, rg->n, nboot, rg->d_qidx, rg->d_ridx, rg->d_rcounts,
+	                            rg->d_nearest, rg->stream);
+	if (rc != MDNS_OK) return rc;
+	return nn_result(rg, nboot, 0, 1, result);
+}
+
+int mdns_region_most_distant_nearest_neighbor(mdns_region *rg, double *result)
+{
+	if (!rg || !result) {
+		set_error("mdns_region_most_distant_nearest_neighbor: need rg and result");
+		return MDNS_EINVAL;
+	}
+	if (rg->ndim == 0 || rg->n <= 0) {
+		set_error("region has no members (cneighbors.c:66 reads nearest_ds[0])");
+		return MDNS_ESTATE;
+	}
+	MDNS_CUDA(cudaSetDevice(rg->device));
+	int rc = nn_buffers(rg, 1);
+	if (rc == MDNS_OK)
+		rc = launch_all_pairs_lists(rg->n, rg->d_qidx, rg->d_ridx, rg->d_rcounts, rg->d_nearest,
+		                            rg->stream);
+	if (rc != MDNS_OK) return rc;
+	return nn_result(rg, 1, 1, 0, result);
+}
+
+}  // extern "C"
+
+// ================================================== legacy one-shot forms ====
+namespace {
+
+std::mutex g_legacy_mutex;
+mdns_region *g_region = nullptr;
+
+int legacy_region(const double *xx, int n, int ndim, mdns_region **out)
+{
+	if (!g_region) {
+		int rc = mdns_region_create(0, &g_region);
+		if (rc != MDNS_OK) return rc;
+	}
+	mdns_region *rg = g_region;
+	const size_t cells = (size_t)n * ndim;
+	const bool same = rg->n == n && rg->ndim == ndim && rg->host_xx.size() == cells &&
+	                  (cells == 0 || std::memcmp(rg->host_xx.data(), xx, cells * sizeof(double)) == 0);
+	if (!same) {
+		int rc = mdns_region_set_members(rg, xx, n, ndim);
+		if (rc != MDNS_OK) return rc;
+	}
+	*out = rg;
+	return MDNS_OK;
+}
+
+struct LegacyKey {
+	const void *yy, *vv;
+	int ndata, nx;
+	bool operator<(const LegacyKey &o) const
+	{
+		if (yy != o.yy) return yy < o.yy;
+		if (vv != o.vv) return vv < o.vv;
+		if (ndata != o.ndata) return ndata < o.ndata;
+		return nx < o.nx;
+	}
+};
+struct LegacyEntry {
+	mdns_dataset *ds = nullptr;
+	uint64_t fp_y = 0, fp_v = 0, fp_x = 0;
+};
+std::map<LegacyKey, LegacyEntry> g_legacy;
+
+void complain(const char *what)
+{
+	fprintf(stderr, "libmdns_b200: %s failed: %s\n", what, mdns_last_error());
+}
+
+int legacy_dataset(const double *x, const double *yy, const double *vv, int ndata, int nx,
+                   mdns_dataset **out)
+{
+	const LegacyKey key{yy, vv, ndata, nx};
+	const long long cells = (long long)ndata * nx;
+	const uint64_t fy = fingerprint(yy, cells);
+	const uint64_t fv = vv ? fingerprint(vv, cells) : 0;
+	const uint64_t fx = x ? fingerprint(x, nx) : 0;
+	auto it = g_legacy.find(key);
+	if (it != g_legacy.end() &&
+	    (it->second.fp_y != fy || it->second.fp_v != fv || it->second.fp_x != fx)) {
+		mdns_dataset_destroy(it->second.ds);   // same address, new content
+		g_legacy.erase(it);
+		it = g_legacy.end();
+	}
+	if (it == g_legacy.end()) {
+		LegacyEntry e;
+		int rc = mdns_dataset_create(x, yy, vv, ndata, nx, nullptr, 0, &e.ds);
+		if (rc != MDNS_OK) return rc;
+		e.fp_y = fy;
+		e.fp_v = fv;
+		e.fp_x = fx;
+		it = g_legacy.emplace(key, e).first;
+	}
+	*out = it->second.ds;
+	return MDNS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+double mdns_most_distant_nearest_neighbor(const void *xx, int nsamples, int ndim)
+{
+	std::lock_guard<std::mutex> lock(g_legacy_mutex);
+	mdns_region *rg;
+	double r = NAN;
+	int rc = legacy_region((const double *)xx, nsamples, ndim, &rg);
+	if (rc == MDNS_OK) rc = mdns_region_most_distant_nearest_neighbor(rg, &r);
+	if (rc != MDNS_OK) {
+		complain("most_distant_nearest_neighbor");
+		return NAN;
+	}
+	return r;
+}
+
+int mdns_is_within_distance_of(const void *xx, int nsamples, int ndim, double maxdistance,
+                               const void *y)
+{
+	std::lock_guard<std::mutex> lock(g_legacy_mutex);
+	mdns_region *rg;
+	int res = 0;
+	int rc = legacy_region((const double *)xx, nsamples, ndim, &rg);
+	if (rc == MDNS_OK) rc = mdns_region_is_within(rg, maxdistance, (const double *)y, &res);
+	if (rc != MDNS_OK) {
+		complain("is_within_distance_of");
+		return -1;
+	}
+	return res;
+}
+
+int mdns_count_within_distance_of(const void *xx, int nsamples, int ndim, double maxdistance,
+                                  const void *yy, int nothers, void *out, int countmax)
+{
+	std::lock_guard<std::mutex> lock(g_legacy_mutex);
+	mdns_region *rg;
+	int rc = legacy_region((const double *)xx, nsamples, ndim, &rg);
+	if (rc == MDNS_OK)
+		rc = mdns_region_count_within(rg, maxdistance, (const double *)yy, nothers, (double *)out,
+		                              countmax);
+	if (rc != MDNS_OK) {
+		complain("count_within_distance_of");
+		return -1;
+	}
+	return 0;
+}
+
+double mdns_bootstrapped_maxdistance(const void *xx, int nsamples, int ndim, const void *chosen,
+                                     int nbootstraps)
+{
+	std::lock_guard<std::mutex> lock(g_legacy_mutex);
+	mdns_region *rg;
+	double r = NAN;
+	int rc = legacy_region((const double *)xx, nsamples, ndim, &rg);
+	if (rc == MDNS_OK)
+		rc = mdns_region_bootstrapped_maxdistance(rg, (const double *)chosen, nbootstraps, &r);
+	if (rc != MDNS_OK) {
+		complain("bootstrapped_maxdistance");
+		return NAN;
+	}
+	return r;
+}
+
+int mdns_clike_like(const void *x, const void *yy, int ndata, int nx, double A, double mu,
+                    double sig, double noise_level, const void *data_mask, void *Lout)
+{
+	std::lock_guard<std::mutex> lock(g_legacy_mutex);
+	mdns_dataset *ds;
+	int rc = legacy_dataset((const double *)x, (const double *)yy, nullptr, ndata, nx, &ds);
+	if (rc != MDNS_OK) {
+		complain("like (clike)");
+		return rc;
+	}
+	const double params[3] = {A, mu, sig};
+	int n_act = 0;
+	rc = mdns_stage_params(ds, params, 1);
+	if (rc == MDNS_OK) rc = mdns_set_mask(ds, (const uint8_t *)data_mask, &n_act);
+	std::vector<double> tmp((size_t)(n_act > 0 ? n_act : 1));
+	if (rc == MDNS_OK && n_act > 0) {
+		rc = mdns_clike_launch(ds, noise_level, 1.0);
+		if (rc == MDNS_OK) rc = mdns_fetch(ds, tmp.data(), n_act);
+	}
+	if (rc != MDNS_OK) {
+		complain("like (clike)");
+		return rc;
+	}
+	double *L = (double *)Lout;
+	for (int k = 0; k < n_act; ++k) L[k] += tmp[k];   // clike.c:72 accumulates
+	return 0;
+}
+
+int mdns_cmuselike_like(const void *yy, const void *vv, const void *ypred, const void *data_mask,
+                        int ndata, int nx, void *Lout)
+{
+	std::lock_guard<std::mutex> lock(g_legacy_mutex);
+	mdns_dataset *ds;
+	int rc = legacy_dataset(nullptr, (const double *)yy, (const double *)vv, ndata, nx, &ds);
+	if (rc == MDNS_OK)
+		rc = mdns_muse_eval_spectra(ds, (const double *)ypred, 1, (const uint8_t *)data_mask,
+		                            (double *)Lout);
+	if (rc != MDNS_OK) complain("like (cmuselike)");
+	return rc;
+}
+
+int mdns_legacy_reset(void)
+{
+	std::lock_guard<std::mutex> lock(g_legacy_mutex);
+	for (auto &kv : g_legacy) mdns_dataset_destroy(kv.second.ds);
+	g_legacy.clear();
+	if (g_region) mdns_region_destroy(g_region);
+	g_region = nullptr;
+	return MDNS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+// kernels.cuh -- host-callable launchers of the sm_100a kernels (internal).
+#pragma once
+#include "common.cuh"
+
+namespace mdns {
+
+// ---------------------------------------------------------------- layout ---
+// Resident layout ("data-set-major rows"): data set i of a shard owns the row
+//   Y[i*pitch .. i*pitch + nx)   (doubles), pitch = round_up(nx, 16)
+// i.e. every row starts on a 128-byte boundary and is padded with zeros.
+// The host matrix is channel-major (clike.c:72: yy[i + j*ndata]); it is
+// transposed once at upload.  Model spectra use the same pitch and padding.
+constexpr int ROW_ALIGN = 16;   // doubles (128 bytes)
+constexpr int KT_MAX = 8;       // candidates per pass kept in registers
+
+// in: channel-major chunk in[j*ld_in + c], j < nx, c < nb  (device staging)
+// out: rows out[c*pitch + j]; recip != 0 stores 1/v (inverse variance)
+int launch_transpose_rows(const double *in, size_t ld_in, int nx, int nb, double *out,
+                          size_t pitch, int recip, cudaStream_t st);
+
+// clike.c:65 -- model[k*mpitch + j] = A_k*exp(-0.5*((mu_k - x_j)/sig_k)^2); zero padding
+// for j >= nx and for k in [K, Kpad).
+int launch_line_model(const double *x, int nx, const double *params, int K, int Kpad,
+                      double *model, int mpitch, cudaStream_t st);
+// zero-pad host-provided spectra: src[K][nx] -> model[Kpad][mpitch]
+int launch_pad_spectra(const double *src, int nx, int K, int Kpad, double *model, int mpitch,
+                       cudaStream_t st);
+
+// mask bytes -> ordered list of active row indices (stable compaction; the rank
+// of i in the mask is the output slot k of clike.c:67-74).
+// scratch must hold ceil(n/4096)+1 ints.
+int launch_compact_mask(const uint8_t *mask, int n, int *scratch, int *active, int *n_active_dev,
+                        cudaStream_t st);
+
+struct LikeArgs {
+	const double *Y;      // rows
+	const double *W;      // inverse-variance rows (muse) or nullptr
+	long long pitch;      // doubles
+	int nx;
+	const int *active;    // nullptr = identity
+	int n_rows;           // number of active rows
+	const double *model;  // [Kpad][mpitch]
+	int mpitch;
+	int K;
+	double noise2;        // noise^2 (clike)
+	double scale;         // clike: multiplies the chi-square sum
+	double *out;          // clike: [K][out_stride] compacted; muse: [K][out_stride] by row index
+	long long out_stride;
+};
+
+struct Tuning {
+	int lanes = 0;   // lanes per data set: 8 or 32 (0 = auto)
+	int unroll = 0;  // 128-bit fragments in flight per lane (0 = auto)
+	int ktile = 0;   // candidates per pass (0 = auto)
+};
+
+int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t st);
+int launch_muse(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t st);
+
+// ------------------------------------------------------------ neighbours ---
+// members in SoA layout xs[k*npad + i]
+int launch_count_within(const double *xs, int n, int npad, int ndim, const double *yy, int m,
+                        double T, int stop_at, int *counts, int sm_count, cudaStream_t st);
+int launch_within_single(const double *xs, int n, int npad, int ndim, const double *y, double T,
+                         int *flag, cudaStream_t st);
+// chosen[n][nboot] doubles -> per round: query list (un-chosen i) and reference list (chosen j).
+// lists: qidx[b*n + p], ridx[b*n + p]; counts[b] (queries), counts[nboot + b] (references);
+// nearest[b*n + p] is initialised to the bit pattern of 1e300 (cneighbors.c:148).
+int launch_bootstrap_lists(const double *chosen, int n, int nboot, int *qidx, int *ridx,
+                           int *counts, unsigned long long *nearest, cudaStream_t st);
+// mode 1: one round, every sample queries every other sample (cneighbors.c:50-64).
+int launch_all_pairs_lists(int n, int *qidx, int *ridx, int *counts, unsigned long long *nearest,
+                           cudaStream_t st);
+int launch_nn_min(const double *xs, int n, int npad, int ndim, const int *qidx, const int *ridx,
+                  const int *counts, int nrounds, int exclude_self, unsigned long long *nearest,
+                  int sm_count, cudaStream_t st);
+// max over rounds and queries of nearest (skip_first: ignore original sample 0, cneighbors.c:162)
+int launch_nn_finalize(const int *qidx, const int *counts, int n, int nrounds, int skip_first,
+                       const unsigned long long *nearest, double *result, cudaStream_t st);
+
+}  // namespace mdns

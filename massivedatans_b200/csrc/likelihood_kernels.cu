@@ -1,0 +1,541 @@
+// likelihood_kernels.cu -- batched Gaussian chi-square likelihood kernels (sm_100a).
+//
+// Reference behaviour being replaced: clike.c:64-76 (scalar noise, compacted output) and
+// cmuselike.c:48-64 (per-element variance, free amplitude).  Design:
+//   * data-set-major resident rows -> every active data set is a contiguous, 128-byte
+//     aligned run in HBM whatever the mask looks like;
+//   * L lanes of a warp (8 or 32) share one data set: 128-bit coalesced streaming loads,
+//     FP64 accumulation, butterfly warp-shuffle reduction per data set;
+//   * the K model spectra of the current candidate batch are staged into shared memory
+//     with one bulk-TMA copy (cp.async.bulk + mbarrier) per CTA;
+//   * stable mask compaction (prefix sum) gives the output slot k of clike.c:67-74.
+#include "kernels.cuh"
+
+namespace mdns {
+
+// ------------------------------------------------------------------ upload ---
+__global__ void __launch_bounds__(256) transpose_rows_kernel(const double *__restrict__ in,
+                                                             size_t ld_in, int nx, int nb,
+                                                             double *__restrict__ out,
+                                                             size_t pitch, int recip)
+{
+	__shared__ double tile[32][33];
+	const int c0 = blockIdx.x * 32;  // data sets
+	const int j0 = blockIdx.y * 32;  // channels
+	for (int dy = threadIdx.y; dy < 32; dy += 8) {
+		const int j = j0 + dy, c = c0 + threadIdx.x;
+		double v = 0.0;
+		if (j < nx && c < nb) {
+			v = in[(size_t)j * ld_in + c];
+			if (recip) v = __ddiv_rn(1.0, v);
+		}
+		tile[dy][threadIdx.x] = v;
+	}
+	__syncthreads();
+	for (int dy = threadIdx.y; dy < 32; dy += 8) {
+		const int c = c0 + dy, j = j0 + threadIdx.x;
+		if (c < nb && j < nx) out[(size_t)c * pitch + j] = tile[threadIdx.x][dy];
+	}
+}
+
+int launch_transpose_rows(const double *in, size_t ld_in, int nx, int nb, double *out,
+                          size_t pitch, int recip, cudaStream_t st)
+{
+	dim3 grid(ceil_div(nb, 32), ceil_div(nx, 32));
+	transpose_rows_kernel<<<grid, dim3(32, 8), 0, st>>>(in, ld_in, nx, nb, out, pitch, recip);
+	MDNS_LAUNCHED("transpose_rows_kernel");
+	return MDNS_OK;
+}
+
+// ------------------------------------------------------------ model batch ---
+__global__ void line_model_kernel(const double *__restrict__ x, int nx,
+                                  const double *__restrict__ params, int K, int Kpad,
+                                  double *__restrict__ model, int mpitch)
+{
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	const int k = blockIdx.y;
+	if (j >= mpitch || k >= Kpad) return;
+	double v = 0.0;
+	if (k < K && j < nx) {
+		const double A = params[3 * k], mu = params[3 * k + 1], sig = params[3 * k + 2];
+		// clike.c:65, un-fused like the reference build
+		const double t = __ddiv_rn(__dsub_rn(mu, x[j]), sig);
+		v = __dmul_rn(A, exp(__dmul_rn(-0.5, __dmul_rn(t, t))));
+	}
+	model[(size_t)k * mpitch + j] = v;
+}
+
+int launch_line_model(const double *x, int nx, const double *params, int K, int Kpad,
+                      double *model, int mpitch, cudaStream_t st)
+{
+	dim3 grid(ceil_div(mpitch, 128), Kpad);
+	line_model_kernel<<<grid, 128, 0, st>>>(x, nx, params, K, Kpad, model, mpitch);
+	MDNS_LAUNCHED("line_model_kernel");
+	return MDNS_OK;
+}
+
+__global__ void pad_spectra_kernel(const double *__restrict__ src, int nx, int K, int Kpad,
+                                   double *__restrict__ model, int mpitch)
+{
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	const int k = blockIdx.y;
+	if (j >= mpitch || k >= Kpad) return;
+	model[(size_t)k * mpitch + j] = (k < K && j < nx) ? src[(size_t)k * nx + j] : 0.0;
+}
+
+int launch_pad_spectra(const double *src, int nx, int K, int Kpad, double *model, int mpitch,
+                       cudaStream_t st)
+{
+	dim3 grid(ceil_div(mpitch, 128), Kpad);
+	pad_spectra_kernel<<<grid, 128, 0, st>>>(src, nx, K, Kpad, model, mpitch);
+	MDNS_LAUNCHED("pad_spectra_kernel");
+	return MDNS_OK;
+}
+
+// -------------------------------------------------------- mask compaction ---
+constexpr int CM_THREADS = 256;
+constexpr int CM_TILE = CM_THREADS * 16;  // mask bytes per block
+
+__device__ __forceinline__ int nonzero_bytes(uint32_t w)
+{
+	w |= w >> 4;
+	w |= w >> 2;
+	w |= w >> 1;
+	return __popc(w & 0x01010101u);
+}
+
+// the mask buffer is allocated zero-padded to a multiple of 16 bytes
+__device__ __forceinline__ uint4 mask_word16(const uint8_t *mask, int n, long long base)
+{
+	if (base >= n) return make_uint4(0, 0, 0, 0);
+	return *reinterpret_cast<const uint4 *>(mask + base);
+}
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total)
+{
+	__shared__ int warp_sums[CM_THREADS / 32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int x = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const int y = __shfl_up_sync(0xffffffffu, x, o);
+		if (lane >= o) x += y;
+	}
+	if (lane == 31) warp_sums[warp] = x;
+	__syncthreads();
+	int before = 0, all = 0;
+#pragma unroll
+	for (int w = 0; w < CM_THREADS / 32; ++w) {
+		const int s = warp_sums[w];
+		if (w < warp) before += s;
+		all += s;
+	}
+	*total = all;
+	return before + x - v;
+}
+
+__global__ void __launch_bounds__(CM_THREADS) mask_count_kernel(const uint8_t *__restrict__ mask,
+                                                                int n, int *__restrict__ block_counts)
+{
+	const long long base = ((long long)blockIdx.x * CM_THREADS + threadIdx.x) * 16;
+	const uint4 w = mask_word16(mask, n, base);
+	const int c = nonzero_bytes(w.x) + nonzero_bytes(w.y) + nonzero_bytes(w.z) + nonzero_bytes(w.w);
+	int total;
+	block_exclusive_scan(c, &total);
+	if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) scan_counts_kernel(int *__restrict__ counts, int nb,
+                                                           int *__restrict__ total_out)
+{
+	__shared__ int warp_sums[32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int carry = 0;
+	for (int base = 0; base < nb; base += 1024) {
+		const int i = base + threadIdx.x;
+		const int v = i < nb ? counts[i] : 0;
+		int x = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const int y = __shfl_up_sync(0xffffffffu, x, o);
+			if (lane >= o) x += y;
+		}
+		if (lane == 31) warp_sums[warp] = x;
+		__syncthreads();
+		int before = 0, all = 0;
+		for (int w = 0; w < 32; ++w) {
+			const int s = warp_sums[w];
+			if (w < warp) before += s;
+			all += s;
+		}
+		if (i < nb) counts[i] = carry + before + x - v;
+		carry += all;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(CM_THREADS) mask_scatter_kernel(const uint8_t *__restrict__ mask,
+                                                                  int n,
+                                                                  const int *__restrict__ block_offsets,
+                                                                  int *__restrict__ active)
+{
+	const long long base = ((long long)blockIdx.x * CM_THREADS + threadIdx.x) * 16;
+	const uint4 w = mask_word16(mask, n, base);
+	const int c = nonzero_bytes(w.x) + nonzero_bytes(w.y) + nonzero_bytes(w.z) + nonzero_bytes(w.w);
+	int total;
+	int pos = block_offsets[blockIdx.x] + block_exclusive_scan(c, &total);
+	if (c == 0) return;
+	const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+	for (int q = 0; q < 4; ++q) {
+#pragma unroll
+		for (int b = 0; b < 4; ++b) {
+			if ((words[q] >> (8 * b)) & 0xffu) active[pos++] = (int)(base + 4 * q + b);
+		}
+	}
+}
+
+int launch_compact_mask(const uint8_t *mask, int n, int *scratch, int *active, int *n_active_dev,
+                        cudaStream_t st)
+{
+	const int nb = ceil_div(n, CM_TILE);
+	mask_count_kernel<<<nb, CM_THREADS, 0, st>>>(mask, n, scratch);
+	MDNS_LAUNCHED("mask_count_kernel");
+	scan_counts_kernel<<<1, 1024, 0, st>>>(scratch, nb, n_active_dev);
+	MDNS_LAUNCHED("scan_counts_kernel");
+	mask_scatter_kernel<<<nb, CM_THREADS, 0, st>>>(mask, n, scratch, active);
+	MDNS_LAUNCHED("mask_scatter_kernel");
+	return MDNS_OK;
+}
+
+// ------------------------------------------------------------ clike kernel ---
+constexpr int LK_THREADS = 256;
+
+// Stage KT model spectra (contiguous rows of the padded model buffer) into shared
+// memory with one bulk-TMA copy; every thread then waits on the mbarrier.
+template <int KT>
+__device__ __forceinline__ void stage_model_tma(double2 *sm, uint64_t *bar, const double *model,
+                                                int mpitch, int k0)
+{
+	if (threadIdx.x == 0) {
+		mbar_init(bar, 1);
+		mbar_fence_init();
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const uint32_t bytes = (uint32_t)KT * (uint32_t)mpitch * 8u;
+		mbar_expect_tx(bar, bytes);
+		tma_load_1d(sm, model + (size_t)k0 * mpitch, bytes, bar);
+	}
+}
+
+// One CTA = 8 warps; each warp serves 32/L data sets at a time, L lanes per data set.
+// Per data set and lane: U 128-bit fragments are requested back to back (memory-level
+// parallelism), then consumed against the KT staged model spectra.
+template <int L, int U, int KT>
+__global__ void __launch_bounds__(LK_THREADS) clike_rows_kernel(const LikeArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	double2 *sm = reinterpret_cast<double2 *>(smem_raw);
+	__shared__ uint64_t bar;
+	constexpr int G = 32 / L;                     // data sets per warp
+	constexpr int RPC = (LK_THREADS / 32) * G;    // data sets per CTA step
+	const int k0 = blockIdx.y * KT;
+	const int mfp = a.mpitch >> 1;                // fragments per model row
+	const int nfrag = (a.nx + 1) >> 1;
+	stage_model_tma<KT>(sm, &bar, a.model, a.mpitch, k0);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int g = lane / L, gl = lane % L;
+	const int nchunks = (nfrag + L * U - 1) / (L * U);
+	const double inv = a.scale / a.noise2;
+	mbar_wait(&bar, 0);
+
+	for (long long rb = (long long)blockIdx.x * RPC + warp * G; rb < a.n_rows;
+	     rb += (long long)gridDim.x * RPC) {
+		const long long r = rb + g;
+		const bool valid = r < a.n_rows;
+		double acc0[KT], acc1[KT];
+#pragma unroll
+		for (int k = 0; k < KT; ++k) acc0[k] = acc1[k] = 0.0;
+		if (valid) {
+			const long long row = a.active ? (long long)a.active[r] : r;
+			const double2 *p = reinterpret_cast<const double2 *>(a.Y + row * a.pitch);
+			for (int c = 0; c < nchunks; ++c) {
+				const int f = c * (L * U) + gl;
+				double2 y[U];
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					const int fi = f + u * L;
+					if (fi < nfrag) y[u] = ldg_stream(p + fi);
+				}
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					const int fi = f + u * L;
+					if (fi < nfrag) {
+#pragma unroll
+						for (int k = 0; k < KT; ++k) {
+							const double2 m = sm[k * mfp + fi];
+							const double d0 = m.x - y[u].x;
+							const double d1 = m.y - y[u].y;
+							acc0[k] = fma(d0, d0, acc0[k]);
+							acc1[k] = fma(d1, d1, acc1[k]);
+						}
+					}
+				}
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < KT; ++k) {
+			double s = acc0[k] + acc1[k];
+#pragma unroll
+			for (int o = L / 2; o > 0; o >>= 1) s += shfl_xor_f64(s, o);
+			if (valid && gl == 0 && k0 + k < a.K)
+				a.out[(long long)(k0 + k) * a.out_stride + r] = s * inv;
+		}
+	}
+}
+
+template <int L, int U, int KT>
+static int launch_clike_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
+{
+	constexpr int RPC = (LK_THREADS / 32) * (32 / L);
+	const size_t smem = (size_t)KT * a.mpitch * 8;
+	auto kern = clike_rows_kernel<L, U, KT>;
+	if (smem > 48 * 1024)   // per device, so set it on every launch that needs it
+		MDNS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                               (int)smem));
+	int occ = 0;
+	MDNS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LK_THREADS, smem));
+	if (occ < 1) {
+		set_error("clike kernel does not fit: %zu bytes of shared memory", smem);
+		return MDNS_EINVAL;
+	}
+	const int ktiles = ceil_div(a.K, KT);
+	long long gx = ceil_div(a.n_rows, RPC);
+	const long long resident = (long long)sm_count * occ;
+	if (gx > resident) gx = resident;
+	if (gx < 1) gx = 1;
+	kern<<<dim3((unsigned)gx, ktiles), LK_THREADS, smem, st>>>(a);
+	MDNS_LAUNCHED("clike_rows_kernel");
+	return MDNS_OK;
+}
+
+template <int L, int U>
+static int launch_clike_k(const LikeArgs &a, int kt, int sm_count, cudaStream_t st)
+{
+	switch (kt) {
+	case 1: return launch_clike_inst<L, U, 1>(a, sm_count, st);
+	case 2: return launch_clike_inst<L, U, 2>(a, sm_count, st);
+	case 4: return launch_clike_inst<L, U, 4>(a, sm_count, st);
+	default: return launch_clike_inst<L, U, 8>(a, sm_count, st);
+	}
+}
+
+template <int L>
+static int launch_clike_u(const LikeArgs &a, int u, int kt, int sm_count, cudaStream_t st)
+{
+	switch (u) {
+	case 1: return launch_clike_k<L, 1>(a, kt, sm_count, st);
+	case 2: return launch_clike_k<L, 2>(a, kt, sm_count, st);
+	case 4: return launch_clike_k<L, 4>(a, kt, sm_count, st);
+	case 8: return launch_clike_k<L, 8>(a, kt, sm_count, st);
+	case 13: return launch_clike_k<L, 13>(a, kt, sm_count, st);
+	default: return launch_clike_k<L, 16>(a, kt, sm_count, st);
+	}
+}
+
+// Choose the number of fragments in flight per lane: the supported value that wastes the
+// fewest issue slots, preferring the larger (more loads in flight) on ties.
+static int pick_unroll(int nfrag, int L)
+{
+	static const int cand[] = {16, 13, 8, 4, 2, 1};
+	const int per_lane = ceil_div(nfrag, L);
+	int best = 1;
+	long long best_cost = -1;
+	for (int u : cand) {
+		const long long cost = (long long)ceil_div(per_lane, u) * u;
+		if (best_cost < 0 || cost < best_cost) {
+			best_cost = cost;
+			best = u;
+		}
+	}
+	return best;
+}
+
+static int pick_ktile(int K, int mpitch, int requested)
+{
+	int kt = requested > 0 ? requested : (K >= 8 ? 8 : K >= 4 ? 4 : K >= 2 ? 2 : 1);
+	if (kt != 1 && kt != 2 && kt != 4 && kt != 8) kt = kt > 8 ? 8 : kt > 4 ? 4 : kt > 2 ? 2 : 1;
+	// keep the staged model tile within ~96 KB so that two CTAs fit per SM
+	while (kt > 1 && (size_t)kt * mpitch * 8 > 96 * 1024) kt >>= 1;
+	return kt;
+}
+
+int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t st)
+{
+	if (a.n_rows <= 0 || a.K <= 0) return MDNS_OK;
+	const int nfrag = (a.nx + 1) >> 1;
+	int L = t.lanes;
+	if (L != 8 && L != 32) L = (a.n_rows >= 16384 && nfrag >= 8) ? 8 : 32;
+	int U = t.unroll;
+	if (U != 1 && U != 2 && U != 4 && U != 8 && U != 13 && U != 16) U = pick_unroll(nfrag, L);
+	const int kt = pick_ktile(a.K, a.mpitch, t.ktile);
+	if ((size_t)kt * a.mpitch * 8 > 200 * 1024) {
+		set_error("model spectrum of %d channels does not fit in shared memory", a.nx);
+		return MDNS_EINVAL;
+	}
+	return L == 8 ? launch_clike_u<8>(a, U, kt, sm_count, st)
+	              : launch_clike_u<32>(a, U, kt, sm_count, st);
+}
+
+// ------------------------------------------------------------- muse kernel ---
+// cmuselike.c:48-64 with resident inverse variance w = 1/v:
+//   s1 = sum y*m*w ; s2 = 1e-10 + sum m*m*w ; s = s1/s2 ; chi = sum (y - s*m)^2 * w
+// Generic variant: the row is streamed twice (second pass served by L1/L2).
+template <int L, int U>
+__global__ void __launch_bounds__(LK_THREADS) muse_rows_kernel(const LikeArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	double2 *sm = reinterpret_cast<double2 *>(smem_raw);
+	__shared__ uint64_t bar;
+	constexpr int G = 32 / L;
+	constexpr int RPC = (LK_THREADS / 32) * G;
+	const int k = blockIdx.y;
+	const int nfrag = (a.nx + 1) >> 1;
+	stage_model_tma<1>(sm, &bar, a.model, a.mpitch, k);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int g = lane / L, gl = lane % L;
+	const int nchunks = (nfrag + L * U - 1) / (L * U);
+	mbar_wait(&bar, 0);
+
+	for (long long rb = (long long)blockIdx.x * RPC + warp * G; rb < a.n_rows;
+	     rb += (long long)gridDim.x * RPC) {
+		const long long r = rb + g;
+		const bool valid = r < a.n_rows;
+		long long row = 0;
+		const double2 *py = nullptr, *pw = nullptr;
+		double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;
+		if (valid) {
+			row = a.active ? (long long)a.active[r] : r;
+			py = reinterpret_cast<const double2 *>(a.Y + row * a.pitch);
+			pw = reinterpret_cast<const double2 *>(a.W + row * a.pitch);
+			for (int c = 0; c < nchunks; ++c) {
+				const int f = c * (L * U) + gl;
+				double2 y[U], w[U];
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					const int fi = f + u * L;
+					if (fi < nfrag) {
+						y[u] = __ldg(py + fi);
+						w[u] = __ldg(pw + fi);
+					}
+				}
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					const int fi = f + u * L;
+					if (fi < nfrag) {
+						const double2 m = sm[fi];
+						const double t0 = m.x * w[u].x, t1 = m.y * w[u].y;
+						s1a = fma(y[u].x, t0, s1a);
+						s1b = fma(y[u].y, t1, s1b);
+						s2a = fma(m.x, t0, s2a);
+						s2b = fma(m.y, t1, s2b);
+					}
+				}
+			}
+		}
+		double s1 = s1a + s1b, s2 = s2a + s2b;
+#pragma unroll
+		for (int o = L / 2; o > 0; o >>= 1) {
+			s1 += shfl_xor_f64(s1, o);
+			s2 += shfl_xor_f64(s2, o);
+		}
+		const double s = s1 / (s2 + 1e-10);
+		double ca = 0.0, cb = 0.0;
+		if (valid) {
+			for (int c = 0; c < nchunks; ++c) {
+				const int f = c * (L * U) + gl;
+				double2 y[U], w[U];
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					const int fi = f + u * L;
+					if (fi < nfrag) {
+						y[u] = __ldg(py + fi);
+						w[u] = __ldg(pw + fi);
+					}
+				}
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					const int fi = f + u * L;
+					if (fi < nfrag) {
+						const double2 m = sm[fi];
+						const double r0 = fma(-s, m.x, y[u].x);
+						const double r1 = fma(-s, m.y, y[u].y);
+						ca = fma(r0 * r0, w[u].x, ca);
+						cb = fma(r1 * r1, w[u].y, cb);
+					}
+				}
+			}
+		}
+		double chi = ca + cb;
+#pragma unroll
+		for (int o = L / 2; o > 0; o >>= 1) chi += shfl_xor_f64(chi, o);
+		if (valid && gl == 0) a.out[(long long)k * a.out_stride + row] = -0.5 * chi;
+	}
+}
+
+template <int L, int U>
+static int launch_muse_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
+{
+	constexpr int RPC = (LK_THREADS / 32) * (32 / L);
+	const size_t smem = (size_t)a.mpitch * 8;
+	auto kern = muse_rows_kernel<L, U>;
+	if (smem > 48 * 1024)
+		MDNS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                               (int)smem));
+	int occ = 0;
+	MDNS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LK_THREADS, smem));
+	if (occ < 1) {
+		set_error("muse kernel does not fit: %zu bytes of shared memory", smem);
+		return MDNS_EINVAL;
+	}
+	long long gx = ceil_div(a.n_rows, RPC);
+	const long long resident = (long long)sm_count * occ;
+	if (gx > resident) gx = resident;
+	if (gx < 1) gx = 1;
+	kern<<<dim3((unsigned)gx, a.K), LK_THREADS, smem, st>>>(a);
+	MDNS_LAUNCHED("muse_rows_kernel");
+	return MDNS_OK;
+}
+
+int launch_muse(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t st)
+{
+	if (a.n_rows <= 0 || a.K <= 0) return MDNS_OK;
+	const int nfrag = (a.nx + 1) >> 1;
+	if ((size_t)a.mpitch * 8 > 200 * 1024) {
+		set_error("model spectrum of %d channels does not fit in shared memory", a.nx);
+		return MDNS_EINVAL;
+	}
+	int L = t.lanes;
+	if (L != 8 && L != 32) L = (a.n_rows >= 16384 && nfrag >= 8) ? 8 : 32;
+	const int per_lane = ceil_div(nfrag, L);
+	int U = t.unroll;
+	if (U != 2 && U != 4 && U != 8) U = per_lane >= 8 ? 8 : per_lane >= 4 ? 4 : 2;
+	if (L == 8) {
+		switch (U) {
+		case 2: return launch_muse_inst<8, 2>(a, sm_count, st);
+		case 4: return launch_muse_inst<8, 4>(a, sm_count, st);
+		default: return launch_muse_inst<8, 8>(a, sm_count, st);
+		}
+	}
+	switch (U) {
+	case 2: return launch_muse_inst<32, 2>(a, sm_count, st);
+	case 4: return launch_muse_inst<32, 4>(a, sm_count, st);
+	default: return launch_muse_inst<32, 8>(a, sm_count, st);
+	}
+}
+
+}  // namespace mdns

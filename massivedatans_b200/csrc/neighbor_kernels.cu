@@ -1,0 +1,432 @@
+// neighbor_kernels.cu -- RadFriends neighbour tests (sm_100a), bit-exact with cneighbors.c.
+//
+// Exactness contract: the squared distance is accumulated in channel order with separately
+// rounded IEEE double sub/mul/add (cneighbors.c:104-107; the reference is built for baseline
+// x86-64, i.e. without FMA contraction), and `sqrt(d) < r` (cneighbors.c:88,109) is evaluated
+// as `d < T` with T = mdns_sqrt_threshold(r), which is the same predicate because the
+// correctly rounded sqrt is monotone.  min/max over distances commute with sqrt for the
+// same reason, so one sqrt is taken at the very end on the host.
+//
+// Mapping: one warp per candidate (or per 4 candidates), lanes over members held in SoA
+// layout -> coalesced member loads, `__ballot_sync` gives the per-candidate hit count of 32
+// members at once and the early exit of cneighbors.c:112.
+#include "kernels.cuh"
+
+namespace mdns {
+
+constexpr int NB_THREADS = 256;
+constexpr int MAX_TEMPLATE_DIM = 8;
+constexpr unsigned long long BITS_1E300 = 0x7E37E43C8800759CULL;  // 1e300 (cneighbors.c:51,148)
+
+template <int D>
+__device__ __forceinline__ double sqdist_reg(const double (&a)[D], const double (&b)[D])
+{
+	double t = __dsub_rn(a[0], b[0]);
+	double d = __dmul_rn(t, t);   // 0 + t*t == t*t exactly
+#pragma unroll
+	for (int k = 1; k < D; ++k) {
+		t = __dsub_rn(a[k], b[k]);
+		d = __dadd_rn(d, __dmul_rn(t, t));
+	}
+	return d;
+}
+
+// ------------------------------------------------------------------ count ---
+template <int D, int CPW>
+__global__ void __launch_bounds__(NB_THREADS) count_within_kernel(const double *__restrict__ xs,
+                                                                  int n, int npad,
+                                                                  const double *__restrict__ yy,
+                                                                  int m, double T, int stop_at,
+                                                                  int *__restrict__ counts)
+{
+	const int lane = threadIdx.x & 31;
+	const long long wid = ((long long)blockIdx.x * NB_THREADS + threadIdx.x) >> 5;
+	const long long j0 = wid * CPW;
+	if (j0 >= m) return;
+	double y[CPW][D];
+	int cnt[CPW];
+#pragma unroll
+	for (int c = 0; c < CPW; ++c) {
+		const long long j = (j0 + c < m) ? j0 + c : (long long)m - 1;
+		cnt[c] = 0;
+#pragma unroll
+		for (int k = 0; k < D; ++k) y[c][k] = __ldg(yy + j * D + k);
+	}
+	for (int base = 0; base < n; base += 32) {
+		const int i = base + lane;
+		const bool valid = i < n;
+		double x[D];
+#pragma unroll
+		for (int k = 0; k < D; ++k) x[k] = valid ? xs[(size_t)k * npad + i] : 0.0;
+		bool all_done = stop_at > 0;
+#pragma unroll
+		for (int c = 0; c < CPW; ++c) {
+			const double d = sqdist_reg<D>(x, y[c]);
+			const unsigned hits = __ballot_sync(0xffffffffu, valid && d < T);
+			cnt[c] += __popc(hits);
+			all_done = all_done && cnt[c] >= stop_at;
+		}
+		if (all_done) break;   // warp-uniform: cnt comes from the ballot
+	}
+	if (lane == 0) {
+#pragma unroll
+		for (int c = 0; c < CPW; ++c)
+			if (j0 + c < m) counts[j0 + c] = cnt[c];
+	}
+}
+
+// any dimensionality: coordinates streamed per channel
+__global__ void __launch_bounds__(NB_THREADS) count_within_generic_kernel(
+    const double *__restrict__ xs, int n, int npad, int ndim, const double *__restrict__ yy, int m,
+    double T, int stop_at, int *__restrict__ counts)
+{
+	const int lane = threadIdx.x & 31;
+	const long long j = ((long long)blockIdx.x * NB_THREADS + threadIdx.x) >> 5;
+	if (j >= m) return;
+	const double *y = yy + j * ndim;
+	int cnt = 0;
+	for (int base = 0; base < n; base += 32) {
+		const int i = base + lane;
+		const bool valid = i < n;
+		double d = 0.0;
+		if (valid) {
+			double t = __dsub_rn(xs[i], __ldg(y));
+			d = __dmul_rn(t, t);
+			for (int k = 1; k < ndim; ++k) {
+				t = __dsub_rn(xs[(size_t)k * npad + i], __ldg(y + k));
+				d = __dadd_rn(d, __dmul_rn(t, t));
+			}
+		}
+		cnt += __popc(__ballot_sync(0xffffffffu, valid && d < T));
+		if (stop_at > 0 && cnt >= stop_at) break;
+	}
+	if (lane == 0) counts[j] = cnt;
+}
+
+template <int D>
+static int launch_count_d(const double *xs, int n, int npad, const double *yy, int m, double T,
+                          int stop_at, int *counts, int sm_count, cudaStream_t st)
+{
+	const long long warps_wanted = (long long)sm_count * 16;
+	if (m >= 4 * warps_wanted) {
+		const int warps = ceil_div(m, 4);
+		count_within_kernel<D, 4><<<ceil_div(warps, NB_THREADS / 32), NB_THREADS, 0, st>>>(
+		    xs, n, npad, yy, m, T, stop_at, counts);
+	} else {
+		count_within_kernel<D, 1><<<ceil_div(m, NB_THREADS / 32), NB_THREADS, 0, st>>>(
+		    xs, n, npad, yy, m, T, stop_at, counts);
+	}
+	MDNS_LAUNCHED("count_within_kernel");
+	return MDNS_OK;
+}
+
+int launch_count_within(const double *xs, int n, int npad, int ndim, const double *yy, int m,
+                        double T, int stop_at, int *counts, int sm_count, cudaStream_t st)
+{
+	if (m <= 0) return MDNS_OK;
+	switch (ndim) {
+	case 1: return launch_count_d<1>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st);
+	case 2: return launch_count_d<2>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st);
+	case 3: return launch_count_d<3>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st);
+	case 4: return launch_count_d<4>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st);
+	case 5: return launch_count_d<5>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st);
+	case 6: return launch_count_d<6>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st);
+	case 7: return launch_count_d<7>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st);
+	case 8: return launch_count_d<8>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st);
+	default:
+		count_within_generic_kernel<<<ceil_div(m, NB_THREADS / 32), NB_THREADS, 0, st>>>(
+		    xs, n, npad, ndim, yy, m, T, stop_at, counts);
+		MDNS_LAUNCHED("count_within_generic_kernel");
+		return MDNS_OK;
+	}
+}
+
+// ------------------------------------------------------- single-point test ---
+// cneighbors.c:77-92: members are spread over the whole grid; any hit raises the flag.
+__global__ void __launch_bounds__(NB_THREADS) within_single_kernel(const double *__restrict__ xs,
+                                                                   int n, int npad, int ndim,
+                                                                   const double *__restrict__ y,
+                                                                   double T, int *__restrict__ flag)
+{
+	bool hit = false;
+	for (long long i = (long long)blockIdx.x * NB_THREADS + threadIdx.x; i < n;
+	     i += (long long)gridDim.x * NB_THREADS) {
+		double t = __dsub_rn(xs[i], __ldg(y));
+		double d = __dmul_rn(t, t);
+		for (int k = 1; k < ndim; ++k) {
+			t = __dsub_rn(xs[(size_t)k * npad + i], __ldg(y + k));
+			d = __dadd_rn(d, __dmul_rn(t, t));
+		}
+		hit = hit || d < T;
+	}
+	if (__ballot_sync(0xffffffffu, hit) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+int launch_within_single(const double *xs, int n, int npad, int ndim, const double *y, double T,
+                         int *flag, cudaStream_t st)
+{
+	if (n <= 0) return MDNS_OK;
+	int blocks = ceil_div(n, NB_THREADS);
+	if (blocks > 1024) blocks = 1024;
+	within_single_kernel<<<blocks, NB_THREADS, 0, st>>>(xs, n, npad, ndim, y, T, flag);
+	MDNS_LAUNCHED("within_single_kernel");
+	return MDNS_OK;
+}
+
+// ------------------------------------------------- bootstrap: round lists ---
+// One CTA per round: ordered compaction of the un-chosen ("query") and chosen
+// ("reference") sample indices of chosen[i*nboot + b] (cneighbors.c:146,150).
+__global__ void __launch_bounds__(1024) bootstrap_lists_kernel(const double *__restrict__ chosen,
+                                                               int n, int nboot,
+                                                               int *__restrict__ qidx,
+                                                               int *__restrict__ ridx,
+                                                               int *__restrict__ counts,
+                                                               unsigned long long *__restrict__ nearest)
+{
+	__shared__ int warp_sums[32];
+	const int b = blockIdx.x;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int carry_r = 0;
+	for (int base = 0; base < n; base += 1024) {
+		const int i = base + threadIdx.x;
+		const bool in = i < n;
+		const int isref = (in && chosen[(size_t)i * nboot + b] != 0.0) ? 1 : 0;
+		int x = isref;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const int y = __shfl_up_sync(0xffffffffu, x, o);
+			if (lane >= o) x += y;
+		}
+		if (lane == 31) warp_sums[warp] = x;
+		__syncthreads();
+		int before = 0, all = 0;
+		for (int w = 0; w < 32; ++w) {
+			const int s = warp_sums[w];
+			if (w < warp) before += s;
+			all += s;
+		}
+		const int rpos = carry_r + before + x - isref;   // references before i
+		if (in) {
+			if (isref)
+				ridx[(size_t)b * n + rpos] = i;
+			else
+				qidx[(size_t)b * n + (i - rpos)] = i;    // queries before i = i - refs before i
+			nearest[(size_t)b * n + i] = BITS_1E300;
+		}
+		carry_r += all;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		counts[b] = n - carry_r;
+		counts[nboot + b] = carry_r;
+	}
+}
+
+int launch_bootstrap_lists(const double *chosen, int n, int nboot, int *qidx, int *ridx,
+                           int *counts, unsigned long long *nearest, cudaStream_t st)
+{
+	bootstrap_lists_kernel<<<nboot, 1024, 0, st>>>(chosen, n, nboot, qidx, ridx, counts, nearest);
+	MDNS_LAUNCHED("bootstrap_lists_kernel");
+	return MDNS_OK;
+}
+
+__global__ void all_pairs_lists_kernel(int n, int *__restrict__ qidx, int *__restrict__ ridx,
+                                       int *__restrict__ counts,
+                                       unsigned long long *__restrict__ nearest)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) {
+		qidx[i] = i;
+		ridx[i] = i;
+		nearest[i] = BITS_1E300;
+	}
+	if (i == 0) {
+		counts[0] = n;
+		counts[1] = n;
+	}
+}
+
+int launch_all_pairs_lists(int n, int *qidx, int *ridx, int *counts, unsigned long long *nearest,
+                           cudaStream_t st)
+{
+	all_pairs_lists_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, qidx, ridx, counts, nearest);
+	MDNS_LAUNCHED("all_pairs_lists_kernel");
+	return MDNS_OK;
+}
+
+// ------------------------------------------- nearest reference per query ---
+// grid = (query tiles, rounds, reference splits).  Each thread owns one query sample of its
+// round; reference samples are staged through shared memory in tiles and broadcast.  The
+// partial minimum of each reference split is merged with atomicMin on the bit pattern
+// (non-negative doubles order like unsigned integers; NaN patterns sort above 1e300 and so
+// are ignored exactly like the `d < nearest_d` test of cneighbors.c:58,157).
+constexpr int NN_THREADS = 128;
+constexpr int NN_TILE = 256;
+
+template <int D>
+__global__ void __launch_bounds__(NN_THREADS) nn_min_kernel(const double *__restrict__ xs, int n,
+                                                            int npad, const int *__restrict__ qidx,
+                                                            const int *__restrict__ ridx,
+                                                            const int *__restrict__ counts,
+                                                            int nrounds, int exclude_self,
+                                                            unsigned long long *__restrict__ nearest)
+{
+	__shared__ double tile[D][NN_TILE];
+	__shared__ int tile_idx[NN_TILE];
+	const int b = blockIdx.y;
+	const int nq = counts[b], nr = counts[nrounds + b];
+	const int q = blockIdx.x * NN_THREADS + threadIdx.x;
+	if (blockIdx.x * NN_THREADS >= nq) return;   // whole CTA idle for this round
+	const bool valid = q < nq;
+	const int qi = valid ? qidx[(size_t)b * n + q] : 0;
+	double x[D];
+#pragma unroll
+	for (int k = 0; k < D; ++k) x[k] = valid ? xs[(size_t)k * npad + qi] : 0.0;
+
+	// this CTA's slice of the reference list
+	const int per = (nr + gridDim.z - 1) / gridDim.z;
+	const int r_begin = blockIdx.z * per;
+	const int r_end = min(nr, r_begin + per);
+	double best = 1e300;
+	for (int t0 = r_begin; t0 < r_end; t0 += NN_TILE) {
+		const int tn = min(NN_TILE, r_end - t0);
+		__syncthreads();
+		for (int s = threadIdx.x; s < tn; s += NN_THREADS) {
+			const int ri = ridx[(size_t)b * n + t0 + s];
+			tile_idx[s] = ri;
+#pragma unroll
+			for (int k = 0; k < D; ++k) tile[k][s] = xs[(size_t)k * npad + ri];
+		}
+		__syncthreads();
+		if (valid) {
+			for (int s = 0; s < tn; ++s) {
+				double y[D];
+#pragma unroll
+				for (int k = 0; k < D; ++k) y[k] = tile[k][s];
+				const double d = sqdist_reg<D>(x, y);
+				if (exclude_self && tile_idx[s] == qi) continue;
+				if (d < best) best = d;
+			}
+		}
+	}
+	if (valid && best < 1e300)
+		atomicMin(nearest + (size_t)b * n + qi, (unsigned long long)__double_as_longlong(best));
+}
+
+__global__ void __launch_bounds__(NN_THREADS) nn_min_generic_kernel(
+    const double *__restrict__ xs, int n, int npad, int ndim, const int *__restrict__ qidx,
+    const int *__restrict__ ridx, const int *__restrict__ counts, int nrounds, int exclude_self,
+    unsigned long long *__restrict__ nearest)
+{
+	const int b = blockIdx.y;
+	const int nq = counts[b], nr = counts[nrounds + b];
+	const int q = blockIdx.x * NN_THREADS + threadIdx.x;
+	if (q >= nq) return;
+	const int qi = qidx[(size_t)b * n + q];
+	const int per = (nr + gridDim.z - 1) / gridDim.z;
+	const int r_begin = blockIdx.z * per;
+	const int r_end = min(nr, r_begin + per);
+	double best = 1e300;
+	for (int s = r_begin; s < r_end; ++s) {
+		const int ri = ridx[(size_t)b * n + s];
+		if (exclude_self && ri == qi) continue;
+		double t = __dsub_rn(xs[qi], xs[ri]);
+		double d = __dmul_rn(t, t);
+		for (int k = 1; k < ndim; ++k) {
+			t = __dsub_rn(xs[(size_t)k * npad + qi], xs[(size_t)k * npad + ri]);
+			d = __dadd_rn(d, __dmul_rn(t, t));
+		}
+		if (d < best) best = d;
+	}
+	if (best < 1e300)
+		atomicMin(nearest + (size_t)b * n + qi, (unsigned long long)__double_as_longlong(best));
+}
+
+template <int D>
+static int launch_nn_d(const double *xs, int n, int npad, const int *qidx, const int *ridx,
+                       const int *counts, int nrounds, int exclude_self,
+                       unsigned long long *nearest, dim3 grid, cudaStream_t st)
+{
+	nn_min_kernel<D><<<grid, NN_THREADS, 0, st>>>(xs, n, npad, qidx, ridx, counts, nrounds,
+	                                             exclude_self, nearest);
+	MDNS_LAUNCHED("nn_min_kernel");
+	return MDNS_OK;
+}
+
+int launch_nn_min(const double *xs, int n, int npad, int ndim, const int *qidx, const int *ridx,
+                  const int *counts, int nrounds, int exclude_self, unsigned long long *nearest,
+                  int sm_count, cudaStream_t st)
+{
+	if (n <= 0 || nrounds <= 0) return MDNS_OK;
+	const int qtiles = ceil_div(n, NN_THREADS);   // upper bound; idle CTAs exit at once
+	// split the reference list so that the grid covers the chip a few times over
+	long long ctas = (long long)qtiles * nrounds;
+	int split = 1;
+	const int max_split = ceil_div(n, NN_TILE);
+	while (ctas * split < (long long)sm_count * 8 && split < max_split) split *= 2;
+	if (split > max_split) split = max_split;
+	if (split < 1) split = 1;
+	dim3 grid(qtiles, nrounds, split);
+#define MDNS_NN_CASE(D) \
+	case D: return launch_nn_d<D>(xs, n, npad, qidx, ridx, counts, nrounds, exclude_self, nearest, grid, st)
+	switch (ndim) {
+		MDNS_NN_CASE(1);
+		MDNS_NN_CASE(2);
+		MDNS_NN_CASE(3);
+		MDNS_NN_CASE(4);
+		MDNS_NN_CASE(5);
+		MDNS_NN_CASE(6);
+		MDNS_NN_CASE(7);
+		MDNS_NN_CASE(8);
+	default:
+		nn_min_generic_kernel<<<grid, NN_THREADS, 0, st>>>(xs, n, npad, ndim, qidx, ridx, counts,
+		                                                  nrounds, exclude_self, nearest);
+		MDNS_LAUNCHED("nn_min_generic_kernel");
+		return MDNS_OK;
+	}
+#undef MDNS_NN_CASE
+}
+
+// ---------------------------------------------------------------- finalize ---
+// max over rounds b and query samples of nearest (bit patterns order like the doubles).
+// skip_first drops original sample 0 (cneighbors.c:162).  A round without queries
+// contributes 0 (cneighbors.c:142), so the running maximum starts at +0.0.
+__global__ void __launch_bounds__(1024) nn_finalize_kernel(const int *__restrict__ qidx,
+                                                           const int *__restrict__ counts, int n,
+                                                           int nrounds, int skip_first,
+                                                           const unsigned long long *__restrict__ nearest,
+                                                           double *__restrict__ result)
+{
+	__shared__ unsigned long long warp_max[32];
+	unsigned long long best = 0ULL;
+	for (int b = 0; b < nrounds; ++b) {
+		const int nq = counts[b];
+		for (int q = threadIdx.x; q < nq; q += 1024) {
+			const int qi = qidx[(size_t)b * n + q];
+			if (skip_first && qi == 0) continue;
+			const unsigned long long v = nearest[(size_t)b * n + qi];
+			best = v > best ? v : best;
+		}
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		const unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o);
+		best = y > best ? y : best;
+	}
+	if ((threadIdx.x & 31) == 0) warp_max[threadIdx.x >> 5] = best;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int w = 0; w < 32; ++w) best = warp_max[w] > best ? warp_max[w] : best;
+		*result = __longlong_as_double((long long)best);
+	}
+}
+
+int launch_nn_finalize(const int *qidx, const int *counts, int n, int nrounds, int skip_first,
+                       const unsigned long long *nearest, double *result, cudaStream_t st)
+{
+	nn_finalize_kernel<<<1, 1024, 0, st>>>(qidx, counts, n, nrounds, skip_first, nearest, result);
+	MDNS_LAUNCHED("nn_finalize_kernel");
+	return MDNS_OK;
+}
+
+}  // namespace mdns

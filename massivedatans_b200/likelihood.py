@@ -1,0 +1,237 @@
+"""Host-side mirror of the reference's likelihood callables on top of the resident-data shim.
+
+Reference surface kept (same names, argument meaning and return values):
+
+* ``multi_loglikelihood(params, data_mask) -> L[n_act]``  -- sample.py:101-108
+  (``params = (A, mu, log_sig)`` after ``priortransform``; ``sig = 10**log_sig``;
+  result is ``-0.5 * Lout`` compacted over the masked-in data sets).
+* ``multi_loglikelihood_clike(params, data_mask)``         -- musefuse.py:520-535
+  (``model(*params)`` on the host, all-zero guard ``-1e100``, result
+  ``Lout[data_mask] + normal(0, 1e-5)`` with the jitter drawn from numpy.random
+  on the host so that seeded runs consume the same RNG stream).
+
+New, additive: ``ResidentDataset.loglike_batch`` scores K candidates in one pass.
+"""
+import ctypes
+import weakref
+
+import numpy
+
+from . import _lib
+
+
+def _addr(a):
+    return a.ctypes.data if a is not None else None
+
+
+class _PinnedPool(object):
+    """Result vectors live in pinned host memory so the D2H copy needs no bounce
+    buffer; blocks are recycled once the numpy array that wraps them is collected."""
+
+    def __init__(self, max_cached_bytes=1 << 30):
+        self.free = {}
+        self.cached = 0
+        self.max_cached = max_cached_bytes
+
+    def empty(self, n):
+        lib = _lib.load()
+        nbytes = max(int(n) * 8, 8)
+        cap = 1 << (nbytes - 1).bit_length()
+        lst = self.free.get(cap)
+        if lst:
+            ptr = lst.pop()
+            self.cached -= cap
+        else:
+            ptr = lib.mdns_host_alloc(cap)
+            if not ptr:
+                raise _lib.MdnsError('pinned allocation failed: ' + _lib.last_error())
+        buf = (ctypes.c_double * (cap // 8)).from_address(ptr)
+        arr = numpy.frombuffer(buf, dtype=numpy.float64, count=int(n))
+        weakref.finalize(buf, self._release, ptr, cap)
+        return arr
+
+    def _release(self, ptr, cap):
+        if self.cached + cap <= self.max_cached:
+            self.free.setdefault(cap, []).append(ptr)
+            self.cached += cap
+        else:
+            _lib.load().mdns_host_free(ptr)
+
+
+_pool = _PinnedPool()
+
+
+class ResidentDataset(object):
+    """Data (and optionally per-element variances) resident in HBM, sharded over `devices`.
+
+    x : [nx] wavelength grid (sample.py:30) or None
+    y : [nx, ndata] C-contiguous float64, data-set index fastest (sample.py:31)
+    variance : [nx, ndata] or None (musefuse.py:205-206 `noise_level`)
+    """
+
+    def __init__(self, x, y, variance=None, devices=None):
+        lib = _lib.load()
+        _lib.require_device()
+        y = numpy.ascontiguousarray(y, dtype=numpy.float64)
+        if y.ndim != 2:
+            raise ValueError('y must be [nx, ndata]')
+        self.nx, self.ndata = y.shape
+        if x is not None:
+            x = numpy.ascontiguousarray(x, dtype=numpy.float64)
+            if x.shape != (self.nx,):
+                raise ValueError('x must have nx entries')
+        if variance is not None:
+            variance = numpy.ascontiguousarray(variance, dtype=numpy.float64)
+            if variance.shape != y.shape:
+                raise ValueError('variance must match y')
+        devs = None
+        ndev = 0
+        if devices is not None:
+            devs = numpy.ascontiguousarray(devices, dtype=numpy.int32)
+            ndev = len(devs)
+        handle = ctypes.c_void_p()
+        _lib.check(lib.mdns_dataset_create(_addr(x), _addr(y), _addr(variance), self.ndata,
+                                           self.nx, _addr(devs), ndev, ctypes.byref(handle)),
+                   'mdns_dataset_create')
+        self._lib = lib
+        self._h = handle
+        self.has_variance = variance is not None
+        self._finalizer = weakref.finalize(self, lib.mdns_dataset_destroy, handle)
+
+    def close(self):
+        self._finalizer()
+
+    # -- staged interface ----------------------------------------------------
+    def set_mask(self, data_mask):
+        n = ctypes.c_int()
+        if data_mask is not None:
+            data_mask = self._mask(data_mask)
+        _lib.check(self._lib.mdns_set_mask(self._h, _addr(data_mask), ctypes.byref(n)),
+                   'mdns_set_mask')
+        return n.value
+
+    def _mask(self, data_mask):
+        m = numpy.ascontiguousarray(data_mask)
+        if m.dtype != numpy.bool_:
+            m = m.astype(numpy.bool_)
+        if m.shape != (self.ndata,):
+            raise ValueError('data_mask must have ndata entries')
+        return m
+
+    def stage_params(self, params):
+        p = numpy.ascontiguousarray(params, dtype=numpy.float64).reshape((-1, 3))
+        _lib.check(self._lib.mdns_stage_params(self._h, _addr(p), len(p)), 'mdns_stage_params')
+        return len(p)
+
+    def stage_spectra(self, ypred):
+        s = numpy.ascontiguousarray(ypred, dtype=numpy.float64).reshape((-1, self.nx))
+        _lib.check(self._lib.mdns_stage_spectra(self._h, _addr(s), len(s)), 'mdns_stage_spectra')
+        return len(s)
+
+    def launch_clike(self, noise, scale=-0.5):
+        _lib.check(self._lib.mdns_clike_launch(self._h, noise, scale), 'mdns_clike_launch')
+
+    def launch_muse(self):
+        _lib.check(self._lib.mdns_muse_launch(self._h), 'mdns_muse_launch')
+
+    def fetch(self, out):
+        _lib.check(self._lib.mdns_fetch(self._h, _addr(out), out.size), 'mdns_fetch')
+        return out
+
+    def sync(self):
+        _lib.check(self._lib.mdns_sync(self._h), 'mdns_sync')
+
+    def timer_start(self):
+        _lib.check(self._lib.mdns_timer_start(self._h), 'mdns_timer_start')
+
+    def timer_stop(self):
+        ms = ctypes.c_float()
+        _lib.check(self._lib.mdns_timer_stop(self._h, ctypes.byref(ms)), 'mdns_timer_stop')
+        return ms.value
+
+    def set_tuning(self, lanes=0, unroll=0, ktile=0):
+        _lib.check(self._lib.mdns_set_tuning(self._h, lanes, unroll, ktile), 'mdns_set_tuning')
+
+    # -- one-call forms ------------------------------------------------------
+    def loglike_batch(self, params, data_mask, noise, scale=-0.5, out=None):
+        """K parameter points (A, mu, sig) x all active data sets -> L[K, n_act]."""
+        K = self.stage_params(params)
+        n_act = self.set_mask(data_mask)
+        if out is None:
+            out = _pool.empty(K * n_act)
+        if n_act > 0:
+            self.launch_clike(noise, scale)
+            self.fetch(out)
+        return out[:K * n_act].reshape((K, n_act))
+
+    def loglike_spectra(self, ypred, data_mask, noise, scale=-0.5, out=None):
+        """K model spectra x all active data sets -> L[K, n_act] (scalar-noise chi-square)."""
+        K = self.stage_spectra(ypred)
+        n_act = self.set_mask(data_mask)
+        if out is None:
+            out = _pool.empty(K * n_act)
+        if n_act > 0:
+            self.launch_clike(noise, scale)
+            self.fetch(out)
+        return out[:K * n_act].reshape((K, n_act))
+
+    def muse_loglike(self, ypred, data_mask, Lout):
+        """cmuselike.c semantics: writes -0.5*chi2 into the masked entries of Lout[K, ndata]."""
+        K = self.stage_spectra(ypred)
+        n_act = self.set_mask(data_mask)
+        if n_act > 0:
+            self.launch_muse()
+            _lib.check(self._lib.mdns_fetch(self._h, _addr(Lout), K * self.ndata), 'mdns_fetch')
+        return Lout
+
+
+def make_multi_loglikelihood(x, y, noise_level=0.01, devices=None):
+    """Build the callable of sample.py:101-108 over a resident copy of (x, y).
+
+    Returns ``multi_loglikelihood(params, data_mask)`` with ``params = (A, mu, log_sig)``;
+    the attribute ``.dataset`` exposes the ResidentDataset and ``.batch(params_list,
+    data_mask)`` evaluates several parameter vectors in one pass.
+    """
+    ds = ResidentDataset(x, y, devices=devices)
+    p = numpy.empty((1, 3))
+
+    def multi_loglikelihood(params, data_mask):
+        A, mu, log_sig_kms = params
+        p[0, 0] = A
+        p[0, 1] = mu
+        p[0, 2] = 10 ** log_sig_kms
+        return ds.loglike_batch(p, data_mask, noise_level)[0]
+
+    def batch(params_list, data_mask):
+        q = numpy.array(params_list, dtype=numpy.float64).reshape((-1, 3))
+        q[:, 2] = 10 ** q[:, 2]
+        return ds.loglike_batch(q, data_mask, noise_level)
+
+    multi_loglikelihood.dataset = ds
+    multi_loglikelihood.batch = batch
+    return multi_loglikelihood
+
+
+def make_muse_loglikelihood(y, noise_level, model, jitter=1e-5, devices=None):
+    """Build ``multi_loglikelihood_clike`` of musefuse.py:520-535.
+
+    `model(*params)` returns the model spectrum ypred[nspec] on the host
+    (musefuse.py:222-284).  `noise_level` is the per-element variance matrix.
+    """
+    ds = ResidentDataset(None, y, variance=noise_level, devices=devices)
+    Lout = numpy.zeros(ds.ndata)       # persistent, as the global at musefuse.py:519
+
+    def multi_loglikelihood_clike(params, data_mask):
+        ypred = model(*params)
+        if not numpy.any(ypred):
+            # musefuse.py:528-530 -- give low probability to solutions with no stars
+            return numpy.ones(data_mask.sum()) * -1e100
+        ds.muse_loglike(ypred, data_mask, Lout)
+        res = Lout[data_mask]
+        if jitter:
+            res = res + numpy.random.normal(0, jitter, size=data_mask.sum())
+        return res
+
+    multi_loglikelihood_clike.dataset = ds
+    multi_loglikelihood_clike.Lout = Lout
+    return multi_loglikelihood_clike
