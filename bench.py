@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the massivedatans hot path on B200.
+
+Metric (BASELINE.json): model x data-set logL evaluations per second, and % of the HBM
+roofline of the batched likelihood kernel.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nproc-per-node N bench.py --gpus N ...      (one rank per GPU)
+
+One "step" = one pass of the batched likelihood over one batch: `--candidates` parameter
+points scored against every data set of the GPU's resident shard (gensimple_horns-style
+synthetic spectra, C=200 channels, N=1e6 data sets per GPU -> 1.6 GB, far beyond the 126 MB
+L2, so every step streams from HBM).  Data sets are sharded contiguously, one shard per
+rank, no data-path collective: weak scaling.
+
+Keys of the JSON line (rank 0 prints exactly one):
+  value      evals/s with inputs (data, mask, parameter points) resident in HBM, device-timed
+             with CUDA events on the shim's stream, max over ranks
+  e2e        the same metric through the public Python callable with HOST buffers: per step
+             the mask and parameter points go host->device and the logL matrix comes back
+  roofline   algorithmic bytes per step / device time per step vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's own clike.so (oracle/_ref, serial: the build sample.py:81-84
+             loads; its OpenMP variant is racy, clike.c:32) on the box's host, bounded sample
+The reference arm (--impl reference) times that same CPU implementation per step.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'model x data-set logL evaluations per second'
+UNIT = 'evals/s'
+HBM_FALLBACK_GBS = 6650.0     # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=300)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--ndata', type=int, default=1000000, help='data sets per GPU')
+    ap.add_argument('--nx', type=int, default=200, help='channels')
+    ap.add_argument('--candidates', type=int, default=8, help='parameter points per step')
+    ap.add_argument('--mask', default='all', choices=['all', 'half', 'sparse', 'prefix'])
+    ap.add_argument('--ref-ndata', type=int, default=100000,
+                    help='data sets per step of the CPU reference arm (bounded sample)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--tuning', default='', help='lanes,unroll,ktile override (experiments)')
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    return rank, world, local
+
+
+class ClockSampler(object):
+    """Samples SM clock and throttle reasons of one GPU through NVML while work runs."""
+
+    def __init__(self, index, period=0.01):
+        self.samples = []
+        self.reasons = set()
+        self.period = period
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.sm_max = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:               # NVML unavailable: report nulls
+            self.nv = None
+
+    def _once(self):
+        nv = self.nv
+        try:
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            names = (('hw_slowdown', 0x8), ('sw_power_cap', 0x4), ('sw_thermal_slowdown', 0x20),
+                     ('hw_thermal_slowdown', 0x40), ('hw_power_brake_slowdown', 0x80),
+                     ('applications_clocks_setting', 0x2), ('sync_boost', 0x10))
+            for name, bit in names:
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            self._once()
+            time.sleep(self.period)
+
+    def start(self):
+        if self.nv is None:
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.nv is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        self._once()
+        self.stop_flag.set()
+        self.thread.join()
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.sm_max,
+                'reasons': sorted(self.reasons), 'samples': len(s)}
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return HBM_FALLBACK_GBS, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic(nx, ndata, candidates):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if the
+    capture was taken on this very configuration (profiles/clike_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'clike_traffic.json')) as f:
+            t = json.load(f)
+        if (t.get('nx'), t.get('ndata'), t.get('candidates')) == (nx, ndata, candidates):
+            return float(t['dram_bytes_per_launch'])
+    except Exception:
+        pass
+    return None
+
+
+def algorithmic_bytes(n_act, ndata, nx, K):
+    # data rows once + K model spectra + K logL vectors + mask
+    return n_act * nx * 8 + K * nx * 8 + K * n_act * 8 + ndata
+
+
+def make_inputs(args, rank):
+    from massivedatans_b200 import synth
+    x, y, _ = synth.horns(args.ndata, nx=args.nx, legacy=False, seed=1000 + rank)
+    pts = synth.parameter_points(args.candidates, seed=7)
+    log_pts = pts.copy()
+    log_pts[:, 2] = numpy.log10(pts[:, 2])       # what the reference callable receives
+    mask = synth.masks(args.ndata, seed=11)[args.mask]
+    return x, y, pts, log_pts, mask
+
+
+def cpu_reference_rate(x, y, pts, mask, budget_s, min_reps=1):
+    """Time the reference's clike.so (serial) on candidates x data sets; returns evals/s."""
+    from oracle import ref
+    nx, ndata = y.shape
+    n_act = int(mask.sum())
+    out = numpy.zeros(n_act)
+    done = 0
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        for p in pts:
+            out[:] = 0
+            ref.clike(x, y, p[0], p[1], p[2], 0.01, mask, Lout=out)
+            done += n_act
+        reps += 1
+        if reps >= min_reps and time.perf_counter() - t0 >= budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, dt, reps
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation, rank 0 only."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from massivedatans_b200 import synth
+    n = args.ref_ndata
+    x, y, _ = synth.horns(n, nx=args.nx, legacy=False, seed=1000)
+    pts = synth.parameter_points(args.candidates, seed=7)
+    mask = synth.masks(n, seed=11)[args.mask]
+    n_act = int(mask.sum())
+    from oracle import ref
+    out = numpy.zeros(n_act)
+
+    def step():
+        for p in pts:
+            out[:] = 0
+            ref.clike(x, y, p[0], p[1], p[2], 0.01, mask, Lout=out)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = args.steps * args.candidates * n_act / dt
+    sample = ('%d data sets x %d channels x %d candidates per step, reference clike.so '
+              '(gcc -O3, serial: the build sample.py:81-84 loads; OpenMP variant is racy)'
+              % (n, args.nx, args.candidates))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': 1, 'kind': 'reference',
+                         'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {
+        'workload': ('gensimple_horns-style spectra: %d data sets per GPU x %d channels, mask=%s, '
+                     '%d candidate parameter points per step (BASELINE configs[2]/[3] shape)'
+                     % (args.ndata, args.nx, args.mask, args.candidates)),
+        'ndata_per_gpu': args.ndata, 'nx': args.nx, 'candidates_per_step': args.candidates,
+        'mask': args.mask,
+        'l2': 'inputs larger than L2 (%.2f GB resident per GPU vs 126 MB L2), no flush needed'
+              % (args.ndata * args.nx * 8 / 1e9),
+        'sharding': 'contiguous data-set ranges, one shard per GPU, no data-path collective',
+    }
+
+
+def run_ours(args):
+    rank, world, local = dist_env()
+    import torch
+    import torch.distributed as dist
+    distributed = world > 1
+    inproc_devices = None
+    if distributed:
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        n_gpus = world
+        device = local
+    else:
+        n_gpus = args.gpus
+        device = 0
+        if n_gpus > 1:        # not under torchrun: one process drives N shards
+            inproc_devices = list(range(n_gpus))
+
+    from massivedatans_b200 import _lib
+    from massivedatans_b200.likelihood import ResidentDataset, make_multi_loglikelihood
+    lib = _lib.load()
+    _lib.require_device()
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if not distributed:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- inputs ------------------------------------------------------------
+    if inproc_devices:
+        import copy
+        big = copy.copy(args)
+        big.ndata = args.ndata * n_gpus
+        x, y, pts, log_pts, mask = make_inputs(big, 0)
+        f = make_multi_loglikelihood(x, y, 0.01, devices=inproc_devices)
+    else:
+        x, y, pts, log_pts, mask = make_inputs(args, rank)
+        f = make_multi_loglikelihood(x, y, 0.01, devices=[device])
+    ds = f.dataset
+    if args.tuning:
+        ds.set_tuning(*[int(v) for v in args.tuning.split(',')])
+    ndata_local = y.shape[1]
+    n_act = int(mask.sum())
+    K = args.candidates
+    sampler = ClockSampler(device)
+    sampler.start()
+
+    # ---- device-resident timing (value) -------------------------------------
+    ds.set_mask(mask)
+    ds.stage_params(pts)
+    for _ in range(max(args.warmup, 3)):
+        ds.launch_clike(0.01, -0.5)
+    ds.sync()
+    barrier()
+    launches0 = lib.mdns_launch_count()
+    ds.timer_start()
+    for _ in range(args.steps):
+        ds.launch_clike(0.01, -0.5)
+    ms = ds.timer_stop()
+    launches = lib.mdns_launch_count() - launches0
+    barrier()
+    ms = max_over_ranks(ms)
+    ms_per_step = ms / args.steps
+    evals_per_step_all = K * n_act * (n_gpus if distributed else 1)
+    value = evals_per_step_all / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public callable (host buffers) -------------
+    log_list = [tuple(p) for p in log_pts]
+    for _ in range(3):
+        L = f.batch(log_list, mask) if K > 1 else f(log_list[0], mask)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        L = f.batch(log_list, mask) if K > 1 else f(log_list[0], mask)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_s = max_over_ranks(e2e_s)
+    assert L.size == K * n_act and numpy.isfinite(L).all()
+    e2e_value = evals_per_step_all * args.steps / e2e_s
+    shards = (n_gpus if distributed else 1)
+    h2d = (ndata_local + K * 24) * shards
+    d2h = K * n_act * 8 * shards
+    clocks = sampler.stop()
+
+    # ---- roofline of the dominant kernel (per GPU) ---------------------------
+    peak, peak_src = hbm_peak()
+    per_gpu_n = ndata_local // (len(inproc_devices) if inproc_devices else 1)
+    per_gpu_act = n_act // (len(inproc_devices) if inproc_devices else 1)
+    bytes_per_launch = algorithmic_bytes(per_gpu_act, per_gpu_n, args.nx, K)
+    achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': ncu_traffic(args.nx, per_gpu_n, K),
+                'kernel': 'clike_rows_kernel', 'algorithmic_bytes_per_launch': bytes_per_launch,
+                'peak_source': peak_src,
+                'note': 'duration = whole step (line_model_kernel + clike_rows_kernel), CUDA events'}
+
+    # ---- CPU baseline beside it (rank 0, single-GPU run only) ------------------
+    cpu = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        try:
+            n_s = min(ndata_local, 500000)
+            ys = numpy.ascontiguousarray(y[:, :n_s])
+            rate, dt, reps = cpu_reference_rate(x, ys, pts, numpy.ascontiguousarray(mask[:n_s]),
+                                                budget_s=10.0)
+            cpu = {'value': rate, 'unit': UNIT, 'cores': 1, 'kind': 'reference',
+                   'sample': '%d data sets x %d channels x %d candidates x %d repetitions '
+                             '(%.1f s), reference clike.so serial (the build sample.py:81-84 '
+                             'loads; its OpenMP variant is racy, clike.c:32)'
+                             % (n_s, args.nx, K, reps, dt)}
+        except Exception as e:      # the oracle must exist; say why if it does not
+            cpu = {'value': None, 'unit': UNIT, 'cores': 1, 'kind': 'reference',
+                   'sample': 'failed: %s' % e}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': n_gpus,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'config': workload_config(args), 'roofline': roofline,
+            'cpu_baseline': cpu,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'ms_per_step': 1e3 * e2e_s / args.steps,
+                    'api': 'massivedatans_b200.likelihood.make_multi_loglikelihood(...)'
+                           + ('.batch' if K > 1 else '') + '(params, data_mask), host numpy in/out'},
+            'gpu_launches': int(launches), 'clocks': clocks,
+        }
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()
