@@ -124,8 +124,9 @@ int mdns_sync(mdns_dataset *ds);
 int mdns_timer_start(mdns_dataset *ds);
 int mdns_timer_stop(mdns_dataset *ds, float *elapsed_ms);
 /* Kernel-variant override for experiments: lanes per data set (0 = auto),
- * fragments in flight per lane (0 = auto), candidates per pass (0 = auto). */
-int mdns_set_tuning(mdns_dataset *ds, int lanes, int unroll, int ktile);
+ * fragments in flight per lane (0 = auto), candidates per pass (0 = auto),
+ * data sets per lane group (0 = auto; > 1 selects the register-blocked kernel). */
+int mdns_set_tuning(mdns_dataset *ds, int lanes, int unroll, int ktile, int rows);
 
 /* ---- RadFriends neighbour tests --------------------------------------- */
 typedef struct mdns_region mdns_region;

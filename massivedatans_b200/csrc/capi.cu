@@ -68,6 +68,9 @@ struct Shard {
 	size_t stage_cap = 0;
 	int n_act = 0;
 	bool all_active = true;
+	alignas(64) unsigned char tmap[128];      // CUtensorMaps of Y (tile kernel), 128-row boxes
+	alignas(64) unsigned char tmap256[128];   // and 256-row boxes
+	bool has_tmap = false;
 };
 
 }  // namespace mdns
@@ -244,6 +247,8 @@ int mdns_dataset_create(const double *x, const double *yy, const double *vv, int
 		}
 		if ((rc = sm_count_of(s.device, &s.sm_count)) != MDNS_OK) return fail(rc);
 		if ((rc = upload_rows(s, yy, ndata, nx, ds->pitch, 0, &s.Y)) != MDNS_OK) return fail(rc);
+		s.has_tmap = !vv && make_row_tensor_map(s.tmap, s.Y, s.n, (long long)ds->pitch, 128) == MDNS_OK &&
+		             make_row_tensor_map(s.tmap256, s.Y, s.n, (long long)ds->pitch, 256) == MDNS_OK;
 		if (vv && (rc = upload_rows(s, vv, ndata, nx, ds->pitch, 1, &s.W)) != MDNS_OK)
 			return fail(rc);
 		ds->resident_bytes += (int64_t)s.n * ds->pitch * 8 * (vv ? 2 : 1);
@@ -293,7 +298,7 @@ int mdns_dataset_info(const mdns_dataset *ds, int *ndata, int *nx, int *nshards,
 	return MDNS_OK;
 }
 
-int mdns_set_tuning(mdns_dataset *ds, int lanes, int unroll, int ktile)
+int mdns_set_tuning(mdns_dataset *ds, int lanes, int unroll, int ktile, int rows)
 {
 	if (!ds) {
 		set_error("null data set");
@@ -302,6 +307,7 @@ int mdns_set_tuning(mdns_dataset *ds, int lanes, int unroll, int ktile)
 	ds->tuning.lanes = lanes;
 	ds->tuning.unroll = unroll;
 	ds->tuning.ktile = ktile;
+	ds->tuning.rows = rows;
 	return MDNS_OK;
 }
 
@@ -408,6 +414,8 @@ static void fill_args(const mdns_dataset *ds, const Shard &s, LikeArgs &a)
 	a.mpitch = (int)ds->pitch;
 	a.K = ds->K;
 	a.out = s.d_out;
+	a.tmap = s.has_tmap ? s.tmap : nullptr;
+	a.tmap256 = s.has_tmap ? s.tmap256 : nullptr;
 }
 
 int mdns_clike_launch(mdns_dataset *ds, double noise, double scale)

@@ -6,12 +6,14 @@ namespace mdns {
 
 // ---------------------------------------------------------------- layout ---
 // Resident layout ("data-set-major rows"): data set i of a shard owns the row
-//   Y[i*pitch .. i*pitch + nx)   (doubles), pitch = round_up(nx, 16)
-// i.e. every row starts on a 128-byte boundary and is padded with zeros.
+//   Y[i*pitch .. i*pitch + nx)   (doubles), pitch = round_up(nx, 2)
+// i.e. every row starts on a 16-byte boundary (128-bit loads, bulk-TMA) and an odd
+// channel count is padded with one zero.  No wider padding: ncu showed that padding
+// rows to 128 bytes is fetched from DRAM anyway (1664 instead of 1600 bytes per row).
 // The host matrix is channel-major (clike.c:72: yy[i + j*ndata]); it is
 // transposed once at upload.  Model spectra use the same pitch and padding.
-constexpr int ROW_ALIGN = 16;   // doubles (128 bytes)
-constexpr int KT_MAX = 8;       // candidates per pass kept in registers
+constexpr int ROW_ALIGN = 2;    // doubles (16 bytes)
+constexpr int KT_MAX = 32;      // model buffers are padded to a multiple of this many candidates
 
 // in: channel-major chunk in[j*ld_in + c], j < nx, c < nb  (device staging)
 // out: rows out[c*pitch + j]; recip != 0 stores 1/v (inverse variance)
@@ -46,16 +48,27 @@ struct LikeArgs {
 	double scale;         // clike: multiplies the chi-square sum
 	double *out;          // clike: [K][out_stride] compacted; muse: [K][out_stride] by row index
 	long long out_stride;
+	const void *tmap;     // host copies of the rows' CUtensorMaps for 128- and 256-row tiles
+	const void *tmap256;  // (tile kernel) or nullptr
 };
 
 struct Tuning {
-	int lanes = 0;   // lanes per data set: 8 or 32 (0 = auto)
+	int lanes = 0;   // lanes per data set: 8 or 32; 1 = tile kernel (unroll = channels per
+	                 // stage 16/32, rows = ring stages 3/4/6, all-active only); 0 = auto
 	int unroll = 0;  // 128-bit fragments in flight per lane (0 = auto)
 	int ktile = 0;   // candidates per pass (0 = auto)
+	int rows = 0;    // data sets per lane group in the block kernel: 1, 2, 4 (0 = auto)
 };
 
 int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t st);
 int launch_muse(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t st);
+// lane-per-data-set kernel fed by a bulk-TMA ring (clike_tile_kernel.cu)
+int launch_clike_tile(const LikeArgs &a, const void *tmap, int kt, int nbox, int stages,
+                      int tile_rows, int sm_count, cudaStream_t st);
+// 128-byte CUtensorMap describing the resident rows Y[n_rows][pitch] (tile kernel)
+int make_row_tensor_map(void *out, const double *Y, long long n_rows, long long pitch,
+                        int tile_rows);
+int tile_constant_capacity();
 
 // ------------------------------------------------------------ neighbours ---
 // members in SoA layout xs[k*npad + i]

@@ -297,6 +297,161 @@ __global__ void __launch_bounds__(LK_THREADS) clike_rows_kernel(const LikeArgs a
 	}
 }
 
+// ---- register-blocked variant for candidate batches (K >= 4) -----------------
+// With KT candidates per pass the streaming kernel above becomes bound by shared-memory
+// bandwidth: every (element, candidate) pair needs 8 bytes of model from shared memory
+// and the crossbar delivers 128 lane-bytes/clk/SM = 16 pairs/clk, half of what the FP64
+// pipe (64 lanes, 2 ops per pair) can retire.  Here each group of L lanes walks R data
+// sets at once, so a model fragment fetched from shared memory is used R times.
+
+// Sum KT per-lane partials over the L lanes of a group with a transposing butterfly:
+// each step halves the number of live values, so 8 values over 8 lanes cost 7 shuffles
+// instead of 24.  On return lane `gl` holds the group total of candidate `kidx` in v[0].
+template <int N, int O>
+struct GroupReduce {
+	template <int KT>
+	static __device__ __forceinline__ void run(double (&v)[KT], int gl, int &kidx)
+	{
+		if constexpr (O >= 1) {
+			if constexpr (N > 1) {
+				constexpr int H = N / 2;
+				const bool upper = (gl & O) != 0;
+#pragma unroll
+				for (int j = 0; j < H; ++j) {
+					const double keep = upper ? v[j + H] : v[j];
+					const double send = upper ? v[j] : v[j + H];
+					v[j] = keep + shfl_xor_f64(send, O);
+				}
+				if (upper) kidx += H;
+				GroupReduce<H, O / 2>::run(v, gl, kidx);
+			} else {
+				v[0] += shfl_xor_f64(v[0], O);
+				GroupReduce<1, O / 2>::run(v, gl, kidx);
+			}
+		}
+	}
+};
+
+template <int L, int U, int R, int KT>
+__global__ void __launch_bounds__(LK_THREADS, 2) clike_block_kernel(const LikeArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	double2 *sm = reinterpret_cast<double2 *>(smem_raw);
+	__shared__ uint64_t bar;
+	constexpr int G = 32 / L;                         // groups per warp
+	constexpr int RPC = (LK_THREADS / 32) * G * R;    // data sets per CTA step
+	// lanes of a group that own a distinct candidate total after the reduction
+	constexpr int OWNERS = KT < L ? KT : L;
+	const int k0 = blockIdx.y * KT;
+	const int mfp = a.mpitch >> 1;
+	const int nfrag = (a.nx + 1) >> 1;
+	stage_model_tma<KT>(sm, &bar, a.model, a.mpitch, k0);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int g = lane / L, gl = lane % L;
+	const int nchunks = (nfrag + L * U - 1) / (L * U);
+	const double inv = a.scale / a.noise2;
+	mbar_wait(&bar, 0);
+
+	for (long long rb = (long long)blockIdx.x * RPC + (warp * G + g) * R; rb - g * R < a.n_rows;
+	     rb += (long long)gridDim.x * RPC) {
+		const double2 *p[R];
+#pragma unroll
+		for (int r = 0; r < R; ++r) {
+			// rows past the end re-read the last row (results discarded) so that the
+			// whole warp stays convergent for the shuffles
+			long long rr = rb + r < a.n_rows ? rb + r : (long long)a.n_rows - 1;
+			const long long row = a.active ? (long long)a.active[rr] : rr;
+			p[r] = reinterpret_cast<const double2 *>(a.Y + row * a.pitch);
+		}
+		double acc[R][KT];
+#pragma unroll
+		for (int r = 0; r < R; ++r)
+#pragma unroll
+			for (int k = 0; k < KT; ++k) acc[r][k] = 0.0;
+		for (int c = 0; c < nchunks; ++c) {
+			const int f = c * (L * U) + gl;
+			double2 y[R][U];
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				const int fi = f + u * L;
+				if (fi < nfrag) {
+#pragma unroll
+					for (int r = 0; r < R; ++r) y[r][u] = ldg_stream(p[r] + fi);
+				}
+			}
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				const int fi = f + u * L;
+				if (fi < nfrag) {
+#pragma unroll
+					for (int k = 0; k < KT; ++k) {
+						const double2 m = sm[k * mfp + fi];
+#pragma unroll
+						for (int r = 0; r < R; ++r) {
+							const double d0 = m.x - y[r][u].x;
+							const double d1 = m.y - y[r][u].y;
+							acc[r][k] = fma(d0, d0, acc[r][k]);
+							acc[r][k] = fma(d1, d1, acc[r][k]);
+						}
+					}
+				}
+			}
+		}
+#pragma unroll
+		for (int r = 0; r < R; ++r) {
+			int kidx = 0;
+			GroupReduce<KT, L / 2>::run(acc[r], gl, kidx);
+			// after the transposing steps the lanes whose low bits are zero own a total
+			const bool owner = (gl & (L / OWNERS - 1)) == 0;
+			if (owner && rb + r < a.n_rows && k0 + kidx < a.K)
+				a.out[(long long)(k0 + kidx) * a.out_stride + rb + r] = acc[r][0] * inv;
+		}
+	}
+}
+
+template <int L, int U, int R, int KT>
+static int launch_clike_block_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
+{
+	constexpr int RPC = (LK_THREADS / 32) * (32 / L) * R;
+	const size_t smem = (size_t)KT * a.mpitch * 8;
+	auto kern = clike_block_kernel<L, U, R, KT>;
+	if (smem > 48 * 1024)
+		MDNS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                               (int)smem));
+	int occ = 0;
+	MDNS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LK_THREADS, smem));
+	if (occ < 1) {
+		set_error("clike block kernel does not fit: %zu bytes of shared memory", smem);
+		return MDNS_EINVAL;
+	}
+	const int ktiles = ceil_div(a.K, KT);
+	long long gx = ceil_div(a.n_rows, RPC);
+	const long long resident = (long long)sm_count * occ;
+	if (gx > resident) gx = resident;
+	if (gx < 1) gx = 1;
+	kern<<<dim3((unsigned)gx, ktiles), LK_THREADS, smem, st>>>(a);
+	MDNS_LAUNCHED("clike_block_kernel");
+	return MDNS_OK;
+}
+
+// supported (rows, unroll) shapes of the block kernel, lanes fixed at 8
+static int launch_clike_block(const LikeArgs &a, int rows, int u, int kt, int sm_count,
+                              cudaStream_t st)
+{
+#define MDNS_BLK(RR, UU)                                                                  \
+	if (rows == RR && u == UU)                                                        \
+		return kt == 4 ? launch_clike_block_inst<8, UU, RR, 4>(a, sm_count, st)   \
+		               : launch_clike_block_inst<8, UU, RR, 8>(a, sm_count, st)
+	MDNS_BLK(2, 2);
+	MDNS_BLK(2, 4);
+	MDNS_BLK(4, 1);
+	MDNS_BLK(4, 2);
+#undef MDNS_BLK
+	set_error("unsupported block-kernel shape rows=%d unroll=%d", rows, u);
+	return MDNS_EINVAL;
+}
+
 template <int L, int U, int KT>
 static int launch_clike_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 {
@@ -378,6 +533,32 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 	if (a.n_rows <= 0 || a.K <= 0) return MDNS_OK;
 	const int nfrag = (a.nx + 1) >> 1;
 	int L = t.lanes;
+	const bool tile_ok = a.tmap && !a.active && 4LL * a.mpitch <= tile_constant_capacity();
+	if (L == 1 && tile_ok) {
+		// lane-per-data-set tile kernel (tensor-TMA ring), all-active rows only
+		int kt = t.ktile;
+		if (kt != 4 && kt != 8 && kt != 16 && kt != 32) kt = a.K >= 16 ? 16 : a.K >= 8 ? 8 : 4;
+		while (kt > 4 && (long long)kt * a.mpitch > tile_constant_capacity()) kt >>= 1;
+		// unroll: 16/32 channels per stage with 128-row tiles, 116/132 with 256-row tiles
+		const int tile_rows = t.unroll >= 100 ? 256 : 128;
+		const int cw = t.unroll >= 100 ? t.unroll - 100 : t.unroll;
+		const int nbox = cw == 32 ? 2 : 1;
+		int stages = (t.rows == 3 || t.rows == 4 || t.rows == 6) ? t.rows : 3;
+		if (tile_rows == 128 && nbox == 1 && stages == 3) stages = 4;
+		return launch_clike_tile(a, tile_rows == 256 ? a.tmap256 : a.tmap, kt, nbox, stages,
+		                         tile_rows, sm_count, st);
+	}
+	if (L == 1) {
+		// tile kernel requested but not applicable (masked rows): automatic choice
+		return launch_clike(a, Tuning(), sm_count, st);
+	}
+	if (L == 0 && t.unroll == 0 && t.ktile == 0 && t.rows == 0 && tile_ok && a.K >= 8 &&
+	    a.n_rows >= 32768 && 8LL * a.mpitch <= tile_constant_capacity()) {
+		// automatic choice for all-active candidate batches (measured at N=1e6, C=200:
+		// K=8 0.29 ms vs 0.35 ms block kernel; K=16 0.51 ms vs 0.71 ms)
+		const int kt = (a.K >= 16 && 16LL * a.mpitch <= tile_constant_capacity()) ? 16 : 8;
+		return launch_clike_tile(a, a.tmap256, kt, 1, 3, 256, sm_count, st);
+	}
 	if (L != 8 && L != 32) L = (a.n_rows >= 16384 && nfrag >= 8) ? 8 : 32;
 	int U = t.unroll;
 	if (U != 1 && U != 2 && U != 4 && U != 8 && U != 13 && U != 16) U = pick_unroll(nfrag, L);
@@ -385,6 +566,16 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 	if ((size_t)kt * a.mpitch * 8 > 200 * 1024) {
 		set_error("model spectrum of %d channels does not fit in shared memory", a.nx);
 		return MDNS_EINVAL;
+	}
+	// candidate batches: register-blocked kernel (R data sets per lane group)
+	int rows = t.rows;
+	// measured at N=1e6, C=200: KT=4 -> R=4,U=2 (0.27 ms); KT=8 -> R=2,U=4 (0.35 ms)
+	if (rows == 0) rows = (kt >= 4 && a.n_rows >= 65536 && nfrag >= 16) ? (kt == 8 ? 2 : 4) : 1;
+	if (rows > 1 && kt >= 4) {
+		int bu = t.unroll;
+		if (rows == 4 && bu != 1 && bu != 2) bu = 2;
+		if (rows == 2 && bu != 2 && bu != 4) bu = 4;
+		return launch_clike_block(a, rows, bu, kt, sm_count, st);
 	}
 	return L == 8 ? launch_clike_u<8>(a, U, kt, sm_count, st)
 	              : launch_clike_u<32>(a, U, kt, sm_count, st);

@@ -149,8 +149,9 @@ class ResidentDataset(object):
         _lib.check(self._lib.mdns_timer_stop(self._h, ctypes.byref(ms)), 'mdns_timer_stop')
         return ms.value
 
-    def set_tuning(self, lanes=0, unroll=0, ktile=0):
-        _lib.check(self._lib.mdns_set_tuning(self._h, lanes, unroll, ktile), 'mdns_set_tuning')
+    def set_tuning(self, lanes=0, unroll=0, ktile=0, rows=0):
+        _lib.check(self._lib.mdns_set_tuning(self._h, lanes, unroll, ktile, rows),
+                   'mdns_set_tuning')
 
     # -- one-call forms ------------------------------------------------------
     def loglike_batch(self, params, data_mask, noise, scale=-0.5, out=None):

@@ -77,19 +77,48 @@ def test_clike_batch_sizes(oracle_port, K):
         assert rel_err(got[k], want) < TOL
 
 
-@pytest.mark.parametrize('lanes,unroll,ktile', [(8, 1, 1), (8, 2, 2), (8, 4, 4), (8, 8, 8),
-                                                (8, 13, 1), (8, 16, 8), (32, 1, 1), (32, 4, 2),
-                                                (32, 8, 8), (32, 13, 4), (32, 16, 1)])
-def test_clike_kernel_variants(oracle_port, lanes, unroll, ktile):
+@pytest.mark.parametrize('lanes,unroll,ktile,rows', [
+    (8, 1, 1, 1), (8, 2, 2, 1), (8, 4, 4, 1), (8, 8, 8, 1), (8, 13, 1, 1), (8, 16, 8, 1),
+    (32, 1, 1, 1), (32, 4, 2, 1), (32, 8, 8, 1), (32, 13, 4, 1), (32, 16, 1, 1),
+    # register-blocked kernel: rows data sets per lane group
+    (8, 2, 8, 2), (8, 4, 8, 2), (8, 1, 8, 4), (8, 2, 8, 4), (8, 2, 4, 2), (8, 4, 4, 2),
+    (8, 1, 4, 4), (8, 2, 4, 4),
+    # lane-per-data-set tile kernel: (1, channels per stage, candidates per pass, ring stages)
+    # (all-active rows only: with a mask these fall back to the lanes-across-channels kernels)
+    (1, 32, 4, 3), (1, 32, 8, 3), (1, 32, 16, 3), (1, 16, 8, 4), (1, 16, 16, 6), (1, 32, 32, 3),
+    (1, 16, 32, 4), (1, 16, 8, 6), (1, 0, 0, 0),
+    # 256-row tiles: unroll = 100 + channels per stage
+    (1, 116, 4, 3), (1, 116, 8, 3), (1, 116, 16, 4), (1, 116, 32, 3), (1, 132, 8, 3),
+    (1, 132, 16, 3)])
+def test_clike_kernel_variants(oracle_port, lanes, unroll, ktile, rows):
     N = 1111
     x, y, _ = synth.horns(N, nx=203, seed=3)      # odd channel count: padded fragment
     ds = ResidentDataset(x, y)
-    ds.set_tuning(lanes, unroll, ktile)
+    ds.set_tuning(lanes, unroll, ktile, rows)
     pts = synth.parameter_points(5, seed=1)
     m = synth.masks(N)['half']
     got = ds.loglike_batch(pts, m, synth.NOISE_LEVEL, scale=1.0)
+    full = ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0)
+    allm = numpy.ones(N, dtype=bool)
     for k, p in enumerate(pts):
         want = oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, m)
+        assert rel_err(got[k], want) < TOL
+        want = oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, allm)
+        assert rel_err(full[k], want) < TOL
+
+
+@pytest.mark.parametrize('N,nx,K', [(128, 16, 4), (129, 18, 9), (5000, 200, 17), (1000, 33, 40),
+                                    (300, 1000, 5), (77, 1599, 4)])
+def test_clike_tile_kernel_shapes(oracle_port, N, nx, K):
+    x, y, _ = synth.horns(N, nx=nx, seed=N)
+    ds = ResidentDataset(x, y)
+    ds.set_tuning(1, 0, 0, 0)
+    pts = synth.parameter_points(K, seed=N)
+    got = ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0)
+    allm = numpy.ones(N, dtype=bool)
+    for k in (0, K // 2, K - 1):
+        p = pts[k]
+        want = oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, allm)
         assert rel_err(got[k], want) < TOL
 
 

@@ -57,31 +57,33 @@ def main():
               % (tag, K, mask_name, tuning, ms, gbs, gbs / peak, row['evals_per_s']), flush=True)
 
     # 1. kernel variants at K=1 and K=8, full mask
-    variants = ['0,0,0', '8,13,0', '8,8,0', '8,16,0', '8,4,0', '32,4,0', '32,8,0', '32,2,0']
+    variants = ['0,0,0,0', '8,4,8,2', '8,2,4,4',
+                '1,32,8,3', '1,16,8,4', '1,16,16,4', '1,116,4,3', '1,116,8,3', '1,116,8,4',
+                '1,116,16,3', '1,116,16,4', '1,116,32,3', '1,132,8,3', '1,132,16,3']
     if args.quick:
-        variants = ['0,0,0']
-    for K in (1, 8):
+        variants = ['0,0,0,0']
+    for K in (4, 8, 16):
         pts = synth.parameter_points(K)
         ds.stage_params(pts)
         ds.set_mask(None)
         for t in variants:
             ds.set_tuning(*[int(v) for v in t.split(',')])
             record('variant', K, 'all', t, time_launch(ds, args.steps, lambda: ds.launch_clike(0.01, -0.5)))
-    ds.set_tuning(0, 0, 0)
+    ds.set_tuning(0, 0, 0, 0)
     # 2. K sweep, full mask (ktile variants for K >= 2)
     for K in (1, 2, 4, 8, 16, 32, 64, 400):
         pts = synth.parameter_points(K)
         ds.stage_params(pts)
         ds.set_mask(None)
         steps = max(3, args.steps // max(1, K // 8))
-        record('ksweep', K, 'all', '0,0,0', time_launch(ds, steps, lambda: ds.launch_clike(0.01, -0.5)))
+        record('ksweep', K, 'all', 'auto', time_launch(ds, steps, lambda: ds.launch_clike(0.01, -0.5)))
     # 3. masks at K=1 and 8
     for K in (1, 8):
         pts = synth.parameter_points(K)
         ds.stage_params(pts)
         for name in ('all', 'half', 'sparse', 'prefix'):
             ds.set_mask(masks[name])
-            record('mask', K, name, '0,0,0', time_launch(ds, args.steps, lambda: ds.launch_clike(0.01, -0.5)))
+            record('mask', K, name, 'auto', time_launch(ds, args.steps, lambda: ds.launch_clike(0.01, -0.5)))
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(rows, open(args.out, 'w'), indent=1)
 
