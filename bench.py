@@ -55,6 +55,8 @@ def parse_args():
                     help='data sets per step of the CPU reference arm (bounded sample)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--tuning', default='', help='lanes,unroll,ktile override (experiments)')
+    ap.add_argument('--sweep', action='store_true',
+                    help='also time K = 1, 2, 4, 16, 64 device-side and add them under "sweep"')
     return ap.parse_args()
 
 
@@ -300,11 +302,34 @@ def run_ours(args):
         ds.launch_clike(0.01, -0.5)
     ms = ds.timer_stop()
     launches = lib.mdns_launch_count() - launches0
+    kernel_name = lib.mdns_last_kernel().decode()
     barrier()
     ms = max_over_ranks(ms)
     ms_per_step = ms / args.steps
     evals_per_step_all = K * n_act * (n_gpus if distributed else 1)
     value = evals_per_step_all / (ms_per_step * 1e-3)
+
+    # ---- optional device-side sweep over the candidate count ----------------
+    sweep = None
+    if args.sweep and not distributed:
+        from massivedatans_b200 import synth
+        sweep = []
+        peak_gbs = hbm_peak()[0]
+        for Ks in (1, 2, 4, 8, 16, 64, 400):
+            ds.stage_params(synth.parameter_points(Ks, seed=7))
+            for _ in range(3):
+                ds.launch_clike(0.01, -0.5)
+            ds.sync()
+            reps = max(3, min(args.steps, 4000 // Ks))
+            ds.timer_start()
+            for _ in range(reps):
+                ds.launch_clike(0.01, -0.5)
+            t = ds.timer_stop() / reps
+            gbs = algorithmic_bytes(n_act, ndata_local, args.nx, Ks) / (t * 1e-3) / 1e9
+            sweep.append({'candidates': Ks, 'ms_per_step': t, 'evals_per_s': Ks * n_act / (t * 1e-3),
+                          'hbm_gbs': gbs, 'hbm_frac': gbs / peak_gbs,
+                          'kernel': lib.mdns_last_kernel().decode()})
+        ds.stage_params(pts)
 
     # ---- end to end through the public callable (host buffers) -------------
     log_list = [tuple(p) for p in log_pts]
@@ -332,9 +357,10 @@ def run_ours(args):
     achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': ncu_traffic(args.nx, per_gpu_n, K),
-                'kernel': 'clike_rows_kernel', 'algorithmic_bytes_per_launch': bytes_per_launch,
+                'kernel': kernel_name, 'algorithmic_bytes_per_launch': bytes_per_launch,
                 'peak_source': peak_src,
-                'note': 'duration = whole step (line_model_kernel + clike_rows_kernel), CUDA events'}
+                'note': 'duration = whole step (line_model_kernel + constant-bank copy + dominant kernel), '
+                        'CUDA events on the shim stream'}
 
     # ---- CPU baseline beside it (rank 0, single-GPU run only) ------------------
     cpu = None
@@ -366,6 +392,8 @@ def run_ours(args):
                            + ('.batch' if K > 1 else '') + '(params, data_mask), host numpy in/out'},
             'gpu_launches': int(launches), 'clocks': clocks,
         }
+        if sweep is not None:
+            line['sweep'] = sweep
         print(json.dumps(line))
     if distributed:
         dist.destroy_process_group()

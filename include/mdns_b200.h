@@ -40,6 +40,8 @@ int         mdns_version(void);          /* 100*major + minor */
 int         mdns_device_count(void);     /* CUDA devices visible; 0 if none */
 /* Kernels launched by this library since load (bench.py's "gpu_launches"). */
 int64_t     mdns_launch_count(void);
+/* Name of the kernel launched most recently by this library (measurement aid). */
+const char *mdns_last_kernel(void);
 /* Host helper of the neighbour path: the smallest double T such that
  * sqrt(T) >= r in IEEE arithmetic, so that  sqrt(d) < r  <=>  d < T  exactly
  * (the compare at cneighbors.c:88,109 without a sqrt in the device loop). */

@@ -22,6 +22,7 @@ SIGNATURES = {
     'mdns_version': (c_int, []),
     'mdns_device_count': (c_int, []),
     'mdns_launch_count': (c_int64, []),
+    'mdns_last_kernel': (c_char_p, []),
     'mdns_sqrt_threshold': (c_double, [c_double]),
     'mdns_host_alloc': (c_void_p, [c_int64]),
     'mdns_host_free': (c_int, [c_void_p]),

@@ -16,6 +16,7 @@ namespace mdns {
 
 static thread_local std::string g_error;
 std::atomic<long long> g_launches{0};
+std::atomic<const char *> g_last_kernel{""};
 
 void set_error(const char *fmt, ...)
 {
@@ -161,6 +162,7 @@ extern "C" {
 const char *mdns_last_error(void) { return g_error.c_str(); }
 int mdns_version(void) { return 100; }
 int64_t mdns_launch_count(void) { return g_launches.load(); }
+const char *mdns_last_kernel(void) { return g_last_kernel.load(); }
 double mdns_sqrt_threshold(double r) { return sqrt_threshold(r); }
 
 int mdns_device_count(void)

@@ -192,7 +192,7 @@ int make_row_tensor_map(void *out, const double *Y, long long n_rows, long long 
 	CUtensorMap tm;
 	const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)Y, dims, strides, box,
 	                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-	                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) {
 		set_error("cuTensorMapEncodeTiled failed with code %d (rows %lld, pitch %lld)", (int)r,
 		          n_rows, pitch);

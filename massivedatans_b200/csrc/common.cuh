@@ -15,6 +15,7 @@ namespace mdns {
 // ---- error plumbing ------------------------------------------------------
 void set_error(const char *fmt, ...);
 extern std::atomic<long long> g_launches;
+extern std::atomic<const char *> g_last_kernel;
 
 #define MDNS_CUDA(call)                                                              \
 	do {                                                                         \
@@ -30,6 +31,7 @@ extern std::atomic<long long> g_launches;
 #define MDNS_LAUNCHED(name)                                                          \
 	do {                                                                         \
 		mdns::g_launches.fetch_add(1, std::memory_order_relaxed);            \
+		mdns::g_last_kernel.store(name, std::memory_order_relaxed);          \
 		cudaError_t e__ = cudaGetLastError();                                \
 		if (e__ != cudaSuccess) {                                            \
 			mdns::set_error("launch of %s failed at %s:%d: %s", name,    \

@@ -266,3 +266,38 @@ def test_muse_callable_matches_reference_wrapper(oracle_port):
     want = oracle_port.cmuselike(y, v, t, mask)
     assert rel_err(Lout[mask], want[mask]) < TOL and (Lout[~mask] == 0).all()
     _lib.load().mdns_legacy_reset()
+
+
+# ------------------------------------------------------------ multi-GPU ----
+def _ndev():
+    return _lib.load().mdns_device_count()
+
+
+@pytest.mark.skipif(_ndev() < 2, reason='needs 2 GPUs')
+@pytest.mark.parametrize('ndev', [2, 4, 8])
+def test_sharded_dataset_matches_single_device(oracle_port, ndev):
+    if _ndev() < ndev:
+        pytest.skip('needs %d GPUs' % ndev)
+    N = 40003                       # not divisible: ragged shards
+    x, y, _ = synth.horns(N, seed=5)
+    single = ResidentDataset(x, y, devices=[0])
+    multi = ResidentDataset(x, y, devices=list(range(ndev)))
+    pts = synth.parameter_points(9, seed=2)
+    for name, m in synth.masks(N, seed=3).items():
+        a = single.loglike_batch(pts, m, synth.NOISE_LEVEL).copy()
+        b = multi.loglike_batch(pts, m, synth.NOISE_LEVEL)
+        assert a.shape == b.shape == (9, int(m.sum()))
+        assert rel_err(b, a) < TOL, name
+    m = synth.masks(N, seed=3)['half']
+    got = multi.loglike_batch(pts[:2], m, synth.NOISE_LEVEL, scale=1.0)
+    for k in range(2):
+        want = oracle_port.clike(x, y, pts[k][0], pts[k][1], pts[k][2], synth.NOISE_LEVEL, m)
+        assert rel_err(got[k], want) < TOL
+    # MUSE-type, un-compacted output across shards
+    ym, vm, t = synth.muse(ndata=1001, nspec=360)
+    dm = ResidentDataset(None, ym, variance=vm, devices=list(range(ndev)))
+    mask = numpy.random.RandomState(1).uniform(size=1001) < 0.6
+    L = numpy.zeros((1, 1001))
+    dm.muse_loglike(t, mask, L)
+    want = oracle_port.cmuselike(ym, vm, t, mask)
+    assert rel_err(L[0][mask], want[mask]) < TOL and (L[0][~mask] == 0).all()

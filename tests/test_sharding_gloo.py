@@ -1,0 +1,81 @@
+"""N > 1 host logic on CPU: world_size-2 gloo run in which every rank scores its contiguous
+shard (with the CPU oracle standing in for the device) and rank 0 reassembles the compacted
+logL vector exactly as mdns_fetch does across shards."""
+import os
+import socket
+
+import numpy
+import pytest
+
+from massivedatans_b200 import sharding, synth
+
+
+def test_shard_ranges_cover_everything():
+    for ndata in (1, 2, 7, 100, 1000003):
+        for g in (1, 2, 3, 8):
+            r = sharding.shard_ranges(ndata, g)
+            assert r[0][0] == 0 and sum(n for _, n in r) == ndata
+            assert all(r[i][0] + r[i][1] == r[i + 1][0] for i in range(len(r) - 1))
+            assert max(n for _, n in r) - min(n for _, n in r) <= 1
+            assert len(r) == min(g, ndata)
+
+
+def test_compaction_offsets():
+    mask = numpy.array([1, 0, 1, 1, 0, 0, 1, 1, 1, 0], dtype=bool)
+    r = sharding.shard_ranges(10, 3)
+    assert r == [(0, 4), (4, 3), (7, 3)]
+    assert sharding.compaction_offsets(mask, r) == [(0, 3), (3, 1), (4, 2)]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, N, out_path):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from oracle import port as oracle_port
+    x, y, _ = synth.horns(N)
+    mask = synth.masks(N)['half']
+    pts = synth.parameter_points(3)
+    ranges = sharding.shard_ranges(N, world)
+    offs = sharding.compaction_offsets(mask, ranges)
+    i0, n = ranges[rank]
+    ys = numpy.ascontiguousarray(y[:, i0:i0 + n])          # this rank's resident shard
+    ms = numpy.ascontiguousarray(mask[i0:i0 + n])
+    part = numpy.array([oracle_port.clike(x, ys, p[0], p[1], p[2], 0.01, ms) for p in pts])
+    # timing plumbing of bench.py: barrier + max over ranks
+    t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+    dist.barrier()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    assert t.item() == float(world)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, part)
+    if rank == 0:
+        n_act = int(mask.sum())
+        full = numpy.empty((len(pts), n_act))
+        for g, (off, cnt) in enumerate(offs):
+            full[:, off:off + cnt] = gathered[g]
+        numpy.save(out_path, full)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_sharded_evaluation_matches_single(tmp_path, oracle_port):
+    import torch.multiprocessing as mp
+    N = 301
+    out = str(tmp_path / 'full.npy')
+    mp.spawn(_worker, args=(2, _free_port(), N, out), nprocs=2, join=True)
+    got = numpy.load(out)
+    x, y, _ = synth.horns(N)
+    mask = synth.masks(N)['half']
+    want = numpy.array([oracle_port.clike(x, y, p[0], p[1], p[2], 0.01, mask)
+                        for p in synth.parameter_points(3)])
+    assert numpy.array_equal(got, want)
