@@ -609,13 +609,13 @@ __global__ void __launch_bounds__(LK_THREADS) muse_rows_kernel(const LikeArgs a)
 		long long row = 0;
 		const double2 *py = nullptr, *pw = nullptr;
 		double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;
+		double2 y[U], w[U];   // kept for pass 2 when the row fits one chunk (single fetch)
 		if (valid) {
 			row = a.active ? (long long)a.active[r] : r;
 			py = reinterpret_cast<const double2 *>(a.Y + row * a.pitch);
 			pw = reinterpret_cast<const double2 *>(a.W + row * a.pitch);
 			for (int c = 0; c < nchunks; ++c) {
 				const int f = c * (L * U) + gl;
-				double2 y[U], w[U];
 #pragma unroll
 				for (int u = 0; u < U; ++u) {
 					const int fi = f + u * L;
@@ -649,13 +649,14 @@ __global__ void __launch_bounds__(LK_THREADS) muse_rows_kernel(const LikeArgs a)
 		if (valid) {
 			for (int c = 0; c < nchunks; ++c) {
 				const int f = c * (L * U) + gl;
-				double2 y[U], w[U];
+				if (nchunks > 1) {   // longer rows are streamed again (served by L1/L2)
 #pragma unroll
-				for (int u = 0; u < U; ++u) {
-					const int fi = f + u * L;
-					if (fi < nfrag) {
-						y[u] = __ldg(py + fi);
-						w[u] = __ldg(pw + fi);
+					for (int u = 0; u < U; ++u) {
+						const int fi = f + u * L;
+						if (fi < nfrag) {
+							y[u] = __ldg(py + fi);
+							w[u] = __ldg(pw + fi);
+						}
 					}
 				}
 #pragma unroll
@@ -711,21 +712,28 @@ int launch_muse(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t s
 		return MDNS_EINVAL;
 	}
 	int L = t.lanes;
-	if (L != 8 && L != 32) L = (a.n_rows >= 16384 && nfrag >= 8) ? 8 : 32;
+	// long rows: one CTA per data set, rows staged once through a bulk-TMA ring
+	if ((L == 0 || L == 256) && muse_block_fits(a) && (L == 256 || nfrag >= 256))
+		return launch_muse_block(a, t.ktile, sm_count, st);
+	if (L != 8 && L != 32) L = (a.n_rows >= 16384 && nfrag >= 8 && nfrag <= 8 * 16) ? 8 : 32;
 	const int per_lane = ceil_div(nfrag, L);
 	int U = t.unroll;
-	if (U != 2 && U != 4 && U != 8) U = per_lane >= 8 ? 8 : per_lane >= 4 ? 4 : 2;
+	// prefer a single chunk (fragments stay in registers for pass 2) up to 16 per lane
+	if (U != 2 && U != 4 && U != 8 && U != 16)
+		U = per_lane > 8 ? 16 : per_lane > 4 ? 8 : per_lane > 2 ? 4 : 2;
 	if (L == 8) {
 		switch (U) {
 		case 2: return launch_muse_inst<8, 2>(a, sm_count, st);
 		case 4: return launch_muse_inst<8, 4>(a, sm_count, st);
-		default: return launch_muse_inst<8, 8>(a, sm_count, st);
+		case 8: return launch_muse_inst<8, 8>(a, sm_count, st);
+		default: return launch_muse_inst<8, 16>(a, sm_count, st);
 		}
 	}
 	switch (U) {
 	case 2: return launch_muse_inst<32, 2>(a, sm_count, st);
 	case 4: return launch_muse_inst<32, 4>(a, sm_count, st);
-	default: return launch_muse_inst<32, 8>(a, sm_count, st);
+	case 8: return launch_muse_inst<32, 8>(a, sm_count, st);
+	default: return launch_muse_inst<32, 16>(a, sm_count, st);
 	}
 }
 

@@ -234,6 +234,26 @@ def test_muse_vs_oracle(oracle_port, ndata, nspec):
             assert rel_err(L[0][mask], want[mask]) < TOL
 
 
+@pytest.mark.parametrize('lanes,unroll,ktile', [(256, 0, 1), (256, 0, 2), (256, 0, 4), (256, 0, 0),
+                                                (8, 2, 0), (8, 16, 0), (32, 4, 0), (32, 16, 0),
+                                                (0, 0, 0)])
+@pytest.mark.parametrize('ndata,nspec', [(3, 2), (50, 37), (700, 360), (90, 3600), (20, 5001)])
+def test_muse_kernel_variants_and_batches(oracle_port, lanes, unroll, ktile, ndata, nspec):
+    y, v, t = synth.muse(ndata=ndata, nspec=nspec, seed=ndata + 1)
+    ds = ResidentDataset(None, y, variance=v)
+    ds.set_tuning(lanes, unroll, ktile, 0)
+    K = 5
+    ypreds = numpy.array([synth.muse_template(nspec, phase=0.3 * k) for k in range(K)])
+    rs = numpy.random.RandomState(ndata)
+    for mask in (numpy.ones(ndata, dtype=bool), rs.uniform(size=ndata) < 0.5):
+        L = numpy.full((K, ndata), 3.0)
+        ds.muse_loglike(ypreds, mask, L)
+        for k in range(K):
+            want = oracle_port.cmuselike(y, v, ypreds[k], mask)
+            assert rel_err(L[k][mask], want[mask]) < TOL
+            assert (L[k][~mask] == 3.0).all()
+
+
 def test_muse_callable_matches_reference_wrapper(oracle_port):
     ndata, nspec = 200, 360
     y, v, t = synth.muse(ndata=ndata, nspec=nspec)
