@@ -120,6 +120,19 @@ int mdns_stage_params(mdns_dataset *ds, const double *params, int K);
 int mdns_stage_spectra(mdns_dataset *ds, const double *ypred, int K);
 int mdns_clike_launch(mdns_dataset *ds, double noise, double scale);
 int mdns_muse_launch(mdns_dataset *ds);
+/* launch + fetch of the clike-type result in one call: the active rows are processed in
+ * chunks and the D2H copy of each finished chunk overlaps the next chunk's kernel. */
+int mdns_clike_launch_fetch(mdns_dataset *ds, double noise, double scale, double *Lout,
+                            int64_t lout_capacity);
+/* Speculative batch of the constrained draw (hiermetriclearn.py:181-196: one candidate at a
+ * time until `numpy.any(L > Lmins)`): scores the K staged candidates in one pass and applies
+ * the accept test on the device.  Lmins[n_act] is aligned with the compacted active order.
+ * accept_counts[K] (may be NULL) = data sets with scale*chi2 > Lmins per candidate;
+ * *first_k = first candidate with a non-zero count, or -1; its logL vector is copied to Lout
+ * (untouched when none accepts).  Only K ints and one vector cross PCIe. */
+int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const double *Lmins,
+                            int *accept_counts, int *first_k, double *Lout,
+                            int64_t lout_capacity);
 int mdns_fetch(mdns_dataset *ds, double *Lout, int64_t lout_capacity);
 int mdns_sync(mdns_dataset *ds);
 /* CUDA-event stopwatch on the data set's own streams (max over shards). */

@@ -40,6 +40,9 @@ SIGNATURES = {
     'mdns_stage_spectra': (c_int, [_P, _P, c_int]),
     'mdns_clike_launch': (c_int, [_P, c_double, c_double]),
     'mdns_muse_launch': (c_int, [_P]),
+    'mdns_clike_launch_fetch': (c_int, [_P, c_double, c_double, _P, c_int64]),
+    'mdns_clike_first_accept': (c_int, [_P, c_double, c_double, _P, _P, POINTER(c_int), _P,
+                                        c_int64]),
     'mdns_fetch': (c_int, [_P, _P, c_int64]),
     'mdns_sync': (c_int, [_P]),
     'mdns_timer_start': (c_int, [_P]),

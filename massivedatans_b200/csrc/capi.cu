@@ -55,7 +55,9 @@ struct Shard {
 	int i0 = 0, n = 0;            // data-set range [i0, i0+n) of the full problem
 	int sm_count = 148;
 	cudaStream_t stream = nullptr;
+	cudaStream_t copy_stream = nullptr;       // D2H of finished row chunks overlaps the next chunk
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaEvent_t ev_chunk[8] = {nullptr};
 	double *Y = nullptr, *W = nullptr, *x = nullptr;
 	uint8_t *d_mask = nullptr;
 	int *d_active = nullptr, *d_scratch = nullptr, *d_nact = nullptr;
@@ -67,6 +69,10 @@ struct Shard {
 	size_t out_cap = 0;
 	double *h_stage = nullptr;    // pinned
 	size_t stage_cap = 0;
+	double *d_lmins = nullptr;    // accept thresholds of the active data sets
+	size_t lmins_cap = 0;
+	int *d_counts = nullptr;      // accepting data sets per candidate
+	size_t counts_cap = 0;
 	int n_act = 0;
 	bool all_active = true;
 	alignas(64) unsigned char tmap[128];      // CUtensorMaps of Y (tile kernel), 128-row boxes
@@ -106,9 +112,14 @@ static void shard_free(Shard &s)
 	cudaFree(s.d_in);
 	cudaFree(s.d_model);
 	cudaFree(s.d_out);
+	cudaFree(s.d_lmins);
+	cudaFree(s.d_counts);
 	if (s.h_stage) cudaFreeHost(s.h_stage);
 	if (s.ev0) cudaEventDestroy(s.ev0);
 	if (s.ev1) cudaEventDestroy(s.ev1);
+	for (auto &e : s.ev_chunk)
+		if (e) cudaEventDestroy(e);
+	if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
 	if (s.stream) cudaStreamDestroy(s.stream);
 	s = Shard();
 }
@@ -241,6 +252,9 @@ int mdns_dataset_create(const double *x, const double *yy, const double *vv, int
 		i0 += s.n;
 		cudaError_t e = cudaSetDevice(s.device);
 		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking);
+		for (auto &ev : s.ev_chunk)
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
 		if (e == cudaSuccess) e = cudaEventCreate(&s.ev0);
 		if (e == cudaSuccess) e = cudaEventCreate(&s.ev1);
 		if (e != cudaSuccess) {
@@ -418,36 +432,175 @@ static void fill_args(const mdns_dataset *ds, const Shard &s, LikeArgs &a)
 	a.out = s.d_out;
 	a.tmap = s.has_tmap ? s.tmap : nullptr;
 	a.tmap256 = s.has_tmap ? s.tmap256 : nullptr;
+	a.row0 = 0;
 }
 
-int mdns_clike_launch(mdns_dataset *ds, double noise, double scale)
+static int clike_check(mdns_dataset *ds, const char *who)
 {
 	if (!ds || ds->staged == 0) {
-		set_error("mdns_clike_launch: stage parameter points or spectra first");
+		set_error("%s: stage parameter points or spectra first", who);
 		return MDNS_ESTATE;
 	}
 	if (ds->has_var) {
 		set_error("data set carries per-element variances: use mdns_muse_launch");
 		return MDNS_ESTATE;
 	}
+	return MDNS_OK;
+}
+
+static int clike_model(mdns_dataset *ds, Shard &s)
+{
+	if (ds->staged != 1) return MDNS_OK;
+	const int Kpad = (int)round_up(ds->K, KT_MAX);
+	return launch_line_model(s.x, ds->nx, s.d_in, ds->K, Kpad, s.d_model, (int)ds->pitch, s.stream);
+}
+
+// chi-square of the active rows [r0, r0+nc) of one shard
+static int clike_rows(mdns_dataset *ds, Shard &s, double noise, double scale, int r0, int nc)
+{
+	LikeArgs a;
+	fill_args(ds, s, a);
+	a.noise2 = noise * noise;
+	a.scale = scale;
+	a.out_stride = s.n_act;
+	a.row0 = r0;
+	a.n_rows = nc;
+	a.out = s.d_out + r0;
+	if (a.active)
+		a.active += r0;
+	else
+		a.Y += (size_t)r0 * ds->pitch;
+	return launch_clike(a, ds->tuning, s.sm_count, s.stream);
+}
+
+int mdns_clike_launch(mdns_dataset *ds, double noise, double scale)
+{
+	int rc = clike_check(ds, "mdns_clike_launch");
+	if (rc != MDNS_OK) return rc;
 	for (auto &s : ds->shards) {
 		MDNS_CUDA(cudaSetDevice(s.device));
-		int rc = MDNS_OK;
-		if (ds->staged == 1) {
-			const int Kpad = (int)round_up(ds->K, KT_MAX);
-			rc = launch_line_model(s.x, ds->nx, s.d_in, ds->K, Kpad, s.d_model, (int)ds->pitch,
-			                       s.stream);
-			if (rc != MDNS_OK) return rc;
-		}
-		LikeArgs a;
-		fill_args(ds, s, a);
-		a.noise2 = noise * noise;
-		a.scale = scale;
-		a.out_stride = s.n_act;
-		if ((rc = launch_clike(a, ds->tuning, s.sm_count, s.stream)) != MDNS_OK) return rc;
+		if ((rc = clike_model(ds, s)) != MDNS_OK) return rc;
+		if ((rc = clike_rows(ds, s, noise, scale, 0, s.n_act)) != MDNS_OK) return rc;
 	}
 	ds->launched = 1;
 	return MDNS_OK;
+}
+
+// Launch + fetch in one call: every shard's active rows are cut into up to 8 chunks; the
+// D2H copy of a finished chunk runs on a second stream while the next chunk computes, so
+// the PCIe transfer of the K x n_act logL matrix hides the kernel time (or vice versa).
+int mdns_clike_launch_fetch(mdns_dataset *ds, double noise, double scale, double *Lout,
+                            int64_t lout_capacity)
+{
+	int rc = clike_check(ds, "mdns_clike_launch_fetch");
+	if (rc != MDNS_OK) return rc;
+	if (!Lout) {
+		set_error("mdns_clike_launch_fetch: Lout is null");
+		return MDNS_EINVAL;
+	}
+	const int K = ds->K;
+	const long long need = (long long)K * ds->n_act_total;
+	if (lout_capacity < need) {
+		set_error("Lout holds %lld doubles, %lld needed (K=%d, n_act=%d)", (long long)lout_capacity,
+		          need, K, ds->n_act_total);
+		return MDNS_EINVAL;
+	}
+	long long off = 0;
+	for (auto &s : ds->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		if (s.n_act > 0) {
+			if ((rc = clike_model(ds, s)) != MDNS_OK) return rc;
+			// ~4 MB of results per chunk, at most 8 chunks, at least 32768 rows each
+			const long long bytes = (long long)K * s.n_act * 8;
+			int nchunk = (int)std::min<long long>(8, std::max<long long>(1, bytes / (4 << 20)));
+			while (nchunk > 1 && s.n_act / nchunk < 32768) --nchunk;
+			const int per = (int)round_up(ceil_div(s.n_act, nchunk), 256);
+			int c = 0;
+			for (int r0 = 0; r0 < s.n_act; r0 += per, ++c) {
+				const int nc = std::min(per, s.n_act - r0);
+				if ((rc = clike_rows(ds, s, noise, scale, r0, nc)) != MDNS_OK) return rc;
+				MDNS_CUDA(cudaEventRecord(s.ev_chunk[c], s.stream));
+				MDNS_CUDA(cudaStreamWaitEvent(s.copy_stream, s.ev_chunk[c], 0));
+				MDNS_CUDA(cudaMemcpy2DAsync(Lout + off + r0, (size_t)ds->n_act_total * sizeof(double),
+				                            s.d_out + r0, (size_t)s.n_act * sizeof(double),
+				                            (size_t)nc * sizeof(double), K, cudaMemcpyDeviceToHost,
+				                            s.copy_stream));
+			}
+		}
+		off += s.n_act;
+	}
+	for (auto &s : ds->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		MDNS_CUDA(cudaStreamSynchronize(s.copy_stream));
+		MDNS_CUDA(cudaStreamSynchronize(s.stream));
+	}
+	ds->launched = 1;
+	return MDNS_OK;
+}
+
+// Speculative batch of the constrained draw (hiermetriclearn.py:181-196): the K staged
+// candidates are scored in one pass; accept_counts[k] receives the number of active data sets
+// with scale*chi2 > Lmins; the logL vector of the FIRST candidate with a non-zero count (the
+// one the reference's one-at-a-time loop would have returned) is copied to Lout.  Only
+// K ints + one vector cross PCIe instead of K vectors.
+int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const double *Lmins,
+                            int *accept_counts, int *first_k, double *Lout, int64_t lout_capacity)
+{
+	int rc = clike_check(ds, "mdns_clike_first_accept");
+	if (rc != MDNS_OK) return rc;
+	if (!Lmins || !first_k || !Lout) {
+		set_error("mdns_clike_first_accept: need Lmins, first_k and Lout");
+		return MDNS_EINVAL;
+	}
+	if (lout_capacity < ds->n_act_total) {
+		set_error("Lout holds %lld doubles, %d needed", (long long)lout_capacity, ds->n_act_total);
+		return MDNS_EINVAL;
+	}
+	const int K = ds->K;
+	std::vector<int> total(K, 0), part(K);
+	long long off = 0;
+	for (auto &s : ds->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		if (s.n_act > 0) {
+			if ((rc = grow(&s.d_lmins, &s.lmins_cap, (size_t)s.n_act, false)) != MDNS_OK) return rc;
+			if ((rc = grow(&s.d_counts, &s.counts_cap, (size_t)K, false)) != MDNS_OK) return rc;
+			MDNS_CUDA(cudaMemcpyAsync(s.d_lmins, Lmins + off, (size_t)s.n_act * sizeof(double),
+			                          cudaMemcpyHostToDevice, s.stream));
+			if ((rc = clike_model(ds, s)) != MDNS_OK) return rc;
+			if ((rc = clike_rows(ds, s, noise, scale, 0, s.n_act)) != MDNS_OK) return rc;
+			if ((rc = launch_accept_count(s.d_out, s.n_act, s.n_act, K, s.d_lmins, s.d_counts,
+			                              s.stream)) != MDNS_OK)
+				return rc;
+		}
+		off += s.n_act;
+	}
+	for (auto &s : ds->shards) {
+		if (s.n_act == 0) continue;
+		MDNS_CUDA(cudaSetDevice(s.device));
+		MDNS_CUDA(cudaMemcpyAsync(part.data(), s.d_counts, (size_t)K * sizeof(int),
+		                          cudaMemcpyDeviceToHost, s.stream));
+		MDNS_CUDA(cudaStreamSynchronize(s.stream));
+		for (int k = 0; k < K; ++k) total[k] += part[k];
+	}
+	ds->launched = 1;
+	int first = -1;
+	for (int k = 0; k < K && first < 0; ++k)
+		if (total[k] > 0) first = k;
+	if (accept_counts)
+		for (int k = 0; k < K; ++k) accept_counts[k] = total[k];
+	*first_k = first;
+	if (first < 0) return MDNS_OK;
+	off = 0;
+	for (auto &s : ds->shards) {
+		if (s.n_act > 0) {
+			MDNS_CUDA(cudaSetDevice(s.device));
+			MDNS_CUDA(cudaMemcpyAsync(Lout + off, s.d_out + (size_t)first * s.n_act,
+			                          (size_t)s.n_act * sizeof(double), cudaMemcpyDeviceToHost,
+			                          s.stream));
+		}
+		off += s.n_act;
+	}
+	return mdns_sync(ds);
 }
 
 int mdns_muse_launch(mdns_dataset *ds)
@@ -626,8 +779,7 @@ int mdns_clike_eval_params(mdns_dataset *ds, const double *params, int K, double
 	}
 	int rc = mdns_stage_params(ds, params, K);
 	if (rc == MDNS_OK) rc = eval_common(ds, K, mask, n_act_out, lout_capacity, true);
-	if (rc == MDNS_OK) rc = mdns_clike_launch(ds, noise, scale);
-	if (rc == MDNS_OK) rc = mdns_fetch(ds, Lout, lout_capacity);
+	if (rc == MDNS_OK) rc = mdns_clike_launch_fetch(ds, noise, scale, Lout, lout_capacity);
 	return rc;
 }
 
@@ -641,8 +793,7 @@ int mdns_clike_eval_spectra(mdns_dataset *ds, const double *ypred, int K, double
 	}
 	int rc = mdns_stage_spectra(ds, ypred, K);
 	if (rc == MDNS_OK) rc = eval_common(ds, K, mask, n_act_out, lout_capacity, true);
-	if (rc == MDNS_OK) rc = mdns_clike_launch(ds, noise, scale);
-	if (rc == MDNS_OK) rc = mdns_fetch(ds, Lout, lout_capacity);
+	if (rc == MDNS_OK) rc = mdns_clike_launch_fetch(ds, noise, scale, Lout, lout_capacity);
 	return rc;
 }
 

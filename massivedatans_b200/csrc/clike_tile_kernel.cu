@@ -24,6 +24,8 @@
 // therefore stay on clike_block_kernel.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace mdns {
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(TILE_ROWS + 32) clike_tile_kernel(
 		if (lane == 0) {
 			int it = 0;
 			for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-				const int r0 = tile * TILE_ROWS;
+				const int r0 = a.row0 + tile * TILE_ROWS;
 				for (int c = 0; c < nchunks; ++c, ++it) {
 					const int stage = it % STAGES;
 					const uint32_t round = (uint32_t)(it / STAGES);
@@ -189,10 +191,19 @@ int make_row_tensor_map(void *out, const double *Y, long long n_rows, long long 
 	const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(double)};
 	const cuuint32_t box[2] = {TILE_BOX_CH, (cuuint32_t)tile_rows};
 	const cuuint32_t estr[2] = {1, 1};
+	// L2 promotion of the box rows (experiment knob MDNS_TMAP_L2 = 0 / 64 / 128 / 256)
+	CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;   // measured best
+	if (const char *e = getenv("MDNS_TMAP_L2")) {
+		const int v = atoi(e);
+		promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+		      : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+		      : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+		                 : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+	}
 	CUtensorMap tm;
 	const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)Y, dims, strides, box,
 	                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-	                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	                          promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) {
 		set_error("cuTensorMapEncodeTiled failed with code %d (rows %lld, pitch %lld)", (int)r,
 		          n_rows, pitch);

@@ -50,6 +50,7 @@ struct LikeArgs {
 	long long out_stride;
 	const void *tmap;     // host copies of the rows' CUtensorMaps for 128- and 256-row tiles
 	const void *tmap256;  // (tile kernel) or nullptr
+	int row0;             // first row of this launch within the shard (tile kernel coordinates)
 };
 
 struct Tuning {
@@ -62,6 +63,9 @@ struct Tuning {
 
 int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t st);
 int launch_muse(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t st);
+// counts[k] = #{r : L[k*stride + r] > lmins[r]}  (hiermetriclearn.py:193 on the device)
+int launch_accept_count(const double *L, long long stride, int n, int K, const double *lmins,
+                        int *counts, cudaStream_t st);
 // MUSE-type, one CTA per data set, rows staged once through a bulk-TMA ring (muse_block_kernel.cu)
 bool muse_block_fits(const LikeArgs &a);
 int launch_muse_block(const LikeArgs &a, int ktile, int sm_count, cudaStream_t st);

@@ -581,6 +581,39 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 	              : launch_clike_u<32>(a, U, kt, sm_count, st);
 }
 
+// ------------------------------------------------------------ accept test ---
+// hiermetriclearn.py:193 `numpy.any(L > Lmins)` on the device: counts[k] = number of active
+// data sets whose logL of candidate k exceeds its threshold.  One CTA per candidate; the logL
+// matrix was just written and is still L2-resident.
+__global__ void __launch_bounds__(256) accept_count_kernel(const double *__restrict__ L,
+                                                           long long stride, int n,
+                                                           const double *__restrict__ lmins,
+                                                           int *__restrict__ counts)
+{
+	__shared__ int warp_counts[8];
+	const double *row = L + (long long)blockIdx.x * stride;
+	int c = 0;
+	for (int i = threadIdx.x; i < n; i += 256) c += row[i] > lmins[i] ? 1 : 0;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+	if ((threadIdx.x & 31) == 0) warp_counts[threadIdx.x >> 5] = c;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int t = 0;
+		for (int w = 0; w < 8; ++w) t += warp_counts[w];
+		counts[blockIdx.x] = t;
+	}
+}
+
+int launch_accept_count(const double *L, long long stride, int n, int K, const double *lmins,
+                        int *counts, cudaStream_t st)
+{
+	if (K <= 0) return MDNS_OK;
+	accept_count_kernel<<<K, 256, 0, st>>>(L, stride, n, lmins, counts);
+	MDNS_LAUNCHED("accept_count_kernel");
+	return MDNS_OK;
+}
+
 // ------------------------------------------------------------- muse kernel ---
 // cmuselike.c:48-64 with resident inverse variance w = 1/v:
 //   s1 = sum y*m*w ; s2 = 1e-10 + sum m*m*w ; s = s1/s2 ; chi = sum (y - s*m)^2 * w

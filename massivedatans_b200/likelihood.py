@@ -161,9 +161,35 @@ class ResidentDataset(object):
         if out is None:
             out = _pool.empty(K * n_act)
         if n_act > 0:
-            self.launch_clike(noise, scale)
-            self.fetch(out)
+            _lib.check(self._lib.mdns_clike_launch_fetch(self._h, noise, scale, _addr(out), out.size),
+                       'mdns_clike_launch_fetch')
         return out[:K * n_act].reshape((K, n_act))
+
+    def first_accepted(self, params, data_mask, Lmins, noise, scale=-0.5):
+        """Speculative batch of the constrained draw (hiermetriclearn.py:181-196).
+
+        Scores the K parameter points in one pass and returns ``(k, L, counts)``: the index of
+        the first candidate for which ``numpy.any(L > Lmins)`` holds (what the reference's
+        one-candidate-at-a-time loop would have stopped at), its logL vector ``L[n_act]``, and
+        the number of accepting data sets of every candidate.  ``(-1, None, counts)`` if none.
+        """
+        K = self.stage_params(params)
+        n_act = self.set_mask(data_mask)
+        Lmins = numpy.ascontiguousarray(Lmins, dtype=numpy.float64)
+        if Lmins.shape != (n_act,):
+            raise ValueError('Lmins must have one entry per active data set')
+        counts = numpy.zeros(K, dtype=numpy.int32)
+        if n_act == 0:
+            return -1, None, counts
+        out = _pool.empty(n_act)
+        first = ctypes.c_int(-1)
+        _lib.check(self._lib.mdns_clike_first_accept(self._h, noise, scale, _addr(Lmins),
+                                                     _addr(counts), ctypes.byref(first),
+                                                     _addr(out), out.size),
+                   'mdns_clike_first_accept')
+        if first.value < 0:
+            return -1, None, counts
+        return first.value, out, counts
 
     def loglike_spectra(self, ypred, data_mask, noise, scale=-0.5, out=None):
         """K model spectra x all active data sets -> L[K, n_act] (scalar-noise chi-square)."""
@@ -172,8 +198,8 @@ class ResidentDataset(object):
         if out is None:
             out = _pool.empty(K * n_act)
         if n_act > 0:
-            self.launch_clike(noise, scale)
-            self.fetch(out)
+            _lib.check(self._lib.mdns_clike_launch_fetch(self._h, noise, scale, _addr(out), out.size),
+                       'mdns_clike_launch_fetch')
         return out[:K * n_act].reshape((K, n_act))
 
     def muse_loglike(self, ypred, data_mask, Lout):

@@ -166,6 +166,33 @@ def test_clike_linearity_property_large():
     assert numpy.array_equal(part, full[:, m])
 
 
+@pytest.mark.parametrize('N', [500, 70000])
+def test_first_accepted_matches_one_at_a_time_loop(oracle_port, N):
+    # hiermetriclearn.py:181-196: candidates are tried in order until numpy.any(L > Lmins)
+    x, y, _ = synth.horns(N, legacy=False, seed=9)
+    ds = ResidentDataset(x, y)
+    m = synth.masks(N)['half']
+    n_act = int(m.sum())
+    pts = synth.parameter_points(12, seed=4)
+    Ls = numpy.array([-0.5 * oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, m)
+                      for p in pts])
+    best = Ls.max(axis=0)
+    # thresholds chosen so that candidates 0..4 are rejected everywhere and 5 is accepted
+    Lmins = Ls[:5].max(axis=0) + 1e-6 * numpy.abs(Ls[:5].max(axis=0))
+    want_counts = (Ls > Lmins).sum(axis=1)
+    want_first = int(numpy.argmax(want_counts > 0)) if (want_counts > 0).any() else -1
+    k, L, counts = ds.first_accepted(pts, m, Lmins, synth.NOISE_LEVEL)
+    assert k == want_first and k >= 5
+    assert numpy.array_equal(counts, want_counts)
+    assert L.shape == (n_act,) and rel_err(L, Ls[k]) < TOL
+    # nothing accepts above the best value of every data set
+    k, L, counts = ds.first_accepted(pts, m, best + 1.0, synth.NOISE_LEVEL)
+    assert k == -1 and L is None and (counts == 0).all()
+    # everything accepts below the worst
+    k, L, counts = ds.first_accepted(pts, m, Ls.min(axis=0) - 1.0, synth.NOISE_LEVEL)
+    assert k == 0 and (counts == n_act).all() and rel_err(L, Ls[0]) < TOL
+
+
 def test_legacy_like_symbol_accumulates(oracle_port):
     # the reference's own argtypes (sample.py:85-96) on the drop-in veneer
     import os
