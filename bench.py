@@ -56,7 +56,9 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--tuning', default='', help='lanes,unroll,ktile override (experiments)')
     ap.add_argument('--sweep', action='store_true',
-                    help='also time K = 1, 2, 4, 16, 64 device-side and add them under "sweep"')
+                    help='also time K = 1 ... 400 device-side and add them under "sweep"')
+    ap.add_argument('--no-expanded', action='store_true',
+                    help='keep candidate batches on the direct-form kernels')
     return ap.parse_args()
 
 
@@ -159,25 +161,70 @@ def make_inputs(args, rank):
     return x, y, pts, log_pts, mask
 
 
-def cpu_reference_rate(x, y, pts, mask, budget_s, min_reps=1):
-    """Time the reference's clike.so (serial) on candidates x data sets; returns evals/s."""
-    from oracle import ref
-    nx, ndata = y.shape
-    n_act = int(mask.sum())
-    out = numpy.zeros(n_act)
-    done = 0
-    t0 = time.perf_counter()
-    reps = 0
-    while True:
+def host_threads():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 64))
+
+
+class ReferencePool(object):
+    """The reference's own clike.so (oracle/_ref, the serial build sample.py:81-84 loads --
+    its OpenMP variant is racy, clike.c:32) driven with every host thread it can use: the
+    sample is cut into contiguous data-set shards (copied once, outside the timed region) and
+    each host thread scores all candidates against its own shard.  ctypes releases the GIL
+    for the duration of each call, so the shards run concurrently; the C code is unmodified."""
+
+    def __init__(self, x, y, mask, threads):
+        from concurrent.futures import ThreadPoolExecutor
+        nx, ndata = y.shape
+        self.threads = max(1, min(threads, ndata))
+        bounds = numpy.linspace(0, ndata, self.threads + 1).astype(int)
+        self.x = x
+        self.shards = []
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            m = numpy.ascontiguousarray(mask[a:b])
+            self.shards.append((numpy.ascontiguousarray(y[:, a:b]), m, numpy.zeros(int(m.sum()))))
+        self.n_act = int(mask.sum())
+        self.pool = ThreadPoolExecutor(self.threads)
+
+    def _work(self, shard, pts):
+        from oracle import ref
+        y, m, out = shard
         for p in pts:
             out[:] = 0
-            ref.clike(x, y, p[0], p[1], p[2], 0.01, mask, Lout=out)
-            done += n_act
+            ref.clike(self.x, y, p[0], p[1], p[2], 0.01, m, Lout=out)
+        return out[0] if out.size else 0.0
+
+    def step(self, pts):
+        list(self.pool.map(lambda sh: self._work(sh, pts), self.shards))
+        return len(pts) * self.n_act
+
+    def close(self):
+        self.pool.shutdown()
+
+
+def cpu_reference_rate(x, y, pts, mask, budget_s, threads, min_reps=1):
+    """Time the reference's clike.so on candidates x data sets; returns evals/s."""
+    pool = ReferencePool(x, y, mask, threads)
+    pool.step(pts[:1])                      # touch the pages, load the library
+    done = 0
+    reps = 0
+    t0 = time.perf_counter()
+    while True:
+        done += pool.step(pts)
         reps += 1
         if reps >= min_reps and time.perf_counter() - t0 >= budget_s:
             break
     dt = time.perf_counter() - t0
+    pool.close()
     return done / dt, dt, reps
+
+
+REF_NOTE = ('reference clike.so (gcc -O3; the serial build sample.py:81-84 loads, its OpenMP '
+            'variant is racy, clike.c:32), unmodified, one contiguous data-set shard per host '
+            'thread')
 
 
 def run_reference(args):
@@ -191,31 +238,25 @@ def run_reference(args):
     pts = synth.parameter_points(args.candidates, seed=7)
     mask = synth.masks(n, seed=11)[args.mask]
     n_act = int(mask.sum())
-    from oracle import ref
-    out = numpy.zeros(n_act)
-
-    def step():
-        for p in pts:
-            out[:] = 0
-            ref.clike(x, y, p[0], p[1], p[2], 0.01, mask, Lout=out)
-
-    for _ in range(args.warmup):
-        step()
+    threads = host_threads()
+    pool = ReferencePool(x, y, mask, threads)
+    for _ in range(max(args.warmup, 1)):
+        pool.step(pts)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        pool.step(pts)
     dt = time.perf_counter() - t0
+    pool.close()
     value = args.steps * args.candidates * n_act / dt
-    sample = ('%d data sets x %d channels x %d candidates per step, reference clike.so '
-              '(gcc -O3, serial: the build sample.py:81-84 loads; OpenMP variant is racy)'
-              % (n, args.nx, args.candidates))
+    sample = ('%d data sets x %d channels x %d candidates per step on %d host threads, %s'
+              % (n, args.nx, args.candidates, pool.threads, REF_NOTE))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(args),
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': 1, 'kind': 'reference',
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': pool.threads, 'kind': 'reference',
                          'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -283,6 +324,8 @@ def run_ours(args):
     ds = f.dataset
     if args.tuning:
         ds.set_tuning(*[int(v) for v in args.tuning.split(',')])
+    if args.no_expanded:
+        ds.set_expanded(False)
     ndata_local = y.shape[1]
     n_act = int(mask.sum())
     K = args.candidates
@@ -315,7 +358,7 @@ def run_ours(args):
         from massivedatans_b200 import synth
         sweep = []
         peak_gbs = hbm_peak()[0]
-        for Ks in (1, 2, 4, 8, 16, 64, 400):
+        for Ks in (1, 2, 4, 8, 16, 32, 64, 400):
             ds.stage_params(synth.parameter_points(Ks, seed=7))
             for _ in range(3):
                 ds.launch_clike(0.01, -0.5)
@@ -344,6 +387,30 @@ def run_ours(args):
     e2e_s = max_over_ranks(e2e_s)
     assert L.size == K * n_act and numpy.isfinite(L).all()
     e2e_value = evals_per_step_all * args.steps / e2e_s
+    # the speculative batch of the constrained draw (hiermetriclearn.py:181-196) through
+    # ResidentDataset.first_accepted: mask, parameter points and thresholds go in, the accept
+    # counts and the logL vector of the first accepted candidate come out.  Thresholds are set
+    # so that only the LAST candidate is accepted: all K are consumed, as in the reference loop.
+    fa = None
+    if K > 1:
+        Lmins = numpy.max(L[:K - 1], axis=0) + 1.0
+        k_acc, L_acc, counts = ds.first_accepted(pts, mask, Lmins, 0.01)
+        for _ in range(2):
+            ds.first_accepted(pts, mask, Lmins, 0.01)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            k_acc, L_acc, counts = ds.first_accepted(pts, mask, Lmins, 0.01)
+        fa_s = time.perf_counter() - t0
+        barrier()
+        fa_s = max_over_ranks(fa_s)
+        ok = bool(k_acc in (-1, K - 1) and (k_acc < 0 or numpy.array_equal(L_acc, L[K - 1])))
+        fa = {'value': evals_per_step_all * args.steps / fa_s, 'unit': UNIT,
+              'ms_per_step': 1e3 * fa_s / args.steps, 'accepted_candidate': int(k_acc),
+              'matches_full_matrix': ok,
+              'h2d_bytes_per_step': (ndata_local + K * 24 + n_act * 8) * (n_gpus if distributed else 1),
+              'd2h_bytes_per_step': (n_act * 8 + K * 4) * (n_gpus if distributed else 1),
+              'api': 'ResidentDataset.first_accepted(params, data_mask, Lmins, noise)'}
     shards = (n_gpus if distributed else 1)
     h2d = (ndata_local + K * 24) * shards
     d2h = K * n_act * 8 * shards
@@ -368,13 +435,16 @@ def run_ours(args):
         try:
             n_s = min(ndata_local, 500000)
             ys = numpy.ascontiguousarray(y[:, :n_s])
+            threads = host_threads()
             rate, dt, reps = cpu_reference_rate(x, ys, pts, numpy.ascontiguousarray(mask[:n_s]),
-                                                budget_s=10.0)
-            cpu = {'value': rate, 'unit': UNIT, 'cores': 1, 'kind': 'reference',
+                                                budget_s=10.0, threads=threads)
+            rate1, dt1, reps1 = cpu_reference_rate(x, ys[:, :100000].copy(), pts,
+                                                   numpy.ascontiguousarray(mask[:100000]),
+                                                   budget_s=3.0, threads=1)
+            cpu = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'reference',
                    'sample': '%d data sets x %d channels x %d candidates x %d repetitions '
-                             '(%.1f s), reference clike.so serial (the build sample.py:81-84 '
-                             'loads; its OpenMP variant is racy, clike.c:32)'
-                             % (n_s, args.nx, K, reps, dt)}
+                             '(%.1f s), %s' % (n_s, args.nx, K, reps, dt, REF_NOTE),
+                   'single_thread_value': rate1}
         except Exception as e:      # the oracle must exist; say why if it does not
             cpu = {'value': None, 'unit': UNIT, 'cores': 1, 'kind': 'reference',
                    'sample': 'failed: %s' % e}
@@ -389,7 +459,8 @@ def run_ours(args):
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': 1e3 * e2e_s / args.steps,
                     'api': 'massivedatans_b200.likelihood.make_multi_loglikelihood(...)'
-                           + ('.batch' if K > 1 else '') + '(params, data_mask), host numpy in/out'},
+                           + ('.batch' if K > 1 else '') + '(params, data_mask), host numpy in/out',
+                    'first_accept': fa},
             'gpu_launches': int(launches), 'clocks': clocks,
         }
         if sweep is not None:

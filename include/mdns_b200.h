@@ -142,6 +142,16 @@ int mdns_timer_stop(mdns_dataset *ds, float *elapsed_ms);
  * fragments in flight per lane (0 = auto), candidates per pass (0 = auto),
  * data sets per lane group (0 = auto; > 1 selects the register-blocked kernel). */
 int mdns_set_tuning(mdns_dataset *ds, int lanes, int unroll, int ktile, int rows);
+/* Expanded form of the candidate-batch kernel (K >= 8, all data sets active):
+ *     sum_j (m_j - y_j)^2 = Syy - 2*Sym + Smm ,  Syy resident per data set,
+ * one FP64 FMA per (element, candidate) instead of two operations.  FP64 throughout; a
+ * result is kept only when the rounding-error bound of the three sums is below rel_tol
+ * (default 1e-10; the parity contract of clike.c:64-76 is 1e-9), anything else is recomputed
+ * in the direct form inside the same launch.  enable = 0 keeps every launch on the direct
+ * kernels; rel_tol <= 0 leaves the tolerance unchanged.  Data that needs more than 2 % of its
+ * rows recomputed switches itself back to the direct form. */
+int mdns_set_expanded(mdns_dataset *ds, int enable, double rel_tol);
+int mdns_expanded_stats(const mdns_dataset *ds, int *enabled, int64_t *redo_rows);
 
 /* ---- RadFriends neighbour tests --------------------------------------- */
 typedef struct mdns_region mdns_region;

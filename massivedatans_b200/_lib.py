@@ -43,6 +43,8 @@ SIGNATURES = {
     'mdns_clike_launch_fetch': (c_int, [_P, c_double, c_double, _P, c_int64]),
     'mdns_clike_first_accept': (c_int, [_P, c_double, c_double, _P, _P, POINTER(c_int), _P,
                                         c_int64]),
+    'mdns_set_expanded': (c_int, [_P, c_int, c_double]),
+    'mdns_expanded_stats': (c_int, [_P, POINTER(c_int), POINTER(c_int64)]),
     'mdns_fetch': (c_int, [_P, _P, c_int64]),
     'mdns_sync': (c_int, [_P]),
     'mdns_timer_start': (c_int, [_P]),

@@ -73,6 +73,10 @@ struct Shard {
 	size_t lmins_cap = 0;
 	int *d_counts = nullptr;      // accepting data sets per candidate
 	size_t counts_cap = 0;
+	double *syy = nullptr;        // expanded form: sum of squares of every resident row
+	double *d_smm = nullptr;      // and of every staged model spectrum
+	size_t smm_cap = 0;
+	int *d_redo = nullptr;        // direct-form recomputations of the expanded kernel
 	int n_act = 0;
 	bool all_active = true;
 	alignas(64) unsigned char tmap[128];      // CUtensorMaps of Y (tile kernel), 128-row boxes
@@ -96,6 +100,8 @@ struct mdns_dataset {
 	std::vector<uint8_t> host_mask;   // copy of the last mask (muse scatter); empty = all
 	Tuning tuning;
 	int64_t resident_bytes = 0;
+	double xp_tol = 1e-10;        // relative error bound enforced by the expanded form
+	long long xp_redo_total = 0;  // rows recomputed in the direct form so far
 };
 
 static void shard_free(Shard &s)
@@ -114,6 +120,9 @@ static void shard_free(Shard &s)
 	cudaFree(s.d_out);
 	cudaFree(s.d_lmins);
 	cudaFree(s.d_counts);
+	cudaFree(s.syy);
+	cudaFree(s.d_smm);
+	cudaFree(s.d_redo);
 	if (s.h_stage) cudaFreeHost(s.h_stage);
 	if (s.ev0) cudaEventDestroy(s.ev0);
 	if (s.ev1) cudaEventDestroy(s.ev1);
@@ -267,6 +276,19 @@ int mdns_dataset_create(const double *x, const double *yy, const double *vv, int
 		             make_row_tensor_map(s.tmap256, s.Y, s.n, (long long)ds->pitch, 256) == MDNS_OK;
 		if (vv && (rc = upload_rows(s, vv, ndata, nx, ds->pitch, 1, &s.W)) != MDNS_OK)
 			return fail(rc);
+		if (s.has_tmap) {
+			// expanded form of the candidate-batch kernel: resident Syy per data set
+			e = cudaMalloc((void **)&s.syy, (size_t)s.n * sizeof(double));
+			if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_redo, sizeof(int));
+			if (e == cudaSuccess) e = cudaMemsetAsync(s.d_redo, 0, sizeof(int), s.stream);
+			if (e != cudaSuccess) {
+				set_error("device %d allocation failed: %s", s.device, cudaGetErrorString(e));
+				return fail(MDNS_ENOMEM);
+			}
+			if ((rc = launch_row_sumsq(s.Y, s.n, (long long)ds->pitch, nx, s.syy, s.stream)) != MDNS_OK)
+				return fail(rc);
+			ds->resident_bytes += (int64_t)s.n * 8;
+		}
 		ds->resident_bytes += (int64_t)s.n * ds->pitch * 8 * (vv ? 2 : 1);
 		const size_t mask_bytes = round_up(s.n, 16) + 16;
 		e = cudaMalloc((void **)&s.d_mask, mask_bytes);
@@ -327,6 +349,34 @@ int mdns_set_tuning(mdns_dataset *ds, int lanes, int unroll, int ktile, int rows
 	return MDNS_OK;
 }
 
+int mdns_set_expanded(mdns_dataset *ds, int enable, double rel_tol)
+{
+	if (!ds) {
+		set_error("null data set");
+		return MDNS_EINVAL;
+	}
+	if (rel_tol > 0.0) {
+		if (rel_tol < 1e-13 || rel_tol > 1e-3) {
+			set_error("mdns_set_expanded: tolerance %g outside [1e-13, 1e-3]", rel_tol);
+			return MDNS_EINVAL;
+		}
+		ds->xp_tol = rel_tol;
+	}
+	ds->tuning.allow_expanded = enable != 0;
+	return MDNS_OK;
+}
+
+int mdns_expanded_stats(const mdns_dataset *ds, int *enabled, int64_t *redo_rows)
+{
+	if (!ds) {
+		set_error("null data set");
+		return MDNS_EINVAL;
+	}
+	if (enabled) *enabled = ds->tuning.allow_expanded ? 1 : 0;
+	if (redo_rows) *redo_rows = ds->xp_redo_total;
+	return MDNS_OK;
+}
+
 int mdns_set_mask(mdns_dataset *ds, const uint8_t *mask, int *n_act_out)
 {
 	if (!ds) {
@@ -370,6 +420,7 @@ static int ensure_batch(mdns_dataset *ds, Shard &s, int K)
 	const int Kpad = (int)round_up(K, KT_MAX);
 	int rc;
 	if ((rc = grow(&s.d_model, &s.model_cap, (size_t)Kpad * ds->pitch, true)) != MDNS_OK) return rc;
+	if ((rc = grow(&s.d_smm, &s.smm_cap, (size_t)Kpad, true)) != MDNS_OK) return rc;
 	return grow(&s.d_out, &s.out_cap, (size_t)K * s.n, false);
 }
 
@@ -433,6 +484,19 @@ static void fill_args(const mdns_dataset *ds, const Shard &s, LikeArgs &a)
 	a.tmap = s.has_tmap ? s.tmap : nullptr;
 	a.tmap256 = s.has_tmap ? s.tmap256 : nullptr;
 	a.row0 = 0;
+	a.syy = s.syy;
+	a.smm = s.d_smm;
+	a.xp_redo = s.d_redo;
+	// error bound of the three sequential FP64 sums relative to Syy+Smm, over the tolerance
+	a.xp_guard = (2.0 * ds->nx + 4.0) * 1.1102230246251565e-16 / ds->xp_tol;
+}
+
+// may this launch take the expanded form? (mirrors the automatic choice of launch_clike)
+static bool xp_candidate(const mdns_dataset *ds, const Shard &s)
+{
+	if (!s.syy || !s.all_active) return false;
+	if (ds->tuning.lanes == 2) return true;               // explicit request
+	return ds->tuning.lanes == 0 && ds->K >= 8 && ds->tuning.allow_expanded;
 }
 
 static int clike_check(mdns_dataset *ds, const char *who)
@@ -450,9 +514,33 @@ static int clike_check(mdns_dataset *ds, const char *who)
 
 static int clike_model(mdns_dataset *ds, Shard &s)
 {
-	if (ds->staged != 1) return MDNS_OK;
 	const int Kpad = (int)round_up(ds->K, KT_MAX);
-	return launch_line_model(s.x, ds->nx, s.d_in, ds->K, Kpad, s.d_model, (int)ds->pitch, s.stream);
+	int rc = MDNS_OK;
+	if (ds->staged == 1)
+		rc = launch_line_model(s.x, ds->nx, s.d_in, ds->K, Kpad, s.d_model, (int)ds->pitch, s.stream);
+	if (rc == MDNS_OK && xp_candidate(ds, s))
+		rc = launch_row_sumsq(s.d_model, Kpad, (long long)ds->pitch, ds->nx, s.d_smm, s.stream);
+	return rc;
+}
+
+// After a synchronising call: collect the expanded kernel's recomputation counter; data that
+// cancels in more than 2 % of the (data set, pass) pairs goes back to the direct kernel.
+static int xp_feedback(mdns_dataset *ds)
+{
+	for (auto &s : ds->shards) {
+		if (!xp_candidate(ds, s) || s.n_act == 0) continue;
+		int redo = 0;
+		MDNS_CUDA(cudaSetDevice(s.device));
+		MDNS_CUDA(cudaMemcpyAsync(&redo, s.d_redo, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+		MDNS_CUDA(cudaStreamSynchronize(s.stream));
+		if (redo > 0) {
+			MDNS_CUDA(cudaMemsetAsync(s.d_redo, 0, sizeof(int), s.stream));
+			ds->xp_redo_total += redo;
+			const long long passes = ceil_div(ds->K, 8);
+			if ((long long)redo * 50 > (long long)s.n_act * passes) ds->tuning.allow_expanded = false;
+		}
+	}
+	return MDNS_OK;
 }
 
 // chi-square of the active rows [r0, r0+nc) of one shard
@@ -535,7 +623,7 @@ int mdns_clike_launch_fetch(mdns_dataset *ds, double noise, double scale, double
 		MDNS_CUDA(cudaStreamSynchronize(s.stream));
 	}
 	ds->launched = 1;
-	return MDNS_OK;
+	return xp_feedback(ds);
 }
 
 // Speculative batch of the constrained draw (hiermetriclearn.py:181-196): the K staged
@@ -589,6 +677,7 @@ int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const 
 	if (accept_counts)
 		for (int k = 0; k < K; ++k) accept_counts[k] = total[k];
 	*first_k = first;
+	if ((rc = xp_feedback(ds)) != MDNS_OK) return rc;
 	if (first < 0) return MDNS_OK;
 	off = 0;
 	for (auto &s : ds->shards) {

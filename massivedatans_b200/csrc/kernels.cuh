@@ -51,11 +51,19 @@ struct LikeArgs {
 	const void *tmap;     // host copies of the rows' CUtensorMaps for 128- and 256-row tiles
 	const void *tmap256;  // (tile kernel) or nullptr
 	int row0;             // first row of this launch within the shard (tile kernel coordinates)
+	// expanded form (clike_xtile_kernel): Syy - 2 Sym + Smm
+	const double *syy;    // resident sum of squares of every row of the shard, or nullptr
+	const double *smm;    // [Kpad] sum of squares of every model spectrum
+	double xp_guard;      // keep a result iff chi2 >= xp_guard*(Syy+Smm), else direct form
+	int *xp_redo;         // device counter of direct-form recomputations
 };
 
 struct Tuning {
+	bool allow_expanded = true;   // false: automatic choice never takes the expanded form
 	int lanes = 0;   // lanes per data set: 8 or 32; 1 = tile kernel (unroll = channels per
-	                 // stage 16/32, rows = ring stages 3/4/6, all-active only); 0 = auto
+	                 // stage 16/32, rows = ring stages 3/4/6, all-active only), 2 = expanded-form
+	                 // tile kernel (unroll = data sets per lane 2/4, rows = ring stages 2/3,
+	                 // all-active only); 0 = auto
 	int unroll = 0;  // 128-bit fragments in flight per lane (0 = auto)
 	int ktile = 0;   // candidates per pass (0 = auto)
 	int rows = 0;    // data sets per lane group in the block kernel: 1, 2, 4 (0 = auto)
@@ -72,6 +80,14 @@ int launch_muse_block(const LikeArgs &a, int ktile, int sm_count, cudaStream_t s
 // lane-per-data-set kernel fed by a bulk-TMA ring (clike_tile_kernel.cu)
 int launch_clike_tile(const LikeArgs &a, const void *tmap, int kt, int nbox, int stages,
                       int tile_rows, int sm_count, cudaStream_t st);
+// expanded form Syy - 2 Sym + Smm, register-blocked over data sets (clike_xtile_kernel.cu);
+// kt in {8, 16, 32}, lane_rows in {2, 4}, stages in {2, 3}
+bool xtile_fits(const LikeArgs &a, int kt, int stages);
+int launch_clike_xtile(const LikeArgs &a, int kt, int lane_rows, int stages, int sm_count,
+                       cudaStream_t st);
+// out[r] = sum_j rows[r*pitch + j]^2 (rows: resident data sets or padded model spectra)
+int launch_row_sumsq(const double *rows, long long n_rows, long long pitch, int nx, double *out,
+                     cudaStream_t st);
 // 128-byte CUtensorMap describing the resident rows Y[n_rows][pitch] (tile kernel)
 int make_row_tensor_map(void *out, const double *Y, long long n_rows, long long pitch,
                         int tile_rows);

@@ -92,6 +92,41 @@ int launch_pad_spectra(const double *src, int nx, int K, int Kpad, double *model
 	return MDNS_OK;
 }
 
+// ---------------------------------------------------------- row sum of squares ---
+// Syy / Smm of the expanded form (clike_tile_kernel<XP>): one warp per row, 128-bit loads,
+// FP64 accumulation, butterfly reduction.  The zero pad of an odd channel count adds 0.
+__global__ void __launch_bounds__(256) row_sumsq_kernel(const double *__restrict__ rows,
+                                                        long long n_rows, long long pitch,
+                                                        int nfrag, double *__restrict__ out)
+{
+	const int lane = threadIdx.x & 31;
+	const long long warps = (long long)gridDim.x * 8;
+	for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < n_rows; r += warps) {
+		const double2 *p = reinterpret_cast<const double2 *>(rows + r * pitch);
+		double s0 = 0.0, s1 = 0.0;
+		for (int f = lane; f < nfrag; f += 32) {
+			const double2 y = __ldg(p + f);
+			s0 = fma(y.x, y.x, s0);
+			s1 = fma(y.y, y.y, s1);
+		}
+		double s = s0 + s1;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) s += shfl_xor_f64(s, o);
+		if (lane == 0) out[r] = s;
+	}
+}
+
+int launch_row_sumsq(const double *rows, long long n_rows, long long pitch, int nx, double *out,
+                     cudaStream_t st)
+{
+	if (n_rows <= 0) return MDNS_OK;
+	long long blocks = (n_rows + 7) / 8;
+	if (blocks > 148 * 16) blocks = 148 * 16;
+	row_sumsq_kernel<<<(unsigned)blocks, 256, 0, st>>>(rows, n_rows, pitch, (nx + 1) >> 1, out);
+	MDNS_LAUNCHED("row_sumsq_kernel");
+	return MDNS_OK;
+}
+
 // -------------------------------------------------------- mask compaction ---
 constexpr int CM_THREADS = 256;
 constexpr int CM_TILE = CM_THREADS * 16;  // mask bytes per block
@@ -534,6 +569,16 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 	const int nfrag = (a.nx + 1) >> 1;
 	int L = t.lanes;
 	const bool tile_ok = a.tmap && !a.active && 4LL * a.mpitch <= tile_constant_capacity();
+	if (L == 2 && !a.active) {
+		// expanded form, register-blocked over data sets (all-active rows only)
+		int kt = t.ktile;
+		if (kt != 8 && kt != 16 && kt != 32) kt = a.K >= 16 ? 16 : 8;
+		int stages = t.rows == 2 ? 2 : 3;
+		while (kt > 8 && !xtile_fits(a, kt, stages)) kt >>= 1;
+		if (!xtile_fits(a, kt, stages)) stages = 2;
+		const int lane_rows = t.unroll == 4 && kt <= 16 ? 4 : 2;
+		return launch_clike_xtile(a, kt, lane_rows, stages, sm_count, st);
+	}
 	if (L == 1 && tile_ok) {
 		// lane-per-data-set tile kernel (tensor-TMA ring), all-active rows only
 		int kt = t.ktile;
@@ -548,16 +593,24 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		return launch_clike_tile(a, tile_rows == 256 ? a.tmap256 : a.tmap, kt, nbox, stages,
 		                         tile_rows, sm_count, st);
 	}
-	if (L == 1) {
+	if (L == 1 || L == 2) {
 		// tile kernel requested but not applicable (masked rows): automatic choice
-		return launch_clike(a, Tuning(), sm_count, st);
+		Tuning d;
+		d.allow_expanded = t.allow_expanded;
+		return launch_clike(a, d, sm_count, st);
 	}
-	if (L == 0 && t.unroll == 0 && t.ktile == 0 && t.rows == 0 && tile_ok && a.K >= 8 &&
-	    a.n_rows >= 32768 && 8LL * a.mpitch <= tile_constant_capacity()) {
-		// automatic choice for all-active candidate batches (measured at N=1e6, C=200:
-		// K=8 0.29 ms vs 0.35 ms block kernel; K=16 0.51 ms vs 0.71 ms)
-		const int kt = (a.K >= 16 && 16LL * a.mpitch <= tile_constant_capacity()) ? 16 : 8;
-		return launch_clike_tile(a, a.tmap256, kt, 1, 3, 256, sm_count, st);
+	if (L == 0 && t.unroll == 0 && t.ktile == 0 && t.rows == 0 && !a.active && a.K >= 8 &&
+	    a.n_rows >= 32768) {
+		// automatic choice for all-active candidate batches: expanded form when allowed ...
+		const int xkt = a.K >= 16 && xtile_fits(a, 16, 2) ? 16 : 8;
+		if (t.allow_expanded && xtile_fits(a, xkt, 2))
+			return launch_clike_xtile(a, xkt, 2, 2, sm_count, st);
+		// ... else the direct-form tile kernel (measured at N=1e6, C=200: K=8 0.29 ms vs
+		// 0.35 ms block kernel; K=16 0.51 ms vs 0.71 ms)
+		if (tile_ok && 8LL * a.mpitch <= tile_constant_capacity()) {
+			const int kt = (a.K >= 16 && 16LL * a.mpitch <= tile_constant_capacity()) ? 16 : 8;
+			return launch_clike_tile(a, a.tmap256, kt, 1, 3, 256, sm_count, st);
+		}
 	}
 	if (L != 8 && L != 32) L = (a.n_rows >= 16384 && nfrag >= 8) ? 8 : 32;
 	int U = t.unroll;

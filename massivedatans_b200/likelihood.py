@@ -153,6 +153,20 @@ class ResidentDataset(object):
         _lib.check(self._lib.mdns_set_tuning(self._h, lanes, unroll, ktile, rows),
                    'mdns_set_tuning')
 
+    def set_expanded(self, enable=True, rel_tol=0.0):
+        """Allow / forbid the expanded form Syy - 2 Sym + Smm of the candidate-batch kernel
+        (K >= 8, all data sets active); rel_tol > 0 sets the error bound it enforces."""
+        _lib.check(self._lib.mdns_set_expanded(self._h, 1 if enable else 0, rel_tol),
+                   'mdns_set_expanded')
+
+    def expanded_stats(self):
+        """(enabled, rows recomputed in the direct form so far)"""
+        en = ctypes.c_int()
+        redo = ctypes.c_int64()
+        _lib.check(self._lib.mdns_expanded_stats(self._h, ctypes.byref(en), ctypes.byref(redo)),
+                   'mdns_expanded_stats')
+        return bool(en.value), int(redo.value)
+
     # -- one-call forms ------------------------------------------------------
     def loglike_batch(self, params, data_mask, noise, scale=-0.5, out=None):
         """K parameter points (A, mu, sig) x all active data sets -> L[K, n_act]."""

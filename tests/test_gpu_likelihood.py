@@ -16,6 +16,7 @@ from massivedatans_b200.likelihood import (ResidentDataset, make_multi_loglikeli
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12          # asserted; the contract is 1e-9 relative
+TOL_XP = 1e-10       # expanded form Syy - 2 Sym + Smm: the bound the kernel itself enforces
 
 
 @pytest.fixture(scope='module')
@@ -120,6 +121,115 @@ def test_clike_tile_kernel_shapes(oracle_port, N, nx, K):
         p = pts[k]
         want = oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, allm)
         assert rel_err(got[k], want) < TOL
+
+
+@pytest.mark.parametrize('N,nx,K,lane_rows,ktile,stages', [
+    (128, 16, 4, 2, 8, 3), (129, 18, 9, 2, 8, 2), (5000, 200, 17, 2, 16, 3),
+    (1000, 33, 40, 2, 32, 3), (300, 1000, 5, 4, 8, 2), (3000, 203, 33, 4, 16, 3),
+    (40000, 200, 16, 0, 0, 0)])
+def test_clike_expanded_form_vs_oracle(oracle_port, N, nx, K, lane_rows, ktile, stages):
+    # explicit selection of the expanded tile kernel (lanes = 2) on ordinary data: nothing
+    # cancels, nothing is recomputed, results within the enforced bound
+    x, y, _ = synth.horns(N, nx=nx, seed=N + 1)
+    ds = ResidentDataset(x, y)
+    ds.set_tuning(2, lane_rows, ktile, stages)
+    pts = synth.parameter_points(K, seed=N)
+    got = ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0)
+    assert _lib.load().mdns_last_kernel() == b'clike_xtile_kernel'
+    allm = numpy.ones(N, dtype=bool)
+    for k in sorted(set((0, 1, K // 2, K - 2, K - 1))):
+        p = pts[k]
+        want = oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, allm)
+        assert rel_err(got[k], want) < TOL_XP
+    assert ds.expanded_stats() == (True, 0)
+    # direct and expanded forms agree far inside the tolerance on this data
+    ds.set_expanded(False)
+    ds.set_tuning(1, 0, 0, 0)
+    direct = ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0)
+    assert _lib.load().mdns_last_kernel() == b'clike_tile_kernel'
+    assert rel_err(got, direct) < TOL_XP
+
+
+@pytest.mark.parametrize('lane_rows,ktile,stages', [(2, 8, 3), (2, 16, 3), (2, 32, 2), (2, 8, 2),
+                                                    (4, 8, 3), (4, 16, 2), (2, 32, 3), (2, 16, 2)])
+@pytest.mark.parametrize('N,nx,K', [(700, 203, 9), (70000, 200, 37)])
+def test_clike_expanded_blocked_variants(oracle_port, lane_rows, ktile, stages, N, nx, K):
+    # expanded form with 2 / 4 data sets per consumer lane
+    x, y, _ = synth.horns(N, nx=nx, legacy=False, seed=N)
+    ds = ResidentDataset(x, y)
+    ds.set_tuning(2, lane_rows, ktile, stages)
+    pts = synth.parameter_points(K, seed=N + 1)
+    got = ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0)
+    assert _lib.load().mdns_last_kernel() == b'clike_xtile_kernel'
+    allm = numpy.ones(N, dtype=bool)
+    for k in sorted(set((0, 7, 8, K // 2, K - 1))):
+        p = pts[k]
+        want = oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, allm)
+        assert rel_err(got[k], want) < TOL_XP
+    assert ds.expanded_stats() == (True, 0)
+
+
+def test_clike_expanded_form_automatic_choice(oracle_port):
+    # all-active batches of >= 8 candidates take the expanded form on their own; masks and
+    # small batches stay on the direct kernels
+    N = 50000
+    x, y, _ = synth.horns(N, legacy=False, seed=21)
+    ds = ResidentDataset(x, y)
+    lib = _lib.load()
+    pts = synth.parameter_points(35, seed=2)
+    got = ds.loglike_batch(pts, None, synth.NOISE_LEVEL)
+    assert lib.mdns_last_kernel() == b'clike_xtile_kernel'
+    allm = numpy.ones(N, dtype=bool)
+    for k in (0, 7, 8, 31, 32, 34):
+        p = pts[k]
+        want = -0.5 * oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, allm)
+        assert rel_err(got[k], want) < TOL_XP
+    ds.loglike_batch(pts[:4], None, synth.NOISE_LEVEL)
+    assert b'xtile' not in lib.mdns_last_kernel()
+    ds.loglike_batch(pts, synth.masks(N)['half'], synth.NOISE_LEVEL)
+    assert b'xtile' not in lib.mdns_last_kernel()
+    ds.set_expanded(False)
+    got = ds.loglike_batch(pts[:9], None, synth.NOISE_LEVEL)
+    assert lib.mdns_last_kernel() == b'clike_tile_kernel'
+    for k in (0, 8):
+        p = pts[k]
+        want = -0.5 * oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, allm)
+        assert rel_err(got[k], want) < TOL
+
+
+def test_clike_expanded_form_cancellation_guard(oracle_port):
+    # data that the candidate fits to ~1e-7 of its amplitude: Syy, Sym and Smm agree to 14
+    # digits and their combination would be rounding noise.  Those (data set, candidate) pairs
+    # must be caught by the guard and recomputed in the direct form.
+    N, nx, K = 4096, 200, 8
+    x = numpy.linspace(400, 800, nx)
+    rs = numpy.random.RandomState(5)
+    pts = synth.parameter_points(K, seed=3)
+    pts[:, 0] = 50.0                      # strong lines
+    pts[:, 2] = rs.uniform(20, 60, size=K)
+    y = rs.normal(0, 1e-2, size=(nx, N))
+    fitted = numpy.arange(N) % 3 == 0     # every third data set is candidate (i % K) + tiny noise
+    # model spectra computed once on the host and handed to both sides (the device exp and
+    # libm's differ in the last bit, which is the whole residual of such a fit)
+    spectra = numpy.array([p[0] * numpy.exp(-0.5 * ((p[1] - x) / p[2]) ** 2) for p in pts])
+    for i in numpy.nonzero(fitted)[0]:
+        y[:, i] = spectra[i % K] + rs.normal(0, 1e-6, size=nx)
+    ds = ResidentDataset(x, y)
+    ds.set_tuning(2, 2, 8, 3)
+    got = ds.loglike_spectra(spectra, None, synth.NOISE_LEVEL, scale=1.0)
+    assert _lib.load().mdns_last_kernel() == b'clike_xtile_kernel'
+    allm = numpy.ones(N, dtype=bool)
+    for k in range(K):
+        want = oracle_port.clike_spectrum(spectra[k], y, synth.NOISE_LEVEL, allm)
+        assert rel_err(got[k], want) < TOL_XP, k
+    enabled, redo = ds.expanded_stats()
+    assert redo >= fitted.sum() // K        # at least the perfectly fitted pairs
+    # more than 2 % of the rows needed the direct form: the data set switches itself back
+    assert not enabled
+    ds.set_tuning(0, 0, 0, 0)
+    again = ds.loglike_spectra(spectra, None, synth.NOISE_LEVEL, scale=1.0)
+    assert b'xtile' not in _lib.load().mdns_last_kernel()
+    assert rel_err(again, got) < TOL_XP
 
 
 def test_clike_spectra_entry_point(oracle_port):
