@@ -76,7 +76,8 @@ struct Shard {
 	double *syy = nullptr;        // expanded form: sum of squares of every resident row
 	double *d_smm = nullptr;      // and of every staged model spectrum
 	size_t smm_cap = 0;
-	int *d_redo = nullptr;        // direct-form recomputations of the expanded kernel
+	int *d_redo = nullptr;        // counters of the expanded kernel's direct-form fix-ups
+	int *d_redo_list = nullptr;   // and the rows to fix up in the current pass
 	int n_act = 0;
 	bool all_active = true;
 	alignas(64) unsigned char tmap[128];      // CUtensorMaps of Y (tile kernel), 128-row boxes
@@ -123,6 +124,7 @@ static void shard_free(Shard &s)
 	cudaFree(s.syy);
 	cudaFree(s.d_smm);
 	cudaFree(s.d_redo);
+	cudaFree(s.d_redo_list);
 	if (s.h_stage) cudaFreeHost(s.h_stage);
 	if (s.ev0) cudaEventDestroy(s.ev0);
 	if (s.ev1) cudaEventDestroy(s.ev1);
@@ -279,8 +281,10 @@ int mdns_dataset_create(const double *x, const double *yy, const double *vv, int
 		if (s.has_tmap) {
 			// expanded form of the candidate-batch kernel: resident Syy per data set
 			e = cudaMalloc((void **)&s.syy, (size_t)s.n * sizeof(double));
-			if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_redo, sizeof(int));
-			if (e == cudaSuccess) e = cudaMemsetAsync(s.d_redo, 0, sizeof(int), s.stream);
+			const size_t cbytes = (size_t)xtile_counter_capacity() * sizeof(int);
+			if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_redo, cbytes);
+			if (e == cudaSuccess) e = cudaMemsetAsync(s.d_redo, 0, cbytes, s.stream);
+			if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_redo_list, (size_t)s.n * sizeof(int));
 			if (e != cudaSuccess) {
 				set_error("device %d allocation failed: %s", s.device, cudaGetErrorString(e));
 				return fail(MDNS_ENOMEM);
@@ -487,6 +491,7 @@ static void fill_args(const mdns_dataset *ds, const Shard &s, LikeArgs &a)
 	a.syy = s.syy;
 	a.smm = s.d_smm;
 	a.xp_redo = s.d_redo;
+	a.xp_list = s.d_redo_list;
 	// error bound of the three sequential FP64 sums relative to Syy+Smm, over the tolerance
 	a.xp_guard = (2.0 * ds->nx + 4.0) * 1.1102230246251565e-16 / ds->xp_tol;
 }

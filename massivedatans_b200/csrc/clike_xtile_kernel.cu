@@ -26,9 +26,11 @@
 // Syy - 2 Sym + Smm is bounded by about (2C+4) * 2^-53 * (Syy + Smm), so a result is kept only
 // when that bound is below the tolerance relative to the result itself (a.xp_guard =
 // (2C+4) * 2^-53 / xp_tol; keep iff chi2 >= xp_guard * (Syy + Smm); default xp_tol 1e-10, the
-// parity contract is 1e-9).  Every other (data set, candidate) pair is recomputed in the direct
-// form right here by its lane (rare: counted in a.xp_redo, and data that needs it for more than
-// 2 % of its rows is sent back to the direct kernel by the host).
+// parity contract is 1e-9).  The data sets of every other pair are appended to a list and
+// recomputed in the direct form by a small follow-up launch (xtile_fixup_kernel; rare: counted in
+// a.xp_redo[0], and data that needs it for more than 2 % of its rows is sent back to the direct
+// kernel by the host).  Keeping the fix-up out of line keeps it out of the main kernel's
+// register budget (135 instead of 167 registers at KT = 16).
 #include <cuda.h>
 
 #include "kernels.cuh"
@@ -38,6 +40,11 @@ namespace mdns {
 constexpr int XT_ROWS = 256;                    // data sets per tile = rows of one TMA box
 constexpr int XT_BOX_CH = 16;                   // channels per box row = 128 bytes (swizzle span)
 constexpr int XT_STAGE_BYTES = XT_ROWS * XT_BOX_CH * 8;
+constexpr int XT_MAX_COUNTERS = 1024;           // ints behind a.xp_redo: total + one per pass
+#ifndef XT_UNROLL
+#define XT_UNROLL 2
+#endif
+constexpr int XT_UNROLL_PAIRS = XT_UNROLL;   // channel pairs unrolled in the inner loop (registers)
 
 __device__ __forceinline__ void xt_mbar_arrive(uint64_t *bar)
 {
@@ -54,37 +61,40 @@ __device__ __forceinline__ void xt_tma_load_2d(void *smem_dst, const CUtensorMap
 	    : "memory");
 }
 
-// Direct-form recomputation of the pairs the expanded form could not vouch for.  Called by a
-// whole warp; lanes with `redo` walk their own row from global memory (uncoalesced, rare),
-// the channel index stays warp-uniform so the model reads remain broadcasts.
-template <int KT>
-__device__ __noinline__ void xt_redo_direct(const double *yrow, int nx, const double *sm_model,
-                                            int mpitch, bool redo, double *out,
-                                            long long out_stride, int kt_valid, double inv,
-                                            int *counter)
+// Direct-form recomputation of the data sets the expanded form could not vouch for in this
+// pass: one warp per listed data set, lanes across channels, candidates k0 .. k0+kt_valid-1.
+// counter[0] accumulates the number of recomputed rows (host feedback), counter[1 + pass] is
+// the length of this pass's list.
+__global__ void __launch_bounds__(256) xtile_fixup_kernel(const LikeArgs a, const int k0,
+                                                          const int kt_valid, const int pass)
 {
-	double acc[KT];
+	const int n = a.xp_redo[1 + pass];
+	if (n == 0) return;
+	const int lane = threadIdx.x & 31;
+	const int warps = gridDim.x * 8;
+	const double inv = a.scale / a.noise2;
+	for (int e = blockIdx.x * 8 + (threadIdx.x >> 5); e < n; e += warps) {
+		const int gr = a.xp_list[e];               // row within this launch
+		const double *yrow = a.Y + (long long)gr * a.pitch;
+		for (int k = 0; k < kt_valid; ++k) {
+			const double *m = a.model + (size_t)(k0 + k) * a.mpitch;
+			double s = 0.0;
+			for (int j = lane; j < a.nx; j += 32) {
+				const double d = m[j] - yrow[j];
+				s = fma(d, d, s);
+			}
 #pragma unroll
-	for (int k = 0; k < KT; ++k) acc[k] = 0.0;
-	for (int j = 0; j < nx; ++j) {
-		const double y = redo ? yrow[j] : 0.0;
-#pragma unroll
-		for (int k = 0; k < KT; ++k) {
-			const double d = sm_model[k * mpitch + j] - y;
-			acc[k] = fma(d, d, acc[k]);
+			for (int o = 16; o > 0; o >>= 1) s += shfl_xor_f64(s, o);
+			if (lane == 0) a.out[(long long)(k0 + k) * a.out_stride + gr] = s * inv;
 		}
 	}
-	if (redo) {
-#pragma unroll
-		for (int k = 0; k < KT; ++k)
-			if (k < kt_valid) out[k * out_stride] = acc[k] * inv;
-		atomicAdd(counter, 1);
-	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.xp_redo, n);
 }
 
 template <int KT, int R, int STAGES>
 __global__ void __launch_bounds__(XT_ROWS / R + 32) clike_xtile_kernel(
-    const __grid_constant__ CUtensorMap tmap, const LikeArgs a, const int k0, const int kt_valid)
+    const __grid_constant__ CUtensorMap tmap, const LikeArgs a, const int k0, const int kt_valid,
+    const int pass)
 {
 	constexpr int LANE_ROWS = XT_ROWS / R;             // distance between the rows of one lane
 	constexpr int CONSUMER_WARPS = LANE_ROWS / 32;
@@ -156,7 +166,7 @@ __global__ void __launch_bounds__(XT_ROWS / R + 32) clike_xtile_kernel(
 				const int left = pitch_even - jbase;     // valid channels of this box (even)
 				const double *mrow = sm_model + jbase;
 				if (left >= XT_BOX_CH) {
-#pragma unroll
+#pragma unroll XT_UNROLL_PAIRS
 					for (int u = 0; u < XT_BOX_CH / 2; ++u) {
 						double2 y[R];
 #pragma unroll
@@ -215,10 +225,7 @@ __global__ void __launch_bounds__(XT_ROWS / R + 32) clike_xtile_kernel(
 							redo = true;
 					}
 				}
-				if (__any_sync(0xffffffffu, redo))
-					xt_redo_direct<KT>(a.Y + (redo ? gr : 0) * a.pitch, a.nx, sm_model, a.mpitch, redo,
-					                   a.out + (long long)k0 * a.out_stride + gr, a.out_stride,
-					                   kt_valid, inv, a.xp_redo);
+				if (redo) a.xp_list[atomicAdd(a.xp_redo + 1 + pass, 1)] = (int)gr;
 			}
 		}
 	}
@@ -249,9 +256,20 @@ static int launch_xtile_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 	long long gx = ntiles;
 	const long long resident = (long long)sm_count * occ;
 	if (gx > resident) gx = resident;
-	for (int k0 = 0; k0 < a.K; k0 += KT) {
+	const int npass = ceil_div(a.K, KT);
+	if (npass + 1 > XT_MAX_COUNTERS) {
+		set_error("expanded tile kernel: %d passes exceed the counter block", npass);
+		return MDNS_EINVAL;
+	}
+	// list lengths of this launch's passes (counter[0], the running total, is left alone)
+	MDNS_CUDA(cudaMemsetAsync(a.xp_redo + 1, 0, (size_t)npass * sizeof(int), st));
+	int fix_blocks = ceil_div(a.n_rows, 8);
+	if (fix_blocks > 2 * sm_count) fix_blocks = 2 * sm_count;
+	for (int k0 = 0, pass = 0; k0 < a.K; k0 += KT, ++pass) {
 		const int kv = a.K - k0 < KT ? a.K - k0 : KT;
-		kern<<<(unsigned)gx, THREADS, smem, st>>>(tm, a, k0, kv);
+		kern<<<(unsigned)gx, THREADS, smem, st>>>(tm, a, k0, kv, pass);
+		MDNS_LAUNCHED("clike_xtile_kernel");
+		xtile_fixup_kernel<<<fix_blocks, 256, 0, st>>>(a, k0, kv, pass);
 		MDNS_LAUNCHED("clike_xtile_kernel");
 	}
 	return MDNS_OK;
@@ -259,12 +277,14 @@ static int launch_xtile_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 
 bool xtile_fits(const LikeArgs &a, int kt, int stages)
 {
-	return a.tmap256 && !a.active && a.syy && a.smm && a.xp_redo &&
+	return a.tmap256 && !a.active && a.syy && a.smm && a.xp_redo && a.xp_list &&
 	       xtile_smem(kt, stages, a.mpitch) <= 220 * 1024 &&
 	       (size_t)kt * a.mpitch * 8 < (1u << 20);   // mbarrier tx-count range
 }
 
 // kt in {8, 16, 32}; lane_rows in {2, 4}; stages in {2, 3}
+int xtile_counter_capacity() { return XT_MAX_COUNTERS; }
+
 int launch_clike_xtile(const LikeArgs &a, int kt, int lane_rows, int stages, int sm_count,
                        cudaStream_t st)
 {

@@ -55,7 +55,9 @@ struct LikeArgs {
 	const double *syy;    // resident sum of squares of every row of the shard, or nullptr
 	const double *smm;    // [Kpad] sum of squares of every model spectrum
 	double xp_guard;      // keep a result iff chi2 >= xp_guard*(Syy+Smm), else direct form
-	int *xp_redo;         // device counter of direct-form recomputations
+	int *xp_redo;         // device counters: [0] rows recomputed in the direct form so far,
+	                      // [1 + pass] list length of each pass of the current launch
+	int *xp_list;         // rows (within the launch) to recompute, capacity = rows of the shard
 };
 
 struct Tuning {
@@ -83,6 +85,7 @@ int launch_clike_tile(const LikeArgs &a, const void *tmap, int kt, int nbox, int
 // expanded form Syy - 2 Sym + Smm, register-blocked over data sets (clike_xtile_kernel.cu);
 // kt in {8, 16, 32}, lane_rows in {2, 4}, stages in {2, 3}
 bool xtile_fits(const LikeArgs &a, int kt, int stages);
+int xtile_counter_capacity();
 int launch_clike_xtile(const LikeArgs &a, int kt, int lane_rows, int stages, int sm_count,
                        cudaStream_t st);
 // out[r] = sum_j rows[r*pitch + j]^2 (rows: resident data sets or padded model spectra)
