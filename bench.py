@@ -385,32 +385,43 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     barrier()
     e2e_s = max_over_ranks(e2e_s)
+    L = numpy.array(L, copy=True).reshape((K, n_act))     # off the recycled pinned block
     assert L.size == K * n_act and numpy.isfinite(L).all()
     e2e_value = evals_per_step_all * args.steps / e2e_s
     # the speculative batch of the constrained draw (hiermetriclearn.py:181-196) through
-    # ResidentDataset.first_accepted: mask, parameter points and thresholds go in, the accept
-    # counts and the logL vector of the first accepted candidate come out.  Thresholds are set
-    # so that only the LAST candidate is accepted: all K are consumed, as in the reference loop.
+    # ResidentDataset.begin_draw / draw_batch: mask and thresholds are constant during one
+    # draw_constrained call (hiermetriclearn.py:173-211) and are staged once, outside the timed
+    # loop; per step the K parameter points go in, the accept counts and the logL vector of the
+    # first accepted candidate come out.  Thresholds are set so that only the LAST candidate is
+    # accepted: all K are consumed, as in the reference's one-at-a-time loop.
     fa = None
     if K > 1:
-        Lmins = numpy.max(L[:K - 1], axis=0) + 1.0
-        k_acc, L_acc, counts = ds.first_accepted(pts, mask, Lmins, 0.01)
-        for _ in range(2):
-            ds.first_accepted(pts, mask, Lmins, 0.01)
+        wins = numpy.bincount(numpy.argmax(L, axis=0), minlength=K)
+        order = numpy.argsort(wins, kind='stable')          # most frequent winner last
+        pts_fa = numpy.ascontiguousarray(pts[order])
+        L_fa = L[order]
+        Lmins = numpy.max(L_fa[:K - 1], axis=0)
+        ds.begin_draw(mask, Lmins)
+        for _ in range(3):
+            k_acc, L_acc, counts = ds.draw_batch(pts_fa, 0.01)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            k_acc, L_acc, counts = ds.first_accepted(pts, mask, Lmins, 0.01)
+            k_acc, L_acc, counts = ds.draw_batch(pts_fa, 0.01)
         fa_s = time.perf_counter() - t0
         barrier()
         fa_s = max_over_ranks(fa_s)
-        ok = bool(k_acc in (-1, K - 1) and (k_acc < 0 or numpy.array_equal(L_acc, L[K - 1])))
+        want_k = K - 1 if (L_fa[K - 1] > Lmins).any() else -1
+        ok = bool(k_acc == want_k and (k_acc < 0 or numpy.array_equal(L_acc, L_fa[K - 1])))
+        nsh = n_gpus if distributed else 1
         fa = {'value': evals_per_step_all * args.steps / fa_s, 'unit': UNIT,
               'ms_per_step': 1e3 * fa_s / args.steps, 'accepted_candidate': int(k_acc),
               'matches_full_matrix': ok,
-              'h2d_bytes_per_step': (ndata_local + K * 24 + n_act * 8) * (n_gpus if distributed else 1),
-              'd2h_bytes_per_step': (n_act * 8 + K * 4) * (n_gpus if distributed else 1),
-              'api': 'ResidentDataset.first_accepted(params, data_mask, Lmins, noise)'}
+              'h2d_bytes_per_step': K * 24 * nsh,
+              'd2h_bytes_per_step': (n_act * 8 + K * 4) * nsh,
+              'staged_once_per_draw_bytes': (ndata_local + n_act * 8) * nsh,
+              'api': 'ResidentDataset.begin_draw(data_mask, Lmins) once, then '
+                     'draw_batch(params, noise) per step'}
     shards = (n_gpus if distributed else 1)
     h2d = (ndata_local + K * 24) * shards
     d2h = K * n_act * 8 * shards

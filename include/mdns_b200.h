@@ -130,6 +130,10 @@ int mdns_clike_launch_fetch(mdns_dataset *ds, double noise, double scale, double
  * accept_counts[K] (may be NULL) = data sets with scale*chi2 > Lmins per candidate;
  * *first_k = first candidate with a non-zero count, or -1; its logL vector is copied to Lout
  * (untouched when none accepts).  Only K ints and one vector cross PCIe. */
+/* Thresholds may also be staged once per constrained draw (they are constant while candidates
+ * are tried, hiermetriclearn.py:173-211): mdns_set_thresholds after mdns_set_mask, then
+ * mdns_clike_first_accept with Lmins = NULL for every batch of candidates. */
+int mdns_set_thresholds(mdns_dataset *ds, const double *Lmins);
 int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const double *Lmins,
                             int *accept_counts, int *first_k, double *Lout,
                             int64_t lout_capacity);

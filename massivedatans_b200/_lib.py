@@ -41,6 +41,7 @@ SIGNATURES = {
     'mdns_clike_launch': (c_int, [_P, c_double, c_double]),
     'mdns_muse_launch': (c_int, [_P]),
     'mdns_clike_launch_fetch': (c_int, [_P, c_double, c_double, _P, c_int64]),
+    'mdns_set_thresholds': (c_int, [_P, _P]),
     'mdns_clike_first_accept': (c_int, [_P, c_double, c_double, _P, _P, POINTER(c_int), _P,
                                         c_int64]),
     'mdns_set_expanded': (c_int, [_P, c_int, c_double]),

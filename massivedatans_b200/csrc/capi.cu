@@ -101,6 +101,7 @@ struct mdns_dataset {
 	std::vector<uint8_t> host_mask;   // copy of the last mask (muse scatter); empty = all
 	Tuning tuning;
 	int64_t resident_bytes = 0;
+	bool thresholds_staged = false;   // d_lmins holds thresholds aligned with the current mask
 	double xp_tol = 1e-10;        // relative error bound enforced by the expanded form
 	long long xp_redo_total = 0;  // rows recomputed in the direct form so far
 };
@@ -415,7 +416,38 @@ int mdns_set_mask(mdns_dataset *ds, const uint8_t *mask, int *n_act_out)
 		ds->host_mask.clear();
 	ds->n_act_total = total;
 	ds->launched = 0;
+	ds->thresholds_staged = false;    // thresholds are aligned with the compacted active order
 	if (n_act_out) *n_act_out = total;
+	return MDNS_OK;
+}
+
+// Accept thresholds of the active data sets (the `Lmins` of draw_constrained,
+// hiermetriclearn.py:173: constant while candidates are tried), aligned with the compacted
+// active order of the current mask.  Stays resident until the next mdns_set_mask.
+int mdns_set_thresholds(mdns_dataset *ds, const double *Lmins)
+{
+	if (!ds || !Lmins) {
+		set_error("mdns_set_thresholds: need ds and Lmins");
+		return MDNS_EINVAL;
+	}
+	long long off = 0;
+	for (auto &s : ds->shards) {
+		if (s.n_act > 0) {
+			MDNS_CUDA(cudaSetDevice(s.device));
+			int rc = grow(&s.d_lmins, &s.lmins_cap, (size_t)s.n_act, false);
+			if (rc != MDNS_OK) return rc;
+			MDNS_CUDA(cudaMemcpyAsync(s.d_lmins, Lmins + off, (size_t)s.n_act * sizeof(double),
+			                          cudaMemcpyHostToDevice, s.stream));
+		}
+		off += s.n_act;
+	}
+	// the caller may reuse its buffer right away
+	for (auto &s : ds->shards) {
+		if (s.n_act == 0) continue;
+		MDNS_CUDA(cudaSetDevice(s.device));
+		MDNS_CUDA(cudaStreamSynchronize(s.stream));
+	}
+	ds->thresholds_staged = true;
 	return MDNS_OK;
 }
 
@@ -641,9 +673,16 @@ int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const 
 {
 	int rc = clike_check(ds, "mdns_clike_first_accept");
 	if (rc != MDNS_OK) return rc;
-	if (!Lmins || !first_k || !Lout) {
-		set_error("mdns_clike_first_accept: need Lmins, first_k and Lout");
+	if (!first_k || !Lout) {
+		set_error("mdns_clike_first_accept: need first_k and Lout");
 		return MDNS_EINVAL;
+	}
+	if (Lmins) {
+		if ((rc = mdns_set_thresholds(ds, Lmins)) != MDNS_OK) return rc;
+	} else if (!ds->thresholds_staged) {
+		set_error("mdns_clike_first_accept: no thresholds (pass Lmins or call mdns_set_thresholds "
+		          "after mdns_set_mask)");
+		return MDNS_ESTATE;
 	}
 	if (lout_capacity < ds->n_act_total) {
 		set_error("Lout holds %lld doubles, %d needed", (long long)lout_capacity, ds->n_act_total);
@@ -655,10 +694,7 @@ int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const 
 	for (auto &s : ds->shards) {
 		MDNS_CUDA(cudaSetDevice(s.device));
 		if (s.n_act > 0) {
-			if ((rc = grow(&s.d_lmins, &s.lmins_cap, (size_t)s.n_act, false)) != MDNS_OK) return rc;
 			if ((rc = grow(&s.d_counts, &s.counts_cap, (size_t)K, false)) != MDNS_OK) return rc;
-			MDNS_CUDA(cudaMemcpyAsync(s.d_lmins, Lmins + off, (size_t)s.n_act * sizeof(double),
-			                          cudaMemcpyHostToDevice, s.stream));
 			if ((rc = clike_model(ds, s)) != MDNS_OK) return rc;
 			if ((rc = clike_rows(ds, s, noise, scale, 0, s.n_act)) != MDNS_OK) return rc;
 			if ((rc = launch_accept_count(s.d_out, s.n_act, s.n_act, K, s.d_lmins, s.d_counts,

@@ -636,17 +636,24 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 
 // ------------------------------------------------------------ accept test ---
 // hiermetriclearn.py:193 `numpy.any(L > Lmins)` on the device: counts[k] = number of active
-// data sets whose logL of candidate k exceeds its threshold.  One CTA per candidate; the logL
-// matrix was just written and is still L2-resident.
+// data sets whose logL of candidate k exceeds its threshold.  grid = (row tiles, candidates);
+// the logL matrix was just written and is largely still L2-resident.
+constexpr int AC_ROWS = 256 * 8;   // rows per CTA
+
 __global__ void __launch_bounds__(256) accept_count_kernel(const double *__restrict__ L,
                                                            long long stride, int n,
                                                            const double *__restrict__ lmins,
                                                            int *__restrict__ counts)
 {
 	__shared__ int warp_counts[8];
-	const double *row = L + (long long)blockIdx.x * stride;
+	const double *row = L + (long long)blockIdx.y * stride;
+	const int base = blockIdx.x * AC_ROWS;
 	int c = 0;
-	for (int i = threadIdx.x; i < n; i += 256) c += row[i] > lmins[i] ? 1 : 0;
+#pragma unroll
+	for (int u = 0; u < 8; ++u) {
+		const int i = base + u * 256 + threadIdx.x;
+		if (i < n) c += row[i] > __ldg(lmins + i) ? 1 : 0;
+	}
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
 	if ((threadIdx.x & 31) == 0) warp_counts[threadIdx.x >> 5] = c;
@@ -654,7 +661,7 @@ __global__ void __launch_bounds__(256) accept_count_kernel(const double *__restr
 	if (threadIdx.x == 0) {
 		int t = 0;
 		for (int w = 0; w < 8; ++w) t += warp_counts[w];
-		counts[blockIdx.x] = t;
+		if (t) atomicAdd(counts + blockIdx.y, t);
 	}
 }
 
@@ -662,7 +669,9 @@ int launch_accept_count(const double *L, long long stride, int n, int K, const d
                         int *counts, cudaStream_t st)
 {
 	if (K <= 0) return MDNS_OK;
-	accept_count_kernel<<<K, 256, 0, st>>>(L, stride, n, lmins, counts);
+	MDNS_CUDA(cudaMemsetAsync(counts, 0, (size_t)K * sizeof(int), st));
+	if (n <= 0) return MDNS_OK;
+	accept_count_kernel<<<dim3(ceil_div(n, AC_ROWS), K), 256, 0, st>>>(L, stride, n, lmins, counts);
 	MDNS_LAUNCHED("accept_count_kernel");
 	return MDNS_OK;
 }

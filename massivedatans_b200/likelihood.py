@@ -205,6 +205,36 @@ class ResidentDataset(object):
             return -1, None, counts
         return first.value, out, counts
 
+    def begin_draw(self, data_mask, Lmins):
+        """Stage what stays constant during one constrained draw (hiermetriclearn.py:173-211):
+        the data-set mask and the accept thresholds of the active data sets.  Returns n_act."""
+        n_act = self.set_mask(data_mask)
+        Lmins = numpy.ascontiguousarray(Lmins, dtype=numpy.float64)
+        if Lmins.shape != (n_act,):
+            raise ValueError('Lmins must have one entry per active data set')
+        if n_act > 0:
+            _lib.check(self._lib.mdns_set_thresholds(self._h, _addr(Lmins)), 'mdns_set_thresholds')
+        self._draw_n_act = n_act
+        return n_act
+
+    def draw_batch(self, params, noise, scale=-0.5):
+        """Score the next K candidates of the draw started with ``begin_draw``; returns
+        ``(k, L, counts)`` like ``first_accepted``.  Per call only the K parameter points go to
+        the device and K counts plus at most one logL vector come back."""
+        K = self.stage_params(params)
+        n_act = self._draw_n_act
+        counts = numpy.zeros(K, dtype=numpy.int32)
+        if n_act == 0:
+            return -1, None, counts
+        out = _pool.empty(n_act)
+        first = ctypes.c_int(-1)
+        _lib.check(self._lib.mdns_clike_first_accept(self._h, noise, scale, None, _addr(counts),
+                                                     ctypes.byref(first), _addr(out), out.size),
+                   'mdns_clike_first_accept')
+        if first.value < 0:
+            return -1, None, counts
+        return first.value, out, counts
+
     def loglike_spectra(self, ypred, data_mask, noise, scale=-0.5, out=None):
         """K model spectra x all active data sets -> L[K, n_act] (scalar-noise chi-square)."""
         K = self.stage_spectra(ypred)

@@ -301,6 +301,16 @@ def test_first_accepted_matches_one_at_a_time_loop(oracle_port, N):
     # everything accepts below the worst
     k, L, counts = ds.first_accepted(pts, m, Ls.min(axis=0) - 1.0, synth.NOISE_LEVEL)
     assert k == 0 and (counts == n_act).all() and rel_err(L, Ls[0]) < TOL
+    # staged form: mask and thresholds once per draw, then batches of candidates
+    assert ds.begin_draw(m, Lmins) == n_act
+    k, L, counts = ds.draw_batch(pts[:4], synth.NOISE_LEVEL)
+    assert k == -1 and L is None and numpy.array_equal(counts, want_counts[:4])
+    k, L, counts = ds.draw_batch(pts[4:], synth.NOISE_LEVEL)
+    assert k == want_first - 4 and numpy.array_equal(counts, want_counts[4:])
+    assert rel_err(L, Ls[want_first]) < TOL
+    ds.set_mask(None)
+    with pytest.raises(_lib.MdnsError):
+        ds.draw_batch(pts, synth.NOISE_LEVEL)       # thresholds do not survive a new mask
 
 
 def test_legacy_like_symbol_accumulates(oracle_port):
