@@ -532,7 +532,7 @@ static void fill_args(const mdns_dataset *ds, const Shard &s, LikeArgs &a)
 static bool xp_candidate(const mdns_dataset *ds, const Shard &s)
 {
 	if (!s.syy || !s.all_active) return false;
-	if (ds->tuning.lanes == 2) return true;               // explicit request
+	if (ds->tuning.lanes == 2 || ds->tuning.lanes == 3) return true;   // explicit request
 	return ds->tuning.lanes == 0 && ds->K >= 8 && ds->tuning.allow_expanded;
 }
 

@@ -1,0 +1,279 @@
+// clike_dmma_kernel.cu -- candidate-batch chi-square, expanded form, cross term on the FP64
+// tensor path (mma.sync m8n8k4 f64 -> SASS DMMA).
+//
+//     sum_j (m_kj - y_ij)^2 = Syy_i - 2 * Sym_ik + Smm_k ,   Sym = Y * M^T
+//
+// Same algebra, guard and fix-up as clike_xtile_kernel.cu (see there for the error bound); what
+// changes is how the K x C x N contraction Sym is issued.  tools/dmma_peak.cu measured the DMMA
+// path of the B200 at 18.5 T FMA/s -- the same rate as the FP64 FMA pipe, and the two do not add
+// up (they share the unit) -- so the tensor path buys no FLOPs.  What it buys is operand
+// traffic: one DMMA performs 8 x 8 x 4 FMAs from ONE double of Y and ONE double of M per lane,
+// where the FMA form needs a shared-memory model fetch per 4 FMAs.  ncu on the FMA form at
+// K = 16 showed the shared-memory pipe busier than the FP64 pipe (55 % vs 47 %, one warp per
+// scheduler); here a warp tile of 32 data sets x 8*NC candidates needs 4 + NC 64-bit fragment
+// loads per 4 channels for 4*NC DMMAs.
+//
+// tcgen05 has no FP64 kind, so this is the only tensor path that keeps the 1e-9 contract; the
+// TF32/BF16 variants of the north star's split cannot (cancellation).
+//
+// Layout:
+//   * producer thread: tensor-TMA ring of [256 data sets] x [16 channels] boxes (128-byte
+//     swizzle) exactly as in clike_tile_kernel; the KT model spectra of the pass are copied once
+//     per CTA into shared memory with a row pitch = 4 mod 16 doubles so that the B fragments
+//     (8 candidates x 4 channels) are bank-conflict free;
+//   * 8 consumer warps, warp w owns data sets [32w, 32w+32) of the tile as 4 row tiles of 8.
+//     Fragment (m8n8k4, f64): A[g][t] = Y[row(g)][4*ks + t], B[t][g] = M[8*nc + g][4*ks + t],
+//     g = lane / 4, t = lane % 4.  The logical row g is mapped to the physical row
+//     perm(g) = 0,2,4,6,1,3,5,7 so that each half-warp touches rows of equal parity: with the
+//     128-byte swizzle (16-byte chunk index ^= row % 8) its 16 lanes then hit 8 distinct chunk
+//     columns and the 64-bit loads are conflict free;
+//   * D[g][2t + {0,1}] accumulates over all channels in registers (2 doubles per tile).
+#include <cuda.h>
+
+#include "kernels.cuh"
+
+namespace mdns {
+
+constexpr int DM_ROWS = 256;                    // data sets per tile = rows of one TMA box
+constexpr int DM_BOX_CH = 16;                   // channels per box row = 128 bytes (swizzle span)
+constexpr int DM_STAGE_BYTES = DM_ROWS * DM_BOX_CH * 8;
+constexpr int DM_WARPS = DM_ROWS / 32;          // consumer warps
+constexpr int DM_MR = 4;                        // row tiles (of 8 data sets) per warp
+
+__device__ __forceinline__ void dm_mbar_arrive(uint64_t *bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void dm_tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int c0,
+                                               int c1, uint64_t *bar)
+{
+	asm volatile(
+	    "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+	    "[%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(smem_dst)),
+	    "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+	    : "memory");
+}
+
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b)
+{
+	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+	             : "+d"(c0), "+d"(c1)
+	             : "d"(a), "d"(b));
+}
+
+// shared-memory pitch of a model row: covers every box column and is 4 mod 16 doubles
+__host__ __device__ inline int dm_model_pitch(int pitch_even)
+{
+	return (pitch_even + DM_BOX_CH - 1) / DM_BOX_CH * DM_BOX_CH + 4;
+}
+
+template <int NC, int STAGES>
+__global__ void __launch_bounds__(DM_ROWS + 32) clike_dmma_kernel(
+    const __grid_constant__ CUtensorMap tmap, const LikeArgs a, const int k0, const int kt_valid,
+    const int pass)
+{
+	constexpr int KT = NC * 8;
+	extern __shared__ __align__(1024) unsigned char smem_raw[];
+	__shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], model_bar;
+	// the swizzle pattern is a function of the shared-memory address: align the ring to 1 KB
+	unsigned char *ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+	double *sm_model = reinterpret_cast<double *>(ring + STAGES * DM_STAGE_BYTES);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int pitch_even = (int)a.pitch;       // channels incl. the zero pad of an odd count
+	const int nchunks = (pitch_even + DM_BOX_CH - 1) / DM_BOX_CH;
+	const int ntiles = (a.n_rows + DM_ROWS - 1) / DM_ROWS;
+	const int mps = dm_model_pitch(pitch_even);
+
+	// zero the tail of every model row (channels the TMA copy below does not write; the data
+	// there is zero-filled by the tensor copy, but 0 * garbage could be NaN)
+	for (int i = threadIdx.x; i < KT * (mps - a.mpitch); i += blockDim.x) {
+		const int k = i / (mps - a.mpitch), j = i % (mps - a.mpitch);
+		sm_model[k * mps + a.mpitch + j] = 0.0;
+	}
+	if (threadIdx.x == 0) {
+#pragma unroll
+		for (int s = 0; s < STAGES; ++s) {
+			mbar_init(&full_bar[s], 1);
+			mbar_init(&empty_bar[s], DM_WARPS);
+		}
+		mbar_init(&model_bar, 1);
+		mbar_fence_init();
+	}
+	__syncthreads();
+
+	if (warp == DM_WARPS) {
+		// ===================== producer (one elected thread) =====================
+		if (lane == 0) {
+			const uint32_t row_bytes = (uint32_t)a.mpitch * 8u;
+			mbar_expect_tx(&model_bar, row_bytes * KT);
+			for (int k = 0; k < KT; ++k)
+				tma_load_1d(sm_model + (size_t)k * mps, a.model + (size_t)(k0 + k) * a.mpitch,
+				            row_bytes, &model_bar);
+			int it = 0;
+			for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+				const int r0 = a.row0 + tile * DM_ROWS;
+				for (int c = 0; c < nchunks; ++c, ++it) {
+					const int stage = it % STAGES;
+					const uint32_t round = (uint32_t)(it / STAGES);
+					mbar_wait(&empty_bar[stage], (round & 1u) ^ 1u);   // first round passes
+					// out-of-bounds parts of a box are zero-filled and still counted
+					mbar_expect_tx(&full_bar[stage], DM_STAGE_BYTES);
+					dm_tma_load_2d(ring + (size_t)stage * DM_STAGE_BYTES, &tmap, c * DM_BOX_CH, r0,
+					               &full_bar[stage]);
+				}
+			}
+		}
+	} else {
+		// ===================== consumer warps =====================
+		const int g = lane >> 2, t = lane & 3;
+		const int pr = ((g & 3) << 1) | (g >> 2);      // physical row of logical row g
+		// byte offset of this lane's A element inside a stage, per channel step ks: row * 128 +
+		// ((2*ks + t/2) ^ pr) * 16 + (t & 1) * 8 ; the row tiles of the warp are 1 KB apart
+		const int a_row_off = (warp * 32 + pr) * 128 + (t & 1) * 8;
+		const int a_chunk = t >> 1;
+		const double *b_base = sm_model + (size_t)g * mps + t;
+		const double inv = a.scale / a.noise2;
+		mbar_wait(&model_bar, 0);
+		int it = 0;
+		for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+			double acc[DM_MR][NC][2];
+#pragma unroll
+			for (int mr = 0; mr < DM_MR; ++mr)
+#pragma unroll
+				for (int nc = 0; nc < NC; ++nc) acc[mr][nc][0] = acc[mr][nc][1] = 0.0;
+			for (int c = 0; c < nchunks; ++c, ++it) {
+				const int stage = it % STAGES;
+				const uint32_t round = (uint32_t)(it / STAGES);
+				mbar_wait(&full_bar[stage], round & 1u);
+				const unsigned char *sbase = ring + (size_t)stage * DM_STAGE_BYTES + a_row_off;
+				const double *bc = b_base + c * DM_BOX_CH;
+#pragma unroll
+				for (int ks = 0; ks < DM_BOX_CH / 4; ++ks) {
+					double fa[DM_MR], fb[NC];
+					const int choff = ((2 * ks + a_chunk) ^ pr) << 4;
+#pragma unroll
+					for (int mr = 0; mr < DM_MR; ++mr)
+						fa[mr] = *reinterpret_cast<const double *>(sbase + mr * 1024 + choff);
+#pragma unroll
+					for (int nc = 0; nc < NC; ++nc) fb[nc] = bc[(size_t)nc * 8 * mps + ks * 4];
+#pragma unroll
+					for (int mr = 0; mr < DM_MR; ++mr)
+#pragma unroll
+						for (int nc = 0; nc < NC; ++nc)
+							dmma_8x8x4(acc[mr][nc][0], acc[mr][nc][1], fa[mr], fb[nc]);
+				}
+				__syncwarp();
+				if (lane == 0) dm_mbar_arrive(&empty_bar[stage]);   // this warp is done with the stage
+			}
+			// epilogue: lane holds D[row(g)][2t + {0,1}] of every (row tile, candidate tile)
+#pragma unroll
+			for (int mr = 0; mr < DM_MR; ++mr) {
+				const long long gr = (long long)tile * DM_ROWS + warp * 32 + mr * 8 + pr;
+				const bool live = gr < a.n_rows;
+				const double syy = live ? __ldg(a.syy + a.row0 + gr) : 0.0;
+				bool redo = false;
+#pragma unroll
+				for (int nc = 0; nc < NC; ++nc) {
+#pragma unroll
+					for (int i = 0; i < 2; ++i) {
+						const int k = nc * 8 + 2 * t + i;
+						const double smm = __ldg(a.smm + k0 + k);
+						const double chi = syy + fma(-2.0, acc[mr][nc][i], smm);
+						const bool ok = chi >= a.xp_guard * (syy + smm);   // false for NaN too
+						if (live && k < kt_valid) {
+							if (ok)
+								a.out[(long long)(k0 + k) * a.out_stride + gr] = chi * inv;
+							else
+								redo = true;
+						}
+					}
+				}
+				// the four lanes of a group share the data set: list it once
+				redo = redo || __shfl_xor_sync(0xffffffffu, redo, 1);
+				redo = redo || __shfl_xor_sync(0xffffffffu, redo, 2);
+				if (redo && t == 0) a.xp_list[atomicAdd(a.xp_redo + 1 + pass, 1)] = (int)gr;
+			}
+		}
+	}
+}
+
+// ---- host side ---------------------------------------------------------------------------
+static size_t dmma_smem(int kt, int stages, int pitch_even)
+{
+	return (size_t)stages * DM_STAGE_BYTES + 1024 + (size_t)kt * dm_model_pitch(pitch_even) * 8;
+}
+
+int launch_xtile_fixup(const LikeArgs &a, int k0, int kv, int pass, int sm_count, cudaStream_t st);
+
+template <int NC, int STAGES>
+static int launch_dmma_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
+{
+	constexpr int KT = NC * 8;
+	constexpr int THREADS = DM_ROWS + 32;
+	const size_t smem = dmma_smem(KT, STAGES, (int)a.pitch);
+	auto kern = clike_dmma_kernel<NC, STAGES>;
+	MDNS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int occ = 0;
+	MDNS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+	if (occ < 1) {
+		set_error("DMMA tile kernel does not fit (%zu bytes of shared memory)", smem);
+		return MDNS_EINVAL;
+	}
+	CUtensorMap tm;
+	memcpy(&tm, a.tmap256, sizeof tm);
+	const int ntiles = ceil_div(a.n_rows, DM_ROWS);
+	long long gx = ntiles;
+	const long long resident = (long long)sm_count * occ;
+	if (gx > resident) gx = resident;
+	const int npass = ceil_div(a.K, KT);
+	if (npass + 1 > xtile_counter_capacity()) {
+		set_error("DMMA tile kernel: %d passes exceed the counter block", npass);
+		return MDNS_EINVAL;
+	}
+	// list lengths of this launch's passes (counter[0], the running total, is left alone)
+	MDNS_CUDA(cudaMemsetAsync(a.xp_redo + 1, 0, (size_t)npass * sizeof(int), st));
+	for (int k0 = 0, pass = 0; k0 < a.K; k0 += KT, ++pass) {
+		const int kv = a.K - k0 < KT ? a.K - k0 : KT;
+		kern<<<(unsigned)gx, THREADS, smem, st>>>(tm, a, k0, kv, pass);
+		MDNS_LAUNCHED("clike_dmma_kernel");
+		const int rc = launch_xtile_fixup(a, k0, kv, pass, sm_count, st);
+		if (rc != MDNS_OK) return rc;
+	}
+	return MDNS_OK;
+}
+
+bool dmma_fits(const LikeArgs &a, int kt, int stages)
+{
+	return a.tmap256 && !a.active && a.syy && a.smm && a.xp_redo && a.xp_list &&
+	       dmma_smem(kt, stages, (int)a.pitch) <= 220 * 1024 &&
+	       (size_t)kt * a.mpitch * 8 < (1u << 20);   // mbarrier tx-count range
+}
+
+// kt in {8, 16, 32}; stages in {2, 3, 4}
+int launch_clike_dmma(const LikeArgs &a, int kt, int stages, int sm_count, cudaStream_t st)
+{
+	if (a.n_rows <= 0 || a.K <= 0) return MDNS_OK;
+	if (!dmma_fits(a, kt, stages)) {
+		set_error("DMMA tile kernel: needs all-active rows, the resident row sums and %zu bytes of "
+		          "shared memory", dmma_smem(kt, stages, (int)a.pitch));
+		return MDNS_EINVAL;
+	}
+#define MDNS_DM(KK, SS) \
+	if (kt == KK && stages == SS) return launch_dmma_inst<KK / 8, SS>(a, sm_count, st)
+	MDNS_DM(8, 2);
+	MDNS_DM(8, 3);
+	MDNS_DM(8, 4);
+	MDNS_DM(16, 2);
+	MDNS_DM(16, 3);
+	MDNS_DM(16, 4);
+	MDNS_DM(32, 2);
+	MDNS_DM(32, 3);
+	MDNS_DM(32, 4);
+#undef MDNS_DM
+	set_error("unsupported DMMA tile-kernel shape kt=%d stages=%d", kt, stages);
+	return MDNS_EINVAL;
+}
+
+}  // namespace mdns

@@ -232,6 +232,8 @@ __global__ void __launch_bounds__(XT_ROWS / R + 32) clike_xtile_kernel(
 }
 
 // ---- host side ---------------------------------------------------------------------------
+int launch_xtile_fixup(const LikeArgs &a, int k0, int kv, int pass, int sm_count, cudaStream_t st);
+
 static size_t xtile_smem(int kt, int stages, int mpitch)
 {
 	return (size_t)stages * XT_STAGE_BYTES + 1024 + (size_t)kt * mpitch * 8;
@@ -263,15 +265,23 @@ static int launch_xtile_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 	}
 	// list lengths of this launch's passes (counter[0], the running total, is left alone)
 	MDNS_CUDA(cudaMemsetAsync(a.xp_redo + 1, 0, (size_t)npass * sizeof(int), st));
-	int fix_blocks = ceil_div(a.n_rows, 8);
-	if (fix_blocks > 2 * sm_count) fix_blocks = 2 * sm_count;
 	for (int k0 = 0, pass = 0; k0 < a.K; k0 += KT, ++pass) {
 		const int kv = a.K - k0 < KT ? a.K - k0 : KT;
 		kern<<<(unsigned)gx, THREADS, smem, st>>>(tm, a, k0, kv, pass);
 		MDNS_LAUNCHED("clike_xtile_kernel");
-		xtile_fixup_kernel<<<fix_blocks, 256, 0, st>>>(a, k0, kv, pass);
-		MDNS_LAUNCHED("clike_xtile_kernel");
+		const int rc = launch_xtile_fixup(a, k0, kv, pass, sm_count, st);
+		if (rc != MDNS_OK) return rc;
 	}
+	return MDNS_OK;
+}
+
+// the direct-form fix-up of one pass (shared with clike_dmma_kernel.cu)
+int launch_xtile_fixup(const LikeArgs &a, int k0, int kv, int pass, int sm_count, cudaStream_t st)
+{
+	int fix_blocks = ceil_div(a.n_rows, 8);
+	if (fix_blocks > 2 * sm_count) fix_blocks = 2 * sm_count;
+	xtile_fixup_kernel<<<fix_blocks, 256, 0, st>>>(a, k0, kv, pass);
+	MDNS_LAUNCHED("xtile_fixup_kernel");
 	return MDNS_OK;
 }
 

@@ -65,7 +65,8 @@ struct Tuning {
 	int lanes = 0;   // lanes per data set: 8 or 32; 1 = tile kernel (unroll = channels per
 	                 // stage 16/32, rows = ring stages 3/4/6, all-active only), 2 = expanded-form
 	                 // tile kernel (unroll = data sets per lane 2/4, rows = ring stages 2/3,
-	                 // all-active only); 0 = auto
+	                 // all-active only), 3 = expanded form on the FP64 tensor path (DMMA;
+	                 // ktile 8/16/32, rows = ring stages 2/3/4); 0 = auto
 	int unroll = 0;  // 128-bit fragments in flight per lane (0 = auto)
 	int ktile = 0;   // candidates per pass (0 = auto)
 	int rows = 0;    // data sets per lane group in the block kernel: 1, 2, 4 (0 = auto)
@@ -86,6 +87,10 @@ int launch_clike_tile(const LikeArgs &a, const void *tmap, int kt, int nbox, int
 // kt in {8, 16, 32}, lane_rows in {2, 4}, stages in {2, 3}
 bool xtile_fits(const LikeArgs &a, int kt, int stages);
 int xtile_counter_capacity();
+// the same expanded form with the cross term on the FP64 tensor path (clike_dmma_kernel.cu);
+// kt in {8, 16, 32}, stages in {2, 3, 4}
+bool dmma_fits(const LikeArgs &a, int kt, int stages);
+int launch_clike_dmma(const LikeArgs &a, int kt, int stages, int sm_count, cudaStream_t st);
 int launch_clike_xtile(const LikeArgs &a, int kt, int lane_rows, int stages, int sm_count,
                        cudaStream_t st);
 // out[r] = sum_j rows[r*pitch + j]^2 (rows: resident data sets or padded model spectra)

@@ -569,6 +569,15 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 	const int nfrag = (a.nx + 1) >> 1;
 	int L = t.lanes;
 	const bool tile_ok = a.tmap && !a.active && 4LL * a.mpitch <= tile_constant_capacity();
+	if (L == 3 && !a.active) {
+		// expanded form, cross term as FP64 tensor-core tiles
+		int kt = t.ktile;
+		if (kt != 8 && kt != 16 && kt != 32) kt = a.K >= 32 ? 32 : a.K >= 16 ? 16 : 8;
+		int stages = (t.rows == 2 || t.rows == 3 || t.rows == 4) ? t.rows : 2;
+		while (kt > 8 && !dmma_fits(a, kt, stages)) kt >>= 1;
+		if (!dmma_fits(a, kt, stages)) stages = 2;
+		return launch_clike_dmma(a, kt, stages, sm_count, st);
+	}
 	if (L == 2 && !a.active) {
 		// expanded form, register-blocked over data sets (all-active rows only)
 		int kt = t.ktile;
@@ -593,7 +602,7 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		return launch_clike_tile(a, tile_rows == 256 ? a.tmap256 : a.tmap, kt, nbox, stages,
 		                         tile_rows, sm_count, st);
 	}
-	if (L == 1 || L == 2) {
+	if (L == 1 || L == 2 || L == 3) {
 		// tile kernel requested but not applicable (masked rows): automatic choice
 		Tuning d;
 		d.allow_expanded = t.allow_expanded;

@@ -135,7 +135,7 @@ def test_clike_expanded_form_vs_oracle(oracle_port, N, nx, K, lane_rows, ktile, 
     ds.set_tuning(2, lane_rows, ktile, stages)
     pts = synth.parameter_points(K, seed=N)
     got = ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0)
-    assert _lib.load().mdns_last_kernel() == b'clike_xtile_kernel'
+    assert _lib.load().mdns_last_kernel() == b'xtile_fixup_kernel'
     allm = numpy.ones(N, dtype=bool)
     for k in sorted(set((0, 1, K // 2, K - 2, K - 1))):
         p = pts[k]
@@ -160,13 +160,35 @@ def test_clike_expanded_blocked_variants(oracle_port, lane_rows, ktile, stages, 
     ds.set_tuning(2, lane_rows, ktile, stages)
     pts = synth.parameter_points(K, seed=N + 1)
     got = ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0)
-    assert _lib.load().mdns_last_kernel() == b'clike_xtile_kernel'
+    assert _lib.load().mdns_last_kernel() == b'xtile_fixup_kernel'
     allm = numpy.ones(N, dtype=bool)
     for k in sorted(set((0, 7, 8, K // 2, K - 1))):
         p = pts[k]
         want = oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, allm)
         assert rel_err(got[k], want) < TOL_XP
     assert ds.expanded_stats() == (True, 0)
+
+
+@pytest.mark.parametrize('ktile,stages', [(8, 2), (16, 2), (16, 3), (32, 2), (32, 3), (8, 4)])
+@pytest.mark.parametrize('N,nx,K', [(128, 16, 4), (700, 203, 9), (300, 1000, 5), (70000, 200, 37),
+                                    (2049, 57, 64)])
+def test_clike_expanded_tensor_path_variants(oracle_port, ktile, stages, N, nx, K):
+    # expanded form with the cross term as FP64 tensor-core tiles (lanes = 3)
+    x, y, _ = synth.horns(N, nx=nx, legacy=False, seed=N + 2)
+    ds = ResidentDataset(x, y)
+    ds.set_tuning(3, 0, ktile, stages)
+    pts = synth.parameter_points(K, seed=N + 3)
+    got = ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0)
+    assert _lib.load().mdns_last_kernel() == b'xtile_fixup_kernel'
+    allm = numpy.ones(N, dtype=bool)
+    for k in sorted(set((0, 1, 7, 8, K // 2, K - 2, K - 1)) & set(range(K))):
+        p = pts[k]
+        want = oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, allm)
+        assert rel_err(got[k], want) < TOL_XP, k
+    assert ds.expanded_stats() == (True, 0)
+    ds.set_tuning(2, 2, 8, 2)
+    fma_form = ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0)
+    assert rel_err(got, fma_form) < TOL_XP
 
 
 def test_clike_expanded_form_automatic_choice(oracle_port):
@@ -178,16 +200,16 @@ def test_clike_expanded_form_automatic_choice(oracle_port):
     lib = _lib.load()
     pts = synth.parameter_points(35, seed=2)
     got = ds.loglike_batch(pts, None, synth.NOISE_LEVEL)
-    assert lib.mdns_last_kernel() == b'clike_xtile_kernel'
+    assert lib.mdns_last_kernel() == b'xtile_fixup_kernel'
     allm = numpy.ones(N, dtype=bool)
     for k in (0, 7, 8, 31, 32, 34):
         p = pts[k]
         want = -0.5 * oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, allm)
         assert rel_err(got[k], want) < TOL_XP
     ds.loglike_batch(pts[:4], None, synth.NOISE_LEVEL)
-    assert b'xtile' not in lib.mdns_last_kernel()
+    assert b'fixup' not in lib.mdns_last_kernel()
     ds.loglike_batch(pts, synth.masks(N)['half'], synth.NOISE_LEVEL)
-    assert b'xtile' not in lib.mdns_last_kernel()
+    assert b'fixup' not in lib.mdns_last_kernel()
     ds.set_expanded(False)
     got = ds.loglike_batch(pts[:9], None, synth.NOISE_LEVEL)
     assert lib.mdns_last_kernel() == b'clike_tile_kernel'
@@ -217,7 +239,7 @@ def test_clike_expanded_form_cancellation_guard(oracle_port):
     ds = ResidentDataset(x, y)
     ds.set_tuning(2, 2, 8, 3)
     got = ds.loglike_spectra(spectra, None, synth.NOISE_LEVEL, scale=1.0)
-    assert _lib.load().mdns_last_kernel() == b'clike_xtile_kernel'
+    assert _lib.load().mdns_last_kernel() == b'xtile_fixup_kernel'
     allm = numpy.ones(N, dtype=bool)
     for k in range(K):
         want = oracle_port.clike_spectrum(spectra[k], y, synth.NOISE_LEVEL, allm)
@@ -228,7 +250,7 @@ def test_clike_expanded_form_cancellation_guard(oracle_port):
     assert not enabled
     ds.set_tuning(0, 0, 0, 0)
     again = ds.loglike_spectra(spectra, None, synth.NOISE_LEVEL, scale=1.0)
-    assert b'xtile' not in _lib.load().mdns_last_kernel()
+    assert b'fixup' not in _lib.load().mdns_last_kernel()
     assert rel_err(again, got) < TOL_XP
 
 
