@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--ndata', type=int, default=1000000, help='data sets per GPU')
     ap.add_argument('--nx', type=int, default=200, help='channels')
-    ap.add_argument('--candidates', type=int, default=8, help='parameter points per step')
+    ap.add_argument('--candidates', type=int, default=16, help='parameter points per step')
     ap.add_argument('--mask', default='all', choices=['all', 'half', 'sparse', 'prefix'])
     ap.add_argument('--ref-ndata', type=int, default=100000,
                     help='data sets per step of the CPU reference arm (bounded sample)')
@@ -437,7 +437,7 @@ def run_ours(args):
                 'frac': achieved / peak, 'traffic': ncu_traffic(args.nx, per_gpu_n, K),
                 'kernel': kernel_name, 'algorithmic_bytes_per_launch': bytes_per_launch,
                 'peak_source': peak_src,
-                'note': 'duration = whole step (line_model_kernel + constant-bank copy + dominant kernel), '
+                'note': 'duration = whole step (line model + dominant kernel + fix-up launch), '
                         'CUDA events on the shim stream'}
 
     # ---- CPU baseline beside it (rank 0, single-GPU run only) ------------------

@@ -78,6 +78,7 @@ struct Shard {
 	size_t smm_cap = 0;
 	int *d_redo = nullptr;        // counters of the expanded kernel's direct-form fix-ups
 	int *d_redo_list = nullptr;   // and the rows to fix up in the current pass
+	bool counters_clear = false;  // per-pass counters already reset by the model kernel
 	int n_act = 0;
 	bool all_active = true;
 	alignas(64) unsigned char tmap[128];      // CUtensorMaps of Y (tile kernel), 128-row boxes
@@ -524,6 +525,7 @@ static void fill_args(const mdns_dataset *ds, const Shard &s, LikeArgs &a)
 	a.smm = s.d_smm;
 	a.xp_redo = s.d_redo;
 	a.xp_list = s.d_redo_list;
+	a.xp_counters_clear = s.counters_clear;
 	// error bound of the three sequential FP64 sums relative to Syy+Smm, over the tolerance
 	a.xp_guard = (2.0 * ds->nx + 4.0) * 1.1102230246251565e-16 / ds->xp_tol;
 }
@@ -552,12 +554,18 @@ static int clike_check(mdns_dataset *ds, const char *who)
 static int clike_model(mdns_dataset *ds, Shard &s)
 {
 	const int Kpad = (int)round_up(ds->K, KT_MAX);
-	int rc = MDNS_OK;
-	if (ds->staged == 1)
-		rc = launch_line_model(s.x, ds->nx, s.d_in, ds->K, Kpad, s.d_model, (int)ds->pitch, s.stream);
-	if (rc == MDNS_OK && xp_candidate(ds, s))
-		rc = launch_row_sumsq(s.d_model, Kpad, (long long)ds->pitch, ds->nx, s.d_smm, s.stream);
-	return rc;
+	const bool xp = xp_candidate(ds, s);
+	const int npass = ceil_div(ds->K, 8);
+	s.counters_clear = false;
+	if (ds->staged == 1) {
+		const bool clear = xp && npass + 1 <= xtile_counter_capacity();
+		int rc = launch_line_model(s.x, ds->nx, s.d_in, ds->K, Kpad, s.d_model, (int)ds->pitch,
+		                           xp ? s.d_smm : nullptr, clear ? s.d_redo : nullptr, npass, s.stream);
+		s.counters_clear = clear;
+		return rc;
+	}
+	if (xp) return launch_row_sumsq(s.d_model, Kpad, (long long)ds->pitch, ds->nx, s.d_smm, s.stream);
+	return MDNS_OK;
 }
 
 // After a synchronising call: collect the expanded kernel's recomputation counter; data that
@@ -595,6 +603,7 @@ static int clike_rows(mdns_dataset *ds, Shard &s, double noise, double scale, in
 		a.active += r0;
 	else
 		a.Y += (size_t)r0 * ds->pitch;
+	s.counters_clear = false;     // the reset by the model kernel covers one launch only
 	return launch_clike(a, ds->tuning, s.sm_count, s.stream);
 }
 

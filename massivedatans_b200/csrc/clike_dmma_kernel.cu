@@ -233,7 +233,8 @@ static int launch_dmma_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 		return MDNS_EINVAL;
 	}
 	// list lengths of this launch's passes (counter[0], the running total, is left alone)
-	MDNS_CUDA(cudaMemsetAsync(a.xp_redo + 1, 0, (size_t)npass * sizeof(int), st));
+	if (!a.xp_counters_clear)
+		MDNS_CUDA(cudaMemsetAsync(a.xp_redo + 1, 0, (size_t)npass * sizeof(int), st));
 	for (int k0 = 0, pass = 0; k0 < a.K; k0 += KT, ++pass) {
 		const int kv = a.K - k0 < KT ? a.K - k0 : KT;
 		kern<<<(unsigned)gx, THREADS, smem, st>>>(tm, a, k0, kv, pass);

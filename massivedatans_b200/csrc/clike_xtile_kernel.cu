@@ -264,7 +264,8 @@ static int launch_xtile_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 		return MDNS_EINVAL;
 	}
 	// list lengths of this launch's passes (counter[0], the running total, is left alone)
-	MDNS_CUDA(cudaMemsetAsync(a.xp_redo + 1, 0, (size_t)npass * sizeof(int), st));
+	if (!a.xp_counters_clear)
+		MDNS_CUDA(cudaMemsetAsync(a.xp_redo + 1, 0, (size_t)npass * sizeof(int), st));
 	for (int k0 = 0, pass = 0; k0 < a.K; k0 += KT, ++pass) {
 		const int kv = a.K - k0 < KT ? a.K - k0 : KT;
 		kern<<<(unsigned)gx, THREADS, smem, st>>>(tm, a, k0, kv, pass);
@@ -281,7 +282,7 @@ int launch_xtile_fixup(const LikeArgs &a, int k0, int kv, int pass, int sm_count
 	int fix_blocks = ceil_div(a.n_rows, 8);
 	if (fix_blocks > 2 * sm_count) fix_blocks = 2 * sm_count;
 	xtile_fixup_kernel<<<fix_blocks, 256, 0, st>>>(a, k0, kv, pass);
-	MDNS_LAUNCHED("xtile_fixup_kernel");
+	MDNS_LAUNCHED_HELPER("xtile_fixup_kernel");
 	return MDNS_OK;
 }
 

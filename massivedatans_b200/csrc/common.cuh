@@ -40,6 +40,18 @@ extern std::atomic<const char *> g_last_kernel;
 		}                                                                    \
 	} while (0)
 
+// The same for helper launches that should not show up as "the kernel of the last launch".
+#define MDNS_LAUNCHED_HELPER(name)                                                   \
+	do {                                                                         \
+		mdns::g_launches.fetch_add(1, std::memory_order_relaxed);            \
+		cudaError_t e__ = cudaGetLastError();                                \
+		if (e__ != cudaSuccess) {                                            \
+			mdns::set_error("launch of %s failed at %s:%d: %s", name,    \
+			                __FILE__, __LINE__, cudaGetErrorString(e__)); \
+			return MDNS_ECUDA;                                           \
+		}                                                                    \
+	} while (0)
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 

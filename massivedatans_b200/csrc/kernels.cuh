@@ -22,8 +22,11 @@ int launch_transpose_rows(const double *in, size_t ld_in, int nx, int nb, double
 
 // clike.c:65 -- model[k*mpitch + j] = A_k*exp(-0.5*((mu_k - x_j)/sig_k)^2); zero padding
 // for j >= nx and for k in [K, Kpad).
+// smm (may be null): sum of squares of every model row; counters (may be null): the expanded
+// kernels' counter block, whose per-pass entries [1, 1+ncounters) are reset.
 int launch_line_model(const double *x, int nx, const double *params, int K, int Kpad,
-                      double *model, int mpitch, cudaStream_t st);
+                      double *model, int mpitch, double *smm, int *counters, int ncounters,
+                      cudaStream_t st);
 // zero-pad host-provided spectra: src[K][nx] -> model[Kpad][mpitch]
 int launch_pad_spectra(const double *src, int nx, int K, int Kpad, double *model, int mpitch,
                        cudaStream_t st);
@@ -58,6 +61,7 @@ struct LikeArgs {
 	int *xp_redo;         // device counters: [0] rows recomputed in the direct form so far,
 	                      // [1 + pass] list length of each pass of the current launch
 	int *xp_list;         // rows (within the launch) to recompute, capacity = rows of the shard
+	bool xp_counters_clear;  // the per-pass counters were already reset by the model kernel
 };
 
 struct Tuning {

@@ -48,28 +48,55 @@ int launch_transpose_rows(const double *in, size_t ld_in, int nx, int nb, double
 }
 
 // ------------------------------------------------------------ model batch ---
-__global__ void line_model_kernel(const double *__restrict__ x, int nx,
-                                  const double *__restrict__ params, int K, int Kpad,
-                                  double *__restrict__ model, int mpitch)
+// One CTA per candidate: the model spectrum, its sum of squares (Smm of the expanded form) and,
+// by CTA 0, the reset of the expanded kernels' per-pass list counters -- one launch per batch.
+__global__ void __launch_bounds__(256) line_model_kernel(const double *__restrict__ x, int nx,
+                                                         const double *__restrict__ params, int K,
+                                                         double *__restrict__ model, int mpitch,
+                                                         double *__restrict__ smm,
+                                                         int *__restrict__ counters, int ncounters)
 {
-	const int j = blockIdx.x * blockDim.x + threadIdx.x;
-	const int k = blockIdx.y;
-	if (j >= mpitch || k >= Kpad) return;
-	double v = 0.0;
-	if (k < K && j < nx) {
-		const double A = params[3 * k], mu = params[3 * k + 1], sig = params[3 * k + 2];
-		// clike.c:65, un-fused like the reference build
-		const double t = __ddiv_rn(__dsub_rn(mu, x[j]), sig);
-		v = __dmul_rn(A, exp(__dmul_rn(-0.5, __dmul_rn(t, t))));
+	__shared__ double warp_sums[8];
+	const int k = blockIdx.x;
+	double A = 0.0, mu = 0.0, sig = 1.0;
+	if (k < K) {
+		A = params[3 * k];
+		mu = params[3 * k + 1];
+		sig = params[3 * k + 2];
 	}
-	model[(size_t)k * mpitch + j] = v;
+	double s = 0.0;
+	for (int j = threadIdx.x; j < mpitch; j += 256) {
+		double v = 0.0;
+		if (k < K && j < nx) {
+			// clike.c:65, un-fused like the reference build
+			const double t = __ddiv_rn(__dsub_rn(mu, x[j]), sig);
+			v = __dmul_rn(A, exp(__dmul_rn(-0.5, __dmul_rn(t, t))));
+		}
+		model[(size_t)k * mpitch + j] = v;
+		s = fma(v, v, s);
+	}
+	if (smm) {
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) s += shfl_xor_f64(s, o);
+		if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			double tot = 0.0;
+#pragma unroll
+			for (int w = 0; w < 8; ++w) tot += warp_sums[w];
+			smm[k] = tot;
+		}
+	}
+	if (counters && k == 0)
+		for (int i = threadIdx.x; i < ncounters; i += 256) counters[1 + i] = 0;
 }
 
 int launch_line_model(const double *x, int nx, const double *params, int K, int Kpad,
-                      double *model, int mpitch, cudaStream_t st)
+                      double *model, int mpitch, double *smm, int *counters, int ncounters,
+                      cudaStream_t st)
 {
-	dim3 grid(ceil_div(mpitch, 128), Kpad);
-	line_model_kernel<<<grid, 128, 0, st>>>(x, nx, params, K, Kpad, model, mpitch);
+	line_model_kernel<<<Kpad, 256, 0, st>>>(x, nx, params, K, model, mpitch, smm, counters,
+	                                        ncounters);
 	MDNS_LAUNCHED("line_model_kernel");
 	return MDNS_OK;
 }
@@ -610,10 +637,17 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 	}
 	if (L == 0 && t.unroll == 0 && t.ktile == 0 && t.rows == 0 && !a.active && a.K >= 8 &&
 	    a.n_rows >= 32768) {
-		// automatic choice for all-active candidate batches: expanded form when allowed ...
-		const int xkt = a.K >= 16 && xtile_fits(a, 16, 2) ? 16 : 8;
-		if (t.allow_expanded && xtile_fits(a, xkt, 2))
-			return launch_clike_xtile(a, xkt, 2, 2, sm_count, st);
+		// automatic choice for all-active candidate batches: expanded form with the cross term
+		// on the FP64 tensor path when allowed (measured at N=1e6, C=200: K=8 0.287 ms, K=16
+		// 0.32 ms, K=32 0.53 ms; FMA form 0.29 / 0.35 / 0.69; direct form 0.30 / 0.56 / 1.1) ...
+		if (t.allow_expanded) {
+			if (a.K >= 32 && dmma_fits(a, 32, 3)) return launch_clike_dmma(a, 32, 3, sm_count, st);
+			if (a.K >= 32 && dmma_fits(a, 32, 2)) return launch_clike_dmma(a, 32, 2, sm_count, st);
+			if (a.K >= 16 && dmma_fits(a, 16, 2)) return launch_clike_dmma(a, 16, 2, sm_count, st);
+			if (dmma_fits(a, 8, 2)) return launch_clike_dmma(a, 8, 2, sm_count, st);
+			const int xkt = a.K >= 16 && xtile_fits(a, 16, 2) ? 16 : 8;
+			if (xtile_fits(a, xkt, 2)) return launch_clike_xtile(a, xkt, 2, 2, sm_count, st);
+		}
 		// ... else the direct-form tile kernel (measured at N=1e6, C=200: K=8 0.29 ms vs
 		// 0.35 ms block kernel; K=16 0.51 ms vs 0.71 ms)
 		if (tile_ok && 8LL * a.mpitch <= tile_constant_capacity()) {

@@ -135,7 +135,7 @@ def test_clike_expanded_form_vs_oracle(oracle_port, N, nx, K, lane_rows, ktile, 
     ds.set_tuning(2, lane_rows, ktile, stages)
     pts = synth.parameter_points(K, seed=N)
     got = ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0)
-    assert _lib.load().mdns_last_kernel() == b'xtile_fixup_kernel'
+    assert _lib.load().mdns_last_kernel() == b'clike_xtile_kernel'
     allm = numpy.ones(N, dtype=bool)
     for k in sorted(set((0, 1, K // 2, K - 2, K - 1))):
         p = pts[k]
@@ -160,7 +160,7 @@ def test_clike_expanded_blocked_variants(oracle_port, lane_rows, ktile, stages, 
     ds.set_tuning(2, lane_rows, ktile, stages)
     pts = synth.parameter_points(K, seed=N + 1)
     got = ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0)
-    assert _lib.load().mdns_last_kernel() == b'xtile_fixup_kernel'
+    assert _lib.load().mdns_last_kernel() == b'clike_xtile_kernel'
     allm = numpy.ones(N, dtype=bool)
     for k in sorted(set((0, 7, 8, K // 2, K - 1))):
         p = pts[k]
@@ -179,7 +179,7 @@ def test_clike_expanded_tensor_path_variants(oracle_port, ktile, stages, N, nx, 
     ds.set_tuning(3, 0, ktile, stages)
     pts = synth.parameter_points(K, seed=N + 3)
     got = ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0)
-    assert _lib.load().mdns_last_kernel() == b'xtile_fixup_kernel'
+    assert _lib.load().mdns_last_kernel() == b'clike_dmma_kernel'
     allm = numpy.ones(N, dtype=bool)
     for k in sorted(set((0, 1, 7, 8, K // 2, K - 2, K - 1)) & set(range(K))):
         p = pts[k]
@@ -200,16 +200,16 @@ def test_clike_expanded_form_automatic_choice(oracle_port):
     lib = _lib.load()
     pts = synth.parameter_points(35, seed=2)
     got = ds.loglike_batch(pts, None, synth.NOISE_LEVEL)
-    assert lib.mdns_last_kernel() == b'xtile_fixup_kernel'
+    assert lib.mdns_last_kernel() == b'clike_dmma_kernel'
     allm = numpy.ones(N, dtype=bool)
     for k in (0, 7, 8, 31, 32, 34):
         p = pts[k]
         want = -0.5 * oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, allm)
         assert rel_err(got[k], want) < TOL_XP
     ds.loglike_batch(pts[:4], None, synth.NOISE_LEVEL)
-    assert b'fixup' not in lib.mdns_last_kernel()
+    assert lib.mdns_last_kernel() not in (b'clike_xtile_kernel', b'clike_dmma_kernel')
     ds.loglike_batch(pts, synth.masks(N)['half'], synth.NOISE_LEVEL)
-    assert b'fixup' not in lib.mdns_last_kernel()
+    assert lib.mdns_last_kernel() not in (b'clike_xtile_kernel', b'clike_dmma_kernel')
     ds.set_expanded(False)
     got = ds.loglike_batch(pts[:9], None, synth.NOISE_LEVEL)
     assert lib.mdns_last_kernel() == b'clike_tile_kernel'
@@ -219,7 +219,9 @@ def test_clike_expanded_form_automatic_choice(oracle_port):
         assert rel_err(got[k], want) < TOL
 
 
-def test_clike_expanded_form_cancellation_guard(oracle_port):
+@pytest.mark.parametrize('tuning,kernel', [((2, 2, 8, 3), b'clike_xtile_kernel'),
+                                           ((3, 0, 8, 2), b'clike_dmma_kernel')])
+def test_clike_expanded_form_cancellation_guard(oracle_port, tuning, kernel):
     # data that the candidate fits to ~1e-7 of its amplitude: Syy, Sym and Smm agree to 14
     # digits and their combination would be rounding noise.  Those (data set, candidate) pairs
     # must be caught by the guard and recomputed in the direct form.
@@ -237,9 +239,9 @@ def test_clike_expanded_form_cancellation_guard(oracle_port):
     for i in numpy.nonzero(fitted)[0]:
         y[:, i] = spectra[i % K] + rs.normal(0, 1e-6, size=nx)
     ds = ResidentDataset(x, y)
-    ds.set_tuning(2, 2, 8, 3)
+    ds.set_tuning(*tuning)
     got = ds.loglike_spectra(spectra, None, synth.NOISE_LEVEL, scale=1.0)
-    assert _lib.load().mdns_last_kernel() == b'xtile_fixup_kernel'
+    assert _lib.load().mdns_last_kernel() == kernel
     allm = numpy.ones(N, dtype=bool)
     for k in range(K):
         want = oracle_port.clike_spectrum(spectra[k], y, synth.NOISE_LEVEL, allm)
@@ -250,7 +252,7 @@ def test_clike_expanded_form_cancellation_guard(oracle_port):
     assert not enabled
     ds.set_tuning(0, 0, 0, 0)
     again = ds.loglike_spectra(spectra, None, synth.NOISE_LEVEL, scale=1.0)
-    assert b'fixup' not in _lib.load().mdns_last_kernel()
+    assert _lib.load().mdns_last_kernel() not in (b'clike_xtile_kernel', b'clike_dmma_kernel')
     assert rel_err(again, got) < TOL_XP
 
 
