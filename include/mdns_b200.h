@@ -157,6 +157,38 @@ int mdns_set_tuning(mdns_dataset *ds, int lanes, int unroll, int ktile, int rows
 int mdns_set_expanded(mdns_dataset *ds, int enable, double rel_tol);
 int mdns_expanded_stats(const mdns_dataset *ds, int *enabled, int64_t *redo_rows);
 
+/* ---- live-point likelihood table (next row of the hot path) ------------ */
+/*
+ * `live_pointsL[nlive_points][ndata]` of multi_nested_sampler.py:111 resident
+ * next to the data it was scored on (same devices, same data-set ranges), so
+ * that the per-iteration reductions of the sampler run where the numbers are.
+ * Row-major like the numpy array (row = live point).  All results are
+ * selections and therefore bit-identical to numpy's.
+ */
+typedef struct mdns_livetable mdns_livetable;
+int mdns_livetable_create(mdns_dataset *ds, int nlive, mdns_livetable **out);
+int mdns_livetable_destroy(mdns_livetable *t);
+int mdns_livetable_upload(mdns_livetable *t, const double *L);      /* [nlive][ndata] */
+int mdns_livetable_download(mdns_livetable *t, double *L);
+/* rows [row0, row0+K) := the K logL vectors of the data set's last clike launch
+ * (every data set active): the initial population of
+ * multi_nested_sampler.py:91-111 without leaving the device. */
+int mdns_livetable_fill_from_launch(mdns_livetable *t, mdns_dataset *ds, int row0);
+/* prepare(), multi_nested_sampler.py:134-137 and :531: per data set the minimum,
+ * the row of its first occurrence (numpy.argmin) and the maximum over the live
+ * points.  Any output may be NULL. */
+int mdns_livetable_colstats(mdns_livetable *t, double *Lmins, int64_t *Lmini, double *Lmax);
+/* advance, multi_nested_sampler.py:520-524: table[rows[d]][d] = values[d] for
+ * every data set d with rows[d] >= 0. */
+int mdns_livetable_replace(mdns_livetable *t, const int64_t *rows, const double *values);
+/* Lmins_higher, multi_nested_sampler.py:438-447 (find_nsmallest :44-47): for the
+ * j-th listed data set d = indices[j] (increasing) with n = shelf_offsets[j+1] -
+ * shelf_offsets[j] queued likelihoods shelf_values[shelf_offsets[j] ...],
+ * out[j] = numpy.partition(concatenate(table[:, d], shelf), n)[n]. */
+int mdns_livetable_lmins_higher(mdns_livetable *t, const int *indices, int nidx,
+                                const int64_t *shelf_offsets, const double *shelf_values,
+                                double *out);
+
 /* ---- RadFriends neighbour tests --------------------------------------- */
 typedef struct mdns_region mdns_region;
 

@@ -47,6 +47,14 @@ SIGNATURES = {
     'mdns_set_expanded': (c_int, [_P, c_int, c_double]),
     'mdns_expanded_stats': (c_int, [_P, POINTER(c_int), POINTER(c_int64)]),
     'mdns_fetch': (c_int, [_P, _P, c_int64]),
+    'mdns_livetable_create': (c_int, [_P, c_int, POINTER(_P)]),
+    'mdns_livetable_destroy': (c_int, [_P]),
+    'mdns_livetable_upload': (c_int, [_P, _P]),
+    'mdns_livetable_download': (c_int, [_P, _P]),
+    'mdns_livetable_fill_from_launch': (c_int, [_P, _P, c_int]),
+    'mdns_livetable_colstats': (c_int, [_P, _P, _P, _P]),
+    'mdns_livetable_replace': (c_int, [_P, _P, _P]),
+    'mdns_livetable_lmins_higher': (c_int, [_P, _P, c_int, _P, _P, _P]),
     'mdns_sync': (c_int, [_P]),
     'mdns_timer_start': (c_int, [_P]),
     'mdns_timer_stop': (c_int, [_P, POINTER(c_float)]),

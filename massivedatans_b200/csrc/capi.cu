@@ -320,6 +320,24 @@ int mdns_dataset_create(const double *x, const double *yy, const double *vv, int
 	return MDNS_OK;
 }
 
+// internal (livetable.cu): geometry and last-launch buffers of one shard
+int mdns_internal_shard_count(const mdns_dataset *ds) { return ds ? (int)ds->shards.size() : 0; }
+
+int mdns_internal_shard_view(mdns_dataset *ds, int shard, int *device, int *i0, int *n, int *n_act,
+                             int *K, const double **d_out, void **stream)
+{
+	if (!ds || shard < 0 || shard >= (int)ds->shards.size()) return MDNS_EINVAL;
+	const Shard &s = ds->shards[shard];
+	if (device) *device = s.device;
+	if (i0) *i0 = s.i0;
+	if (n) *n = s.n;
+	if (n_act) *n_act = s.n_act;
+	if (K) *K = ds->launched == 1 ? ds->K : 0;
+	if (d_out) *d_out = ds->launched == 1 ? s.d_out : nullptr;
+	if (stream) *stream = (void *)s.stream;
+	return MDNS_OK;
+}
+
 int mdns_dataset_destroy(mdns_dataset *ds)
 {
 	if (!ds) return MDNS_OK;

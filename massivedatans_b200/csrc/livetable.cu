@@ -1,0 +1,421 @@
+// livetable.cu -- the sampler's live-point likelihood table resident next to the data
+// (the accept / shelf epilogue of the hot path).
+//
+// Reference: `live_pointsL[nlive_points, ndata]` of multi_nested_sampler.py:111 (3.2 GB at
+// nlive = 400, ndata = 1e6, kept in host RAM and walked with numpy every iteration):
+//   * prepare()  multi_nested_sampler.py:134-137  Lmins = min(axis 0), Lmini = argmin(axis 0)
+//                and :531 Lmax = max(axis 0);
+//   * Lmins_higher  :438-447 via find_nsmallest :44-47: the element of rank n of
+//                live_pointsL[:, d] joined with the n likelihoods on data set d's shelf;
+//   * advance    :520-524 live_pointsL[Lmini[d], d] = Lj (one replacement per data set);
+//   * initial population :91-111: nlive full-mask likelihood calls fill the table.
+//
+// Layout: row-major like the numpy array (row = live point, data set index fastest), sharded
+// over the same devices and data-set ranges as the data set it was created from, so the
+// batched likelihood can write its result rows straight into the table.  Every operation is a
+// selection (comparisons only): results are bit-identical to numpy's.
+#include <algorithm>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace mdns {
+
+// ---- kernels -----------------------------------------------------------------------------
+// one thread per data set; rows are walked with UNROLL loads in flight (coalesced across d)
+__global__ void __launch_bounds__(256) lt_colstats_kernel(const double *__restrict__ T, int nlive,
+                                                          int n, double *__restrict__ cmin,
+                                                          long long *__restrict__ cargmin,
+                                                          double *__restrict__ cmax)
+{
+	const int d = blockIdx.x * 256 + threadIdx.x;
+	if (d >= n) return;
+	double lo = T[d], hi = T[d];
+	int at = 0;
+	int i = 1;
+	for (; i + 4 <= nlive; i += 4) {
+		double v[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) v[u] = T[(size_t)(i + u) * n + d];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			if (v[u] < lo) {        // strict: first occurrence wins, like numpy.argmin
+				lo = v[u];
+				at = i + u;
+			}
+			if (v[u] > hi) hi = v[u];
+		}
+	}
+	for (; i < nlive; ++i) {
+		const double v = T[(size_t)i * n + d];
+		if (v < lo) {
+			lo = v;
+			at = i;
+		}
+		if (v > hi) hi = v;
+	}
+	if (cmin) cmin[d] = lo;
+	if (cargmin) cargmin[d] = at;
+	if (cmax) cmax[d] = hi;
+}
+
+__global__ void __launch_bounds__(256) lt_replace_kernel(double *__restrict__ T, int nlive, int n,
+                                                         const long long *__restrict__ rows,
+                                                         const double *__restrict__ values)
+{
+	const int d = blockIdx.x * 256 + threadIdx.x;
+	if (d >= n) return;
+	const long long r = rows[d];
+	if (r >= 0 && r < nlive) T[(size_t)r * n + d] = values[d];
+}
+
+// find_nsmallest (multi_nested_sampler.py:44-47) for a list of data sets: one thread each.
+// Single pass with a sorted buffer of the m = n_shelf + 1 smallest values seen so far while
+// m <= NB; longer shelves take the threshold walk below (exact, duplicates included).
+template <int NB>
+__global__ void __launch_bounds__(128) lt_rank_kernel(const double *__restrict__ T, int nlive, int n,
+                                                      const int *__restrict__ cols, int ncols,
+                                                      const long long *__restrict__ off,
+                                                      const double *__restrict__ shelf,
+                                                      double *__restrict__ out)
+{
+	const int j = blockIdx.x * 128 + threadIdx.x;
+	if (j >= ncols) return;
+	const int d = cols[j];
+	const long long s0 = off[j], s1 = off[j + 1];
+	const int ns = (int)(s1 - s0);
+	const int m = ns + 1;
+	const int total = nlive + ns;
+	auto value = [&](int i) { return i < nlive ? T[(size_t)i * n + d] : shelf[s0 + (i - nlive)]; };
+	if (m <= NB) {
+		double buf[NB];
+		int cnt = 0;
+		for (int i = 0; i < total; ++i) {
+			const double v = value(i);
+			if (cnt < m) {
+				int p = cnt++;
+				while (p > 0 && buf[p - 1] > v) {
+					buf[p] = buf[p - 1];
+					--p;
+				}
+				buf[p] = v;
+			} else if (v < buf[m - 1]) {
+				int p = m - 1;
+				while (p > 0 && buf[p - 1] > v) {
+					buf[p] = buf[p - 1];
+					--p;
+				}
+				buf[p] = v;
+			}
+		}
+		out[j] = buf[m - 1];
+		return;
+	}
+	// rank walk: repeatedly take the smallest value above the current one
+	double cur = 0.0;
+	bool have = false;
+	int remaining = ns;       // rank still to skip
+	for (;;) {
+		double best = 0.0;
+		int count = 0;
+		for (int i = 0; i < total; ++i) {
+			const double v = value(i);
+			if (have && !(v > cur)) continue;
+			if (count == 0 || v < best) {
+				best = v;
+				count = 1;
+			} else if (v == best) {
+				++count;
+			}
+		}
+		if (count == 0 || remaining < count) {
+			out[j] = count ? best : cur;
+			return;
+		}
+		remaining -= count;
+		cur = best;
+		have = true;
+	}
+}
+
+}  // namespace mdns
+
+using namespace mdns;
+
+// internal view of a data set's shards (capi.cu)
+extern "C" int mdns_internal_shard_view(mdns_dataset *ds, int shard, int *device, int *i0, int *n,
+                                        int *n_act, int *K, const double **d_out, void **stream);
+extern "C" int mdns_internal_shard_count(const mdns_dataset *ds);
+
+struct LtShard {
+	int device = 0, i0 = 0, n = 0;
+	cudaStream_t stream = nullptr;
+	double *T = nullptr;
+	double *d_min = nullptr, *d_max = nullptr, *d_vals = nullptr;
+	long long *d_arg = nullptr, *d_rows = nullptr;
+	int *d_cols = nullptr;
+	long long *d_off = nullptr;
+	double *d_shelf = nullptr, *d_rank = nullptr;
+	size_t cols_cap = 0, off_cap = 0, rank_cap = 0, shelf_cap = 0;
+};
+
+struct mdns_livetable {
+	int nlive = 0, ndata = 0;
+	std::vector<LtShard> shards;
+};
+
+static void lt_free(mdns_livetable *t)
+{
+	for (auto &s : t->shards) {
+		cudaSetDevice(s.device);
+		if (s.stream) cudaStreamSynchronize(s.stream);
+		cudaFree(s.T);
+		cudaFree(s.d_min);
+		cudaFree(s.d_max);
+		cudaFree(s.d_vals);
+		cudaFree(s.d_arg);
+		cudaFree(s.d_rows);
+		cudaFree(s.d_cols);
+		cudaFree(s.d_off);
+		cudaFree(s.d_shelf);
+		cudaFree(s.d_rank);
+		if (s.stream) cudaStreamDestroy(s.stream);
+	}
+	delete t;
+}
+
+template <typename T>
+static int lt_grow(T **p, size_t *cap, size_t want)
+{
+	if (want <= *cap) return MDNS_OK;
+	if (*p) MDNS_CUDA(cudaFree(*p));
+	*p = nullptr;
+	*cap = 0;
+	const size_t n = want + want / 2 + 16;
+	MDNS_CUDA(cudaMalloc((void **)p, n * sizeof(T)));
+	*cap = n;
+	return MDNS_OK;
+}
+
+static int lt_sync(mdns_livetable *t)
+{
+	for (auto &s : t->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		MDNS_CUDA(cudaStreamSynchronize(s.stream));
+	}
+	return MDNS_OK;
+}
+
+extern "C" {
+
+int mdns_livetable_create(mdns_dataset *ds, int nlive, mdns_livetable **out)
+{
+	if (!ds || !out || nlive <= 0) {
+		set_error("mdns_livetable_create: need a data set, out and nlive > 0");
+		return MDNS_EINVAL;
+	}
+	mdns_livetable *t = new mdns_livetable();
+	t->nlive = nlive;
+	const int nshards = mdns_internal_shard_count(ds);
+	t->shards.resize(nshards);
+	for (int k = 0; k < nshards; ++k) {
+		LtShard &s = t->shards[k];
+		mdns_internal_shard_view(ds, k, &s.device, &s.i0, &s.n, nullptr, nullptr, nullptr, nullptr);
+		t->ndata += s.n;
+		cudaError_t e = cudaSetDevice(s.device);
+		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+		if (e == cudaSuccess) e = cudaMalloc((void **)&s.T, (size_t)nlive * s.n * sizeof(double));
+		if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_min, (size_t)s.n * sizeof(double));
+		if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_max, (size_t)s.n * sizeof(double));
+		if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_vals, (size_t)s.n * sizeof(double));
+		if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_arg, (size_t)s.n * sizeof(long long));
+		if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_rows, (size_t)s.n * sizeof(long long));
+		if (e != cudaSuccess) {
+			set_error("live table (%d x %d doubles) on device %d failed: %s", nlive, s.n, s.device,
+			          cudaGetErrorString(e));
+			lt_free(t);
+			return e == cudaErrorMemoryAllocation ? MDNS_ENOMEM : MDNS_ECUDA;
+		}
+	}
+	*out = t;
+	return MDNS_OK;
+}
+
+int mdns_livetable_destroy(mdns_livetable *t)
+{
+	if (t) lt_free(t);
+	return MDNS_OK;
+}
+
+int mdns_livetable_upload(mdns_livetable *t, const double *L)
+{
+	if (!t || !L) {
+		set_error("mdns_livetable_upload: need the table and L");
+		return MDNS_EINVAL;
+	}
+	for (auto &s : t->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		MDNS_CUDA(cudaMemcpy2DAsync(s.T, (size_t)s.n * sizeof(double), L + s.i0,
+		                            (size_t)t->ndata * sizeof(double), (size_t)s.n * sizeof(double),
+		                            t->nlive, cudaMemcpyHostToDevice, s.stream));
+	}
+	return lt_sync(t);
+}
+
+int mdns_livetable_download(mdns_livetable *t, double *L)
+{
+	if (!t || !L) {
+		set_error("mdns_livetable_download: need the table and L");
+		return MDNS_EINVAL;
+	}
+	for (auto &s : t->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		MDNS_CUDA(cudaMemcpy2DAsync(L + s.i0, (size_t)t->ndata * sizeof(double), s.T,
+		                            (size_t)s.n * sizeof(double), (size_t)s.n * sizeof(double),
+		                            t->nlive, cudaMemcpyDeviceToHost, s.stream));
+	}
+	return lt_sync(t);
+}
+
+int mdns_livetable_fill_from_launch(mdns_livetable *t, mdns_dataset *ds, int row0)
+{
+	if (!t || !ds) {
+		set_error("mdns_livetable_fill_from_launch: need the table and the data set");
+		return MDNS_EINVAL;
+	}
+	for (size_t k = 0; k < t->shards.size(); ++k) {
+		LtShard &s = t->shards[k];
+		int n_act = 0, K = 0, n = 0;
+		const double *d_out = nullptr;
+		void *stream = nullptr;
+		if (mdns_internal_shard_view(ds, (int)k, nullptr, nullptr, &n, &n_act, &K, &d_out, &stream) !=
+		    MDNS_OK)
+			return MDNS_EINVAL;
+		if (n != s.n || n_act != n || !d_out) {
+			set_error("fill_from_launch needs a launch with every data set active on the table's own "
+			          "data set (shard %zu: %d of %d active)", k, n_act, n);
+			return MDNS_ESTATE;
+		}
+		if (row0 < 0 || row0 + K > t->nlive) {
+			set_error("rows [%d, %d) outside the table of %d live points", row0, row0 + K, t->nlive);
+			return MDNS_EINVAL;
+		}
+		MDNS_CUDA(cudaSetDevice(s.device));
+		// on the data set's stream: ordered after the launch that produced the rows
+		MDNS_CUDA(cudaMemcpyAsync(s.T + (size_t)row0 * s.n, d_out, (size_t)K * s.n * sizeof(double),
+		                          cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+		MDNS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+	}
+	return MDNS_OK;
+}
+
+int mdns_livetable_colstats(mdns_livetable *t, double *Lmins, int64_t *Lmini, double *Lmax)
+{
+	if (!t) {
+		set_error("null live table");
+		return MDNS_EINVAL;
+	}
+	for (auto &s : t->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		lt_colstats_kernel<<<ceil_div(s.n, 256), 256, 0, s.stream>>>(s.T, t->nlive, s.n, s.d_min, s.d_arg,
+		                                                            s.d_max);
+		MDNS_LAUNCHED("lt_colstats_kernel");
+		if (Lmins)
+			MDNS_CUDA(cudaMemcpyAsync(Lmins + s.i0, s.d_min, (size_t)s.n * sizeof(double),
+			                          cudaMemcpyDeviceToHost, s.stream));
+		if (Lmini)
+			MDNS_CUDA(cudaMemcpyAsync(Lmini + s.i0, s.d_arg, (size_t)s.n * sizeof(long long),
+			                          cudaMemcpyDeviceToHost, s.stream));
+		if (Lmax)
+			MDNS_CUDA(cudaMemcpyAsync(Lmax + s.i0, s.d_max, (size_t)s.n * sizeof(double),
+			                          cudaMemcpyDeviceToHost, s.stream));
+	}
+	return lt_sync(t);
+}
+
+int mdns_livetable_replace(mdns_livetable *t, const int64_t *rows, const double *values)
+{
+	if (!t || !rows || !values) {
+		set_error("mdns_livetable_replace: need the table, rows and values");
+		return MDNS_EINVAL;
+	}
+	for (auto &s : t->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		MDNS_CUDA(cudaMemcpyAsync(s.d_rows, rows + s.i0, (size_t)s.n * sizeof(long long),
+		                          cudaMemcpyHostToDevice, s.stream));
+		MDNS_CUDA(cudaMemcpyAsync(s.d_vals, values + s.i0, (size_t)s.n * sizeof(double),
+		                          cudaMemcpyHostToDevice, s.stream));
+		lt_replace_kernel<<<ceil_div(s.n, 256), 256, 0, s.stream>>>(s.T, t->nlive, s.n, s.d_rows, s.d_vals);
+		MDNS_LAUNCHED("lt_replace_kernel");
+	}
+	return lt_sync(t);
+}
+
+int mdns_livetable_lmins_higher(mdns_livetable *t, const int *indices, int nidx,
+                                const int64_t *shelf_offsets, const double *shelf_values,
+                                double *out)
+{
+	if (!t || (nidx > 0 && (!indices || !shelf_offsets || !out))) {
+		set_error("mdns_livetable_lmins_higher: need the table, indices, shelf_offsets and out");
+		return MDNS_EINVAL;
+	}
+	if (nidx <= 0) return MDNS_OK;
+	for (int j = 0; j < nidx; ++j) {
+		if (indices[j] < 0 || indices[j] >= t->ndata || shelf_offsets[j + 1] < shelf_offsets[j]) {
+			set_error("lmins_higher: entry %d (data set %d) is malformed", j, indices[j]);
+			return MDNS_EINVAL;
+		}
+		if (j > 0 && indices[j] <= indices[j - 1]) {
+			set_error("lmins_higher: data-set indices must be increasing");
+			return MDNS_EINVAL;
+		}
+	}
+	// the listed data sets are increasing, so each shard owns one contiguous run of the list
+	int j0 = 0;
+	for (auto &s : t->shards) {
+		int j1 = j0;
+		while (j1 < nidx && indices[j1] < s.i0 + s.n) ++j1;
+		const int cnt = j1 - j0;
+		if (cnt > 0) {
+			MDNS_CUDA(cudaSetDevice(s.device));
+			std::vector<int> cols(cnt);
+			std::vector<long long> off(cnt + 1);
+			const long long base = shelf_offsets[j0];
+			long long longest = 0;
+			for (int j = 0; j < cnt; ++j) {
+				cols[j] = indices[j0 + j] - s.i0;
+				off[j] = shelf_offsets[j0 + j] - base;
+				longest = std::max<long long>(longest, shelf_offsets[j0 + j + 1] - shelf_offsets[j0 + j]);
+			}
+			off[cnt] = shelf_offsets[j1] - base;
+			const size_t nshelf = (size_t)off[cnt];
+			int rc = lt_grow(&s.d_cols, &s.cols_cap, (size_t)cnt + 1);
+			if (rc == MDNS_OK) rc = lt_grow(&s.d_off, &s.off_cap, (size_t)cnt + 1);
+			if (rc == MDNS_OK) rc = lt_grow(&s.d_rank, &s.rank_cap, (size_t)cnt + 1);
+			if (rc == MDNS_OK) rc = lt_grow(&s.d_shelf, &s.shelf_cap, nshelf + 1);
+			if (rc != MDNS_OK) return rc;
+			MDNS_CUDA(cudaMemcpyAsync(s.d_cols, cols.data(), (size_t)cnt * sizeof(int),
+			                          cudaMemcpyHostToDevice, s.stream));
+			MDNS_CUDA(cudaMemcpyAsync(s.d_off, off.data(), (size_t)(cnt + 1) * sizeof(long long),
+			                          cudaMemcpyHostToDevice, s.stream));
+			if (nshelf)
+				MDNS_CUDA(cudaMemcpyAsync(s.d_shelf, shelf_values + base, nshelf * sizeof(double),
+				                          cudaMemcpyHostToDevice, s.stream));
+			if (longest + 1 <= 8)
+				lt_rank_kernel<8><<<ceil_div(cnt, 128), 128, 0, s.stream>>>(s.T, t->nlive, s.n, s.d_cols, cnt,
+				                                                           s.d_off, s.d_shelf, s.d_rank);
+			else
+				lt_rank_kernel<32><<<ceil_div(cnt, 128), 128, 0, s.stream>>>(s.T, t->nlive, s.n, s.d_cols, cnt,
+				                                                            s.d_off, s.d_shelf, s.d_rank);
+			MDNS_LAUNCHED("lt_rank_kernel");
+			MDNS_CUDA(cudaMemcpyAsync(out + j0, s.d_rank, (size_t)cnt * sizeof(double),
+			                          cudaMemcpyDeviceToHost, s.stream));
+			// cols/off live on the host stack of this call: finish before they go away
+			MDNS_CUDA(cudaStreamSynchronize(s.stream));
+		}
+		j0 = j1;
+	}
+	return MDNS_OK;
+}
+
+}  // extern "C"

@@ -206,3 +206,56 @@ double oracle_bootstrapped_maxdistance(const double *xx, int n, int ndim,
 	}
 	return best;
 }
+
+/* ---- live-point table (multi_nested_sampler.py) --------------------------- */
+#include <stdlib.h>
+
+/*
+ * prepare(), multi_nested_sampler.py:134-137, and Lmax, :531, on
+ * live_pointsL[nlive][ndata] (C order): per data set the minimum over the live
+ * points, the row of its first occurrence (numpy.argmin) and the maximum.
+ */
+void oracle_live_colstats(const double *L, int nlive, int ndata, double *Lmins,
+                          long long *Lmini, double *Lmax)
+{
+	for (int d = 0; d < ndata; d++) {
+		double lo = L[d], hi = L[d];
+		long long at = 0;
+		for (int i = 1; i < nlive; i++) {
+			const double v = L[(size_t)i * ndata + d];
+			if (v < lo) {
+				lo = v;
+				at = i;
+			}
+			if (v > hi)
+				hi = v;
+		}
+		Lmins[d] = lo;
+		Lmini[d] = at;
+		Lmax[d] = hi;
+	}
+}
+
+static int cmp_double(const void *a, const void *b)
+{
+	const double x = *(const double *)a, y = *(const double *)b;
+	return (x > y) - (x < y);
+}
+
+/*
+ * find_nsmallest, multi_nested_sampler.py:38-42 (the "old version": join the
+ * two arrays, sort everything, return element n; the new version :44-47 uses
+ * numpy.partition and returns the same element).
+ */
+double oracle_find_nsmallest(int n, const double *arr1, int n1, const double *arr2, int n2)
+{
+	double *arr = (double *)malloc(sizeof(double) * (size_t)(n1 + n2));
+	for (int i = 0; i < n1; i++)
+		arr[i] = arr1[i];
+	for (int i = 0; i < n2; i++)
+		arr[n1 + i] = arr2[i];
+	qsort(arr, (size_t)(n1 + n2), sizeof(double), cmp_double);
+	const double r = arr[n];
+	free(arr);
+	return r;
+}

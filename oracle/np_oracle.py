@@ -74,3 +74,14 @@ def bootstrapped_maxdistance(u, chosen):
             furthest = 0.0
         best = furthest if best is None or furthest > best else best
     return best
+
+
+def live_colstats(live_pointsL):
+    """multi_nested_sampler.py:134-137 and :531."""
+    return live_pointsL.min(axis=0), live_pointsL.argmin(axis=0), live_pointsL.max(axis=0)
+
+
+def find_nsmallest(n, arr1, arr2):
+    """multi_nested_sampler.py:44-47 (the numpy.partition version)."""
+    arr = numpy.concatenate((arr1, arr2))
+    return numpy.partition(arr, n)[n]

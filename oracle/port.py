@@ -36,6 +36,12 @@ def lib():
                                                       c_int, _f1, c_int]
         L.oracle_bootstrapped_maxdistance.argtypes = [_f2, c_int, c_int, _f2, c_int]
         L.oracle_bootstrapped_maxdistance.restype = c_double
+        L.oracle_live_colstats.argtypes = [_f2, c_int, c_int, _f1,
+                                           ndpointer(dtype=numpy.int64, ndim=1, flags='C_CONTIGUOUS'),
+                                           _f1]
+        L.oracle_live_colstats.restype = None
+        L.oracle_find_nsmallest.argtypes = [c_int, _f1, c_int, _f1, c_int]
+        L.oracle_find_nsmallest.restype = c_double
         _lib = L
     return _lib
 
@@ -91,3 +97,20 @@ def any_within_distance_of(xx, maxdistance, yy):
 def bootstrapped_maxdistance_chosen(xx, chosen):
     n, d = xx.shape
     return lib().oracle_bootstrapped_maxdistance(xx, n, d, chosen, chosen.shape[1])
+
+
+def live_colstats(live_pointsL):
+    """(Lmins, Lmini, Lmax) of live_pointsL[nlive, ndata] -- multi_nested_sampler.py:134-137, :531."""
+    L = numpy.ascontiguousarray(live_pointsL, dtype=numpy.float64)
+    nlive, ndata = L.shape
+    lo, hi = numpy.empty(ndata), numpy.empty(ndata)
+    at = numpy.empty(ndata, dtype=numpy.int64)
+    lib().oracle_live_colstats(L, nlive, ndata, lo, at, hi)
+    return lo, at, hi
+
+
+def find_nsmallest(n, arr1, arr2):
+    """multi_nested_sampler.py:38-47."""
+    a1 = numpy.ascontiguousarray(arr1, dtype=numpy.float64)
+    a2 = numpy.ascontiguousarray(arr2, dtype=numpy.float64)
+    return lib().oracle_find_nsmallest(n, a1, len(a1), a2, len(a2))

@@ -117,3 +117,21 @@ def test_neighbors_quirk_sample0_skipped(golden, oracle_port):
     got = oracle_port.bootstrapped_maxdistance_chosen(g['quirk_x'], g['quirk_chosen'])
     assert got == float(g['quirk_r'])
     assert got < 1.0          # the outlier at index 0 (distance ~14) is ignored
+
+
+def test_live_table_oracle_matches_numpy_twin(oracle_port):
+    # multi_nested_sampler.py:38-47,134-137,531: C restatement vs the numpy expressions
+    from oracle import np_oracle
+    rs = numpy.random.RandomState(11)
+    L = rs.normal(size=(60, 41)) * 10
+    L[9, 4] = L[3, 4] = L[:, 4].min() - 1          # tie: first occurrence
+    got = oracle_port.live_colstats(L)
+    want = np_oracle.live_colstats(L)
+    for g, w in zip(got, want):
+        assert numpy.array_equal(g, w)
+    for n in (0, 1, 2, 7, 25):
+        shelf = rs.normal(size=n) * 10
+        if n > 1:
+            shelf[0] = L[5, 0]
+        assert oracle_port.find_nsmallest(n, numpy.ascontiguousarray(L[:, 0]), shelf) == \
+            np_oracle.find_nsmallest(n, L[:, 0], shelf)
