@@ -189,6 +189,23 @@ int mdns_livetable_lmins_higher(mdns_livetable *t, const int *indices, int nidx,
                                 const int64_t *shelf_offsets, const double *shelf_values,
                                 double *out);
 
+/*
+ * Subset partition, generate_subsets_graph / generate_subsets_nograph
+ * (multi_nested_sampler.py:204-355): groups of data sets that share live points,
+ * i.e. connected components of the data set <-> live point graph.
+ *   upload_points   live_pointsp[nlive][ndata] (int64 indices into the point pile,
+ *                   multi_nested_sampler.py:111); kept as int32 on the first device
+ *   replace_points  live_pointsp[rows[d]][d] = ids[d] for rows[d] >= 0 (:523)
+ *   subsets         labels[d] = smallest data-set index of d's group (-1 outside the
+ *                   mask; NULL mask = all); groups in increasing label order are the
+ *                   order the reference yields them in (:239).  npoints = size of the
+ *                   point pile (every id < npoints).
+ */
+int mdns_livetable_upload_points(mdns_livetable *t, const int64_t *live_pointsp);
+int mdns_livetable_replace_points(mdns_livetable *t, const int64_t *rows, const int64_t *ids);
+int mdns_livetable_subsets(mdns_livetable *t, const uint8_t *data_mask, int64_t npoints,
+                           int32_t *labels, int *ncomponents, int *nrounds);
+
 /* ---- RadFriends neighbour tests --------------------------------------- */
 typedef struct mdns_region mdns_region;
 

@@ -55,6 +55,9 @@ SIGNATURES = {
     'mdns_livetable_colstats': (c_int, [_P, _P, _P, _P]),
     'mdns_livetable_replace': (c_int, [_P, _P, _P]),
     'mdns_livetable_lmins_higher': (c_int, [_P, _P, c_int, _P, _P, _P]),
+    'mdns_livetable_upload_points': (c_int, [_P, _P]),
+    'mdns_livetable_replace_points': (c_int, [_P, _P, _P]),
+    'mdns_livetable_subsets': (c_int, [_P, _P, c_int64, _P, POINTER(c_int), POINTER(c_int)]),
     'mdns_sync': (c_int, [_P]),
     'mdns_timer_start': (c_int, [_P]),
     'mdns_timer_stop': (c_int, [_P, POINTER(c_float)]),

@@ -138,6 +138,89 @@ __global__ void __launch_bounds__(128) lt_rank_kernel(const double *__restrict__
 	}
 }
 
+// ---- subset partition: connected components of the data set <-> live point graph ----------
+// generate_subsets_graph / generate_subsets_nograph (multi_nested_sampler.py:204-355): two
+// data sets belong to the same group when they share a live point (directly or through a chain
+// of data sets).  Label propagation with the smallest data-set index as the label: every
+// round each live point learns the smallest label among the data sets that hold it
+// (atomicMin), every data set takes the smallest label among its points, and pointer jumping
+// flattens label chains; rounds repeat until nothing changes.  The final label of a group is
+// its smallest member index, which is also the order in which the reference yields the groups
+// (`firstmember`, :239).
+__global__ void __launch_bounds__(256) cc_init_kernel(const uint8_t *__restrict__ mask, int n,
+                                                      int *__restrict__ label)
+{
+	const int d = blockIdx.x * 256 + threadIdx.x;
+	if (d < n) label[d] = (!mask || mask[d]) ? d : -1;
+}
+
+__global__ void __launch_bounds__(256) cc_push_kernel(const int *__restrict__ P, int nlive, int n,
+                                                      const int *__restrict__ label,
+                                                      int *__restrict__ pointmin)
+{
+	const int d = blockIdx.x * 256 + threadIdx.x;
+	if (d >= n) return;
+	const int l = label[d];
+	if (l < 0) return;
+	for (int i = 0; i < nlive; ++i) {
+		int *slot = pointmin + P[(size_t)i * n + d];
+		if (*slot > l) atomicMin(slot, l);     // plain read first: most points are settled
+	}
+}
+
+__global__ void __launch_bounds__(256) cc_pull_kernel(const int *__restrict__ P, int nlive, int n,
+                                                      int *__restrict__ label,
+                                                      const int *__restrict__ pointmin,
+                                                      int *__restrict__ changed)
+{
+	const int d = blockIdx.x * 256 + threadIdx.x;
+	if (d >= n) return;
+	const int l = label[d];
+	if (l < 0) return;
+	int m = l;
+	for (int i = 0; i < nlive; ++i) m = min(m, pointmin[P[(size_t)i * n + d]]);
+	if (m < l) {
+		label[d] = m;
+		*changed = 1;
+	}
+}
+
+__global__ void __launch_bounds__(256) cc_jump_kernel(int n, int *__restrict__ label)
+{
+	const int d = blockIdx.x * 256 + threadIdx.x;
+	if (d >= n) return;
+	int l = label[d];
+	if (l < 0) return;
+	// labels only ever decrease and label[x] <= x, so the chain ends at a root
+	int r = label[l];
+	while (r != l) {
+		l = r;
+		r = label[l];
+	}
+	label[d] = l;
+}
+
+__global__ void __launch_bounds__(256) lt_replace_points_kernel(int *__restrict__ P, int nlive, int n,
+                                                                const long long *__restrict__ rows,
+                                                                const long long *__restrict__ ids)
+{
+	const int d = blockIdx.x * 256 + threadIdx.x;
+	if (d >= n) return;
+	const long long r = rows[d];
+	if (r >= 0 && r < nlive) P[(size_t)r * n + d] = (int)ids[d];
+}
+
+__global__ void __launch_bounds__(256) lt_narrow_points_kernel(const long long *__restrict__ in,
+                                                               size_t count, int *__restrict__ out,
+                                                               int *__restrict__ bad)
+{
+	const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+	if (i >= count) return;
+	const long long v = in[i];
+	if (v < 0 || v > 0x7ffffffeLL) *bad = 1;
+	out[i] = (int)v;
+}
+
 }  // namespace mdns
 
 using namespace mdns;
@@ -162,10 +245,28 @@ struct LtShard {
 struct mdns_livetable {
 	int nlive = 0, ndata = 0;
 	std::vector<LtShard> shards;
+	// live_pointsp[nlive][ndata] (multi_nested_sampler.py:111) as int32, whole on the first
+	// shard's device: the groups of the subset partition span the shards
+	int *P = nullptr;
+	int *d_label = nullptr, *d_pointmin = nullptr, *d_flag = nullptr;
+	uint8_t *d_cmask = nullptr;
+	long long *d_prow = nullptr, *d_pid = nullptr;
+	size_t pointmin_cap = 0;
 };
 
 static void lt_free(mdns_livetable *t)
 {
+	if (!t->shards.empty()) {
+		cudaSetDevice(t->shards[0].device);
+		if (t->shards[0].stream) cudaStreamSynchronize(t->shards[0].stream);
+		cudaFree(t->P);
+		cudaFree(t->d_label);
+		cudaFree(t->d_pointmin);
+		cudaFree(t->d_flag);
+		cudaFree(t->d_cmask);
+		cudaFree(t->d_prow);
+		cudaFree(t->d_pid);
+	}
 	for (auto &s : t->shards) {
 		cudaSetDevice(s.device);
 		if (s.stream) cudaStreamSynchronize(s.stream);
@@ -415,6 +516,133 @@ int mdns_livetable_lmins_higher(mdns_livetable *t, const int *indices, int nidx,
 		}
 		j0 = j1;
 	}
+	return MDNS_OK;
+}
+
+int mdns_livetable_upload_points(mdns_livetable *t, const int64_t *live_pointsp)
+{
+	if (!t || !live_pointsp) {
+		set_error("mdns_livetable_upload_points: need the table and live_pointsp");
+		return MDNS_EINVAL;
+	}
+	LtShard &s = t->shards[0];
+	MDNS_CUDA(cudaSetDevice(s.device));
+	const size_t count = (size_t)t->nlive * t->ndata;
+	if (!t->P) {
+		MDNS_CUDA(cudaMalloc((void **)&t->P, count * sizeof(int)));
+		MDNS_CUDA(cudaMalloc((void **)&t->d_label, (size_t)t->ndata * sizeof(int)));
+		MDNS_CUDA(cudaMalloc((void **)&t->d_flag, 2 * sizeof(int)));
+		MDNS_CUDA(cudaMalloc((void **)&t->d_cmask, (size_t)t->ndata));
+		MDNS_CUDA(cudaMalloc((void **)&t->d_prow, (size_t)t->ndata * sizeof(long long)));
+		MDNS_CUDA(cudaMalloc((void **)&t->d_pid, (size_t)t->ndata * sizeof(long long)));
+	}
+	// stage the int64 table in chunks and narrow it to int32 on the device
+	const size_t chunk = (size_t)1 << 24;
+	long long *stage = nullptr;
+	MDNS_CUDA(cudaMalloc((void **)&stage, std::min(chunk, count) * sizeof(long long)));
+	MDNS_CUDA(cudaMemsetAsync(t->d_flag, 0, 2 * sizeof(int), s.stream));
+	cudaError_t e = cudaSuccess;
+	for (size_t o = 0; o < count && e == cudaSuccess; o += chunk) {
+		const size_t c = std::min(chunk, count - o);
+		e = cudaMemcpyAsync(stage, live_pointsp + o, c * sizeof(long long), cudaMemcpyHostToDevice,
+		                    s.stream);
+		if (e == cudaSuccess) {
+			lt_narrow_points_kernel<<<(unsigned)((c + 255) / 256), 256, 0, s.stream>>>(stage, c, t->P + o,
+			                                                                      t->d_flag);
+			e = cudaGetLastError();
+		}
+	}
+	int bad = 0;
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(&bad, t->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s.stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+	cudaFree(stage);
+	if (e != cudaSuccess) {
+		set_error("upload of live_pointsp failed: %s", cudaGetErrorString(e));
+		return MDNS_ECUDA;
+	}
+	if (bad) {
+		set_error("live_pointsp holds ids outside [0, 2^31-2]");
+		return MDNS_EINVAL;
+	}
+	g_launches.fetch_add(1);
+	return MDNS_OK;
+}
+
+int mdns_livetable_replace_points(mdns_livetable *t, const int64_t *rows, const int64_t *ids)
+{
+	if (!t || !rows || !ids || !t->P) {
+		set_error("mdns_livetable_replace_points: need the table with uploaded points, rows and ids");
+		return MDNS_EINVAL;
+	}
+	LtShard &s = t->shards[0];
+	MDNS_CUDA(cudaSetDevice(s.device));
+	MDNS_CUDA(cudaMemcpyAsync(t->d_prow, rows, (size_t)t->ndata * sizeof(long long),
+	                          cudaMemcpyHostToDevice, s.stream));
+	MDNS_CUDA(cudaMemcpyAsync(t->d_pid, ids, (size_t)t->ndata * sizeof(long long),
+	                          cudaMemcpyHostToDevice, s.stream));
+	lt_replace_points_kernel<<<ceil_div(t->ndata, 256), 256, 0, s.stream>>>(t->P, t->nlive, t->ndata,
+	                                                                       t->d_prow, t->d_pid);
+	MDNS_LAUNCHED("lt_replace_points_kernel");
+	MDNS_CUDA(cudaStreamSynchronize(s.stream));
+	return MDNS_OK;
+}
+
+int mdns_livetable_subsets(mdns_livetable *t, const uint8_t *data_mask, int64_t npoints,
+                           int32_t *labels, int *ncomponents, int *nrounds)
+{
+	if (!t || !labels || !t->P || npoints <= 0 || npoints > 0x7ffffffeLL) {
+		set_error("mdns_livetable_subsets: need the table with uploaded points, labels and the "
+		          "size of the point pile");
+		return MDNS_EINVAL;
+	}
+	LtShard &s = t->shards[0];
+	const int n = t->ndata;
+	MDNS_CUDA(cudaSetDevice(s.device));
+	if ((size_t)npoints > t->pointmin_cap) {
+		if (t->d_pointmin) MDNS_CUDA(cudaFree(t->d_pointmin));
+		t->d_pointmin = nullptr;
+		t->pointmin_cap = 0;
+		const size_t cap = (size_t)npoints + (size_t)npoints / 2 + 1024;
+		MDNS_CUDA(cudaMalloc((void **)&t->d_pointmin, cap * sizeof(int)));
+		t->pointmin_cap = cap;
+	}
+	if (data_mask)
+		MDNS_CUDA(cudaMemcpyAsync(t->d_cmask, data_mask, (size_t)n, cudaMemcpyHostToDevice, s.stream));
+	const int blocks = ceil_div(n, 256);
+	cc_init_kernel<<<blocks, 256, 0, s.stream>>>(data_mask ? t->d_cmask : nullptr, n, t->d_label);
+	MDNS_LAUNCHED("cc_init_kernel");
+	int rounds = 0;
+	for (;;) {
+		++rounds;
+		// 0x7f7f7f7f > any label
+		MDNS_CUDA(cudaMemsetAsync(t->d_pointmin, 0x7f, (size_t)npoints * sizeof(int), s.stream));
+		MDNS_CUDA(cudaMemsetAsync(t->d_flag, 0, sizeof(int), s.stream));
+		cc_push_kernel<<<blocks, 256, 0, s.stream>>>(t->P, t->nlive, n, t->d_label, t->d_pointmin);
+		MDNS_LAUNCHED("cc_push_kernel");
+		cc_pull_kernel<<<blocks, 256, 0, s.stream>>>(t->P, t->nlive, n, t->d_label, t->d_pointmin,
+		                                            t->d_flag);
+		MDNS_LAUNCHED("cc_pull_kernel");
+		cc_jump_kernel<<<blocks, 256, 0, s.stream>>>(n, t->d_label);
+		MDNS_LAUNCHED("cc_jump_kernel");
+		int changed = 0;
+		MDNS_CUDA(cudaMemcpyAsync(&changed, t->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+		MDNS_CUDA(cudaStreamSynchronize(s.stream));
+		if (!changed) break;
+		if (rounds > n + 2) {
+			set_error("subset partition did not converge");
+			return MDNS_ECUDA;
+		}
+	}
+	MDNS_CUDA(cudaMemcpyAsync(labels, t->d_label, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost,
+	                          s.stream));
+	MDNS_CUDA(cudaStreamSynchronize(s.stream));
+	if (ncomponents) {
+		int c = 0;
+		for (int d = 0; d < n; ++d) c += labels[d] == d;
+		*ncomponents = c;
+	}
+	if (nrounds) *nrounds = rounds;
 	return MDNS_OK;
 }
 

@@ -6,6 +6,8 @@ Host-side mirror of what multi_nested_sampler.py does with ``live_pointsL[nlive,
 * ``LiveTable.lmins_higher(...)`` -- the ``Lmins_higher`` loop :438-447 (``find_nsmallest`` :44-47)
 * ``LiveTable.replace(...)``     -- the replacement of the dead points :520-524
 * ``LiveTable.fill_from_launch`` -- the initial population :91-111, K rows per batched launch
+* ``LiveTable.subsets(...)`` / ``generate_subsets(...)`` -- ``generate_subsets_graph`` /
+  ``generate_subsets_nograph`` :204-355: groups of data sets that share live points
 
 All results are selections and bit-identical to the numpy expressions they replace.
 """
@@ -93,3 +95,54 @@ class LiveTable(object):
                                                          _addr(vals), _addr(out)),
                    'mdns_livetable_lmins_higher')
         return out
+
+    # -- live-point indices and the subset partition ---------------------------------------
+    def upload_points(self, live_pointsp):
+        """``live_pointsp[nlive, ndata]``: indices into the point pile (:111)."""
+        P = numpy.ascontiguousarray(live_pointsp, dtype=numpy.int64)
+        if P.shape != (self.nlive, self.ndata):
+            raise ValueError('live_pointsp must be [nlive, ndata]')
+        _lib.check(self._lib.mdns_livetable_upload_points(self._h, _addr(P)),
+                   'mdns_livetable_upload_points')
+
+    def replace_points(self, rows, point_ids):
+        """live_pointsp[rows[d], d] = point_ids[d] for every data set d with rows[d] >= 0 (:523)."""
+        rows = numpy.ascontiguousarray(rows, dtype=numpy.int64)
+        ids = numpy.ascontiguousarray(point_ids, dtype=numpy.int64)
+        if rows.shape != (self.ndata,) or ids.shape != (self.ndata,):
+            raise ValueError('rows and point_ids must have one entry per data set')
+        _lib.check(self._lib.mdns_livetable_replace_points(self._h, _addr(rows), _addr(ids)),
+                   'mdns_livetable_replace_points')
+
+    def subsets(self, data_mask, npoints):
+        """labels[d] = smallest data-set index of the group of d (-1 outside the mask)."""
+        m = None
+        if data_mask is not None:
+            m = numpy.ascontiguousarray(data_mask, dtype=numpy.bool_)
+            if m.shape != (self.ndata,):
+                raise ValueError('data_mask must have ndata entries')
+        labels = numpy.empty(self.ndata, dtype=numpy.int32)
+        ncomp = ctypes.c_int()
+        rounds = ctypes.c_int()
+        _lib.check(self._lib.mdns_livetable_subsets(self._h, _addr(m), int(npoints), _addr(labels),
+                                                    ctypes.byref(ncomp), ctypes.byref(rounds)),
+                   'mdns_livetable_subsets')
+        self.last_rounds = rounds.value
+        return labels
+
+
+def generate_subsets(data_mask, live_pointsp, labels):
+    """Yield ``(member_data_mask, member_live_pointsp)`` per group like
+    ``generate_subsets_nograph`` (multi_nested_sampler.py:237-260), in the same group order
+    (increasing first member).  The live points of a group come sorted (``numpy.unique``); the
+    reference lists the same set in discovery order."""
+    ndata = len(data_mask)
+    order = numpy.argsort(labels, kind='stable')
+    order = order[labels[order] >= 0]
+    bounds = numpy.nonzero(numpy.diff(labels[order]))[0] + 1
+    for members in numpy.split(order, bounds):
+        if len(members) == 0:
+            continue
+        member_data_mask = numpy.zeros(ndata, dtype=bool)
+        member_data_mask[members] = True
+        yield member_data_mask, numpy.unique(live_pointsp[:, members])

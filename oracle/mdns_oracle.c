@@ -259,3 +259,50 @@ double oracle_find_nsmallest(int n, const double *arr1, int n1, const double *ar
 	free(arr);
 	return r;
 }
+
+/*
+ * Subset partition, multi_nested_sampler.py:204-260 (generate_subsets_nograph;
+ * the igraph variant :262-355 yields the same groups): data sets that share live
+ * points, transitively.  Restated as union-find over the point -> first holder
+ * map; labels[d] = smallest data-set index of d's group (the reference yields the
+ * groups in that order, `firstmember` :239), -1 outside the mask.
+ */
+static int uf_find(int *parent, int a)
+{
+	while (parent[a] != a) {
+		parent[a] = parent[parent[a]];
+		a = parent[a];
+	}
+	return a;
+}
+
+void oracle_subsets_labels(const long long *live_pointsp, int nlive, int ndata,
+                           const unsigned char *mask, long long npoints, int *labels)
+{
+	int *parent = (int *)malloc(sizeof(int) * (size_t)ndata);
+	int *holder = (int *)malloc(sizeof(int) * (size_t)npoints);
+	for (int d = 0; d < ndata; d++)
+		parent[d] = d;
+	for (long long p = 0; p < npoints; p++)
+		holder[p] = -1;
+	for (int d = 0; d < ndata; d++) {
+		if (mask && !mask[d])
+			continue;
+		for (int i = 0; i < nlive; i++) {
+			const long long p = live_pointsp[(size_t)i * ndata + d];
+			if (holder[p] < 0) {
+				holder[p] = d;
+			} else {
+				int a = uf_find(parent, holder[p]), b = uf_find(parent, d);
+				if (a < b)
+					parent[b] = a;
+				else
+					parent[a] = b;      /* the smaller index stays the root */
+			}
+		}
+	}
+	for (int d = 0; d < ndata; d++)
+		labels[d] = (mask && !mask[d]) ? -1 : uf_find(parent, d);
+	free(parent);
+	free(holder);
+}

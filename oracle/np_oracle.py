@@ -85,3 +85,23 @@ def find_nsmallest(n, arr1, arr2):
     """multi_nested_sampler.py:44-47 (the numpy.partition version)."""
     arr = numpy.concatenate((arr1, arr2))
     return numpy.partition(arr, n)[n]
+
+
+def subsets_labels(live_pointsp, data_mask, npoints):
+    """Groups of multi_nested_sampler.py:204-355 as labels (smallest member index, -1 outside
+    the mask), via scipy's connected components of the data set <-> live point graph."""
+    import scipy.sparse
+    import scipy.sparse.csgraph
+    nlive, ndata = live_pointsp.shape
+    sel = numpy.nonzero(data_mask)[0]
+    rows = numpy.repeat(sel, nlive)
+    cols = ndata + live_pointsp[:, sel].T.reshape(-1)
+    g = scipy.sparse.coo_matrix((numpy.ones(len(rows)), (rows, cols)),
+                                shape=(ndata + npoints, ndata + npoints))
+    _, comp = scipy.sparse.csgraph.connected_components(g, directed=False)
+    labels = numpy.full(ndata, -1, dtype=numpy.int32)
+    first = {}
+    for d in sel:
+        first.setdefault(comp[d], d)
+        labels[d] = first[comp[d]]
+    return labels

@@ -1,7 +1,7 @@
 """ctypes bindings of oracle/mdns_oracle.c (liboracle.so) -- test infrastructure."""
 import os
 import subprocess
-from ctypes import c_double, c_int, cdll
+from ctypes import c_double, c_int, c_longlong as ctypes_longlong, cdll
 
 import numpy
 from numpy.ctypeslib import ndpointer
@@ -42,6 +42,10 @@ def lib():
         L.oracle_live_colstats.restype = None
         L.oracle_find_nsmallest.argtypes = [c_int, _f1, c_int, _f1, c_int]
         L.oracle_find_nsmallest.restype = c_double
+        L.oracle_subsets_labels.argtypes = [
+            ndpointer(dtype=numpy.int64, ndim=2, flags='C_CONTIGUOUS'), c_int, c_int, _b1,
+            ctypes_longlong, ndpointer(dtype=numpy.int32, ndim=1, flags='C_CONTIGUOUS')]
+        L.oracle_subsets_labels.restype = None
         _lib = L
     return _lib
 
@@ -114,3 +118,13 @@ def find_nsmallest(n, arr1, arr2):
     a1 = numpy.ascontiguousarray(arr1, dtype=numpy.float64)
     a2 = numpy.ascontiguousarray(arr2, dtype=numpy.float64)
     return lib().oracle_find_nsmallest(n, a1, len(a1), a2, len(a2))
+
+
+def subsets_labels(live_pointsp, data_mask, npoints):
+    """labels[d] = smallest data-set index of d's group -- multi_nested_sampler.py:204-355."""
+    P = numpy.ascontiguousarray(live_pointsp, dtype=numpy.int64)
+    nlive, ndata = P.shape
+    m = numpy.ascontiguousarray(data_mask, dtype=numpy.bool_)
+    labels = numpy.empty(ndata, dtype=numpy.int32)
+    lib().oracle_subsets_labels(P, nlive, ndata, m, int(npoints), labels)
+    return labels

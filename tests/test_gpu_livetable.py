@@ -121,3 +121,66 @@ def test_sharded_table_matches_single_device():
     for j, d in enumerate(idx):
         n = len(shelves[j])
         assert got[j] == numpy.partition(numpy.concatenate((L[:, d], shelves[j])), n)[n]
+
+
+def _grouped_points(nlive, ndata, ngroups, rs, chain=False):
+    """live_pointsp with a known group structure: data sets of a group draw their live points
+    from the group's own pool (plus, with `chain`, one point shared with the next data set only,
+    so that labels must travel along a chain)."""
+    group = rs.randint(0, ngroups, size=ndata)
+    pool = 3 * nlive
+    P = numpy.empty((nlive, ndata), dtype=numpy.int64)
+    for d in range(ndata):
+        P[:, d] = group[d] * pool + rs.choice(pool, size=nlive, replace=False)
+    npoints = ngroups * pool
+    if chain:
+        # every data set owns private points; neighbours d, d+1 share exactly one
+        P = numpy.arange(nlive * ndata, dtype=numpy.int64).reshape((nlive, ndata))
+        for d in range(ndata - 1):
+            if (d + 1) % 97:                 # break the chain now and then
+                P[0, d + 1] = P[1, d]
+        npoints = nlive * ndata
+    return P, npoints
+
+
+@pytest.mark.parametrize('nlive,ndata,ngroups,chain', [(20, 300, 7, False), (400, 2000, 50, False),
+                                                       (5, 5000, 1, True), (50, 20000, 900, False),
+                                                       (3, 1, 1, False)])
+def test_subsets_match_oracle_components(oracle_port, nlive, ndata, ngroups, chain):
+    from oracle import np_oracle
+    from massivedatans_b200.livepoints import generate_subsets
+    rs = numpy.random.RandomState(ndata + nlive)
+    P, npoints = _grouped_points(nlive, ndata, ngroups, rs, chain)
+    x, y, _ = synth.horns(ndata, legacy=False, seed=1)
+    t = LiveTable(ResidentDataset(x, y), nlive)
+    t.upload_points(P)
+    masks = {'all': numpy.ones(ndata, dtype=bool), 'half': rs.uniform(size=ndata) < 0.5}
+    for name, m in masks.items():
+        if not m.any():
+            continue
+        got = t.subsets(m if name != 'all' else None, npoints)
+        want = oracle_port.subsets_labels(P, m, npoints)
+        assert numpy.array_equal(got, want), name
+        if ndata <= 5000:
+            assert numpy.array_equal(got, np_oracle.subsets_labels(P, m, npoints))
+        groups = list(generate_subsets(m, P, got))
+        assert len(groups) == len(numpy.unique(want[want >= 0]))
+        seen = numpy.zeros(ndata, dtype=bool)
+        firsts = []
+        for gm, gp in groups:
+            assert not (seen & gm).any()
+            seen |= gm
+            firsts.append(numpy.nonzero(gm)[0][0])
+            assert numpy.array_equal(gp, numpy.unique(P[:, gm]))
+        assert numpy.array_equal(seen, m) and firsts == sorted(firsts)
+    # replacing points merges groups: give data set 0 a point of the last data set
+    if ndata > 1:
+        rows = numpy.full(ndata, -1, dtype=numpy.int64)
+        ids = numpy.zeros(ndata, dtype=numpy.int64)
+        rows[0] = 0
+        ids[0] = P[-1, ndata - 1]
+        t.replace_points(rows, ids)
+        P2 = P.copy()
+        P2[0, 0] = ids[0]
+        allm = numpy.ones(ndata, dtype=bool)
+        assert numpy.array_equal(t.subsets(None, npoints), oracle_port.subsets_labels(P2, allm, npoints))

@@ -135,3 +135,18 @@ def test_live_table_oracle_matches_numpy_twin(oracle_port):
             shelf[0] = L[5, 0]
         assert oracle_port.find_nsmallest(n, numpy.ascontiguousarray(L[:, 0]), shelf) == \
             np_oracle.find_nsmallest(n, L[:, 0], shelf)
+
+
+def test_subsets_oracle_matches_scipy_components(oracle_port):
+    # multi_nested_sampler.py:204-355: union-find restatement vs scipy connected components
+    from oracle import np_oracle
+    rs = numpy.random.RandomState(3)
+    nlive, ndata, ngroups = 10, 200, 9
+    group = rs.randint(0, ngroups, size=ndata)
+    P = numpy.empty((nlive, ndata), dtype=numpy.int64)
+    for d in range(ndata):
+        P[:, d] = group[d] * 40 + rs.choice(40, size=nlive, replace=False)
+    for m in (numpy.ones(ndata, dtype=bool), rs.uniform(size=ndata) < 0.3):
+        got = oracle_port.subsets_labels(P, m, ngroups * 40)
+        assert numpy.array_equal(got, np_oracle.subsets_labels(P, m, ngroups * 40))
+        assert (got[~m] == -1).all() and (got[m] <= numpy.nonzero(m)[0]).all()
