@@ -662,9 +662,10 @@ int mdns_clike_launch_fetch(mdns_dataset *ds, double noise, double scale, double
 		MDNS_CUDA(cudaSetDevice(s.device));
 		if (s.n_act > 0) {
 			if ((rc = clike_model(ds, s)) != MDNS_OK) return rc;
-			// ~4 MB of results per chunk, at most 8 chunks, at least 32768 rows each
+			// >= 1 MB of results per chunk, at most 8 chunks, at least 32768 rows each: the
+			// un-overlapped tail is the download of the last chunk
 			const long long bytes = (long long)K * s.n_act * 8;
-			int nchunk = (int)std::min<long long>(8, std::max<long long>(1, bytes / (4 << 20)));
+			int nchunk = (int)std::min<long long>(8, std::max<long long>(1, bytes / (1 << 20)));
 			while (nchunk > 1 && s.n_act / nchunk < 32768) --nchunk;
 			const int per = (int)round_up(ceil_div(s.n_act, nchunk), 256);
 			int c = 0;

@@ -17,16 +17,19 @@
 // TF32/BF16 variants of the north star's split cannot (cancellation).
 //
 // Layout:
-//   * producer thread: tensor-TMA ring of [256 data sets] x [16 channels] boxes (128-byte
-//     swizzle) exactly as in clike_tile_kernel; the KT model spectra of the pass are copied once
-//     per CTA into shared memory with a row pitch = 4 mod 16 doubles so that the B fragments
-//     (8 candidates x 4 channels) are bank-conflict free;
+//   * producer thread: tensor-TMA ring; every stage holds a [256 data sets] x [16 channels] box
+//     of the resident rows and the matching [KT candidates] x [16 channels] box of the model
+//     batch (both 128-byte swizzled, one mbarrier transaction).  The model slice is re-fetched
+//     from L2 per tile (KT*128 B beside 32 KB of data), which keeps the shared-memory footprint
+//     independent of the channel count: a first version kept the whole model batch in shared
+//     memory and fell to one CTA per SM at 1000 channels (0.67 of the HBM roofline at K = 16);
 //   * 8 consumer warps, warp w owns data sets [32w, 32w+32) of the tile as 4 row tiles of 8.
 //     Fragment (m8n8k4, f64): A[g][t] = Y[row(g)][4*ks + t], B[t][g] = M[8*nc + g][4*ks + t],
 //     g = lane / 4, t = lane % 4.  The logical row g is mapped to the physical row
 //     perm(g) = 0,2,4,6,1,3,5,7 so that each half-warp touches rows of equal parity: with the
 //     128-byte swizzle (16-byte chunk index ^= row % 8) its 16 lanes then hit 8 distinct chunk
-//     columns and the 64-bit loads are conflict free;
+//     columns and the 64-bit loads are conflict free; the candidates of a B fragment are
+//     permuted the same way;
 //   * D[g][2t + {0,1}] accumulates over all channels in registers (2 doubles per tile).
 #include <cuda.h>
 
@@ -62,43 +65,30 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
 	             : "d"(a), "d"(b));
 }
 
-// shared-memory pitch of a model row: covers every box column and is 4 mod 16 doubles
-__host__ __device__ inline int dm_model_pitch(int pitch_even)
-{
-	return (pitch_even + DM_BOX_CH - 1) / DM_BOX_CH * DM_BOX_CH + 4;
-}
-
 template <int NC, int STAGES>
 __global__ void __launch_bounds__(DM_ROWS + 32) clike_dmma_kernel(
-    const __grid_constant__ CUtensorMap tmap, const LikeArgs a, const int k0, const int kt_valid,
-    const int pass)
+    const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap mmap,
+    const LikeArgs a, const int k0, const int kt_valid, const int pass)
 {
 	constexpr int KT = NC * 8;
+	constexpr int MODEL_BYTES = KT * DM_BOX_CH * 8;             // model slice of one stage
+	constexpr int STAGE_BYTES = DM_STAGE_BYTES + MODEL_BYTES;   // multiple of 1 KB
 	extern __shared__ __align__(1024) unsigned char smem_raw[];
-	__shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], model_bar;
+	__shared__ uint64_t full_bar[STAGES], empty_bar[STAGES];
 	// the swizzle pattern is a function of the shared-memory address: align the ring to 1 KB
 	unsigned char *ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-	double *sm_model = reinterpret_cast<double *>(ring + STAGES * DM_STAGE_BYTES);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int pitch_even = (int)a.pitch;       // channels incl. the zero pad of an odd count
 	const int nchunks = (pitch_even + DM_BOX_CH - 1) / DM_BOX_CH;
 	const int ntiles = (a.n_rows + DM_ROWS - 1) / DM_ROWS;
-	const int mps = dm_model_pitch(pitch_even);
 
-	// zero the tail of every model row (channels the TMA copy below does not write; the data
-	// there is zero-filled by the tensor copy, but 0 * garbage could be NaN)
-	for (int i = threadIdx.x; i < KT * (mps - a.mpitch); i += blockDim.x) {
-		const int k = i / (mps - a.mpitch), j = i % (mps - a.mpitch);
-		sm_model[k * mps + a.mpitch + j] = 0.0;
-	}
 	if (threadIdx.x == 0) {
 #pragma unroll
 		for (int s = 0; s < STAGES; ++s) {
 			mbar_init(&full_bar[s], 1);
 			mbar_init(&empty_bar[s], DM_WARPS);
 		}
-		mbar_init(&model_bar, 1);
 		mbar_fence_init();
 	}
 	__syncthreads();
@@ -106,11 +96,6 @@ __global__ void __launch_bounds__(DM_ROWS + 32) clike_dmma_kernel(
 	if (warp == DM_WARPS) {
 		// ===================== producer (one elected thread) =====================
 		if (lane == 0) {
-			const uint32_t row_bytes = (uint32_t)a.mpitch * 8u;
-			mbar_expect_tx(&model_bar, row_bytes * KT);
-			for (int k = 0; k < KT; ++k)
-				tma_load_1d(sm_model + (size_t)k * mps, a.model + (size_t)(k0 + k) * a.mpitch,
-				            row_bytes, &model_bar);
 			int it = 0;
 			for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
 				const int r0 = a.row0 + tile * DM_ROWS;
@@ -119,9 +104,10 @@ __global__ void __launch_bounds__(DM_ROWS + 32) clike_dmma_kernel(
 					const uint32_t round = (uint32_t)(it / STAGES);
 					mbar_wait(&empty_bar[stage], (round & 1u) ^ 1u);   // first round passes
 					// out-of-bounds parts of a box are zero-filled and still counted
-					mbar_expect_tx(&full_bar[stage], DM_STAGE_BYTES);
-					dm_tma_load_2d(ring + (size_t)stage * DM_STAGE_BYTES, &tmap, c * DM_BOX_CH, r0,
-					               &full_bar[stage]);
+					mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+					unsigned char *dst = ring + (size_t)stage * STAGE_BYTES;
+					dm_tma_load_2d(dst, &tmap, c * DM_BOX_CH, r0, &full_bar[stage]);
+					dm_tma_load_2d(dst + DM_STAGE_BYTES, &mmap, c * DM_BOX_CH, k0, &full_bar[stage]);
 				}
 			}
 		}
@@ -133,9 +119,9 @@ __global__ void __launch_bounds__(DM_ROWS + 32) clike_dmma_kernel(
 		// ((2*ks + t/2) ^ pr) * 16 + (t & 1) * 8 ; the row tiles of the warp are 1 KB apart
 		const int a_row_off = (warp * 32 + pr) * 128 + (t & 1) * 8;
 		const int a_chunk = t >> 1;
-		const double *b_base = sm_model + (size_t)g * mps + t;
+		// B element: candidate perm(g) of the tile (same permutation, same swizzle), 128 B per row
+		const int b_row_off = DM_STAGE_BYTES + pr * 128 + (t & 1) * 8;
 		const double inv = a.scale / a.noise2;
-		mbar_wait(&model_bar, 0);
 		int it = 0;
 		for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
 			double acc[DM_MR][NC][2];
@@ -147,17 +133,17 @@ __global__ void __launch_bounds__(DM_ROWS + 32) clike_dmma_kernel(
 				const int stage = it % STAGES;
 				const uint32_t round = (uint32_t)(it / STAGES);
 				mbar_wait(&full_bar[stage], round & 1u);
-				const unsigned char *sbase = ring + (size_t)stage * DM_STAGE_BYTES + a_row_off;
-				const double *bc = b_base + c * DM_BOX_CH;
+				const unsigned char *sbase = ring + (size_t)stage * STAGE_BYTES;
 #pragma unroll
 				for (int ks = 0; ks < DM_BOX_CH / 4; ++ks) {
 					double fa[DM_MR], fb[NC];
 					const int choff = ((2 * ks + a_chunk) ^ pr) << 4;
 #pragma unroll
 					for (int mr = 0; mr < DM_MR; ++mr)
-						fa[mr] = *reinterpret_cast<const double *>(sbase + mr * 1024 + choff);
+						fa[mr] = *reinterpret_cast<const double *>(sbase + a_row_off + mr * 1024 + choff);
 #pragma unroll
-					for (int nc = 0; nc < NC; ++nc) fb[nc] = bc[(size_t)nc * 8 * mps + ks * 4];
+					for (int nc = 0; nc < NC; ++nc)
+						fb[nc] = *reinterpret_cast<const double *>(sbase + b_row_off + nc * 1024 + choff);
 #pragma unroll
 					for (int mr = 0; mr < DM_MR; ++mr)
 #pragma unroll
@@ -178,7 +164,8 @@ __global__ void __launch_bounds__(DM_ROWS + 32) clike_dmma_kernel(
 				for (int nc = 0; nc < NC; ++nc) {
 #pragma unroll
 					for (int i = 0; i < 2; ++i) {
-						const int k = nc * 8 + 2 * t + i;
+						const int col = 2 * t + i;      // logical column -> physical candidate
+						const int k = nc * 8 + (((col & 3) << 1) | (col >> 2));
 						const double smm = __ldg(a.smm + k0 + k);
 						const double chi = syy + fma(-2.0, acc[mr][nc][i], smm);
 						const bool ok = chi >= a.xp_guard * (syy + smm);   // false for NaN too
@@ -191,8 +178,11 @@ __global__ void __launch_bounds__(DM_ROWS + 32) clike_dmma_kernel(
 					}
 				}
 				// the four lanes of a group share the data set: list it once
-				redo = redo || __shfl_xor_sync(0xffffffffu, redo, 1);
-				redo = redo || __shfl_xor_sync(0xffffffffu, redo, 2);
+				// (no short-circuit: every lane must take part in both shuffles)
+				int flag = redo ? 1 : 0;
+				flag |= __shfl_xor_sync(0xffffffffu, flag, 1);
+				flag |= __shfl_xor_sync(0xffffffffu, flag, 2);
+				redo = flag != 0;
 				if (redo && t == 0) a.xp_list[atomicAdd(a.xp_redo + 1 + pass, 1)] = (int)gr;
 			}
 		}
@@ -200,10 +190,13 @@ __global__ void __launch_bounds__(DM_ROWS + 32) clike_dmma_kernel(
 }
 
 // ---- host side ---------------------------------------------------------------------------
-static size_t dmma_smem(int kt, int stages, int pitch_even)
+static size_t dmma_smem(int kt, int stages)
 {
-	return (size_t)stages * DM_STAGE_BYTES + 1024 + (size_t)kt * dm_model_pitch(pitch_even) * 8;
+	return (size_t)stages * (DM_STAGE_BYTES + (size_t)kt * DM_BOX_CH * 8) + 1024;
 }
+
+int make_row_tensor_map_box(void *out, const double *Y, long long n_rows, long long pitch,
+                            int box_rows);
 
 int launch_xtile_fixup(const LikeArgs &a, int k0, int kv, int pass, int sm_count, cudaStream_t st);
 
@@ -212,7 +205,7 @@ static int launch_dmma_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 {
 	constexpr int KT = NC * 8;
 	constexpr int THREADS = DM_ROWS + 32;
-	const size_t smem = dmma_smem(KT, STAGES, (int)a.pitch);
+	const size_t smem = dmma_smem(KT, STAGES);
 	auto kern = clike_dmma_kernel<NC, STAGES>;
 	MDNS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int occ = 0;
@@ -221,8 +214,13 @@ static int launch_dmma_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 		set_error("DMMA tile kernel does not fit (%zu bytes of shared memory)", smem);
 		return MDNS_EINVAL;
 	}
-	CUtensorMap tm;
+	CUtensorMap tm, mm;
 	memcpy(&tm, a.tmap256, sizeof tm);
+	// the model batch [Kpad][mpitch] as boxes of KT candidates x 16 channels (Kpad is a multiple
+	// of 32, so a box never leaves the buffer)
+	const long long kpad = (long long)round_up(a.K, KT_MAX);
+	int rcm = make_row_tensor_map_box(&mm, a.model, kpad, a.mpitch, KT);
+	if (rcm != MDNS_OK) return rcm;
 	const int ntiles = ceil_div(a.n_rows, DM_ROWS);
 	long long gx = ntiles;
 	const long long resident = (long long)sm_count * occ;
@@ -237,7 +235,7 @@ static int launch_dmma_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 		MDNS_CUDA(cudaMemsetAsync(a.xp_redo + 1, 0, (size_t)npass * sizeof(int), st));
 	for (int k0 = 0, pass = 0; k0 < a.K; k0 += KT, ++pass) {
 		const int kv = a.K - k0 < KT ? a.K - k0 : KT;
-		kern<<<(unsigned)gx, THREADS, smem, st>>>(tm, a, k0, kv, pass);
+		kern<<<(unsigned)gx, THREADS, smem, st>>>(tm, mm, a, k0, kv, pass);
 		MDNS_LAUNCHED("clike_dmma_kernel");
 		const int rc = launch_xtile_fixup(a, k0, kv, pass, sm_count, st);
 		if (rc != MDNS_OK) return rc;
@@ -248,8 +246,7 @@ static int launch_dmma_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 bool dmma_fits(const LikeArgs &a, int kt, int stages)
 {
 	return a.tmap256 && !a.active && a.syy && a.smm && a.xp_redo && a.xp_list &&
-	       dmma_smem(kt, stages, (int)a.pitch) <= 220 * 1024 &&
-	       (size_t)kt * a.mpitch * 8 < (1u << 20);   // mbarrier tx-count range
+	       dmma_smem(kt, stages) <= 220 * 1024;
 }
 
 // kt in {8, 16, 32}; stages in {2, 3, 4}
@@ -258,7 +255,7 @@ int launch_clike_dmma(const LikeArgs &a, int kt, int stages, int sm_count, cudaS
 	if (a.n_rows <= 0 || a.K <= 0) return MDNS_OK;
 	if (!dmma_fits(a, kt, stages)) {
 		set_error("DMMA tile kernel: needs all-active rows, the resident row sums and %zu bytes of "
-		          "shared memory", dmma_smem(kt, stages, (int)a.pitch));
+		          "shared memory", dmma_smem(kt, stages));
 		return MDNS_EINVAL;
 	}
 #define MDNS_DM(KK, SS) \

@@ -213,6 +213,13 @@ int make_row_tensor_map(void *out, const double *Y, long long n_rows, long long 
 	return MDNS_OK;
 }
 
+// the same descriptor for any box height (model batches: KT candidates x 16 channels)
+int make_row_tensor_map_box(void *out, const double *Y, long long n_rows, long long pitch,
+                            int box_rows)
+{
+	return make_row_tensor_map(out, Y, n_rows, pitch, box_rows);
+}
+
 template <int KT, int NBOX, int STAGES, int TILE_ROWS>
 static int launch_tile_inst(const LikeArgs &a, const void *tmap, int sm_count, cudaStream_t st)
 {

@@ -563,22 +563,18 @@ static int launch_clike_u(const LikeArgs &a, int u, int kt, int sm_count, cudaSt
 	}
 }
 
-// Choose the number of fragments in flight per lane: the supported value that wastes the
-// fewest issue slots, preferring the larger (more loads in flight) on ties.
+// Choose the number of fragments in flight per lane: the largest supported value that wastes
+// at most ~7 % of the issue slots (a first version minimised the waste alone and picked U = 1
+// for 1000-channel rows: 0.74 of the HBM roofline instead of 0.99).
 static int pick_unroll(int nfrag, int L)
 {
 	static const int cand[] = {16, 13, 8, 4, 2, 1};
 	const int per_lane = ceil_div(nfrag, L);
-	int best = 1;
-	long long best_cost = -1;
 	for (int u : cand) {
 		const long long cost = (long long)ceil_div(per_lane, u) * u;
-		if (best_cost < 0 || cost < best_cost) {
-			best_cost = cost;
-			best = u;
-		}
+		if (cost * 100 <= (long long)per_lane * 107) return u;
 	}
-	return best;
+	return 1;
 }
 
 static int pick_ktile(int K, int mpitch, int requested)
@@ -600,7 +596,7 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		// expanded form, cross term as FP64 tensor-core tiles
 		int kt = t.ktile;
 		if (kt != 8 && kt != 16 && kt != 32) kt = a.K >= 32 ? 32 : a.K >= 16 ? 16 : 8;
-		int stages = (t.rows == 2 || t.rows == 3 || t.rows == 4) ? t.rows : 2;
+		int stages = (t.rows == 2 || t.rows == 3 || t.rows == 4) ? t.rows : 3;
 		while (kt > 8 && !dmma_fits(a, kt, stages)) kt >>= 1;
 		if (!dmma_fits(a, kt, stages)) stages = 2;
 		return launch_clike_dmma(a, kt, stages, sm_count, st);
@@ -638,13 +634,13 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 	if (L == 0 && t.unroll == 0 && t.ktile == 0 && t.rows == 0 && !a.active && a.K >= 8 &&
 	    a.n_rows >= 32768) {
 		// automatic choice for all-active candidate batches: expanded form with the cross term
-		// on the FP64 tensor path when allowed (measured at N=1e6, C=200: K=8 0.287 ms, K=16
-		// 0.32 ms, K=32 0.53 ms; FMA form 0.29 / 0.35 / 0.69; direct form 0.30 / 0.56 / 1.1) ...
+		// on the FP64 tensor path when allowed (measured at N=1e6, C=200: K=8 0.277 ms, K=16
+		// 0.313 ms, K=32 0.46 ms; FMA form 0.29 / 0.35 / 0.69; direct form 0.30 / 0.56 / 1.1) ...
 		if (t.allow_expanded) {
+			// ring depth: K=8 4 stages (0.277 ms vs 0.291 with 2), K=16 3 stages (0.313 vs 0.352)
 			if (a.K >= 32 && dmma_fits(a, 32, 3)) return launch_clike_dmma(a, 32, 3, sm_count, st);
-			if (a.K >= 32 && dmma_fits(a, 32, 2)) return launch_clike_dmma(a, 32, 2, sm_count, st);
-			if (a.K >= 16 && dmma_fits(a, 16, 2)) return launch_clike_dmma(a, 16, 2, sm_count, st);
-			if (dmma_fits(a, 8, 2)) return launch_clike_dmma(a, 8, 2, sm_count, st);
+			if (a.K >= 16 && dmma_fits(a, 16, 3)) return launch_clike_dmma(a, 16, 3, sm_count, st);
+			if (dmma_fits(a, 8, 4)) return launch_clike_dmma(a, 8, 4, sm_count, st);
 			const int xkt = a.K >= 16 && xtile_fits(a, 16, 2) ? 16 : 8;
 			if (xtile_fits(a, xkt, 2)) return launch_clike_xtile(a, xkt, 2, 2, sm_count, st);
 		}
@@ -655,7 +651,9 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 			return launch_clike_tile(a, a.tmap256, kt, 1, 3, 256, sm_count, st);
 		}
 	}
-	if (L != 8 && L != 32) L = (a.n_rows >= 16384 && nfrag >= 8) ? 8 : 32;
+	// 8 lanes per data set for short rows (more data sets in flight per warp), a whole warp for
+	// long ones (measured at 1000 channels: 0.150 ms vs 0.155 ms for 1 GB)
+	if (L != 8 && L != 32) L = (a.n_rows >= 16384 && nfrag >= 8 && nfrag < 256) ? 8 : 32;
 	int U = t.unroll;
 	if (U != 1 && U != 2 && U != 4 && U != 8 && U != 13 && U != 16) U = pick_unroll(nfrag, L);
 	const int kt = pick_ktile(a.K, a.mpitch, t.ktile);

@@ -492,3 +492,39 @@ def test_sharded_dataset_matches_single_device(oracle_port, ndev):
     dm.muse_loglike(t, mask, L)
     want = oracle_port.cmuselike(ym, vm, t, mask)
     assert rel_err(L[0][mask], want[mask]) < TOL and (L[0][~mask] == 0).all()
+
+
+def test_clike_full_size_properties():
+    # BASELINE full size (1e6 data sets x 200 channels, the bench configuration) through
+    # size-independent properties, on the automatically chosen kernels:
+    N = 1000000
+    x, y = synth.nothing(N, legacy=False)
+    ds = ResidentDataset(x, y)
+    lib = _lib.load()
+    pts = synth.parameter_points(16, seed=3)
+    pts[5, 0] = 0.0                                    # a candidate without a line
+    full = ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0).copy()
+    assert lib.mdns_last_kernel() == b'clike_dmma_kernel'
+    # (1) chi2(A=0) = sum (y/noise)^2 (plotevidences.py:17), numpy column sums in blocks
+    want = numpy.empty(N)
+    for lo in range(0, N, 100000):
+        want[lo:lo + 100000] = ((y[:, lo:lo + 100000] / synth.NOISE_LEVEL) ** 2).sum(axis=0)
+    assert rel_err(full[5], want) < TOL_XP
+    # (2) batch == one candidate at a time on the streaming kernel (direct form)
+    for k in (0, 5, 15):
+        one = ds.loglike_batch(pts[k:k + 1], None, synth.NOISE_LEVEL, scale=1.0)[0]
+        assert lib.mdns_last_kernel() == b'clike_rows_kernel'
+        assert rel_err(full[k], one) < TOL_XP
+    # (3) a masked evaluation is the compaction of the full one (direct-form kernels on both
+    # sides: bit for bit)
+    ds.set_expanded(False)
+    direct = ds.loglike_batch(pts[:8], None, synth.NOISE_LEVEL, scale=1.0).copy()
+    assert rel_err(direct, full[:8]) < TOL_XP
+    m = synth.masks(N)['half']
+    part = ds.loglike_batch(pts[:3], m, synth.NOISE_LEVEL, scale=1.0)
+    one = ds.loglike_batch(pts[:1], None, synth.NOISE_LEVEL, scale=1.0)[0]
+    assert numpy.array_equal(part[0], one[m])
+    # (4) idempotence: the same launch twice gives the same bits
+    ds.set_expanded(True)
+    again = ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0)
+    assert numpy.array_equal(again, full)

@@ -28,11 +28,11 @@ def main():
     lib = _lib.load()
     rows = []
     variants = {
-        8: ['0,0,0,0', '1,116,8,3', '2,2,8,2', '3,0,8,2', '3,0,8,3', '3,0,8,4'],
-        16: ['0,0,0,0', '1,116,16,3', '2,2,16,2', '3,0,16,2', '3,0,16,3', '3,0,16,4', '3,0,8,3'],
-        32: ['0,0,0,0', '2,2,16,2', '3,0,32,2', '3,0,32,3', '3,0,16,2', '3,0,16,3'],
-        64: ['0,0,0,0', '3,0,32,2', '3,0,32,3', '3,0,16,3'],
-        400: ['0,0,0,0', '3,0,32,2', '3,0,32,3', '3,0,16,3'],
+        8: ['0,0,0,0', '3,0,8,2', '3,0,8,3', '3,0,8,4'],
+        16: ['0,0,0,0', '3,0,16,2', '3,0,16,3', '3,0,16,4'],
+        32: ['0,0,0,0', '3,0,32,2', '3,0,32,3', '3,0,32,4', '3,0,16,3'],
+        64: ['0,0,0,0', '3,0,32,3', '3,0,16,3'],
+        400: ['0,0,0,0', '3,0,32,3'],
     }
     for K, vs in variants.items():
         ds.stage_params(synth.parameter_points(K, seed=7))
