@@ -52,21 +52,36 @@ __global__ void __launch_bounds__(NB_THREADS) count_within_kernel(const double *
 #pragma unroll
 		for (int k = 0; k < D; ++k) y[c][k] = __ldg(yy + j * D + k);
 	}
-	for (int base = 0; base < n; base += 32) {
-		const int i = base + lane;
-		const bool valid = i < n;
-		double x[D];
+	// two chunks of 32 members per iteration: the loads of the second are in flight while the
+	// first is tested (ncu on the one-chunk loop: 25 % long-scoreboard stalls, FP64 pipe 64 %)
+	for (int base = 0; base < n; base += 64) {
+		const int i0 = base + lane, i1 = base + 32 + lane;
+		const bool valid0 = i0 < n, valid1 = i1 < n;
+		double x0[D], x1[D];
 #pragma unroll
-		for (int k = 0; k < D; ++k) x[k] = valid ? xs[(size_t)k * npad + i] : 0.0;
+		for (int k = 0; k < D; ++k) {
+			x0[k] = valid0 ? xs[(size_t)k * npad + i0] : 0.0;
+			x1[k] = valid1 ? xs[(size_t)k * npad + i1] : 0.0;
+		}
 		bool all_done = stop_at > 0;
 #pragma unroll
 		for (int c = 0; c < CPW; ++c) {
-			const double d = sqdist_reg<D>(x, y[c]);
-			const unsigned hits = __ballot_sync(0xffffffffu, valid && d < T);
+			const double d = sqdist_reg<D>(x0, y[c]);
+			const unsigned hits = __ballot_sync(0xffffffffu, valid0 && d < T);
 			cnt[c] += __popc(hits);
 			all_done = all_done && cnt[c] >= stop_at;
 		}
 		if (all_done) break;   // warp-uniform: cnt comes from the ballot
+		if (base + 32 >= n) break;
+		all_done = stop_at > 0;
+#pragma unroll
+		for (int c = 0; c < CPW; ++c) {
+			const double d = sqdist_reg<D>(x1, y[c]);
+			const unsigned hits = __ballot_sync(0xffffffffu, valid1 && d < T);
+			cnt[c] += __popc(hits);
+			all_done = all_done && cnt[c] >= stop_at;
+		}
+		if (all_done) break;
 	}
 	if (lane == 0) {
 #pragma unroll
