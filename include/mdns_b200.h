@@ -146,7 +146,7 @@ int mdns_timer_stop(mdns_dataset *ds, float *elapsed_ms);
  * fragments in flight per lane (0 = auto), candidates per pass (0 = auto),
  * data sets per lane group (0 = auto; > 1 selects the register-blocked kernel). */
 int mdns_set_tuning(mdns_dataset *ds, int lanes, int unroll, int ktile, int rows);
-/* Expanded form of the candidate-batch kernel (K >= 8, all data sets active):
+/* Expanded form of the candidate-batch kernel (K >= 3, all data sets active, >= 32768 of them):
  *     sum_j (m_j - y_j)^2 = Syy - 2*Sym + Smm ,  Syy resident per data set,
  * one FP64 FMA per (element, candidate) instead of two operations.  FP64 throughout; a
  * result is kept only when the rounding-error bound of the three sums is below rel_tol

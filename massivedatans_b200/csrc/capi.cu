@@ -553,7 +553,7 @@ static bool xp_candidate(const mdns_dataset *ds, const Shard &s)
 {
 	if (!s.syy || !s.all_active) return false;
 	if (ds->tuning.lanes == 2 || ds->tuning.lanes == 3) return true;   // explicit request
-	return ds->tuning.lanes == 0 && ds->K >= 8 && ds->tuning.allow_expanded;
+	return ds->tuning.lanes == 0 && ds->K >= XP_MIN_K && ds->tuning.allow_expanded;
 }
 
 static int clike_check(mdns_dataset *ds, const char *who)

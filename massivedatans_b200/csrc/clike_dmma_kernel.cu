@@ -40,8 +40,6 @@ namespace mdns {
 constexpr int DM_ROWS = 256;                    // data sets per tile = rows of one TMA box
 constexpr int DM_BOX_CH = 16;                   // channels per box row = 128 bytes (swizzle span)
 constexpr int DM_STAGE_BYTES = DM_ROWS * DM_BOX_CH * 8;
-constexpr int DM_WARPS = DM_ROWS / 32;          // consumer warps
-constexpr int DM_MR = 4;                        // row tiles (of 8 data sets) per warp
 
 __device__ __forceinline__ void dm_mbar_arrive(uint64_t *bar)
 {
@@ -65,12 +63,15 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
 	             : "d"(a), "d"(b));
 }
 
-template <int NC, int STAGES>
-__global__ void __launch_bounds__(DM_ROWS + 32) clike_dmma_kernel(
+// NC candidate tiles (of 8) and DM_MR row tiles (of 8 data sets) per consumer warp;
+// DM_ROWS / (8 * DM_MR) consumer warps per CTA
+template <int NC, int STAGES, int DM_MR>
+__global__ void __launch_bounds__(DM_ROWS / (8 * DM_MR) * 32 + 32) clike_dmma_kernel(
     const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap mmap,
     const LikeArgs a, const int k0, const int kt_valid, const int pass)
 {
 	constexpr int KT = NC * 8;
+	constexpr int DM_WARPS = DM_ROWS / (8 * DM_MR);             // consumer warps
 	constexpr int MODEL_BYTES = KT * DM_BOX_CH * 8;             // model slice of one stage
 	constexpr int STAGE_BYTES = DM_STAGE_BYTES + MODEL_BYTES;   // multiple of 1 KB
 	extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(DM_ROWS + 32) clike_dmma_kernel(
 		const int pr = ((g & 3) << 1) | (g >> 2);      // physical row of logical row g
 		// byte offset of this lane's A element inside a stage, per channel step ks: row * 128 +
 		// ((2*ks + t/2) ^ pr) * 16 + (t & 1) * 8 ; the row tiles of the warp are 1 KB apart
-		const int a_row_off = (warp * 32 + pr) * 128 + (t & 1) * 8;
+		const int a_row_off = (warp * (8 * DM_MR) + pr) * 128 + (t & 1) * 8;
 		const int a_chunk = t >> 1;
 		// B element: candidate perm(g) of the tile (same permutation, same swizzle), 128 B per row
 		const int b_row_off = DM_STAGE_BYTES + pr * 128 + (t & 1) * 8;
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(DM_ROWS + 32) clike_dmma_kernel(
 			// epilogue: lane holds D[row(g)][2t + {0,1}] of every (row tile, candidate tile)
 #pragma unroll
 			for (int mr = 0; mr < DM_MR; ++mr) {
-				const long long gr = (long long)tile * DM_ROWS + warp * 32 + mr * 8 + pr;
+				const long long gr = (long long)tile * DM_ROWS + warp * (8 * DM_MR) + mr * 8 + pr;
 				const bool live = gr < a.n_rows;
 				const double syy = live ? __ldg(a.syy + a.row0 + gr) : 0.0;
 				bool redo = false;
@@ -200,13 +201,13 @@ int make_row_tensor_map_box(void *out, const double *Y, long long n_rows, long l
 
 int launch_xtile_fixup(const LikeArgs &a, int k0, int kv, int pass, int sm_count, cudaStream_t st);
 
-template <int NC, int STAGES>
+template <int NC, int STAGES, int DM_MR>
 static int launch_dmma_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 {
 	constexpr int KT = NC * 8;
-	constexpr int THREADS = DM_ROWS + 32;
+	constexpr int THREADS = DM_ROWS / (8 * DM_MR) * 32 + 32;
 	const size_t smem = dmma_smem(KT, STAGES);
-	auto kern = clike_dmma_kernel<NC, STAGES>;
+	auto kern = clike_dmma_kernel<NC, STAGES, DM_MR>;
 	MDNS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int occ = 0;
 	MDNS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
@@ -245,11 +246,13 @@ static int launch_dmma_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 
 bool dmma_fits(const LikeArgs &a, int kt, int stages)
 {
+	if (stages > 10) stages -= 10;
 	return a.tmap256 && !a.active && a.syy && a.smm && a.xp_redo && a.xp_list &&
 	       dmma_smem(kt, stages) <= 220 * 1024;
 }
 
-// kt in {8, 16, 32}; stages in {2, 3, 4}
+// kt in {8, 16, 32}; stages in {2, 3, 4}, + 10 for 16 consumer warps of 16 data sets each
+// instead of 8 warps of 32
 int launch_clike_dmma(const LikeArgs &a, int kt, int stages, int sm_count, cudaStream_t st)
 {
 	if (a.n_rows <= 0 || a.K <= 0) return MDNS_OK;
@@ -258,8 +261,9 @@ int launch_clike_dmma(const LikeArgs &a, int kt, int stages, int sm_count, cudaS
 		          "shared memory", dmma_smem(kt, stages));
 		return MDNS_EINVAL;
 	}
-#define MDNS_DM(KK, SS) \
-	if (kt == KK && stages == SS) return launch_dmma_inst<KK / 8, SS>(a, sm_count, st)
+#define MDNS_DM(KK, SS)                                                                     \
+	if (kt == KK && stages == SS) return launch_dmma_inst<KK / 8, SS, 4>(a, sm_count, st); \
+	if (kt == KK && stages == SS + 10) return launch_dmma_inst<KK / 8, SS, 2>(a, sm_count, st)
 	MDNS_DM(8, 2);
 	MDNS_DM(8, 3);
 	MDNS_DM(8, 4);

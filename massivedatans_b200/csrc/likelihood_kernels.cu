@@ -596,7 +596,7 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		// expanded form, cross term as FP64 tensor-core tiles
 		int kt = t.ktile;
 		if (kt != 8 && kt != 16 && kt != 32) kt = a.K >= 32 ? 32 : a.K >= 16 ? 16 : 8;
-		int stages = (t.rows == 2 || t.rows == 3 || t.rows == 4) ? t.rows : 3;
+		int stages = ((t.rows >= 2 && t.rows <= 4) || (t.rows >= 12 && t.rows <= 14)) ? t.rows : 3;
 		while (kt > 8 && !dmma_fits(a, kt, stages)) kt >>= 1;
 		if (!dmma_fits(a, kt, stages)) stages = 2;
 		return launch_clike_dmma(a, kt, stages, sm_count, st);
@@ -631,22 +631,26 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		d.allow_expanded = t.allow_expanded;
 		return launch_clike(a, d, sm_count, st);
 	}
-	if (L == 0 && t.unroll == 0 && t.ktile == 0 && t.rows == 0 && !a.active && a.K >= 8 &&
+	if (L == 0 && t.unroll == 0 && t.ktile == 0 && t.rows == 0 && !a.active && a.K >= XP_MIN_K &&
 	    a.n_rows >= 32768) {
 		// automatic choice for all-active candidate batches: expanded form with the cross term
 		// on the FP64 tensor path when allowed (measured at N=1e6, C=200: K=8 0.277 ms, K=16
 		// 0.313 ms, K=32 0.46 ms; FMA form 0.29 / 0.35 / 0.69; direct form 0.30 / 0.56 / 1.1) ...
 		if (t.allow_expanded) {
-			// ring depth: K=8 4 stages (0.277 ms vs 0.291 with 2), K=16 3 stages (0.313 vs 0.352)
+			// K=32: 8 consumer warps x 32 data sets, 3 stages (0.46 ms); K=16: 16 warps x 16 data
+			// sets, 3 stages (0.295 ms; 8 warps 0.300); K=8: 16 warps, 4 stages (0.263 ms; 8 warps
+			// 0.277).  Stage counts + 10 select the 16-warp shape.  From K = 3 on a pass of 8
+			// (padded) candidates on the tensor path beats the lanes-across-channels kernels
+			// (K=4: 0.266 ms vs 0.289 ms block kernel).
 			if (a.K >= 32 && dmma_fits(a, 32, 3)) return launch_clike_dmma(a, 32, 3, sm_count, st);
-			if (a.K >= 16 && dmma_fits(a, 16, 3)) return launch_clike_dmma(a, 16, 3, sm_count, st);
-			if (dmma_fits(a, 8, 4)) return launch_clike_dmma(a, 8, 4, sm_count, st);
+			if (a.K >= 16 && dmma_fits(a, 16, 13)) return launch_clike_dmma(a, 16, 13, sm_count, st);
+			if (dmma_fits(a, 8, 14)) return launch_clike_dmma(a, 8, 14, sm_count, st);
 			const int xkt = a.K >= 16 && xtile_fits(a, 16, 2) ? 16 : 8;
 			if (xtile_fits(a, xkt, 2)) return launch_clike_xtile(a, xkt, 2, 2, sm_count, st);
 		}
 		// ... else the direct-form tile kernel (measured at N=1e6, C=200: K=8 0.29 ms vs
 		// 0.35 ms block kernel; K=16 0.51 ms vs 0.71 ms)
-		if (tile_ok && 8LL * a.mpitch <= tile_constant_capacity()) {
+		if (a.K >= 8 && tile_ok && 8LL * a.mpitch <= tile_constant_capacity()) {
 			const int kt = (a.K >= 16 && 16LL * a.mpitch <= tile_constant_capacity()) ? 16 : 8;
 			return launch_clike_tile(a, a.tmap256, kt, 1, 3, 256, sm_count, st);
 		}

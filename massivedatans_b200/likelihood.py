@@ -155,7 +155,7 @@ class ResidentDataset(object):
 
     def set_expanded(self, enable=True, rel_tol=0.0):
         """Allow / forbid the expanded form Syy - 2 Sym + Smm of the candidate-batch kernel
-        (K >= 8, all data sets active); rel_tol > 0 sets the error bound it enforces."""
+        (K >= 3, all data sets active); rel_tol > 0 sets the error bound it enforces."""
         _lib.check(self._lib.mdns_set_expanded(self._h, 1 if enable else 0, rel_tol),
                    'mdns_set_expanded')
 

@@ -59,9 +59,11 @@ def test_clike_vs_oracle_shapes(oracle_port, N, nx):
     for name, m in synth.masks(N, seed=N).items():
         got = ds.loglike_batch(pts, m, synth.NOISE_LEVEL, scale=1.0)
         assert got.shape == (3, int(m.sum()))
+        # all-active batches of >= 3 candidates over >= 32768 data sets take the expanded form
+        tol = TOL_XP if (m.all() and N >= 32768) else TOL
         for k, p in enumerate(pts):
             want = oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, m)
-            assert rel_err(got[k], want) < TOL, (name, k)
+            assert rel_err(got[k], want) < tol, (name, k)
 
 
 @pytest.mark.parametrize('K', [1, 2, 3, 5, 8, 9, 17, 64])
@@ -169,7 +171,8 @@ def test_clike_expanded_blocked_variants(oracle_port, lane_rows, ktile, stages, 
     assert ds.expanded_stats() == (True, 0)
 
 
-@pytest.mark.parametrize('ktile,stages', [(8, 2), (16, 2), (16, 3), (32, 2), (32, 3), (8, 4)])
+@pytest.mark.parametrize('ktile,stages', [(8, 2), (16, 2), (16, 3), (32, 2), (32, 3), (8, 4),
+                                          (8, 14), (16, 13), (32, 12), (16, 12)])
 @pytest.mark.parametrize('N,nx,K', [(128, 16, 4), (700, 203, 9), (300, 1000, 5), (70000, 200, 37),
                                     (2049, 57, 64)])
 def test_clike_expanded_tensor_path_variants(oracle_port, ktile, stages, N, nx, K):
@@ -192,8 +195,8 @@ def test_clike_expanded_tensor_path_variants(oracle_port, ktile, stages, N, nx, 
 
 
 def test_clike_expanded_form_automatic_choice(oracle_port):
-    # all-active batches of >= 8 candidates take the expanded form on their own; masks and
-    # small batches stay on the direct kernels
+    # all-active batches of >= 3 candidates take the expanded form on their own; masks and
+    # smaller batches stay on the direct kernels
     N = 50000
     x, y, _ = synth.horns(N, legacy=False, seed=21)
     ds = ResidentDataset(x, y)
@@ -206,7 +209,7 @@ def test_clike_expanded_form_automatic_choice(oracle_port):
         p = pts[k]
         want = -0.5 * oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, allm)
         assert rel_err(got[k], want) < TOL_XP
-    ds.loglike_batch(pts[:4], None, synth.NOISE_LEVEL)
+    ds.loglike_batch(pts[:2], None, synth.NOISE_LEVEL)
     assert lib.mdns_last_kernel() not in (b'clike_xtile_kernel', b'clike_dmma_kernel')
     ds.loglike_batch(pts, synth.masks(N)['half'], synth.NOISE_LEVEL)
     assert lib.mdns_last_kernel() not in (b'clike_xtile_kernel', b'clike_dmma_kernel')

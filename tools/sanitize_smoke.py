@@ -34,7 +34,8 @@ def main():
     seen = set()
     for tuning, K in (((0, 0, 0, 0), 1), ((0, 0, 0, 0), 3), ((8, 2, 4, 4), 5), ((8, 4, 8, 2), 9),
                       ((1, 116, 8, 3), 9), ((1, 32, 16, 3), 17), ((2, 2, 8, 3), 9), ((2, 4, 16, 2), 17),
-                      ((3, 0, 8, 4), 9), ((3, 0, 16, 3), 17), ((3, 0, 32, 2), 33)):
+                      ((3, 0, 8, 4), 9), ((3, 0, 16, 3), 17), ((3, 0, 32, 2), 33), ((3, 0, 8, 14), 9),
+                      ((3, 0, 16, 13), 17)):
         ds.set_tuning(*tuning)
         pts = synth.parameter_points(K, seed=K)
         for mname in ('all', 'half'):

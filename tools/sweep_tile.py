@@ -28,11 +28,11 @@ def main():
     lib = _lib.load()
     rows = []
     variants = {
-        8: ['0,0,0,0', '3,0,8,2', '3,0,8,3', '3,0,8,4'],
-        16: ['0,0,0,0', '3,0,16,2', '3,0,16,3', '3,0,16,4'],
-        32: ['0,0,0,0', '3,0,32,2', '3,0,32,3', '3,0,32,4', '3,0,16,3'],
-        64: ['0,0,0,0', '3,0,32,3', '3,0,16,3'],
-        400: ['0,0,0,0', '3,0,32,3'],
+        8: ['0,0,0,0', '3,0,8,4', '3,0,8,13', '3,0,8,14'],
+        16: ['0,0,0,0', '3,0,16,3', '3,0,16,12', '3,0,16,13'],
+        32: ['0,0,0,0', '3,0,32,3', '3,0,32,12', '3,0,32,13', '3,0,32,14'],
+        64: ['0,0,0,0', '3,0,32,3', '3,0,32,13'],
+        400: ['0,0,0,0', '3,0,32,3', '3,0,32,13'],
     }
     for K, vs in variants.items():
         ds.stage_params(synth.parameter_points(K, seed=7))
