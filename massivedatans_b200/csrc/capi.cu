@@ -83,6 +83,8 @@ struct Shard {
 	bool all_active = true;
 	alignas(64) unsigned char tmap[128];      // CUtensorMaps of Y (tile kernel), 128-row boxes
 	alignas(64) unsigned char tmap256[128];   // and 256-row boxes
+	alignas(64) unsigned char tmap_gather[128];   // one-row boxes (tile::gather4 of masked rows)
+	bool has_gather = false;
 	bool has_tmap = false;
 };
 
@@ -278,6 +280,8 @@ int mdns_dataset_create(const double *x, const double *yy, const double *vv, int
 		if ((rc = upload_rows(s, yy, ndata, nx, ds->pitch, 0, &s.Y)) != MDNS_OK) return fail(rc);
 		s.has_tmap = !vv && make_row_tensor_map(s.tmap, s.Y, s.n, (long long)ds->pitch, 128) == MDNS_OK &&
 		             make_row_tensor_map(s.tmap256, s.Y, s.n, (long long)ds->pitch, 256) == MDNS_OK;
+		s.has_gather = s.has_tmap &&
+		               make_row_tensor_map(s.tmap_gather, s.Y, s.n, (long long)ds->pitch, 1) == MDNS_OK;
 		if (vv && (rc = upload_rows(s, vv, ndata, nx, ds->pitch, 1, &s.W)) != MDNS_OK)
 			return fail(rc);
 		if (s.has_tmap) {
@@ -538,6 +542,7 @@ static void fill_args(const mdns_dataset *ds, const Shard &s, LikeArgs &a)
 	a.out = s.d_out;
 	a.tmap = s.has_tmap ? s.tmap : nullptr;
 	a.tmap256 = s.has_tmap ? s.tmap256 : nullptr;
+	a.tmap_gather = s.has_gather ? s.tmap_gather : nullptr;
 	a.row0 = 0;
 	a.syy = s.syy;
 	a.smm = s.d_smm;
@@ -551,7 +556,13 @@ static void fill_args(const mdns_dataset *ds, const Shard &s, LikeArgs &a)
 // may this launch take the expanded form? (mirrors the automatic choice of launch_clike)
 static bool xp_candidate(const mdns_dataset *ds, const Shard &s)
 {
-	if (!s.syy || !s.all_active) return false;
+	if (!s.syy) return false;
+	if (!s.all_active) {
+		// masked batches: only the tensor path has a gather form
+		if (!s.has_gather) return false;
+		if (ds->tuning.lanes == 3) return true;
+		return ds->tuning.lanes == 0 && ds->K >= 16 && ds->tuning.allow_expanded;
+	}
 	if (ds->tuning.lanes == 2 || ds->tuning.lanes == 3) return true;   // explicit request
 	return ds->tuning.lanes == 0 && ds->K >= XP_MIN_K && ds->tuning.allow_expanded;
 }

@@ -56,6 +56,18 @@ __device__ __forceinline__ void dm_tma_load_2d(void *smem_dst, const CUtensorMap
 	    : "memory");
 }
 
+// four arbitrary rows of the 2-D tensor (tile::gather4, sm_100): columns [c0, c0+16) of rows
+// r0..r3 land as four consecutive 128-byte rows, swizzled like a tiled box
+__device__ __forceinline__ void dm_tma_gather4(void *smem_dst, const CUtensorMap *tmap, int c0,
+                                               int r0, int r1, int r2, int r3, uint64_t *bar)
+{
+	asm volatile(
+	    "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes "
+	    "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(smem_u32(smem_dst)),
+	    "l"(tmap), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+	    : "memory");
+}
+
 __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b)
 {
 	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -64,8 +76,12 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
 }
 
 // NC candidate tiles (of 8) and DM_MR row tiles (of 8 data sets) per consumer warp;
-// DM_ROWS / (8 * DM_MR) consumer warps per CTA
-template <int NC, int STAGES, int DM_MR>
+// DM_ROWS / (8 * DM_MR) consumer warps per CTA.
+// GATHER: the active data sets are listed in a.active (masked batch); the 32 lanes of the
+// producer warp fill a stage with 64 gather4 copies of four listed rows each (`tmap` then is the
+// one-row-box descriptor of the resident matrix).  Consumers do not change: the rows of a tile
+// land in list order, results go to the compacted slots.
+template <int NC, int STAGES, int DM_MR, bool GATHER>
 __global__ void __launch_bounds__(DM_ROWS / (8 * DM_MR) * 32 + 32) clike_dmma_kernel(
     const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap mmap,
     const LikeArgs a, const int k0, const int kt_valid, const int pass)
@@ -95,8 +111,37 @@ __global__ void __launch_bounds__(DM_ROWS / (8 * DM_MR) * 32 + 32) clike_dmma_ke
 	__syncthreads();
 
 	if (warp == DM_WARPS) {
-		// ===================== producer (one elected thread) =====================
-		if (lane == 0) {
+		// ===================== producer =====================
+		if (GATHER) {
+			int it = 0;
+			for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+				// this lane's two groups of four listed rows (clamped at the end of the list: the
+				// surplus rows of the last tile are computed and dropped)
+				int rows[2][4];
+#pragma unroll
+				for (int q = 0; q < 2; ++q)
+#pragma unroll
+					for (int j = 0; j < 4; ++j) {
+						const long long r = (long long)tile * DM_ROWS + (lane + 32 * q) * 4 + j;
+						rows[q][j] = a.active[r < a.n_rows ? r : a.n_rows - 1];
+					}
+				for (int c = 0; c < nchunks; ++c, ++it) {
+					const int stage = it % STAGES;
+					const uint32_t round = (uint32_t)(it / STAGES);
+					unsigned char *dst = ring + (size_t)stage * STAGE_BYTES;
+					if (lane == 0) {
+						mbar_wait(&empty_bar[stage], (round & 1u) ^ 1u);   // first round passes
+						mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+						dm_tma_load_2d(dst + DM_STAGE_BYTES, &mmap, c * DM_BOX_CH, k0, &full_bar[stage]);
+					}
+					__syncwarp();
+#pragma unroll
+					for (int q = 0; q < 2; ++q)
+						dm_tma_gather4(dst + (lane + 32 * q) * 512, &tmap, c * DM_BOX_CH, rows[q][0],
+						               rows[q][1], rows[q][2], rows[q][3], &full_bar[stage]);
+				}
+			}
+		} else if (lane == 0) {
 			int it = 0;
 			for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
 				const int r0 = a.row0 + tile * DM_ROWS;
@@ -159,7 +204,9 @@ __global__ void __launch_bounds__(DM_ROWS / (8 * DM_MR) * 32 + 32) clike_dmma_ke
 			for (int mr = 0; mr < DM_MR; ++mr) {
 				const long long gr = (long long)tile * DM_ROWS + warp * (8 * DM_MR) + mr * 8 + pr;
 				const bool live = gr < a.n_rows;
-				const double syy = live ? __ldg(a.syy + a.row0 + gr) : 0.0;
+				const double syy = !live ? 0.0
+				                   : GATHER ? __ldg(a.syy + a.active[gr])
+				                            : __ldg(a.syy + a.row0 + gr);
 				bool redo = false;
 #pragma unroll
 				for (int nc = 0; nc < NC; ++nc) {
@@ -201,13 +248,13 @@ int make_row_tensor_map_box(void *out, const double *Y, long long n_rows, long l
 
 int launch_xtile_fixup(const LikeArgs &a, int k0, int kv, int pass, int sm_count, cudaStream_t st);
 
-template <int NC, int STAGES, int DM_MR>
+template <int NC, int STAGES, int DM_MR, bool GATHER>
 static int launch_dmma_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 {
 	constexpr int KT = NC * 8;
 	constexpr int THREADS = DM_ROWS / (8 * DM_MR) * 32 + 32;
 	const size_t smem = dmma_smem(KT, STAGES);
-	auto kern = clike_dmma_kernel<NC, STAGES, DM_MR>;
+	auto kern = clike_dmma_kernel<NC, STAGES, DM_MR, GATHER>;
 	MDNS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int occ = 0;
 	MDNS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
@@ -216,7 +263,7 @@ static int launch_dmma_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 		return MDNS_EINVAL;
 	}
 	CUtensorMap tm, mm;
-	memcpy(&tm, a.tmap256, sizeof tm);
+	memcpy(&tm, GATHER ? a.tmap_gather : a.tmap256, sizeof tm);
 	// the model batch [Kpad][mpitch] as boxes of KT candidates x 16 channels (Kpad is a multiple
 	// of 32, so a box never leaves the buffer)
 	const long long kpad = (long long)round_up(a.K, KT_MAX);
@@ -237,7 +284,7 @@ static int launch_dmma_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 	for (int k0 = 0, pass = 0; k0 < a.K; k0 += KT, ++pass) {
 		const int kv = a.K - k0 < KT ? a.K - k0 : KT;
 		kern<<<(unsigned)gx, THREADS, smem, st>>>(tm, mm, a, k0, kv, pass);
-		MDNS_LAUNCHED("clike_dmma_kernel");
+		MDNS_LAUNCHED(GATHER ? "clike_dmma_kernel(gather)" : "clike_dmma_kernel");
 		const int rc = launch_xtile_fixup(a, k0, kv, pass, sm_count, st);
 		if (rc != MDNS_OK) return rc;
 	}
@@ -247,8 +294,8 @@ static int launch_dmma_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 bool dmma_fits(const LikeArgs &a, int kt, int stages)
 {
 	if (stages > 10) stages -= 10;
-	return a.tmap256 && !a.active && a.syy && a.smm && a.xp_redo && a.xp_list &&
-	       dmma_smem(kt, stages) <= 220 * 1024;
+	return (a.active ? a.tmap_gather != nullptr : a.tmap256 != nullptr) && a.syy && a.smm &&
+	       a.xp_redo && a.xp_list && dmma_smem(kt, stages) <= 220 * 1024;
 }
 
 // kt in {8, 16, 32}; stages in {2, 3, 4}, + 10 for 16 consumer warps of 16 data sets each
@@ -257,13 +304,17 @@ int launch_clike_dmma(const LikeArgs &a, int kt, int stages, int sm_count, cudaS
 {
 	if (a.n_rows <= 0 || a.K <= 0) return MDNS_OK;
 	if (!dmma_fits(a, kt, stages)) {
-		set_error("DMMA tile kernel: needs all-active rows, the resident row sums and %zu bytes of "
+		set_error("DMMA tile kernel: needs the tensor maps, the resident row sums and %zu bytes of "
 		          "shared memory", dmma_smem(kt, stages));
 		return MDNS_EINVAL;
 	}
-#define MDNS_DM(KK, SS)                                                                     \
-	if (kt == KK && stages == SS) return launch_dmma_inst<KK / 8, SS, 4>(a, sm_count, st); \
-	if (kt == KK && stages == SS + 10) return launch_dmma_inst<KK / 8, SS, 2>(a, sm_count, st)
+#define MDNS_DM(KK, SS)                                                                              \
+	if (kt == KK && stages == SS)                                                                \
+		return a.active ? launch_dmma_inst<KK / 8, SS, 4, true>(a, sm_count, st)             \
+		                : launch_dmma_inst<KK / 8, SS, 4, false>(a, sm_count, st);           \
+	if (kt == KK && stages == SS + 10)                                                           \
+		return a.active ? launch_dmma_inst<KK / 8, SS, 2, true>(a, sm_count, st)             \
+		                : launch_dmma_inst<KK / 8, SS, 2, false>(a, sm_count, st)
 	MDNS_DM(8, 2);
 	MDNS_DM(8, 3);
 	MDNS_DM(8, 4);

@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(256) xtile_fixup_kernel(const LikeArgs a, cons
 	const int warps = gridDim.x * 8;
 	const double inv = a.scale / a.noise2;
 	for (int e = blockIdx.x * 8 + (threadIdx.x >> 5); e < n; e += warps) {
-		const int gr = a.xp_list[e];               // row within this launch
-		const double *yrow = a.Y + (long long)gr * a.pitch;
+		const int gr = a.xp_list[e];               // (compacted) row within this launch
+		const double *yrow = a.Y + (long long)(a.active ? a.active[gr] : gr) * a.pitch;
 		for (int k = 0; k < kt_valid; ++k) {
 			const double *m = a.model + (size_t)(k0 + k) * a.mpitch;
 			double s = 0.0;

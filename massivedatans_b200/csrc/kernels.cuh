@@ -54,6 +54,7 @@ struct LikeArgs {
 	long long out_stride;
 	const void *tmap;     // host copies of the rows' CUtensorMaps for 128- and 256-row tiles
 	const void *tmap256;  // (tile kernel) or nullptr
+	const void *tmap_gather;  // one-row boxes of the whole shard for tile::gather4, or nullptr
 	int row0;             // first row of this launch within the shard (tile kernel coordinates)
 	// expanded form (clike_xtile_kernel): Syy - 2 Sym + Smm
 	const double *syy;    // resident sum of squares of every row of the shard, or nullptr

@@ -592,7 +592,7 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 	const int nfrag = (a.nx + 1) >> 1;
 	int L = t.lanes;
 	const bool tile_ok = a.tmap && !a.active && 4LL * a.mpitch <= tile_constant_capacity();
-	if (L == 3 && !a.active) {
+	if (L == 3 && (!a.active || a.tmap_gather)) {
 		// expanded form, cross term as FP64 tensor-core tiles
 		int kt = t.ktile;
 		if (kt != 8 && kt != 16 && kt != 32) kt = a.K >= 32 ? 32 : a.K >= 16 ? 16 : 8;
@@ -624,6 +624,16 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		if (tile_rows == 128 && nbox == 1 && stages == 3) stages = 4;
 		return launch_clike_tile(a, tile_rows == 256 ? a.tmap256 : a.tmap, kt, nbox, stages,
 		                         tile_rows, sm_count, st);
+	}
+	if (L == 0 && t.unroll == 0 && t.ktile == 0 && t.rows == 0 && a.active && a.tmap_gather &&
+	    t.allow_expanded && a.K >= 16 && a.n_rows >= 32768) {
+		// masked candidate batches: the tensor path fed by gather4 copies of the listed rows.
+		// The gather is bound by the issue rate of its 512-byte copies (~0.58 of the HBM roofline
+		// with two producer warps per SM), so it only pays where the block kernel is bound by
+		// shared memory and the FP64 pipe (measured, 5e5 active of 1e6 data sets: K=8 0.219 ms vs
+		// 0.185 ms block kernel; K=16 0.234 vs 0.362; K=32 0.43 vs 0.71).
+		if (a.K >= 32 && dmma_fits(a, 32, 3)) return launch_clike_dmma(a, 32, 3, sm_count, st);
+		if (dmma_fits(a, 16, 3)) return launch_clike_dmma(a, 16, 3, sm_count, st);
 	}
 	if (L == 1 || L == 2 || L == 3) {
 		// tile kernel requested but not applicable (masked rows): automatic choice

@@ -194,6 +194,53 @@ def test_clike_expanded_tensor_path_variants(oracle_port, ktile, stages, N, nx, 
     assert rel_err(got, fma_form) < TOL_XP
 
 
+@pytest.mark.parametrize('ktile,stages', [(8, 2), (8, 14), (16, 3), (16, 13), (32, 3), (32, 12)])
+@pytest.mark.parametrize('N,nx,K', [(700, 203, 9), (70000, 200, 37), (2049, 57, 20)])
+def test_clike_expanded_tensor_path_masked_gather(oracle_port, ktile, stages, N, nx, K):
+    # masked batches on the tensor path: rows fetched with gather4 copies of the active list
+    x, y, _ = synth.horns(N, nx=nx, legacy=False, seed=N + 5)
+    ds = ResidentDataset(x, y)
+    ds.set_tuning(3, 0, ktile, stages)
+    pts = synth.parameter_points(K, seed=N + 6)
+    for name, m in synth.masks(N, seed=N).items():
+        if name == 'all' or not m.any():
+            continue
+        got = ds.loglike_batch(pts, m, synth.NOISE_LEVEL, scale=1.0)
+        assert _lib.load().mdns_last_kernel() == b'clike_dmma_kernel(gather)'
+        assert got.shape == (K, int(m.sum()))
+        for k in sorted(set((0, 7, 8, K // 2, K - 1))):
+            p = pts[k]
+            want = oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, m)
+            assert rel_err(got[k], want) < TOL_XP, (name, k)
+    assert ds.expanded_stats() == (True, 0)
+
+
+def test_clike_masked_batches_automatic_choice(oracle_port):
+    # masked batches: block kernel below 16 candidates, gather-fed tensor path from 16 on
+    N = 80000
+    x, y, _ = synth.horns(N, legacy=False, seed=8)
+    ds = ResidentDataset(x, y)
+    lib = _lib.load()
+    m = synth.masks(N)['half']
+    pts = synth.parameter_points(20, seed=9)
+    got = ds.loglike_batch(pts, m, synth.NOISE_LEVEL)
+    assert lib.mdns_last_kernel() == b'clike_dmma_kernel(gather)'
+    for k in (0, 15, 16, 19):
+        p = pts[k]
+        want = -0.5 * oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, m)
+        assert rel_err(got[k], want) < TOL_XP
+    small = ds.loglike_batch(pts[:8], m, synth.NOISE_LEVEL)
+    assert lib.mdns_last_kernel() in (b'clike_block_kernel', b'clike_rows_kernel')
+    assert rel_err(small, got[:8]) < TOL_XP
+    # first-accept on a masked batch of 20 goes through the same kernel
+    Ls = numpy.array(got)
+    Lmins = Ls[:18].max(axis=0) + 1e-9 * numpy.abs(Ls[:18].max(axis=0))
+    k, L, counts = ds.first_accepted(pts, m, Lmins, synth.NOISE_LEVEL)
+    want_counts = (Ls > Lmins).sum(axis=1)
+    assert numpy.array_equal(counts, want_counts)
+    assert k == (int(numpy.argmax(want_counts > 0)) if (want_counts > 0).any() else -1)
+
+
 def test_clike_expanded_form_automatic_choice(oracle_port):
     # all-active batches of >= 3 candidates take the expanded form on their own; masks and
     # smaller batches stay on the direct kernels
@@ -223,7 +270,8 @@ def test_clike_expanded_form_automatic_choice(oracle_port):
 
 
 @pytest.mark.parametrize('tuning,kernel', [((2, 2, 8, 3), b'clike_xtile_kernel'),
-                                           ((3, 0, 8, 2), b'clike_dmma_kernel')])
+                                           ((3, 0, 8, 2), b'clike_dmma_kernel'),
+                                           ((3, 0, 8, 13), b'clike_dmma_kernel')])
 def test_clike_expanded_form_cancellation_guard(oracle_port, tuning, kernel):
     # data that the candidate fits to ~1e-7 of its amplitude: Syy, Sym and Smm agree to 14
     # digits and their combination would be rounding noise.  Those (data set, candidate) pairs
