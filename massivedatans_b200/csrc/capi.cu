@@ -411,6 +411,14 @@ int mdns_set_mask(mdns_dataset *ds, const uint8_t *mask, int *n_act_out)
 		set_error("null data set");
 		return MDNS_EINVAL;
 	}
+	// The same partial mask as last time (one constrained draw keeps calling with the same
+	// joint_data_mask, hiermetriclearn.py:185): the active lists on the devices, the staged
+	// thresholds and the launch state all stay valid.
+	if (mask && ds->host_mask.size() == (size_t)ds->ndata &&
+	    memcmp(mask, ds->host_mask.data(), (size_t)ds->ndata) == 0) {
+		if (n_act_out) *n_act_out = ds->n_act_total;
+		return MDNS_OK;
+	}
 	int total = 0;
 	bool all = true;
 	for (auto &s : ds->shards) {

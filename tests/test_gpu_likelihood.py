@@ -333,6 +333,36 @@ def test_clike_empty_mask_and_reuse(horns257):
     assert got.shape == (2, 1) and numpy.isfinite(got).all()
 
 
+def test_clike_mask_cache_and_changes(oracle_port):
+    # the shim skips the upload/compaction of a mask it already holds; a changed mask of the same
+    # size, the all-true mask and None must all take effect
+    N = 3001
+    x, y, _ = synth.horns(N, seed=2)
+    ds = ResidentDataset(x, y)
+    p = synth.parameter_points(2, seed=1)
+    rs = numpy.random.RandomState(0)
+    m1 = rs.uniform(size=N) < 0.4
+    m2 = m1.copy()
+    m2[5] = not m2[5]
+    seq = [m1, m1, m2, m2, numpy.ones(N, dtype=bool), m1, None, m2, m1.copy()]
+    for m in seq:
+        got = ds.loglike_batch(p, m, synth.NOISE_LEVEL, scale=1.0)
+        mm = numpy.ones(N, dtype=bool) if m is None else m
+        assert got.shape == (2, int(mm.sum()))
+        for k in range(2):
+            want = oracle_port.clike(x, y, p[k][0], p[k][1], p[k][2], synth.NOISE_LEVEL, mm)
+            assert rel_err(got[k], want) < TOL
+    # staged draw: thresholds survive a repeated identical mask, not a different one
+    Lm = numpy.full(int(m1.sum()), -1e300)
+    ds.begin_draw(m1, Lm)
+    ds.set_mask(m1)
+    k, L, counts = ds.draw_batch(p, synth.NOISE_LEVEL)
+    assert k == 0 and (counts == int(m1.sum())).all()
+    ds.set_mask(m2)
+    with pytest.raises(_lib.MdnsError):
+        ds.draw_batch(p, synth.NOISE_LEVEL)
+
+
 def test_clike_linearity_property_large():
     # size-independent property at a size the oracle would not finish quickly:
     # chi2(A=0) = sum (y/noise)^2 (plotevidences.py:17), checked with numpy column sums
