@@ -85,7 +85,8 @@ int launch_accept_count(const double *L, long long stride, int n, int K, const d
                         int *counts, cudaStream_t st);
 // MUSE-type, one CTA per data set, rows staged once through a bulk-TMA ring (muse_block_kernel.cu)
 bool muse_block_fits(const LikeArgs &a);
-int launch_muse_block(const LikeArgs &a, int ktile, int sm_count, cudaStream_t st);
+// groups: 1 or 2 data sets in flight per CTA (0 = automatic)
+int launch_muse_block(const LikeArgs &a, int ktile, int groups, int sm_count, cudaStream_t st);
 // lane-per-data-set kernel fed by a bulk-TMA ring (clike_tile_kernel.cu)
 int launch_clike_tile(const LikeArgs &a, const void *tmap, int kt, int nbox, int stages,
                       int tile_rows, int sm_count, cudaStream_t st);

@@ -864,7 +864,7 @@ int launch_muse(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t s
 	int L = t.lanes;
 	// long rows: one CTA per data set, rows staged once through a bulk-TMA ring
 	if ((L == 0 || L == 256) && muse_block_fits(a) && (L == 256 || nfrag >= 256))
-		return launch_muse_block(a, t.ktile, sm_count, st);
+		return launch_muse_block(a, t.ktile, t.rows, sm_count, st);
 	if (L != 8 && L != 32) L = (a.n_rows >= 16384 && nfrag >= 8 && nfrag <= 8 * 16) ? 8 : 32;
 	const int per_lane = ceil_div(nfrag, L);
 	int U = t.unroll;

@@ -14,8 +14,13 @@
 //     while both passes run out of registers; KT candidate spectra are register-blocked per
 //     pass and come from L1/L2 through the read-only path.  Longer rows (NF = 0) re-read
 //     the slot from shared memory in both passes;
-//   * block-wide FP64 reductions: warp butterfly + fixed-order sum of the 8 warp partials,
-//     so the result does not depend on scheduling.
+//   * block-wide FP64 reductions: warp butterfly + fixed-order sum of the warp partials,
+//     so the result does not depend on scheduling;
+//   * G = 2: the CTA is split into two groups of 256 threads that work on alternate data sets
+//     of the CTA's list with their own named barriers.  With one data set at a time the two
+//     passes and their two block-wide reductions form a latency chain of ~1.8 us per row, longer
+//     than the 1.3 us the row takes to arrive at the SM's share of HBM bandwidth (measured on the
+//     4223 x 3600 cube: 52 us = 0.71 of the roofline); two rows in flight hide it.
 //
 // The resident W holds 1/v (computed once at upload with a correctly rounded division), so
 // the kernel multiplies where the reference divides: y*m/v -> y*(m*w).  Differences to the
@@ -29,11 +34,19 @@ constexpr int MB_WARPS = MB_THREADS / 32;
 constexpr int MB_STAGES = 3;
 constexpr size_t MB_SMEM_LIMIT = 220 * 1024;
 
-template <int N, int NCOL>
-__device__ __forceinline__ void block_sum(double (&v)[N], double (*red)[MB_WARPS][NCOL])
+// named barrier of one thread group (barrier 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(int group, int nthreads)
 {
-	// red points at one of two alternating scratch buffers (see caller)
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(nthreads) : "memory");
+}
+
+// sum over the TG threads of one group; `red` is one of the group's two alternating buffers
+template <int N, int NCOL, int TG>
+__device__ __forceinline__ void group_sum(double (&v)[N], double (*red)[MB_WARPS][NCOL], int group,
+                                          int gtid)
+{
+	constexpr int GW = TG / 32;
+	const int warp = gtid >> 5, lane = gtid & 31;
 #pragma unroll
 	for (int i = 0; i < N; ++i) {
 #pragma unroll
@@ -43,35 +56,41 @@ __device__ __forceinline__ void block_sum(double (&v)[N], double (*red)[MB_WARPS
 #pragma unroll
 		for (int i = 0; i < N; ++i) (*red)[warp][i] = v[i];
 	}
-	__syncthreads();
+	group_sync(group, TG);
 #pragma unroll
 	for (int i = 0; i < N; ++i) {
 		double s = 0.0;
 #pragma unroll
-		for (int w = 0; w < MB_WARPS; ++w) s += (*red)[w][i];
+		for (int w = 0; w < GW; ++w) s += (*red)[w][i];
 		v[i] = s;
 	}
 }
 
-template <int KT, int NF>
+template <int KT, int NF, int G>
 __global__ void __launch_bounds__(MB_THREADS, 1) muse_block_kernel(const LikeArgs a)
 {
+	constexpr int TG = MB_THREADS / G;            // threads per group
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	__shared__ uint64_t full_bar[MB_STAGES];
-	__shared__ double red[2][MB_WARPS][2 * KT];
+	constexpr int PERIOD = (G == 1 || MB_STAGES % 2 == 0) ? MB_STAGES : 2 * MB_STAGES;
+	static_assert(G == 1 || G == 2, "one or two data sets in flight");
+	__shared__ uint64_t full_bar[G][MB_STAGES];
+	__shared__ double red[G][2][MB_WARPS][2 * KT];
 	const int nfrag = (a.nx + 1) >> 1;
 	const int mfp = a.mpitch >> 1;
 	const uint32_t row_bytes = (uint32_t)a.pitch * 8u;
 	const size_t slot_bytes = 2 * (size_t)row_bytes;
+	const int group = threadIdx.x / TG, gtid = threadIdx.x % TG;
 
 	if (threadIdx.x == 0) {
 #pragma unroll
-		for (int s = 0; s < MB_STAGES; ++s) mbar_init(&full_bar[s], 1);
+		for (int s = 0; s < MB_STAGES; ++s)
+#pragma unroll
+			for (int g = 0; g < G; ++g) mbar_init(&full_bar[g][s], 1);
 		mbar_fence_init();
 	}
 	__syncthreads();
 
-	// rows of this CTA: r = blockIdx.x + it * gridDim.x
+	// rows of this CTA: r = blockIdx.x + it * gridDim.x; group g takes it = g, g + G, ...
 	const long long nmine = a.n_rows > (long long)blockIdx.x
 	                            ? (a.n_rows - blockIdx.x + gridDim.x - 1) / gridDim.x
 	                            : 0;
@@ -80,9 +99,10 @@ __global__ void __launch_bounds__(MB_THREADS, 1) muse_block_kernel(const LikeArg
 		const long long row = a.active ? (long long)a.active[r] : r;
 		const int slot = (int)(it % MB_STAGES);
 		unsigned char *dst = smem_raw + slot * slot_bytes;
-		mbar_expect_tx(&full_bar[slot], 2 * row_bytes);
-		tma_load_1d(dst, a.Y + row * a.pitch, row_bytes, &full_bar[slot]);
-		tma_load_1d(dst + row_bytes, a.W + row * a.pitch, row_bytes, &full_bar[slot]);
+		uint64_t *bar = &full_bar[it % G][slot];      // the barrier of the group that will read it
+		mbar_expect_tx(bar, 2 * row_bytes);
+		tma_load_1d(dst, a.Y + row * a.pitch, row_bytes, bar);
+		tma_load_1d(dst + row_bytes, a.W + row * a.pitch, row_bytes, bar);
 	};
 	if (threadIdx.x == 0) {
 		for (long long it = 0; it < MB_STAGES && it < nmine; ++it) issue(it);
@@ -90,11 +110,16 @@ __global__ void __launch_bounds__(MB_THREADS, 1) muse_block_kernel(const LikeArg
 
 	const double2 *model = reinterpret_cast<const double2 *>(a.model);
 	int flip = 0;
-	for (long long it = 0; it < nmine; ++it) {
+	for (long long it = group; it < nmine; it += G) {
 		const int slot = (int)(it % MB_STAGES);
 		const long long r = (long long)blockIdx.x + it * gridDim.x;
 		const long long row = a.active ? (long long)a.active[r] : r;
-		mbar_wait(&full_bar[slot], (uint32_t)((it / MB_STAGES) & 1));
+		// Every (group, slot) pair has its own barrier: with two groups a slot alternates
+		// between them, and a parity wait is only sound for a waiter that consumed the
+		// immediately preceding phase of the barrier it waits on (a shared per-slot barrier
+		// let a group that was two phases behind pass on the phase in between: wrong rows,
+		// then a launch failure).  Row `it` returns to the same (group, slot) every PERIOD rows.
+		mbar_wait(&full_bar[group][slot], (uint32_t)((it / PERIOD) & 1));
 		const double2 *sy = reinterpret_cast<const double2 *>(smem_raw + slot * slot_bytes);
 		const double2 *sw = reinterpret_cast<const double2 *>(smem_raw + slot * slot_bytes + row_bytes);
 
@@ -104,17 +129,17 @@ __global__ void __launch_bounds__(MB_THREADS, 1) muse_block_kernel(const LikeArg
 		if (NF > 0) {
 #pragma unroll
 			for (int i = 0; i < NR; ++i) {
-				const int f = threadIdx.x + i * MB_THREADS;
+				const int f = gtid + i * TG;
 				ry[i] = rw[i] = make_double2(0.0, 0.0);
 				if (f < nfrag) {
 					ry[i] = sy[f];
 					rw[i] = sw[f];
 				}
 			}
-			__syncthreads();   // everybody has its fragments: refill the slot
-			if (threadIdx.x == 0 && it + MB_STAGES < nmine) issue(it + MB_STAGES);
+			group_sync(group, TG);   // the whole group has its fragments: refill the slot
+			if (gtid == 0 && it + MB_STAGES < nmine) issue(it + MB_STAGES);
 		}
-		const int niter = NF > 0 ? NF : (nfrag + MB_THREADS - 1) / MB_THREADS;
+		const int niter = NF > 0 ? NF : (nfrag + TG - 1) / TG;
 
 		for (int k0 = 0; k0 < a.K; k0 += KT) {
 			// ---- pass 1: s1 = sum y*m*w, s2 = sum m*m*w (cmuselike.c:51-56)
@@ -123,7 +148,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) muse_block_kernel(const LikeArg
 			for (int i = 0; i < 2 * KT; ++i) acc[i] = 0.0;
 #pragma unroll
 			for (int i = 0; i < niter; ++i) {
-				const int f = threadIdx.x + i * MB_THREADS;
+				const int f = gtid + i * TG;
 				if (f < nfrag) {
 					const double2 y = NF > 0 ? ry[NF > 0 ? i : 0] : sy[f];
 					const double2 w = NF > 0 ? rw[NF > 0 ? i : 0] : sw[f];
@@ -138,7 +163,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) muse_block_kernel(const LikeArg
 					}
 				}
 			}
-			block_sum<2 * KT, 2 * KT>(acc, &red[flip]);
+			group_sum<2 * KT, 2 * KT, TG>(acc, &red[group][flip], group, gtid);
 			flip ^= 1;
 			double s[KT];
 #pragma unroll
@@ -149,7 +174,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) muse_block_kernel(const LikeArg
 			for (int k = 0; k < KT; ++k) chi[k] = 0.0;
 #pragma unroll
 			for (int i = 0; i < niter; ++i) {
-				const int f = threadIdx.x + i * MB_THREADS;
+				const int f = gtid + i * TG;
 				if (f < nfrag) {
 					const double2 y = NF > 0 ? ry[NF > 0 ? i : 0] : sy[f];
 					const double2 w = NF > 0 ? rw[NF > 0 ? i : 0] : sw[f];
@@ -163,17 +188,17 @@ __global__ void __launch_bounds__(MB_THREADS, 1) muse_block_kernel(const LikeArg
 					}
 				}
 			}
-			block_sum<KT, 2 * KT>(chi, &red[flip]);
+			group_sum<KT, 2 * KT, TG>(chi, &red[group][flip], group, gtid);
 			flip ^= 1;
-			if (threadIdx.x == 0) {
+			if (gtid == 0) {
 #pragma unroll
 				for (int k = 0; k < KT; ++k)
 					if (k0 + k < a.K) a.out[(long long)(k0 + k) * a.out_stride + row] = -0.5 * chi[k];
 			}
 		}
 		if (NF == 0) {
-			__syncthreads();   // everybody is done with the slot: refill it
-			if (threadIdx.x == 0 && it + MB_STAGES < nmine) issue(it + MB_STAGES);
+			group_sync(group, TG);   // the group is done with the slot: refill it
+			if (gtid == 0 && it + MB_STAGES < nmine) issue(it + MB_STAGES);
 		}
 	}
 }
@@ -184,11 +209,11 @@ bool muse_block_fits(const LikeArgs &a)
 	       (size_t)a.pitch * 8 < (1u << 19);   // mbarrier tx-count range
 }
 
-template <int KT, int NF>
+template <int KT, int NF, int G>
 static int launch_muse_block_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 {
 	const size_t smem = MB_STAGES * 2 * (size_t)a.pitch * 8;
-	auto kern = muse_block_kernel<KT, NF>;
+	auto kern = muse_block_kernel<KT, NF, G>;
 	MDNS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int occ = 0;
 	MDNS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MB_THREADS, smem));
@@ -205,28 +230,40 @@ static int launch_muse_block_inst(const LikeArgs &a, int sm_count, cudaStream_t 
 }
 
 template <int KT>
-static int launch_muse_block_k(const LikeArgs &a, int sm_count, cudaStream_t st)
+static int launch_muse_block_k(const LikeArgs &a, int groups, int sm_count, cudaStream_t st)
 {
 	const int nfrag = (a.nx + 1) >> 1;
+	if (groups == 2) {
+		// two data sets in flight per CTA, 256 threads each
+		const int per_thread = ceil_div(nfrag, MB_THREADS / 2);
+		if (per_thread <= 2) return launch_muse_block_inst<KT, 2, 2>(a, sm_count, st);
+		if (per_thread <= 4) return launch_muse_block_inst<KT, 4, 2>(a, sm_count, st);
+		if (per_thread <= 8) return launch_muse_block_inst<KT, 8, 2>(a, sm_count, st);
+		return launch_muse_block_inst<KT, 0, 2>(a, sm_count, st);
+	}
 	const int per_thread = ceil_div(nfrag, MB_THREADS);
-	if (per_thread <= 1) return launch_muse_block_inst<KT, 1>(a, sm_count, st);
-	if (per_thread <= 2) return launch_muse_block_inst<KT, 2>(a, sm_count, st);
-	if (per_thread <= 4) return launch_muse_block_inst<KT, 4>(a, sm_count, st);
-	if (per_thread <= 8) return launch_muse_block_inst<KT, 8>(a, sm_count, st);
-	return launch_muse_block_inst<KT, 0>(a, sm_count, st);
+	if (per_thread <= 1) return launch_muse_block_inst<KT, 1, 1>(a, sm_count, st);
+	if (per_thread <= 2) return launch_muse_block_inst<KT, 2, 1>(a, sm_count, st);
+	if (per_thread <= 4) return launch_muse_block_inst<KT, 4, 1>(a, sm_count, st);
+	if (per_thread <= 8) return launch_muse_block_inst<KT, 8, 1>(a, sm_count, st);
+	return launch_muse_block_inst<KT, 0, 1>(a, sm_count, st);
 }
 
-int launch_muse_block(const LikeArgs &a, int ktile, int sm_count, cudaStream_t st)
+int launch_muse_block(const LikeArgs &a, int ktile, int groups, int sm_count, cudaStream_t st)
 {
 	if (a.n_rows <= 0 || a.K <= 0) return MDNS_OK;
 	int kt = ktile;
 	// 512 threads cap the kernel at 128 registers: four candidates per pass spill once the
 	// row fragments live in registers, so the automatic choice stops at two
 	if (kt != 1 && kt != 2 && kt != 4) kt = a.K >= 2 ? 2 : 1;
+	if (groups != 1 && groups != 2) groups = 2;
+	// two groups hold twice the fragments per thread: one candidate per pass keeps them in
+	// registers
+	if (groups == 2 && kt > 1 && ktile == 0) kt = 1;
 	switch (kt) {
-	case 1: return launch_muse_block_k<1>(a, sm_count, st);
-	case 2: return launch_muse_block_k<2>(a, sm_count, st);
-	default: return launch_muse_block_k<4>(a, sm_count, st);
+	case 1: return launch_muse_block_k<1>(a, groups, sm_count, st);
+	case 2: return launch_muse_block_k<2>(a, groups, sm_count, st);
+	default: return launch_muse_block_k<4>(a, groups, sm_count, st);
 	}
 }
 

@@ -473,7 +473,8 @@ def test_muse_golden(golden):
     assert (Ls[0, ~sm] == 5.0).all()
 
 
-@pytest.mark.parametrize('ndata,nspec', [(1, 2), (50, 37), (3000, 360), (20000, 64), (300, 3600)])
+@pytest.mark.parametrize('ndata,nspec', [(1, 2), (50, 37), (3000, 360), (20000, 64), (300, 3600),
+                                         (4223, 3600), (6000, 1030), (2500, 8190)])
 def test_muse_vs_oracle(oracle_port, ndata, nspec):
     y, v, t = synth.muse(ndata=ndata, nspec=nspec, seed=ndata)
     ds = ResidentDataset(None, y, variance=v)
@@ -504,6 +505,26 @@ def test_muse_kernel_variants_and_batches(oracle_port, lanes, unroll, ktile, nda
             want = oracle_port.cmuselike(y, v, ypreds[k], mask)
             assert rel_err(L[k][mask], want[mask]) < TOL
             assert (L[k][~mask] == 3.0).all()
+
+
+@pytest.mark.parametrize('groups', [1, 2])
+@pytest.mark.parametrize('K', [1, 3])
+def test_muse_block_kernel_many_rows_per_cta(oracle_port, groups, K):
+    # more rows than resident CTAs: the ring is refilled many times; with two groups of threads
+    # per CTA the data sets of a CTA alternate between the groups (per-group mbarriers)
+    ndata, nspec = 5000, 2048
+    y, v, t = synth.muse(ndata=ndata, nspec=nspec, seed=21)
+    ds = ResidentDataset(None, y, variance=v)
+    ds.set_tuning(256, 0, 0, groups)
+    ypreds = numpy.array([synth.muse_template(nspec, phase=0.3 * k) for k in range(K)])
+    mask = numpy.random.RandomState(4).uniform(size=ndata) < 0.8
+    L = numpy.zeros((K, ndata))
+    for _ in range(3):                       # repeated launches: no state is carried over
+        ds.muse_loglike(ypreds, mask, L)
+    assert _lib.load().mdns_last_kernel() == b'muse_block_kernel'
+    for k in range(K):
+        want = oracle_port.cmuselike(y, v, ypreds[k], mask)
+        assert rel_err(L[k][mask], want[mask]) < TOL
 
 
 def test_muse_callable_matches_reference_wrapper(oracle_port):
