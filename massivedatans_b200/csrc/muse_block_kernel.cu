@@ -257,9 +257,6 @@ int launch_muse_block(const LikeArgs &a, int ktile, int groups, int sm_count, cu
 	// row fragments live in registers, so the automatic choice stops at two
 	if (kt != 1 && kt != 2 && kt != 4) kt = a.K >= 2 ? 2 : 1;
 	if (groups != 1 && groups != 2) groups = 2;
-	// two groups hold twice the fragments per thread: one candidate per pass keeps them in
-	// registers
-	if (groups == 2 && kt > 1 && ktile == 0) kt = 1;
 	switch (kt) {
 	case 1: return launch_muse_block_k<1>(a, groups, sm_count, st);
 	case 2: return launch_muse_block_k<2>(a, groups, sm_count, st);
