@@ -79,6 +79,24 @@ struct Shard {
 	int *d_redo = nullptr;        // counters of the expanded kernel's direct-form fix-ups
 	int *d_redo_list = nullptr;   // and the rows to fix up in the current pass
 	bool counters_clear = false;  // per-pass counters already reset by the model kernel
+	// mdns_clike_launch as a CUDA graph (model kernel -> likelihood kernel(s) -> fix-up): replayed
+	// while nothing it was captured with has changed
+	cudaGraphExec_t graph = nullptr;
+	long long graph_launches = 0;     // kernel launches one replay stands for
+	const char *graph_kernel = "";
+	struct GraphKey {
+		int K = -1, staged = 0, n_act = -1, all_active = 0;
+		int lanes = 0, unroll = 0, ktile = 0, rows = 0, allow_expanded = 0;
+		double noise = 0, scale = 0, xp_tol = 0;
+		const void *model = nullptr, *out = nullptr, *in = nullptr, *smm = nullptr;
+		bool operator==(const GraphKey &o) const
+		{
+			return K == o.K && staged == o.staged && n_act == o.n_act && all_active == o.all_active &&
+			       lanes == o.lanes && unroll == o.unroll && ktile == o.ktile && rows == o.rows &&
+			       allow_expanded == o.allow_expanded && noise == o.noise && scale == o.scale &&
+			       xp_tol == o.xp_tol && model == o.model && out == o.out && in == o.in && smm == o.smm;
+		}
+	} graph_key;
 	int n_act = 0;
 	bool all_active = true;
 	alignas(64) unsigned char tmap[128];      // CUtensorMaps of Y (tile kernel), 128-row boxes
@@ -129,6 +147,7 @@ static void shard_free(Shard &s)
 	cudaFree(s.d_smm);
 	cudaFree(s.d_redo);
 	cudaFree(s.d_redo_list);
+	if (s.graph) cudaGraphExecDestroy(s.graph);
 	if (s.h_stage) cudaFreeHost(s.h_stage);
 	if (s.ev0) cudaEventDestroy(s.ev0);
 	if (s.ev1) cudaEventDestroy(s.ev1);
@@ -648,10 +667,73 @@ int mdns_clike_launch(mdns_dataset *ds, double noise, double scale)
 {
 	int rc = clike_check(ds, "mdns_clike_launch");
 	if (rc != MDNS_OK) return rc;
+	static const bool use_graph = []() {
+		const char *e = getenv("MDNS_NO_GRAPH");
+		return !(e && *e && *e != '0');
+	}();
 	for (auto &s : ds->shards) {
 		MDNS_CUDA(cudaSetDevice(s.device));
-		if ((rc = clike_model(ds, s)) != MDNS_OK) return rc;
-		if ((rc = clike_rows(ds, s, noise, scale, 0, s.n_act)) != MDNS_OK) return rc;
+		if (!use_graph) {
+			if ((rc = clike_model(ds, s)) != MDNS_OK) return rc;
+			if ((rc = clike_rows(ds, s, noise, scale, 0, s.n_act)) != MDNS_OK) return rc;
+			continue;
+		}
+		// The launch sequence (model kernel, likelihood kernel per pass, fix-up) depends only on
+		// what the key holds; the inputs it reads (parameter points, active list, data) live in
+		// device buffers whose contents may change between replays.
+		Shard::GraphKey key;
+		key.K = ds->K;
+		key.staged = ds->staged;
+		key.n_act = s.n_act;
+		key.all_active = s.all_active ? 1 : 0;
+		key.lanes = ds->tuning.lanes;
+		key.unroll = ds->tuning.unroll;
+		key.ktile = ds->tuning.ktile;
+		key.rows = ds->tuning.rows;
+		key.allow_expanded = ds->tuning.allow_expanded ? 1 : 0;
+		key.noise = noise;
+		key.scale = scale;
+		key.xp_tol = ds->xp_tol;
+		key.model = s.d_model;
+		key.out = s.d_out;
+		key.in = s.d_in;
+		key.smm = s.d_smm;
+		if (s.graph && key == s.graph_key) {
+			MDNS_CUDA(cudaGraphLaunch(s.graph, s.stream));
+			g_launches.fetch_add(s.graph_launches, std::memory_order_relaxed);
+			g_last_kernel.store(s.graph_kernel, std::memory_order_relaxed);
+			continue;
+		}
+		if (s.graph) {
+			cudaGraphExecDestroy(s.graph);
+			s.graph = nullptr;
+		}
+		const long long before = g_launches.load();
+		MDNS_CUDA(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+		rc = clike_model(ds, s);
+		if (rc == MDNS_OK) rc = clike_rows(ds, s, noise, scale, 0, s.n_act);
+		cudaGraph_t g = nullptr;
+		const cudaError_t e = cudaStreamEndCapture(s.stream, &g);
+		if (rc != MDNS_OK) {
+			if (g) cudaGraphDestroy(g);
+			cudaGetLastError();
+			return rc;
+		}
+		if (e != cudaSuccess || !g) {
+			set_error("stream capture of the likelihood launch failed: %s", cudaGetErrorString(e));
+			return MDNS_ECUDA;
+		}
+		const cudaError_t ei = cudaGraphInstantiate(&s.graph, g, 0);
+		cudaGraphDestroy(g);
+		if (ei != cudaSuccess) {
+			s.graph = nullptr;
+			set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+			return MDNS_ECUDA;
+		}
+		s.graph_key = key;
+		s.graph_launches = g_launches.load() - before;   // counted once at capture: the first replay
+		s.graph_kernel = g_last_kernel.load();
+		MDNS_CUDA(cudaGraphLaunch(s.graph, s.stream));
 	}
 	ds->launched = 1;
 	return MDNS_OK;
