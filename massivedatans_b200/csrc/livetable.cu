@@ -540,8 +540,7 @@ int mdns_livetable_upload_points(mdns_livetable *t, const int64_t *live_pointsp)
 	const size_t chunk = (size_t)1 << 24;
 	long long *stage = nullptr;
 	MDNS_CUDA(cudaMalloc((void **)&stage, std::min(chunk, count) * sizeof(long long)));
-	MDNS_CUDA(cudaMemsetAsync(t->d_flag, 0, 2 * sizeof(int), s.stream));
-	cudaError_t e = cudaSuccess;
+	cudaError_t e = cudaMemsetAsync(t->d_flag, 0, 2 * sizeof(int), s.stream);
 	for (size_t o = 0; o < count && e == cudaSuccess; o += chunk) {
 		const size_t c = std::min(chunk, count - o);
 		e = cudaMemcpyAsync(stage, live_pointsp + o, c * sizeof(long long), cudaMemcpyHostToDevice,
