@@ -588,7 +588,7 @@ static bool xp_candidate(const mdns_dataset *ds, const Shard &s)
 		// masked batches: only the tensor path has a gather form
 		if (!s.has_gather) return false;
 		if (ds->tuning.lanes == 3) return true;
-		return ds->tuning.lanes == 0 && ds->K >= 16 && ds->tuning.allow_expanded;
+		return ds->tuning.lanes == 0 && ds->K >= XP_MIN_K_MASKED && ds->tuning.allow_expanded;
 	}
 	if (ds->tuning.lanes == 2 || ds->tuning.lanes == 3) return true;   // explicit request
 	return ds->tuning.lanes == 0 && ds->K >= XP_MIN_K && ds->tuning.allow_expanded;

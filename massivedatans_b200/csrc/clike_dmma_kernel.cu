@@ -77,12 +77,14 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
 
 // NC candidate tiles (of 8) and DM_MR row tiles (of 8 data sets) per consumer warp;
 // DM_ROWS / (8 * DM_MR) consumer warps per CTA.
-// GATHER: the active data sets are listed in a.active (masked batch); the 32 lanes of the
-// producer warp fill a stage with 64 gather4 copies of four listed rows each (`tmap` then is the
-// one-row-box descriptor of the resident matrix).  Consumers do not change: the rows of a tile
-// land in list order, results go to the compacted slots.
+// GATHER: the active data sets are listed in a.active (masked batch); the 64 lanes of TWO
+// producer warps fill a stage with 64 gather4 copies of four listed rows each (`tmap` then is
+// the one-row-box descriptor of the resident matrix).  The gather is bound by the issue rate of
+// these 512-byte copies per producer warp (one warp per CTA: 0.215 ms for 5e5 active rows at
+// K = 8, twice that with one CTA per SM), hence the second warp.  Consumers do not change: the
+// rows of a tile land in list order, results go to the compacted slots.
 template <int NC, int STAGES, int DM_MR, bool GATHER>
-__global__ void __launch_bounds__(DM_ROWS / (8 * DM_MR) * 32 + 32) clike_dmma_kernel(
+__global__ void __launch_bounds__(DM_ROWS / (8 * DM_MR) * 32 + (GATHER ? 64 : 32)) clike_dmma_kernel(
     const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap mmap,
     const LikeArgs a, const int k0, const int kt_valid, const int pass)
 {
@@ -110,35 +112,34 @@ __global__ void __launch_bounds__(DM_ROWS / (8 * DM_MR) * 32 + 32) clike_dmma_ke
 	}
 	__syncthreads();
 
-	if (warp == DM_WARPS) {
+	if (warp >= DM_WARPS) {
 		// ===================== producer =====================
 		if (GATHER) {
+			const int pl = (warp - DM_WARPS) * 32 + lane;     // 0..63: one group of four rows each
 			int it = 0;
 			for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-				// this lane's two groups of four listed rows (clamped at the end of the list: the
-				// surplus rows of the last tile are computed and dropped)
-				int rows[2][4];
+				// this lane's four listed rows (clamped at the end of the list: the surplus rows
+				// of the last tile are computed and dropped)
+				int rows[4];
 #pragma unroll
-				for (int q = 0; q < 2; ++q)
-#pragma unroll
-					for (int j = 0; j < 4; ++j) {
-						const long long r = (long long)tile * DM_ROWS + (lane + 32 * q) * 4 + j;
-						rows[q][j] = a.active[r < a.n_rows ? r : a.n_rows - 1];
-					}
+				for (int j = 0; j < 4; ++j) {
+					const long long r = (long long)tile * DM_ROWS + pl * 4 + j;
+					rows[j] = a.active[r < a.n_rows ? r : a.n_rows - 1];
+				}
 				for (int c = 0; c < nchunks; ++c, ++it) {
 					const int stage = it % STAGES;
 					const uint32_t round = (uint32_t)(it / STAGES);
 					unsigned char *dst = ring + (size_t)stage * STAGE_BYTES;
-					if (lane == 0) {
+					if (pl == 0) {
 						mbar_wait(&empty_bar[stage], (round & 1u) ^ 1u);   // first round passes
 						mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
 						dm_tma_load_2d(dst + DM_STAGE_BYTES, &mmap, c * DM_BOX_CH, k0, &full_bar[stage]);
 					}
+					// the two producer warps meet on named barrier 1 once the stage is free
 					__syncwarp();
-#pragma unroll
-					for (int q = 0; q < 2; ++q)
-						dm_tma_gather4(dst + (lane + 32 * q) * 512, &tmap, c * DM_BOX_CH, rows[q][0],
-						               rows[q][1], rows[q][2], rows[q][3], &full_bar[stage]);
+					asm volatile("bar.sync 1, 64;" ::: "memory");
+					dm_tma_gather4(dst + pl * 512, &tmap, c * DM_BOX_CH, rows[0], rows[1], rows[2],
+					               rows[3], &full_bar[stage]);
 				}
 			}
 		} else if (lane == 0) {
@@ -252,7 +253,7 @@ template <int NC, int STAGES, int DM_MR, bool GATHER>
 static int launch_dmma_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 {
 	constexpr int KT = NC * 8;
-	constexpr int THREADS = DM_ROWS / (8 * DM_MR) * 32 + 32;
+	constexpr int THREADS = DM_ROWS / (8 * DM_MR) * 32 + (GATHER ? 64 : 32);
 	const size_t smem = dmma_smem(KT, STAGES);
 	auto kern = clike_dmma_kernel<NC, STAGES, DM_MR, GATHER>;
 	MDNS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -14,6 +14,7 @@ namespace mdns {
 // transposed once at upload.  Model spectra use the same pitch and padding.
 constexpr int ROW_ALIGN = 2;    // doubles (16 bytes)
 constexpr int XP_MIN_K = 3;     // smallest all-active batch that takes the expanded form by itself
+constexpr int XP_MIN_K_MASKED = 5;   // and the smallest masked one (gather4-fed tensor path)
 constexpr int KT_MAX = 32;      // model buffers are padded to a multiple of this many candidates
 
 // in: channel-major chunk in[j*ld_in + c], j < nx, c < nb  (device staging)

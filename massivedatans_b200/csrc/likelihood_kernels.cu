@@ -626,14 +626,14 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		                         tile_rows, sm_count, st);
 	}
 	if (L == 0 && t.unroll == 0 && t.ktile == 0 && t.rows == 0 && a.active && a.tmap_gather &&
-	    t.allow_expanded && a.K >= 16 && a.n_rows >= 32768) {
-		// masked candidate batches: the tensor path fed by gather4 copies of the listed rows.
-		// The gather is bound by the issue rate of its 512-byte copies (~0.58 of the HBM roofline
-		// with two producer warps per SM), so it only pays where the block kernel is bound by
-		// shared memory and the FP64 pipe (measured, 5e5 active of 1e6 data sets: K=8 0.219 ms vs
-		// 0.185 ms block kernel; K=16 0.234 vs 0.362; K=32 0.43 vs 0.71).
+	    t.allow_expanded && a.K >= XP_MIN_K_MASKED && a.n_rows >= 32768) {
+		// masked candidate batches: the tensor path fed by gather4 copies of the listed rows
+		// (two producer warps).  Measured, 5e5 active of 1e6 data sets: K=8 0.152 ms (block kernel
+		// 0.180), K=16 0.173 ms (0.358), K=32 0.43 ms (0.71); up to 4 candidates the block kernel
+		// wins (K=4 0.141 ms).
 		if (a.K >= 32 && dmma_fits(a, 32, 3)) return launch_clike_dmma(a, 32, 3, sm_count, st);
-		if (dmma_fits(a, 16, 3)) return launch_clike_dmma(a, 16, 3, sm_count, st);
+		if (a.K >= 16 && dmma_fits(a, 16, 13)) return launch_clike_dmma(a, 16, 13, sm_count, st);
+		if (dmma_fits(a, 8, 13)) return launch_clike_dmma(a, 8, 13, sm_count, st);
 	}
 	if (L == 1 || L == 2 || L == 3) {
 		// tile kernel requested but not applicable (masked rows): automatic choice

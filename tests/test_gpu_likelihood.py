@@ -216,7 +216,8 @@ def test_clike_expanded_tensor_path_masked_gather(oracle_port, ktile, stages, N,
 
 
 def test_clike_masked_batches_automatic_choice(oracle_port):
-    # masked batches: block kernel below 16 candidates, gather-fed tensor path from 16 on
+    # masked batches: lanes-across-channels kernels up to 4 candidates, gather-fed tensor path
+    # from 5 on
     N = 80000
     x, y, _ = synth.horns(N, legacy=False, seed=8)
     ds = ResidentDataset(x, y)
@@ -229,9 +230,12 @@ def test_clike_masked_batches_automatic_choice(oracle_port):
         p = pts[k]
         want = -0.5 * oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, m)
         assert rel_err(got[k], want) < TOL_XP
-    small = ds.loglike_batch(pts[:8], m, synth.NOISE_LEVEL)
+    mid = ds.loglike_batch(pts[:8], m, synth.NOISE_LEVEL)
+    assert lib.mdns_last_kernel() == b'clike_dmma_kernel(gather)'
+    assert rel_err(mid, got[:8]) < TOL_XP
+    small = ds.loglike_batch(pts[:4], m, synth.NOISE_LEVEL)
     assert lib.mdns_last_kernel() in (b'clike_block_kernel', b'clike_rows_kernel')
-    assert rel_err(small, got[:8]) < TOL_XP
+    assert rel_err(small, got[:4]) < TOL_XP
     # first-accept on a masked batch of 20 goes through the same kernel
     Ls = numpy.array(got)
     Lmins = Ls[:18].max(axis=0) + 1e-9 * numpy.abs(Ls[:18].max(axis=0))
