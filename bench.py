@@ -411,6 +411,26 @@ def run_ours(args):
         fa_s = time.perf_counter() - t0
         barrier()
         fa_s = max_over_ranks(fa_s)
+        # the sparse form: only the accepting data sets of the accepted candidate come back.
+        # Thresholds raised so that the accepted candidate wins for ~1 % of the data sets (late in
+        # a run a new point is accepted for few data sets; early for most of them -- the dense
+        # form above is that case).
+        margin = L_fa[K - 1] - Lmins
+        Lmins_s = Lmins + max(float(numpy.quantile(margin, 0.99)), 0.0)
+        ds.begin_draw(mask, Lmins_s)
+        for _ in range(3):
+            ks, js, Ljs, cs = ds.draw_batch_sparse(pts_fa, 0.01)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ks, js, Ljs, cs = ds.draw_batch_sparse(pts_fa, 0.01)
+        fs_s = time.perf_counter() - t0
+        barrier()
+        fs_s = max_over_ranks(fs_s)
+        want_j = numpy.nonzero(L_fa[K - 1] > Lmins_s)[0]
+        sparse_ok = bool(ks == (K - 1 if len(want_j) else -1) and
+                         (ks < 0 or (numpy.array_equal(js, want_j) and
+                                     numpy.array_equal(Ljs, L_fa[K - 1][want_j]))))
         want_k = K - 1 if (L_fa[K - 1] > Lmins).any() else -1
         ok = bool(k_acc == want_k and (k_acc < 0 or numpy.array_equal(L_acc, L_fa[K - 1])))
         nsh = n_gpus if distributed else 1
@@ -421,7 +441,14 @@ def run_ours(args):
               'd2h_bytes_per_step': (n_act * 8 + K * 4) * nsh,
               'staged_once_per_draw_bytes': (ndata_local + n_act * 8) * nsh,
               'api': 'ResidentDataset.begin_draw(data_mask, Lmins) once, then '
-                     'draw_batch(params, noise) per step'}
+                     'draw_batch(params, noise) per step',
+              'sparse': {'value': evals_per_step_all * args.steps / fs_s, 'unit': UNIT,
+                         'ms_per_step': 1e3 * fs_s / args.steps,
+                         'accepting_data_sets': int(len(want_j)), 'matches_full_matrix': sparse_ok,
+                         'd2h_bytes_per_step': (int(len(want_j)) * 12 + K * 4) * nsh,
+                         'api': 'draw_batch_sparse(params, noise): indices and logL of the data '
+                                'sets the accepted candidate is accepted for '
+                                '(multi_nested_sampler.py:482-485)'}}
     shards = (n_gpus if distributed else 1)
     h2d = (ndata_local + K * 24) * shards
     d2h = K * n_act * 8 * shards

@@ -137,6 +137,15 @@ int mdns_set_thresholds(mdns_dataset *ds, const double *Lmins);
 int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const double *Lmins,
                             int *accept_counts, int *first_k, double *Lout,
                             int64_t lout_capacity);
+/* The same decision, returning only what the sampler consumes (multi_nested_sampler.py:482-485
+ * pushes the new point onto the shelves of the data sets with Lj[j] > Lmins[j]): idx_out[0..n)
+ * = positions j (in the compacted active order, increasing) of the data sets the first accepted
+ * candidate is accepted for, val_out = their logL.  12 bytes per accepting data set cross PCIe
+ * instead of the whole vector.  capacity = entries idx_out / val_out can hold (n_act is always
+ * enough). */
+int mdns_clike_first_accept_sparse(mdns_dataset *ds, double noise, double scale, const double *Lmins,
+                                   int *accept_counts, int *first_k, int32_t *idx_out,
+                                   double *val_out, int64_t capacity, int *n_out);
 int mdns_fetch(mdns_dataset *ds, double *Lout, int64_t lout_capacity);
 int mdns_sync(mdns_dataset *ds);
 /* CUDA-event stopwatch on the data set's own streams (max over shards). */

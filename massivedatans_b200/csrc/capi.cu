@@ -73,6 +73,10 @@ struct Shard {
 	size_t lmins_cap = 0;
 	int *d_counts = nullptr;      // accepting data sets per candidate
 	size_t counts_cap = 0;
+	uint8_t *d_flags = nullptr;   // sparse accept: flag per active data set, accepted list
+	int *d_acc_idx = nullptr, *d_nacc = nullptr;
+	double *d_acc_val = nullptr;
+	size_t flags_cap = 0, acc_idx_cap = 0, acc_val_cap = 0;
 	double *syy = nullptr;        // expanded form: sum of squares of every resident row
 	double *d_smm = nullptr;      // and of every staged model spectrum
 	size_t smm_cap = 0;
@@ -143,6 +147,10 @@ static void shard_free(Shard &s)
 	cudaFree(s.d_out);
 	cudaFree(s.d_lmins);
 	cudaFree(s.d_counts);
+	cudaFree(s.d_flags);
+	cudaFree(s.d_acc_idx);
+	cudaFree(s.d_acc_val);
+	cudaFree(s.d_nacc);
 	cudaFree(s.syy);
 	cudaFree(s.d_smm);
 	cudaFree(s.d_redo);
@@ -797,29 +805,25 @@ int mdns_clike_launch_fetch(mdns_dataset *ds, double noise, double scale, double
 // with scale*chi2 > Lmins; the logL vector of the FIRST candidate with a non-zero count (the
 // one the reference's one-at-a-time loop would have returned) is copied to Lout.  Only
 // K ints + one vector cross PCIe instead of K vectors.
-int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const double *Lmins,
-                            int *accept_counts, int *first_k, double *Lout, int64_t lout_capacity)
+// Common part of the first-accept calls: score the staged candidates, count the accepting data
+// sets of every candidate on the device, find the first candidate with a non-zero count.
+// shard_counts[shard] = accepting data sets of that candidate on the shard.
+static int first_accept_core(mdns_dataset *ds, const char *who, double noise, double scale,
+                             const double *Lmins, int *accept_counts, int *first_k,
+                             std::vector<int> &shard_counts)
 {
-	int rc = clike_check(ds, "mdns_clike_first_accept");
+	int rc = clike_check(ds, who);
 	if (rc != MDNS_OK) return rc;
-	if (!first_k || !Lout) {
-		set_error("mdns_clike_first_accept: need first_k and Lout");
-		return MDNS_EINVAL;
-	}
 	if (Lmins) {
 		if ((rc = mdns_set_thresholds(ds, Lmins)) != MDNS_OK) return rc;
 	} else if (!ds->thresholds_staged) {
-		set_error("mdns_clike_first_accept: no thresholds (pass Lmins or call mdns_set_thresholds "
-		          "after mdns_set_mask)");
+		set_error("%s: no thresholds (pass Lmins or call mdns_set_thresholds after mdns_set_mask)",
+		          who);
 		return MDNS_ESTATE;
 	}
-	if (lout_capacity < ds->n_act_total) {
-		set_error("Lout holds %lld doubles, %d needed", (long long)lout_capacity, ds->n_act_total);
-		return MDNS_EINVAL;
-	}
 	const int K = ds->K;
-	std::vector<int> total(K, 0), part(K);
-	long long off = 0;
+	const size_t nsh = ds->shards.size();
+	std::vector<int> total(K, 0), part(K * nsh, 0);
 	for (auto &s : ds->shards) {
 		MDNS_CUDA(cudaSetDevice(s.device));
 		if (s.n_act > 0) {
@@ -830,15 +834,15 @@ int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const 
 			                              s.stream)) != MDNS_OK)
 				return rc;
 		}
-		off += s.n_act;
 	}
-	for (auto &s : ds->shards) {
+	for (size_t i = 0; i < nsh; ++i) {
+		Shard &s = ds->shards[i];
 		if (s.n_act == 0) continue;
 		MDNS_CUDA(cudaSetDevice(s.device));
-		MDNS_CUDA(cudaMemcpyAsync(part.data(), s.d_counts, (size_t)K * sizeof(int),
+		MDNS_CUDA(cudaMemcpyAsync(part.data() + i * K, s.d_counts, (size_t)K * sizeof(int),
 		                          cudaMemcpyDeviceToHost, s.stream));
 		MDNS_CUDA(cudaStreamSynchronize(s.stream));
-		for (int k = 0; k < K; ++k) total[k] += part[k];
+		for (int k = 0; k < K; ++k) total[k] += part[i * K + k];
 	}
 	ds->launched = 1;
 	int first = -1;
@@ -847,9 +851,29 @@ int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const 
 	if (accept_counts)
 		for (int k = 0; k < K; ++k) accept_counts[k] = total[k];
 	*first_k = first;
-	if ((rc = xp_feedback(ds)) != MDNS_OK) return rc;
-	if (first < 0) return MDNS_OK;
-	off = 0;
+	shard_counts.assign(nsh, 0);
+	if (first >= 0)
+		for (size_t i = 0; i < nsh; ++i) shard_counts[i] = part[i * K + first];
+	return xp_feedback(ds);
+}
+
+int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const double *Lmins,
+                            int *accept_counts, int *first_k, double *Lout, int64_t lout_capacity)
+{
+	if (!ds || !first_k || !Lout) {
+		set_error("mdns_clike_first_accept: need ds, first_k and Lout");
+		return MDNS_EINVAL;
+	}
+	if (lout_capacity < ds->n_act_total) {
+		set_error("Lout holds %lld doubles, %d needed", (long long)lout_capacity, ds->n_act_total);
+		return MDNS_EINVAL;
+	}
+	std::vector<int> shard_counts;
+	int rc = first_accept_core(ds, "mdns_clike_first_accept", noise, scale, Lmins, accept_counts,
+	                           first_k, shard_counts);
+	if (rc != MDNS_OK || *first_k < 0) return rc;
+	const int first = *first_k;
+	long long off = 0;
 	for (auto &s : ds->shards) {
 		if (s.n_act > 0) {
 			MDNS_CUDA(cudaSetDevice(s.device));
@@ -860,6 +884,71 @@ int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const 
 		off += s.n_act;
 	}
 	return mdns_sync(ds);
+}
+
+// The same, returning only what multi_nested_sampler.py:482-485 consumes: the data sets the
+// first accepted candidate is accepted for (positions in the compacted active order,
+// increasing) and their logL.  A stable device compaction keeps the order; only
+// 12 bytes per accepting data set cross PCIe.
+int mdns_clike_first_accept_sparse(mdns_dataset *ds, double noise, double scale, const double *Lmins,
+                                   int *accept_counts, int *first_k, int32_t *idx_out,
+                                   double *val_out, int64_t capacity, int *n_out)
+{
+	if (!ds || !first_k || !idx_out || !val_out || !n_out) {
+		set_error("mdns_clike_first_accept_sparse: need ds, first_k, idx_out, val_out and n_out");
+		return MDNS_EINVAL;
+	}
+	*n_out = 0;
+	std::vector<int> shard_counts;
+	int rc = first_accept_core(ds, "mdns_clike_first_accept_sparse", noise, scale, Lmins,
+	                           accept_counts, first_k, shard_counts);
+	if (rc != MDNS_OK || *first_k < 0) return rc;
+	const int first = *first_k;
+	long long n_total = 0;
+	for (int c : shard_counts) n_total += c;
+	if (n_total > capacity) {
+		set_error("the accepted candidate is accepted for %lld data sets, the output holds %lld",
+		          n_total, (long long)capacity);
+		return MDNS_EINVAL;
+	}
+	long long pos = 0;
+	std::vector<long long> pos_of(ds->shards.size(), 0);
+	for (size_t i = 0; i < ds->shards.size(); ++i) {
+		Shard &s = ds->shards[i];
+		const int cnt = shard_counts[i];
+		pos_of[i] = pos;
+		if (cnt > 0) {
+			MDNS_CUDA(cudaSetDevice(s.device));
+			const size_t fbytes = round_up(s.n_act, 16) + 16;
+			if ((rc = grow(&s.d_flags, &s.flags_cap, fbytes, true)) != MDNS_OK) return rc;
+			if ((rc = grow(&s.d_acc_idx, &s.acc_idx_cap, (size_t)s.n_act, false)) != MDNS_OK) return rc;
+			if ((rc = grow(&s.d_acc_val, &s.acc_val_cap, (size_t)s.n_act, false)) != MDNS_OK) return rc;
+			if (!s.d_nacc) MDNS_CUDA(cudaMalloc((void **)&s.d_nacc, sizeof(int)));
+			const double *row = s.d_out + (size_t)first * s.n_act;
+			if ((rc = launch_accept_flags(row, s.n_act, s.d_lmins, s.d_flags, s.stream)) != MDNS_OK)
+				return rc;
+			if ((rc = launch_compact_mask(s.d_flags, s.n_act, s.d_scratch, s.d_acc_idx, s.d_nacc,
+			                              s.stream)) != MDNS_OK)
+				return rc;
+			if ((rc = launch_gather_values(row, s.d_acc_idx, cnt, s.d_acc_val, s.stream)) != MDNS_OK)
+				return rc;
+			MDNS_CUDA(cudaMemcpyAsync(idx_out + pos, s.d_acc_idx, (size_t)cnt * sizeof(int),
+			                          cudaMemcpyDeviceToHost, s.stream));
+			MDNS_CUDA(cudaMemcpyAsync(val_out + pos, s.d_acc_val, (size_t)cnt * sizeof(double),
+			                          cudaMemcpyDeviceToHost, s.stream));
+		}
+		pos += cnt;
+	}
+	if ((rc = mdns_sync(ds)) != MDNS_OK) return rc;
+	// positions within the whole compacted order: add the active data sets of earlier shards
+	long long off = 0;
+	for (size_t i = 0; i < ds->shards.size(); ++i) {
+		if (off)
+			for (long long p = pos_of[i]; p < pos_of[i] + shard_counts[i]; ++p) idx_out[p] += (int32_t)off;
+		off += ds->shards[i].n_act;
+	}
+	*n_out = (int)n_total;
+	return MDNS_OK;
 }
 
 int mdns_muse_launch(mdns_dataset *ds)

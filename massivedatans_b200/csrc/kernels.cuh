@@ -84,6 +84,9 @@ int launch_muse(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t s
 // counts[k] = #{r : L[k*stride + r] > lmins[r]}  (hiermetriclearn.py:193 on the device)
 int launch_accept_count(const double *L, long long stride, int n, int K, const double *lmins,
                         int *counts, cudaStream_t st);
+// sparse accept: flags[r] = L[r] > lmins[r]; out[i] = L[idx[i]]
+int launch_accept_flags(const double *L, int n, const double *lmins, uint8_t *flags, cudaStream_t st);
+int launch_gather_values(const double *L, const int *idx, int n, double *out, cudaStream_t st);
 // MUSE-type, one CTA per data set, rows staged once through a bulk-TMA ring (muse_block_kernel.cu)
 bool muse_block_fits(const LikeArgs &a);
 // groups: 1 or 2 data sets in flight per CTA (0 = automatic)

@@ -731,6 +731,42 @@ int launch_accept_count(const double *L, long long stride, int n, int K, const d
 	return MDNS_OK;
 }
 
+// flags[r] = L[r] > lmins[r] (one candidate); the flag buffer is zero-padded for the compaction
+__global__ void __launch_bounds__(256) accept_flags_kernel(const double *__restrict__ L, int n,
+                                                           const double *__restrict__ lmins,
+                                                           uint8_t *__restrict__ flags)
+{
+	// also clears the tail up to the next multiple of 16 bytes (the compaction reads 16-byte
+	// words and the number of active data sets changes from mask to mask)
+	const int i = blockIdx.x * 256 + threadIdx.x;
+	const int npad = (n + 15) / 16 * 16;
+	if (i < npad) flags[i] = (i < n && L[i] > lmins[i]) ? 1 : 0;
+}
+
+int launch_accept_flags(const double *L, int n, const double *lmins, uint8_t *flags, cudaStream_t st)
+{
+	if (n <= 0) return MDNS_OK;
+	accept_flags_kernel<<<ceil_div((n + 15) / 16 * 16, 256), 256, 0, st>>>(L, n, lmins, flags);
+	MDNS_LAUNCHED_HELPER("accept_flags_kernel");
+	return MDNS_OK;
+}
+
+__global__ void __launch_bounds__(256) gather_values_kernel(const double *__restrict__ L,
+                                                            const int *__restrict__ idx, int n,
+                                                            double *__restrict__ out)
+{
+	const int i = blockIdx.x * 256 + threadIdx.x;
+	if (i < n) out[i] = L[idx[i]];
+}
+
+int launch_gather_values(const double *L, const int *idx, int n, double *out, cudaStream_t st)
+{
+	if (n <= 0) return MDNS_OK;
+	gather_values_kernel<<<ceil_div(n, 256), 256, 0, st>>>(L, idx, n, out);
+	MDNS_LAUNCHED_HELPER("gather_values_kernel");
+	return MDNS_OK;
+}
+
 // ------------------------------------------------------------- muse kernel ---
 // cmuselike.c:48-64 with resident inverse variance w = 1/v:
 //   s1 = sum y*m*w ; s2 = 1e-10 + sum m*m*w ; s = s1/s2 ; chi = sum (y - s*m)^2 * w

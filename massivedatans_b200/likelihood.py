@@ -235,6 +235,27 @@ class ResidentDataset(object):
             return -1, None, counts
         return first.value, out, counts
 
+    def draw_batch_sparse(self, params, noise, scale=-0.5):
+        """Like ``draw_batch`` but returns only what the sampler consumes
+        (multi_nested_sampler.py:482-485): ``(k, j, Lj, counts)`` with ``j`` the positions (in the
+        compacted active order, increasing) of the data sets candidate ``k`` is accepted for and
+        ``Lj`` their logL; ``(-1, None, None, counts)`` if no candidate is accepted."""
+        K = self.stage_params(params)
+        n_act = self._draw_n_act
+        counts = numpy.zeros(K, dtype=numpy.int32)
+        if n_act == 0:
+            return -1, None, None, counts
+        idx = numpy.empty(n_act, dtype=numpy.int32)
+        val = _pool.empty(n_act)
+        first = ctypes.c_int(-1)
+        n = ctypes.c_int(0)
+        _lib.check(self._lib.mdns_clike_first_accept_sparse(
+            self._h, noise, scale, None, _addr(counts), ctypes.byref(first), _addr(idx), _addr(val),
+            n_act, ctypes.byref(n)), 'mdns_clike_first_accept_sparse')
+        if first.value < 0:
+            return -1, None, None, counts
+        return first.value, idx[:n.value], val[:n.value], counts
+
     def loglike_spectra(self, ypred, data_mask, noise, scale=-0.5, out=None):
         """K model spectra x all active data sets -> L[K, n_act] (scalar-noise chi-square)."""
         K = self.stage_spectra(ypred)

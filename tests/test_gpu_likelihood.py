@@ -417,6 +417,29 @@ def test_first_accepted_matches_one_at_a_time_loop(oracle_port, N):
     k, L, counts = ds.draw_batch(pts[4:], synth.NOISE_LEVEL)
     assert k == want_first - 4 and numpy.array_equal(counts, want_counts[4:])
     assert rel_err(L, Ls[want_first]) < TOL
+    # sparse form: only the accepting data sets of the first accepted candidate come back
+    ds.begin_draw(m, Lmins)
+    k, j, Lj, counts = ds.draw_batch_sparse(pts, synth.NOISE_LEVEL)
+    assert k == want_first and numpy.array_equal(counts, want_counts)
+    want_j = numpy.nonzero(Ls[want_first] > Lmins)[0]
+    assert j.dtype == numpy.int32 and numpy.array_equal(j, want_j)
+    assert rel_err(Lj, Ls[want_first][want_j]) < TOL
+    # ... with a shorter mask afterwards (stale flags beyond the new length must not count)
+    m_short = m.copy()
+    m_short[N // 3:] = False
+    n_short = int(m_short.sum())
+    Ls_short = Ls[:, :n_short]
+    ds.begin_draw(m_short, Lmins[:n_short])
+    k, j, Lj, counts = ds.draw_batch_sparse(pts, synth.NOISE_LEVEL)
+    wc = (Ls_short > Lmins[:n_short]).sum(axis=1)
+    assert numpy.array_equal(counts, wc)
+    if (wc > 0).any():
+        kk = int(numpy.argmax(wc > 0))
+        assert k == kk and numpy.array_equal(j, numpy.nonzero(Ls_short[kk] > Lmins[:n_short])[0])
+    else:
+        assert k == -1 and j is None
+    ds.begin_draw(m, numpy.full(n_act, 1e300))
+    assert ds.draw_batch_sparse(pts, synth.NOISE_LEVEL)[0] == -1
     ds.set_mask(None)
     with pytest.raises(_lib.MdnsError):
         ds.draw_batch(pts, synth.NOISE_LEVEL)       # thresholds do not survive a new mask
