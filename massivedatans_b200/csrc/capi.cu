@@ -127,6 +127,7 @@ struct mdns_dataset {
 	Tuning tuning;
 	int64_t resident_bytes = 0;
 	bool thresholds_staged = false;   // d_lmins holds thresholds aligned with the current mask
+	double single[3] = {0, 0, 0};     // the candidate of a K = 1 batch, passed by value
 	double xp_tol = 1e-10;        // relative error bound enforced by the expanded form
 	long long xp_redo_total = 0;  // rows recomputed in the direct form so far
 };
@@ -533,9 +534,12 @@ int mdns_stage_params(mdns_dataset *ds, const double *params, int K)
 		int rc = ensure_batch(ds, s, K);
 		if (rc == MDNS_OK) rc = grow(&s.d_in, &s.in_cap, (size_t)K * 3, false);
 		if (rc != MDNS_OK) return rc;
-		MDNS_CUDA(cudaMemcpyAsync(s.d_in, params, (size_t)K * 3 * sizeof(double),
-		                          cudaMemcpyHostToDevice, s.stream));
+		// a single candidate travels by value with the kernel launch (K = 1 fast path)
+		if (K > 1)
+			MDNS_CUDA(cudaMemcpyAsync(s.d_in, params, (size_t)K * 3 * sizeof(double),
+			                          cudaMemcpyHostToDevice, s.stream));
 	}
+	if (K == 1) memcpy(ds->single, params, sizeof ds->single);
 	ds->K = K;
 	ds->staged = 1;
 	ds->launched = 0;
@@ -579,6 +583,11 @@ static void fill_args(const mdns_dataset *ds, const Shard &s, LikeArgs &a)
 	a.tmap256 = s.has_tmap ? s.tmap256 : nullptr;
 	a.tmap_gather = s.has_gather ? s.tmap_gather : nullptr;
 	a.row0 = 0;
+	a.inline_model = (ds->K == 1 && ds->staged == 1) ? 1 : 0;
+	a.x = s.x;
+	a.line_A = ds->single[0];
+	a.line_mu = ds->single[1];
+	a.line_sig = ds->single[2];
 	a.syy = s.syy;
 	a.smm = s.d_smm;
 	a.xp_redo = s.d_redo;
@@ -617,6 +626,8 @@ static int clike_check(mdns_dataset *ds, const char *who)
 
 static int clike_model(mdns_dataset *ds, Shard &s)
 {
+	s.counters_clear = false;
+	if (ds->K == 1 && ds->staged == 1) return MDNS_OK;    // built inside the likelihood kernel
 	const int Kpad = (int)round_up(ds->K, KT_MAX);
 	const bool xp = xp_candidate(ds, s);
 	const int npass = ceil_div(ds->K, 8);
@@ -681,7 +692,7 @@ int mdns_clike_launch(mdns_dataset *ds, double noise, double scale)
 	}();
 	for (auto &s : ds->shards) {
 		MDNS_CUDA(cudaSetDevice(s.device));
-		if (!use_graph) {
+		if (!use_graph || (ds->K == 1 && ds->staged == 1)) {    // (a by-value candidate is a kernel argument)
 			if ((rc = clike_model(ds, s)) != MDNS_OK) return rc;
 			if ((rc = clike_rows(ds, s, noise, scale, 0, s.n_act)) != MDNS_OK) return rc;
 			continue;
@@ -781,12 +792,17 @@ int mdns_clike_launch_fetch(mdns_dataset *ds, double noise, double scale, double
 			for (int r0 = 0; r0 < s.n_act; r0 += per, ++c) {
 				const int nc = std::min(per, s.n_act - r0);
 				if ((rc = clike_rows(ds, s, noise, scale, r0, nc)) != MDNS_OK) return rc;
-				MDNS_CUDA(cudaEventRecord(s.ev_chunk[c], s.stream));
-				MDNS_CUDA(cudaStreamWaitEvent(s.copy_stream, s.ev_chunk[c], 0));
+				// one chunk: download on the launch stream; several: on the copy stream, behind
+				// an event, while the next chunk computes
+				cudaStream_t cs = s.stream;
+				if (nchunk > 1) {
+					MDNS_CUDA(cudaEventRecord(s.ev_chunk[c], s.stream));
+					MDNS_CUDA(cudaStreamWaitEvent(s.copy_stream, s.ev_chunk[c], 0));
+					cs = s.copy_stream;
+				}
 				MDNS_CUDA(cudaMemcpy2DAsync(Lout + off + r0, (size_t)ds->n_act_total * sizeof(double),
 				                            s.d_out + r0, (size_t)s.n_act * sizeof(double),
-				                            (size_t)nc * sizeof(double), K, cudaMemcpyDeviceToHost,
-				                            s.copy_stream));
+				                            (size_t)nc * sizeof(double), K, cudaMemcpyDeviceToHost, cs));
 			}
 		}
 		off += s.n_act;

@@ -57,6 +57,11 @@ struct LikeArgs {
 	const void *tmap256;  // (tile kernel) or nullptr
 	const void *tmap_gather;  // one-row boxes of the whole shard for tile::gather4, or nullptr
 	int row0;             // first row of this launch within the shard (tile kernel coordinates)
+	// one candidate given by value (K = 1 fast path of clike_rows_kernel): the kernel builds the
+	// model spectrum itself, no parameter upload and no model kernel
+	int inline_model;
+	const double *x;      // wavelength grid
+	double line_A, line_mu, line_sig;
 	// expanded form (clike_xtile_kernel): Syy - 2 Sym + Smm
 	const double *syy;    // resident sum of squares of every row of the shard, or nullptr
 	const double *smm;    // [Kpad] sum of squares of every model spectrum

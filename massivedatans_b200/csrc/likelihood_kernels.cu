@@ -295,7 +295,10 @@ __device__ __forceinline__ void stage_model_tma(double2 *sm, uint64_t *bar, cons
 // One CTA = 8 warps; each warp serves 32/L data sets at a time, L lanes per data set.
 // Per data set and lane: U 128-bit fragments are requested back to back (memory-level
 // parallelism), then consumed against the KT staged model spectra.
-template <int L, int U, int KT>
+// IM (KT = 1 only): the single candidate comes by value and every CTA builds the model spectrum
+// in shared memory itself (clike.c:65, the same un-fused operations as line_model_kernel, so
+// the spectrum is bit-identical): one launch per call instead of upload + model kernel + this.
+template <int L, int U, int KT, bool IM>
 __global__ void __launch_bounds__(LK_THREADS) clike_rows_kernel(const LikeArgs a)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -306,13 +309,26 @@ __global__ void __launch_bounds__(LK_THREADS) clike_rows_kernel(const LikeArgs a
 	const int k0 = blockIdx.y * KT;
 	const int mfp = a.mpitch >> 1;                // fragments per model row
 	const int nfrag = (a.nx + 1) >> 1;
-	stage_model_tma<KT>(sm, &bar, a.model, a.mpitch, k0);
+	if (IM) {
+		double *smd = reinterpret_cast<double *>(smem_raw);
+		for (int j = threadIdx.x; j < a.mpitch; j += LK_THREADS) {
+			double v = 0.0;
+			if (j < a.nx) {
+				const double t = __ddiv_rn(__dsub_rn(a.line_mu, a.x[j]), a.line_sig);
+				v = __dmul_rn(a.line_A, exp(__dmul_rn(-0.5, __dmul_rn(t, t))));
+			}
+			smd[j] = v;
+		}
+		__syncthreads();
+	} else {
+		stage_model_tma<KT>(sm, &bar, a.model, a.mpitch, k0);
+	}
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int g = lane / L, gl = lane % L;
 	const int nchunks = (nfrag + L * U - 1) / (L * U);
 	const double inv = a.scale / a.noise2;
-	mbar_wait(&bar, 0);
+	if (!IM) mbar_wait(&bar, 0);
 
 	for (long long rb = (long long)blockIdx.x * RPC + warp * G; rb < a.n_rows;
 	     rb += (long long)gridDim.x * RPC) {
@@ -519,7 +535,8 @@ static int launch_clike_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 {
 	constexpr int RPC = (LK_THREADS / 32) * (32 / L);
 	const size_t smem = (size_t)KT * a.mpitch * 8;
-	auto kern = clike_rows_kernel<L, U, KT>;
+	const bool im = KT == 1 && a.inline_model && a.K == 1;
+	auto kern = im ? clike_rows_kernel<L, U, 1, true> : clike_rows_kernel<L, U, KT, false>;
 	if (smem > 48 * 1024)   // per device, so set it on every launch that needs it
 		MDNS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		                               (int)smem));
