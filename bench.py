@@ -397,17 +397,33 @@ def run_ours(args):
     fa = None
     if K > 1:
         wins = numpy.bincount(numpy.argmax(L, axis=0), minlength=K)
+        if distributed:       # the same candidate order on every rank
+            tw = torch.as_tensor(wins, dtype=torch.int64).cuda()
+            dist.all_reduce(tw)
+            wins = tw.cpu().numpy()
         order = numpy.argsort(wins, kind='stable')          # most frequent winner last
         pts_fa = numpy.ascontiguousarray(pts[order])
         L_fa = L[order]
         Lmins = numpy.max(L_fa[:K - 1], axis=0)
         ds.begin_draw(mask, Lmins)
+        from massivedatans_b200 import sharding
+
+        def fa_step():
+            if not distributed:
+                return ds.draw_batch(pts_fa, 0.01)
+            # one process per GPU: local counts -> all-reduce of K integers over NCCL (the one
+            # exchange step of the sharded path) -> every rank fetches the globally first
+            # accepted candidate from its own shard
+            c = ds.draw_counts(pts_fa, 0.01)
+            k, tot = sharding.global_first_accepted(c, device=torch.device('cuda', local))
+            return k, (ds.fetch_candidate(k) if k >= 0 else None), tot
+
         for _ in range(3):
-            k_acc, L_acc, counts = ds.draw_batch(pts_fa, 0.01)
+            k_acc, L_acc, counts = fa_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            k_acc, L_acc, counts = ds.draw_batch(pts_fa, 0.01)
+            k_acc, L_acc, counts = fa_step()
         fa_s = time.perf_counter() - t0
         barrier()
         fa_s = max_over_ranks(fa_s)
@@ -431,7 +447,7 @@ def run_ours(args):
         sparse_ok = bool(ks == (K - 1 if len(want_j) else -1) and
                          (ks < 0 or (numpy.array_equal(js, want_j) and
                                      numpy.array_equal(Ljs, L_fa[K - 1][want_j]))))
-        want_k = K - 1 if (L_fa[K - 1] > Lmins).any() else -1
+        want_k = K - 1 if (distributed or (L_fa[K - 1] > Lmins).any()) else -1
         ok = bool(k_acc == want_k and (k_acc < 0 or numpy.array_equal(L_acc, L_fa[K - 1])))
         nsh = n_gpus if distributed else 1
         fa = {'value': evals_per_step_all * args.steps / fa_s, 'unit': UNIT,
@@ -440,8 +456,11 @@ def run_ours(args):
               'h2d_bytes_per_step': K * 24 * nsh,
               'd2h_bytes_per_step': (n_act * 8 + K * 4) * nsh,
               'staged_once_per_draw_bytes': (ndata_local + n_act * 8) * nsh,
-              'api': 'ResidentDataset.begin_draw(data_mask, Lmins) once, then '
-                     'draw_batch(params, noise) per step',
+              'api': ('ResidentDataset.begin_draw(data_mask, Lmins) once, then per step draw_counts + '
+                      'NCCL all-reduce of the K accept counts + fetch_candidate'
+                      if distributed else
+                      'ResidentDataset.begin_draw(data_mask, Lmins) once, then '
+                      'draw_batch(params, noise) per step'),
               'sparse': {'value': evals_per_step_all * args.steps / fs_s, 'unit': UNIT,
                          'ms_per_step': 1e3 * fs_s / args.steps,
                          'accepting_data_sets': int(len(want_j)), 'matches_full_matrix': sparse_ok,

@@ -146,6 +146,12 @@ int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const 
 int mdns_clike_first_accept_sparse(mdns_dataset *ds, double noise, double scale, const double *Lmins,
                                    int *accept_counts, int *first_k, int32_t *idx_out,
                                    double *val_out, int64_t capacity, int *n_out);
+/* Two-step form for one process per GPU: accept_counts[K] of this process's data sets (to be
+ * summed over the processes: an all-reduce of K integers is the only exchange of the sharded
+ * path), then the logL vector of candidate k of the same launch. */
+int mdns_clike_accept_counts(mdns_dataset *ds, double noise, double scale, const double *Lmins,
+                             int *accept_counts);
+int mdns_fetch_candidate(mdns_dataset *ds, int k, double *Lout, int64_t lout_capacity);
 int mdns_fetch(mdns_dataset *ds, double *Lout, int64_t lout_capacity);
 int mdns_sync(mdns_dataset *ds);
 /* CUDA-event stopwatch on the data set's own streams (max over shards). */

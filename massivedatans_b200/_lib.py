@@ -46,6 +46,8 @@ SIGNATURES = {
                                         c_int64]),
     'mdns_clike_first_accept_sparse': (c_int, [_P, c_double, c_double, _P, _P, POINTER(c_int), _P, _P,
                                                c_int64, POINTER(c_int)]),
+    'mdns_clike_accept_counts': (c_int, [_P, c_double, c_double, _P, _P]),
+    'mdns_fetch_candidate': (c_int, [_P, c_int, _P, c_int64]),
     'mdns_set_expanded': (c_int, [_P, c_int, c_double]),
     'mdns_expanded_stats': (c_int, [_P, POINTER(c_int), POINTER(c_int64)]),
     'mdns_fetch': (c_int, [_P, _P, c_int64]),

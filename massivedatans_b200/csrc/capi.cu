@@ -902,6 +902,46 @@ int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const 
 	return mdns_sync(ds);
 }
 
+// Two-step form for one process per GPU (torchrun): every rank counts the accepting data sets
+// of its own shard; the ranks add their K counts up (the one exchange step of the sharded path:
+// an all-reduce of K integers) and then fetch the logL vector of the globally first accepted
+// candidate from their shard.
+int mdns_clike_accept_counts(mdns_dataset *ds, double noise, double scale, const double *Lmins,
+                             int *accept_counts)
+{
+	if (!ds || !accept_counts) {
+		set_error("mdns_clike_accept_counts: need ds and accept_counts");
+		return MDNS_EINVAL;
+	}
+	int first = -1;
+	std::vector<int> shard_counts;
+	return first_accept_core(ds, "mdns_clike_accept_counts", noise, scale, Lmins, accept_counts,
+	                         &first, shard_counts);
+}
+
+int mdns_fetch_candidate(mdns_dataset *ds, int k, double *Lout, int64_t lout_capacity)
+{
+	if (!ds || !Lout || ds->launched != 1 || k < 0 || k >= ds->K) {
+		set_error("mdns_fetch_candidate: need a clike launch, Lout and 0 <= k < K");
+		return ds && Lout ? MDNS_ESTATE : MDNS_EINVAL;
+	}
+	if (lout_capacity < ds->n_act_total) {
+		set_error("Lout holds %lld doubles, %d needed", (long long)lout_capacity, ds->n_act_total);
+		return MDNS_EINVAL;
+	}
+	long long off = 0;
+	for (auto &s : ds->shards) {
+		if (s.n_act > 0) {
+			MDNS_CUDA(cudaSetDevice(s.device));
+			MDNS_CUDA(cudaMemcpyAsync(Lout + off, s.d_out + (size_t)k * s.n_act,
+			                          (size_t)s.n_act * sizeof(double), cudaMemcpyDeviceToHost,
+			                          s.stream));
+		}
+		off += s.n_act;
+	}
+	return mdns_sync(ds);
+}
+
 // The same, returning only what multi_nested_sampler.py:482-485 consumes: the data sets the
 // first accepted candidate is accepted for (positions in the compacted active order,
 // increasing) and their logL.  A stable device compaction keeps the order; only

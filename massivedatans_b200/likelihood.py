@@ -235,6 +235,25 @@ class ResidentDataset(object):
             return -1, None, counts
         return first.value, out, counts
 
+    def draw_counts(self, params, noise, scale=-0.5):
+        """First step of the two-step form (one process per GPU): score the next K candidates of
+        the draw started with ``begin_draw`` and return the accept counts of THIS process's data
+        sets; see ``sharding.global_first_accepted`` for the exchange."""
+        K = self.stage_params(params)
+        counts = numpy.zeros(K, dtype=numpy.int32)
+        if self._draw_n_act > 0:
+            _lib.check(self._lib.mdns_clike_accept_counts(self._h, noise, scale, None, _addr(counts)),
+                       'mdns_clike_accept_counts')
+        return counts
+
+    def fetch_candidate(self, k):
+        """Second step: the logL vector of candidate k of the launch behind ``draw_counts``."""
+        out = _pool.empty(self._draw_n_act)
+        if self._draw_n_act > 0:
+            _lib.check(self._lib.mdns_fetch_candidate(self._h, int(k), _addr(out), out.size),
+                       'mdns_fetch_candidate')
+        return out
+
     def draw_batch_sparse(self, params, noise, scale=-0.5):
         """Like ``draw_batch`` but returns only what the sampler consumes
         (multi_nested_sampler.py:482-485): ``(k, j, Lj, counts)`` with ``j`` the positions (in the

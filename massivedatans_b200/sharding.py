@@ -26,3 +26,26 @@ def compaction_offsets(data_mask, ranges):
     counts = [int(numpy.count_nonzero(data_mask[i0:i0 + n])) for i0, n in ranges]
     offs = numpy.concatenate([[0], numpy.cumsum(counts)[:-1]]).astype(int)
     return list(zip(offs.tolist(), counts))
+
+
+def first_accepted_from_counts(counts):
+    """Index of the first candidate accepted for at least one data set, or -1
+    (hiermetriclearn.py:181-196: candidates are tried in order until numpy.any(L > Lmins))."""
+    nz = numpy.nonzero(numpy.asarray(counts) > 0)[0]
+    return int(nz[0]) if len(nz) else -1
+
+
+def global_first_accepted(local_counts, device=None, group=None):
+    """One process per GPU: add the per-candidate accept counts of all ranks (the only exchange
+    step of the sharded path -- K integers through torch.distributed, NCCL over NVLink when
+    `device` is a CUDA device, gloo on the host otherwise) and return (k, global_counts); every
+    rank then fetches candidate k from its own shard."""
+    import torch
+    import torch.distributed as dist
+    t = torch.as_tensor(numpy.asarray(local_counts, dtype=numpy.int64))
+    if device is not None:
+        t = t.to(device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    total = t.cpu().numpy()
+    return first_accepted_from_counts(total), total

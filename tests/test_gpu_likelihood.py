@@ -440,6 +440,17 @@ def test_first_accepted_matches_one_at_a_time_loop(oracle_port, N):
         assert k == -1 and j is None
     ds.begin_draw(m, numpy.full(n_act, 1e300))
     assert ds.draw_batch_sparse(pts, synth.NOISE_LEVEL)[0] == -1
+    # two-step form (one process per GPU): counts, then any candidate of the same launch
+    from massivedatans_b200 import sharding
+    ds.begin_draw(m, Lmins)
+    c = ds.draw_counts(pts, synth.NOISE_LEVEL)
+    assert numpy.array_equal(c, want_counts)
+    kk, tot = sharding.global_first_accepted(c)          # no process group: the local decision
+    assert kk == want_first and numpy.array_equal(tot, want_counts)
+    for cand in (0, want_first, len(pts) - 1):
+        assert rel_err(ds.fetch_candidate(cand), Ls[cand]) < TOL
+    with pytest.raises(_lib.MdnsError):
+        ds.fetch_candidate(len(pts))
     ds.set_mask(None)
     with pytest.raises(_lib.MdnsError):
         ds.draw_batch(pts, synth.NOISE_LEVEL)       # thresholds do not survive a new mask

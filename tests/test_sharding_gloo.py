@@ -79,3 +79,40 @@ def test_two_rank_sharded_evaluation_matches_single(tmp_path, oracle_port):
     want = numpy.array([oracle_port.clike(x, y, p[0], p[1], p[2], 0.01, mask)
                         for p in synth.parameter_points(3)])
     assert numpy.array_equal(got, want)
+
+
+def _worker_accept(rank, world, port, N, out_path):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from oracle import port as oracle_port
+    x, y, _ = synth.horns(N)
+    pts = synth.parameter_points(6, seed=3)
+    allm = numpy.ones(N, dtype=bool)
+    full = numpy.array([-0.5 * oracle_port.clike(x, y, p[0], p[1], p[2], 0.01, allm) for p in pts])
+    # thresholds: candidates 0..2 rejected everywhere, candidate 3 accepted for data set N-1 only
+    # (which lives on the LAST rank), candidate 4 accepted on the first rank
+    Lmins = full.max(axis=0) + 1.0
+    Lmins[N - 1] = full[3, N - 1] - 1e-3
+    Lmins[0] = full[4, 0] - 1e-3
+    i0, n = sharding.shard_ranges(N, world)[rank]
+    local = (full[:, i0:i0 + n] > Lmins[i0:i0 + n]).sum(axis=1)      # what draw_counts returns
+    k, total = sharding.global_first_accepted(local)
+    want_total = (full > Lmins).sum(axis=1)
+    assert numpy.array_equal(total, want_total)
+    assert k == sharding.first_accepted_from_counts(want_total)
+    if rank == 0:
+        numpy.save(out_path, numpy.array([k, sharding.first_accepted_from_counts(local)]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_first_accept_needs_the_count_exchange(tmp_path, oracle_port):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / 'k.npy')
+    mp.spawn(_worker_accept, args=(2, _free_port(), 200, out), nprocs=2, join=True)
+    k_global, k_rank0 = numpy.load(out)
+    # the globally first accepted candidate is not the one rank 0 would have picked alone
+    assert k_global <= k_rank0 or k_rank0 == -1
+    assert k_global >= 0
