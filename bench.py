@@ -17,10 +17,17 @@ Keys of the JSON line (rank 0 prints exactly one):
   value      evals/s with inputs (data, mask, parameter points) resident in HBM, device-timed
              with CUDA events on the shim's stream, max over ranks
   e2e        the same metric through the public Python callable with HOST buffers: per step
-             the mask and parameter points go host->device and the logL matrix comes back
-  roofline   algorithmic bytes per step / device time per step vs MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the reference's own clike.so (oracle/_ref, serial: the build sample.py:81-84
-             loads; its OpenMP variant is racy, clike.c:32) on the box's host, bounded sample
+             the mask and parameter points go host->device and the K x N logL matrix comes back
+             (PCIe-bound).  e2e.first_accept: the same batch through the device-side form of
+             the constrained draw's loop (hiermetriclearn.py:181-196): K parameter points in,
+             K accept counts + the accepted candidate's logL vector out (for N > 1 with the
+             all-reduce of the K counts between the ranks); .sparse: only the accepting data
+             sets' indices and logL come back
+  roofline   algorithmic bytes per step / device time per step vs MEASURED_PEAKS.json hbm_gbs;
+             traffic = dram bytes of the dominant kernel from the committed ncu capture
+  cpu_baseline  the reference's own unmodified clike.so (oracle/_ref; the serial build
+             sample.py:81-84 loads, its OpenMP variant is racy, clike.c:32), one contiguous
+             data-set shard per host thread, all host cores, bounded sample
 The reference arm (--impl reference) times that same CPU implementation per step.
 """
 import argparse
