@@ -510,6 +510,15 @@ int mdns_set_thresholds(mdns_dataset *ds, const double *Lmins)
 	return MDNS_OK;
 }
 
+// rows too long for a model row in shared memory: only the tensor-path kernel applies
+static bool long_rows(const mdns_dataset *ds) { return ds->pitch * 8 > 200 * 1024; }
+
+// a single candidate travels by value and the likelihood kernel builds its spectrum itself
+static bool inline_single(const mdns_dataset *ds)
+{
+	return ds->K == 1 && ds->staged == 1 && !long_rows(ds);
+}
+
 static int ensure_batch(mdns_dataset *ds, Shard &s, int K)
 {
 	const int Kpad = (int)round_up(K, KT_MAX);
@@ -535,7 +544,7 @@ int mdns_stage_params(mdns_dataset *ds, const double *params, int K)
 		if (rc == MDNS_OK) rc = grow(&s.d_in, &s.in_cap, (size_t)K * 3, false);
 		if (rc != MDNS_OK) return rc;
 		// a single candidate travels by value with the kernel launch (K = 1 fast path)
-		if (K > 1)
+		if (K > 1 || long_rows(ds))
 			MDNS_CUDA(cudaMemcpyAsync(s.d_in, params, (size_t)K * 3 * sizeof(double),
 			                          cudaMemcpyHostToDevice, s.stream));
 	}
@@ -583,7 +592,7 @@ static void fill_args(const mdns_dataset *ds, const Shard &s, LikeArgs &a)
 	a.tmap256 = s.has_tmap ? s.tmap256 : nullptr;
 	a.tmap_gather = s.has_gather ? s.tmap_gather : nullptr;
 	a.row0 = 0;
-	a.inline_model = (ds->K == 1 && ds->staged == 1) ? 1 : 0;
+	a.inline_model = inline_single(ds) ? 1 : 0;
 	a.x = s.x;
 	a.line_A = ds->single[0];
 	a.line_mu = ds->single[1];
@@ -601,6 +610,7 @@ static void fill_args(const mdns_dataset *ds, const Shard &s, LikeArgs &a)
 static bool xp_candidate(const mdns_dataset *ds, const Shard &s)
 {
 	if (!s.syy) return false;
+	if (long_rows(ds) && ds->tuning.allow_expanded && (s.all_active || s.has_gather)) return true;
 	if (!s.all_active) {
 		// masked batches: only the tensor path has a gather form
 		if (!s.has_gather) return false;
@@ -627,7 +637,7 @@ static int clike_check(mdns_dataset *ds, const char *who)
 static int clike_model(mdns_dataset *ds, Shard &s)
 {
 	s.counters_clear = false;
-	if (ds->K == 1 && ds->staged == 1) return MDNS_OK;    // built inside the likelihood kernel
+	if (inline_single(ds)) return MDNS_OK;    // built inside the likelihood kernel
 	const int Kpad = (int)round_up(ds->K, KT_MAX);
 	const bool xp = xp_candidate(ds, s);
 	const int npass = ceil_div(ds->K, 8);
@@ -692,7 +702,7 @@ int mdns_clike_launch(mdns_dataset *ds, double noise, double scale)
 	}();
 	for (auto &s : ds->shards) {
 		MDNS_CUDA(cudaSetDevice(s.device));
-		if (!use_graph || (ds->K == 1 && ds->staged == 1)) {    // (a by-value candidate is a kernel argument)
+		if (!use_graph || inline_single(ds)) {    // (a by-value candidate is a kernel argument)
 			if ((rc = clike_model(ds, s)) != MDNS_OK) return rc;
 			if ((rc = clike_rows(ds, s, noise, scale, 0, s.n_act)) != MDNS_OK) return rc;
 			continue;

@@ -689,6 +689,9 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 	if (U != 1 && U != 2 && U != 4 && U != 8 && U != 13 && U != 16) U = pick_unroll(nfrag, L);
 	const int kt = pick_ktile(a.K, a.mpitch, t.ktile);
 	if ((size_t)kt * a.mpitch * 8 > 200 * 1024) {
+		// spectra too long for a whole model row in shared memory: the tensor-path kernel
+		// streams the model in 16-channel slices beside the data, whatever the channel count
+		if (t.allow_expanded && dmma_fits(a, 8, 3)) return launch_clike_dmma(a, 8, 3, sm_count, st);
 		set_error("model spectrum of %d channels does not fit in shared memory", a.nx);
 		return MDNS_EINVAL;
 	}

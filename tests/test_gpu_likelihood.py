@@ -311,6 +311,24 @@ def test_clike_expanded_form_cancellation_guard(oracle_port, tuning, kernel):
     assert rel_err(again, got) < TOL_XP
 
 
+@pytest.mark.parametrize('K', [1, 5])
+def test_clike_very_long_spectra(oracle_port, K):
+    # a model row of 30001 channels (240 KB) does not fit in shared memory: every batch size and
+    # mask goes to the tensor-path kernel, which streams the model in 16-channel slices
+    N, nx = 300, 30001
+    x, y, _ = synth.horns(N, nx=nx, seed=6)
+    ds = ResidentDataset(x, y)
+    pts = synth.parameter_points(K, seed=2)
+    for name in ('all', 'half'):
+        m = synth.masks(N)[name]
+        got = ds.loglike_batch(pts, m, synth.NOISE_LEVEL, scale=1.0)
+        assert _lib.load().mdns_last_kernel().startswith(b'clike_dmma_kernel')
+        for k in range(K):
+            p = pts[k]
+            want = oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, m)
+            assert rel_err(got[k], want) < TOL_XP, (name, k)
+
+
 def test_clike_spectra_entry_point(oracle_port):
     N = 999
     x, y, _ = synth.horns(N)
