@@ -476,7 +476,11 @@ def run_ours(args):
                                 'sets the accepted candidate is accepted for '
                                 '(multi_nested_sampler.py:482-485)'}}
     shards = (n_gpus if distributed else 1)
-    h2d = (ndata_local + K * 24) * shards
+    # bytes that really cross PCIe per step: the K parameter points; an all-true mask is
+    # recognised by a host scan and needs no device list, a partial mask is uploaded once and
+    # recognised (memcmp) when it comes again -- both checks run inside the timed region
+    mask_bytes_uploaded_each_step = 0
+    h2d = (K * 24 + mask_bytes_uploaded_each_step) * shards
     d2h = K * n_act * 8 * shards
     clocks = sampler.stop()
 
@@ -522,6 +526,7 @@ def run_ours(args):
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': 1e3 * e2e_s / args.steps,
+                    'mask_bytes_scanned_on_host_per_step': ndata_local * shards,
                     'api': 'massivedatans_b200.likelihood.make_multi_loglikelihood(...)'
                            + ('.batch' if K > 1 else '') + '(params, data_mask), host numpy in/out',
                     'first_accept': fa},
