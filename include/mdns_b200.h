@@ -193,6 +193,10 @@ int mdns_livetable_fill_from_launch(mdns_livetable *t, mdns_dataset *ds, int row
  * the row of its first occurrence (numpy.argmin) and the maximum over the live
  * points.  Any output may be NULL. */
 int mdns_livetable_colstats(mdns_livetable *t, double *Lmins, int64_t *Lmini, double *Lmax);
+/* The column minima become the accept thresholds of `ds` (every data set active) on the
+ * devices, without a host round trip: table -> thresholds -> mdns_clike_first_accept with
+ * Lmins = NULL. */
+int mdns_livetable_stage_thresholds(mdns_livetable *t, mdns_dataset *ds);
 /* advance, multi_nested_sampler.py:520-524: table[rows[d]][d] = values[d] for
  * every data set d with rows[d] >= 0. */
 int mdns_livetable_replace(mdns_livetable *t, const int64_t *rows, const double *values);

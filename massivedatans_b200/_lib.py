@@ -58,6 +58,7 @@ SIGNATURES = {
     'mdns_livetable_fill_from_launch': (c_int, [_P, _P, c_int]),
     'mdns_livetable_colstats': (c_int, [_P, _P, _P, _P]),
     'mdns_livetable_replace': (c_int, [_P, _P, _P]),
+    'mdns_livetable_stage_thresholds': (c_int, [_P, _P]),
     'mdns_livetable_lmins_higher': (c_int, [_P, _P, c_int, _P, _P, _P]),
     'mdns_livetable_upload_points': (c_int, [_P, _P]),
     'mdns_livetable_replace_points': (c_int, [_P, _P, _P]),

@@ -370,6 +370,24 @@ int mdns_internal_shard_view(mdns_dataset *ds, int shard, int *device, int *i0, 
 	return MDNS_OK;
 }
 
+// internal (livetable.cu): device buffer that receives the accept thresholds of shard `shard`
+// when every data set is active (n doubles); marks the thresholds as staged
+int mdns_internal_threshold_buffer(mdns_dataset *ds, int shard, double **d_lmins)
+{
+	if (!ds || shard < 0 || shard >= (int)ds->shards.size() || !d_lmins) return MDNS_EINVAL;
+	Shard &s = ds->shards[shard];
+	if (!s.all_active) {
+		set_error("thresholds from the live table need every data set active (mask = all)");
+		return MDNS_ESTATE;
+	}
+	MDNS_CUDA(cudaSetDevice(s.device));
+	int rc = grow(&s.d_lmins, &s.lmins_cap, (size_t)s.n, false);
+	if (rc != MDNS_OK) return rc;
+	*d_lmins = s.d_lmins;
+	if (shard == (int)ds->shards.size() - 1) ds->thresholds_staged = true;
+	return MDNS_OK;
+}
+
 int mdns_dataset_destroy(mdns_dataset *ds)
 {
 	if (!ds) return MDNS_OK;

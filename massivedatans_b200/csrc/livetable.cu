@@ -229,6 +229,7 @@ using namespace mdns;
 extern "C" int mdns_internal_shard_view(mdns_dataset *ds, int shard, int *device, int *i0, int *n,
                                         int *n_act, int *K, const double **d_out, void **stream);
 extern "C" int mdns_internal_shard_count(const mdns_dataset *ds);
+extern "C" int mdns_internal_threshold_buffer(mdns_dataset *ds, int shard, double **d_lmins);
 
 struct LtShard {
 	int device = 0, i0 = 0, n = 0;
@@ -432,6 +433,42 @@ int mdns_livetable_colstats(mdns_livetable *t, double *Lmins, int64_t *Lmini, do
 			                          cudaMemcpyDeviceToHost, s.stream));
 	}
 	return lt_sync(t);
+}
+
+// The current minimum of every data set's live points becomes its accept threshold on the data
+// set's devices (the `Lmins` of a superset draw, multi_nested_sampler.py:134-137 -> :462-472 ->
+// hiermetriclearn.py:193) without a round trip through the host: live table -> thresholds ->
+// mdns_clike_first_accept(..., Lmins = NULL, ...).  Needs the all-active mask.
+int mdns_livetable_stage_thresholds(mdns_livetable *t, mdns_dataset *ds)
+{
+	if (!t || !ds) {
+		set_error("mdns_livetable_stage_thresholds: need the table and its data set");
+		return MDNS_EINVAL;
+	}
+	if (mdns_internal_shard_count(ds) != (int)t->shards.size()) {
+		set_error("the live table belongs to a data set with another sharding");
+		return MDNS_EINVAL;
+	}
+	for (size_t k = 0; k < t->shards.size(); ++k) {
+		LtShard &s = t->shards[k];
+		int n = 0;
+		void *stream = nullptr;
+		mdns_internal_shard_view(ds, (int)k, nullptr, nullptr, &n, nullptr, nullptr, nullptr, &stream);
+		if (n != s.n) {
+			set_error("the live table belongs to a data set with another sharding");
+			return MDNS_EINVAL;
+		}
+		double *d_lmins = nullptr;
+		int rc = mdns_internal_threshold_buffer(ds, (int)k, &d_lmins);
+		if (rc != MDNS_OK) return rc;
+		MDNS_CUDA(cudaSetDevice(s.device));
+		lt_colstats_kernel<<<ceil_div(s.n, 256), 256, 0, s.stream>>>(s.T, t->nlive, s.n, d_lmins, nullptr,
+		                                                            nullptr);
+		MDNS_LAUNCHED("lt_colstats_kernel");
+		// the data set's stream consumes the thresholds: order it behind this kernel
+		MDNS_CUDA(cudaStreamSynchronize(s.stream));
+	}
+	return MDNS_OK;
 }
 
 int mdns_livetable_replace(mdns_livetable *t, const int64_t *rows, const double *values)

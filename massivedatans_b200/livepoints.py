@@ -66,6 +66,15 @@ class LiveTable(object):
                    'mdns_livetable_colstats')
         return lo, at, hi
 
+    def stage_thresholds(self):
+        """The column minima become the accept thresholds of the data set (all data sets active),
+        device to device: afterwards ``dataset.draw_batch(params, noise)`` tests candidates
+        against ``Lmins = live_pointsL.min(axis=0)`` without the vector ever visiting the host."""
+        self._dataset.set_mask(None)
+        _lib.check(self._lib.mdns_livetable_stage_thresholds(self._h, self._dataset._h),
+                   'mdns_livetable_stage_thresholds')
+        self._dataset._draw_n_act = self.ndata
+
     def replace(self, rows, values):
         """live_pointsL[rows[d], d] = values[d] for every data set d with rows[d] >= 0."""
         rows = numpy.ascontiguousarray(rows, dtype=numpy.int64)

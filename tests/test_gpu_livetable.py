@@ -184,3 +184,32 @@ def test_subsets_match_oracle_components(oracle_port, nlive, ndata, ngroups, cha
         P2[0, 0] = ids[0]
         allm = numpy.ones(ndata, dtype=bool)
         assert numpy.array_equal(t.subsets(None, npoints), oracle_port.subsets_labels(P2, allm, npoints))
+
+
+def test_thresholds_staged_from_the_table_match_the_host_path(oracle_port):
+    # live table -> thresholds -> device-side accept test, no host round trip of Lmins
+    nlive, ndata = 20, 40000
+    x, y, _ = synth.horns(ndata, legacy=False, seed=12)
+    ds = ResidentDataset(x, y)
+    t = LiveTable(ds, nlive)
+    init = synth.parameter_points(nlive, seed=3)
+    for r0 in range(0, nlive, 10):
+        ds.stage_params(init[r0:r0 + 10])
+        ds.set_mask(None)
+        ds.launch_clike(synth.NOISE_LEVEL, -0.5)
+        t.fill_from_launch(r0)
+    Lmins, _, _ = t.prepare()
+    cands = synth.parameter_points(12, seed=99)
+    ds.begin_draw(None, Lmins)                       # host path
+    k1, L1, c1 = ds.draw_batch(cands, synth.NOISE_LEVEL)
+    t.stage_thresholds()                             # device path
+    k2, L2, c2 = ds.draw_batch(cands, synth.NOISE_LEVEL)
+    assert k1 == k2 and numpy.array_equal(c1, c2)
+    if k1 >= 0:
+        assert numpy.array_equal(L1, L2)
+    # the counts are what numpy gives on the downloaded table
+    full = ds.loglike_batch(cands, None, synth.NOISE_LEVEL)
+    assert numpy.array_equal(c2, (full > t.download().min(axis=0)).sum(axis=1))
+    ds.set_mask(synth.masks(ndata)['half'])
+    with pytest.raises(_lib.MdnsError):
+        _lib.check(_lib.load().mdns_livetable_stage_thresholds(t._h, ds._h), 'stage_thresholds')
