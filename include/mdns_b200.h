@@ -240,6 +240,14 @@ int mdns_region_set_members(mdns_region *rg, const double *xx, int n, int ndim);
 int mdns_region_count_within(mdns_region *rg, double maxdistance,
                              const double *yy, int m, double *out, int countmax);
 /* cneighbors.c:77-92: *result = 1 if any member is within maxdistance of y. */
+/* Candidate generation on the device (the ball draws of RadFriendsRegion.generate,
+ * radfriendsregion.py:156-178, fused with the neighbour count): proposals
+ * first_proposal .. first_proposal+nproposals-1 of the stream keyed by `seed` (counter-based
+ * Philox, not the numpy stream: statistical parity only); the accepted points (uniform in the
+ * union of balls of radius maxdistance around the members) land in points_out[n_out][ndim], in
+ * proposal order.  capacity = points points_out can hold (nproposals is always enough). */
+int mdns_region_generate(mdns_region *rg, double maxdistance, uint64_t seed, uint64_t first_proposal,
+                         int nproposals, double *points_out, int64_t capacity, int *n_out);
 int mdns_region_is_within(mdns_region *rg, double maxdistance, const double *y,
                           int *result);
 /* cneighbors.c:125-179: chosen[n][nboot] float64 0/1 (round index fastest). */

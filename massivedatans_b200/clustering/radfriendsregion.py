@@ -59,6 +59,16 @@ class ResidentMembers(object):
                                                    ctypes.byref(res)), 'mdns_region_is_within')
         return res.value == 1
 
+    def generate(self, maxdistance, nproposals, seed, first_proposal=0):
+        """``nproposals`` ball draws fused with the neighbour count on the device; returns the
+        accepted points [k, ndim] (uniform in the union of balls), in proposal order."""
+        out = numpy.empty((int(nproposals), self.ndim))
+        n = ctypes.c_int(0)
+        _lib.check(self._lib.mdns_region_generate(self._h, maxdistance, int(seed), int(first_proposal),
+                                                  int(nproposals), out.ctypes.data, int(nproposals),
+                                                  ctypes.byref(n)), 'mdns_region_generate')
+        return out[:n.value]
+
     def bootstrapped_maxdistance(self, nbootstraps):
         # selection matrix drawn on the host exactly as clustering/neighbors.py:172-174
         chosen = numpy.zeros((self.n, nbootstraps))
@@ -127,6 +137,13 @@ class RadFriendsRegion(object):
         with numpy.errstate(divide='ignore'):
             keep = coin < 1. / nnear
         return us[keep, :]
+
+    def generate_device(self, nproposals, seed, first_proposal=0):
+        """Device-side candidate generation: ball draws, neighbour count
+        and 1/count thinning in one kernel; the random numbers are Philox(seed, proposal index),
+        NOT numpy's, so this is a statistically equivalent alternative to ``generate`` -- use the
+        latter where a seeded run must reproduce the reference draw by draw."""
+        return self._resident.generate(self.maxdistance, nproposals, seed, first_proposal)
 
     def generate(self, nmax=0):
         """Yield ``(accepted points [k, ndim], proposals spent since the last yield)`` like

@@ -1271,6 +1271,12 @@ struct mdns_region {
 	size_t rcounts_cap = 0;
 	double *d_result = nullptr;       // 1 double
 	int *d_flag = nullptr;            // 1 int
+	// device-side candidate generation
+	double *d_gen_points = nullptr, *d_gen_out = nullptr;
+	uint8_t *d_gen_keep = nullptr;
+	int *d_gen_nnear = nullptr, *d_gen_idx = nullptr, *d_gen_scratch = nullptr, *d_gen_count = nullptr;
+	size_t gen_points_cap = 0, gen_out_cap = 0, gen_keep_cap = 0, gen_nnear_cap = 0, gen_idx_cap = 0,
+	       gen_scratch_cap = 0;
 };
 
 extern "C" {
@@ -1326,6 +1332,13 @@ int mdns_region_destroy(mdns_region *rg)
 	cudaFree(rg->d_rcounts);
 	cudaFree(rg->d_result);
 	cudaFree(rg->d_flag);
+	cudaFree(rg->d_gen_points);
+	cudaFree(rg->d_gen_out);
+	cudaFree(rg->d_gen_keep);
+	cudaFree(rg->d_gen_nnear);
+	cudaFree(rg->d_gen_idx);
+	cudaFree(rg->d_gen_scratch);
+	cudaFree(rg->d_gen_count);
 	if (rg->stream) cudaStreamDestroy(rg->stream);
 	delete rg;
 	return MDNS_OK;
@@ -1404,6 +1417,60 @@ int mdns_region_count_within(mdns_region *rg, double maxdistance, const double *
 			}
 		}
 	}
+	return MDNS_OK;
+}
+
+int mdns_region_generate(mdns_region *rg, double maxdistance, uint64_t seed, uint64_t first_proposal,
+                         int nproposals, double *points_out, int64_t capacity, int *n_out)
+{
+	if (!rg || !points_out || !n_out || nproposals < 0) {
+		set_error("mdns_region_generate: need rg, points_out, n_out, nproposals >= 0");
+		return MDNS_EINVAL;
+	}
+	*n_out = 0;
+	if (rg->ndim == 0 || rg->n == 0) {
+		set_error("region has no members: call mdns_region_set_members first");
+		return MDNS_ESTATE;
+	}
+	if (!(maxdistance > 0.0)) {
+		set_error("mdns_region_generate: maxdistance must be positive");
+		return MDNS_EINVAL;
+	}
+	const int m = nproposals, D = rg->ndim;
+	if (m == 0) return MDNS_OK;
+	MDNS_CUDA(cudaSetDevice(rg->device));
+	int rc = grow(&rg->d_gen_points, &rg->gen_points_cap, (size_t)m * D, false);
+	if (rc == MDNS_OK) rc = grow(&rg->d_gen_out, &rg->gen_out_cap, (size_t)m * D, false);
+	if (rc == MDNS_OK) rc = grow(&rg->d_gen_keep, &rg->gen_keep_cap, round_up(m, 16) + 16, true);
+	if (rc == MDNS_OK) rc = grow(&rg->d_gen_nnear, &rg->gen_nnear_cap, (size_t)m, false);
+	if (rc == MDNS_OK) rc = grow(&rg->d_gen_idx, &rg->gen_idx_cap, (size_t)m, false);
+	if (rc == MDNS_OK) rc = grow(&rg->d_gen_scratch, &rg->gen_scratch_cap, (size_t)ceil_div(m, 4096) + 1, false);
+	if (rc != MDNS_OK) return rc;
+	if (!rg->d_gen_count) MDNS_CUDA(cudaMalloc((void **)&rg->d_gen_count, sizeof(int)));
+	// the compaction reads 16-byte words: clear the tail of the flag buffer
+	MDNS_CUDA(cudaMemsetAsync(rg->d_gen_keep, 0, round_up(m, 16) + 16, rg->stream));
+	rc = launch_region_generate(rg->d_xs, rg->n, rg->npad, D, maxdistance, sqrt_threshold(maxdistance),
+	                            seed, first_proposal, m, rg->d_gen_points, rg->d_gen_keep,
+	                            rg->d_gen_nnear, rg->stream);
+	if (rc == MDNS_OK)
+		rc = launch_compact_mask(rg->d_gen_keep, m, rg->d_gen_scratch, rg->d_gen_idx, rg->d_gen_count,
+		                         rg->stream);
+	if (rc != MDNS_OK) return rc;
+	int kept = 0;
+	MDNS_CUDA(cudaMemcpyAsync(&kept, rg->d_gen_count, sizeof(int), cudaMemcpyDeviceToHost, rg->stream));
+	MDNS_CUDA(cudaStreamSynchronize(rg->stream));
+	if ((int64_t)kept > capacity) {
+		set_error("%d points accepted, the output holds %lld", kept, (long long)capacity);
+		return MDNS_EINVAL;
+	}
+	if (kept > 0) {
+		rc = launch_gather_points(rg->d_gen_points, D, rg->d_gen_idx, kept, rg->d_gen_out, rg->stream);
+		if (rc != MDNS_OK) return rc;
+		MDNS_CUDA(cudaMemcpyAsync(points_out, rg->d_gen_out, (size_t)kept * D * sizeof(double),
+		                          cudaMemcpyDeviceToHost, rg->stream));
+		MDNS_CUDA(cudaStreamSynchronize(rg->stream));
+	}
+	*n_out = kept;
 	return MDNS_OK;
 }
 

@@ -121,6 +121,13 @@ int tile_constant_capacity();
 // members in SoA layout xs[k*npad + i]
 int launch_count_within(const double *xs, int n, int npad, int ndim, const double *yy, int m,
                         double T, int stop_at, int *counts, int sm_count, cudaStream_t st);
+// m ball draws of RadFriendsRegion.generate fused with the neighbour count: points[m][ndim],
+// keep[m] (accepted with probability 1/nnear), nnear[m]; Philox keyed by (seed, first + j)
+int launch_region_generate(const double *xs, int n, int npad, int ndim, double r, double T,
+                           unsigned long long seed, unsigned long long first, int m, double *points,
+                           uint8_t *keep, int *nnear, cudaStream_t st);
+int launch_gather_points(const double *points, int ndim, const int *idx, int n, double *out,
+                         cudaStream_t st);
 int launch_within_single(const double *xs, int n, int npad, int ndim, const double *y, double T,
                          int *flag, cudaStream_t st);
 // chosen[n][nboot] doubles -> per round: query list (un-chosen i) and reference list (chosen j).

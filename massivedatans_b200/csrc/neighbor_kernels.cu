@@ -156,6 +156,155 @@ int launch_count_within(const double *xs, int n, int npad, int ndim, const doubl
 	}
 }
 
+// ------------------------------------------- candidate generation (fused) ---
+// the ball draws of RadFriendsRegion.generate
+// (radfriendsregion.py:156-178) fused with the neighbour count on the device.  Proposal p picks a
+// member, a direction (normalised normal vector) and a radius r*u^(1/D), counts the members
+// within r of the proposed point and keeps it with probability 1/count -- a uniform draw from
+// the union of balls.  The random numbers come from a counter-based generator (Philox4x32-10
+// keyed by the seed, counter = proposal index), so the result depends only on (seed, first
+// proposal index), not on the launch shape.  This is NOT the numpy stream of the reference:
+// parity with radfriendsregion.py is statistical (tests/test_gpu_region.py), the seed-exact
+// mirror stays clustering/radfriendsregion.py on the host RNG.
+struct Philox {
+	uint32_t c[4], k[2];
+	__device__ __forceinline__ void round()
+	{
+		const uint32_t lo0 = 0xD2511F53u * c[0], hi0 = __umulhi(0xD2511F53u, c[0]);
+		const uint32_t lo1 = 0xCD9E8D57u * c[2], hi1 = __umulhi(0xCD9E8D57u, c[2]);
+		const uint32_t n0 = hi1 ^ c[1] ^ k[0], n2 = hi0 ^ c[3] ^ k[1];
+		c[0] = n0;
+		c[1] = lo1;
+		c[2] = n2;
+		c[3] = lo0;
+		k[0] += 0x9E3779B9u;
+		k[1] += 0xBB67AE85u;
+	}
+};
+
+// four 32-bit words for (seed, proposal, block)
+__device__ __forceinline__ uint4 philox4(unsigned long long seed, unsigned long long idx, uint32_t block)
+{
+	Philox p;
+	p.c[0] = (uint32_t)idx;
+	p.c[1] = (uint32_t)(idx >> 32);
+	p.c[2] = block;
+	p.c[3] = 0x5eed5eedu;
+	p.k[0] = (uint32_t)seed;
+	p.k[1] = (uint32_t)(seed >> 32);
+#pragma unroll
+	for (int r = 0; r < 10; ++r) p.round();
+	return make_uint4(p.c[0], p.c[1], p.c[2], p.c[3]);
+}
+
+// uniform in (0, 1) from 53 random bits
+__device__ __forceinline__ double u01(uint32_t a, uint32_t b)
+{
+	const unsigned long long bits = ((unsigned long long)a << 21) ^ (unsigned long long)(b >> 11);
+	return ((double)(bits & ((1ULL << 53) - 1)) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+template <int D>
+__global__ void __launch_bounds__(NB_THREADS) region_generate_kernel(
+    const double *__restrict__ xs, int n, int npad, double r, double T, unsigned long long seed,
+    unsigned long long first, int m, double *__restrict__ points, uint8_t *__restrict__ keep,
+    int *__restrict__ nnear_out)
+{
+	const int lane = threadIdx.x & 31;
+	const long long j = ((long long)blockIdx.x * NB_THREADS + threadIdx.x) >> 5;   // proposal
+	if (j >= m) return;
+	const unsigned long long idx = first + (unsigned long long)j;
+	// every lane computes the same proposal (cheap), then the warp shares the member scan
+	const uint4 w0 = philox4(seed, idx, 0);
+	const int centre = (int)(((unsigned long long)w0.x * (unsigned long long)n) >> 32);
+	const double urad = u01(w0.y, w0.z);
+	double y[D];
+	double norm2 = 0.0;
+#pragma unroll
+	for (int k = 0; k < D; k += 2) {
+		const uint4 w = philox4(seed, idx, 1 + k / 2);
+		const double u1 = u01(w.x, w.y), u2 = u01(w.z, w.w);
+		const double rad = sqrt(-2.0 * log(u1));
+		double s, c;
+		sincospi(2.0 * u2, &s, &c);
+		y[k] = rad * c;
+		norm2 += y[k] * y[k];
+		if (k + 1 < D) {
+			y[k + 1] = rad * s;
+			norm2 += y[k + 1] * y[k + 1];
+		}
+	}
+	const uint4 wc = philox4(seed, idx, 1 + (D + 1) / 2);
+	const double coin = u01(wc.x, wc.y);
+	const double scale = r * pow(urad, 1.0 / D) / sqrt(norm2);
+#pragma unroll
+	for (int k = 0; k < D; ++k) y[k] = xs[(size_t)k * npad + centre] + y[k] * scale;
+	int cnt = 0;
+	for (int base = 0; base < n; base += 32) {
+		const int i = base + lane;
+		const bool valid = i < n;
+		double x[D];
+#pragma unroll
+		for (int k = 0; k < D; ++k) x[k] = valid ? xs[(size_t)k * npad + i] : 0.0;
+		const double d = sqdist_reg<D>(x, y);
+		cnt += __popc(__ballot_sync(0xffffffffu, valid && d < T));
+	}
+	if (lane == 0) {
+#pragma unroll
+		for (int k = 0; k < D; ++k) points[(size_t)j * D + k] = y[k];
+		// the centre itself is within r, so cnt >= 1 up to rounding at the surface
+		keep[j] = (cnt <= 1 || coin * cnt < 1.0) ? 1 : 0;
+		nnear_out[j] = cnt;
+	}
+}
+
+__global__ void __launch_bounds__(256) gather_points_kernel(const double *__restrict__ points, int D,
+                                                            const int *__restrict__ idx, int n,
+                                                            double *__restrict__ out)
+{
+	const int i = blockIdx.x * 256 + threadIdx.x;
+	if (i >= n * D) return;
+	out[i] = points[(size_t)idx[i / D] * D + i % D];
+}
+
+int launch_region_generate(const double *xs, int n, int npad, int ndim, double r, double T,
+                           unsigned long long seed, unsigned long long first, int m, double *points,
+                           uint8_t *keep, int *nnear, cudaStream_t st)
+{
+	if (m <= 0) return MDNS_OK;
+	const int blocks = ceil_div(m, NB_THREADS / 32);
+#define MDNS_GEN_CASE(D)                                                                       \
+	case D:                                                                                \
+		region_generate_kernel<D><<<blocks, NB_THREADS, 0, st>>>(xs, n, npad, r, T, seed, first, m, \
+		                                                        points, keep, nnear);         \
+		break
+	switch (ndim) {
+		MDNS_GEN_CASE(1);
+		MDNS_GEN_CASE(2);
+		MDNS_GEN_CASE(3);
+		MDNS_GEN_CASE(4);
+		MDNS_GEN_CASE(5);
+		MDNS_GEN_CASE(6);
+		MDNS_GEN_CASE(7);
+		MDNS_GEN_CASE(8);
+	default:
+		set_error("device candidate generation supports 1..8 dimensions, not %d", ndim);
+		return MDNS_EINVAL;
+	}
+#undef MDNS_GEN_CASE
+	MDNS_LAUNCHED("region_generate_kernel");
+	return MDNS_OK;
+}
+
+int launch_gather_points(const double *points, int ndim, const int *idx, int n, double *out,
+                         cudaStream_t st)
+{
+	if (n <= 0) return MDNS_OK;
+	gather_points_kernel<<<ceil_div((long long)n * ndim, 256), 256, 0, st>>>(points, ndim, idx, n, out);
+	MDNS_LAUNCHED_HELPER("gather_points_kernel");
+	return MDNS_OK;
+}
+
 // ------------------------------------------------------- single-point test ---
 // cneighbors.c:77-92: members are spread over the whole grid; any hit raises the flag.
 __global__ void __launch_bounds__(NB_THREADS) within_single_kernel(const double *__restrict__ xs,

@@ -43,3 +43,39 @@ def test_region_given_radius_and_far_point():
     assert (region.count_nearby_members(members) >= 1).all()
     with pytest.raises(NotImplementedError):
         RadFriendsRegion(members=members, metric='chebyshev')
+
+
+@pytest.mark.parametrize('ndim,n', [(3, 400), (2, 60), (5, 300)])
+def test_device_generation_is_uniform_in_the_region(ndim, n):
+    # statistical parity with the host generator (radfriendsregion.py:156-178): both draw
+    # uniformly from the union of balls
+    rs = numpy.random.RandomState(ndim)
+    members = rs.uniform(size=(n, ndim))
+    region = RadFriendsRegion(members=members, maxdistance=0.18 if ndim == 3 else 0.25)
+    m = 200000
+    dev = region.generate_device(m, seed=7)
+    numpy.random.seed(5)
+    host = numpy.vstack([region._ball_round(1000, ndim) for _ in range(m // 1000)])
+    # (1) every generated point lies in the region
+    assert region.are_inside(dev).all()
+    # (2) same acceptance rate (binomial error)
+    p_dev, p_host = len(dev) / m, len(host) / m
+    sigma = numpy.sqrt(p_host * (1 - p_host) / m * 2)
+    assert abs(p_dev - p_host) < 5 * sigma, (p_dev, p_host)
+    # (3) same first and second moments
+    se = host.std(axis=0) / numpy.sqrt(len(host)) * numpy.sqrt(2)
+    assert (numpy.abs(dev.mean(axis=0) - host.mean(axis=0)) < 5 * se).all()
+    assert numpy.allclose(numpy.cov(dev.T), numpy.cov(host.T), rtol=0.05, atol=2e-3)
+    # (4) uniform density: the number of members near a generated point is distributed alike
+    nd = numpy.bincount(region.count_nearby_members(dev[:50000]), minlength=40)[:40]
+    nh = numpy.bincount(region.count_nearby_members(host[:50000]), minlength=40)[:40]
+    fd, fh = nd / nd.sum(), nh / nh.sum()
+    err = numpy.sqrt((fd + fh) / min(nd.sum(), nh.sum())) + 1e-4
+    assert (numpy.abs(fd - fh) < 6 * err).all()
+    # (5) the stream is counter-based: same seed -> same points, split launches concatenate
+    again = region.generate_device(m, seed=7)
+    assert numpy.array_equal(dev, again)
+    a = region.generate_device(50000, seed=7, first_proposal=0)
+    b = region.generate_device(m - 50000, seed=7, first_proposal=50000)
+    assert numpy.array_equal(numpy.vstack([a, b]), dev)
+    assert not numpy.array_equal(region.generate_device(1000, seed=8)[:5], dev[:5])
