@@ -9,8 +9,9 @@ them are bit-exact with cneighbors.c).  What changes: the members are uploaded t
 once per region (``mdns_region_set_members``) instead of once per neighbour call.
 
 SURVEY.md section 8(f) rank 3 asks for candidate generation fused with the neighbour test on
-the device; that would change the RNG stream (statistical parity only), so this mirror keeps the
-host RNG and moves only the member set.
+the device; that changes the RNG stream (statistical parity only), so ``generate`` keeps the
+host RNG and moves only the member set, and the fused device form is the separate
+``generate_device`` (counter-based Philox stream, ``mdns_region_generate``).
 """
 import ctypes
 import weakref
@@ -85,6 +86,7 @@ class RadFriendsRegion(object):
     """Union of balls of radius ``maxdistance`` around ``members`` (radfriendsregion.py:58-70)."""
 
     PROPOSALS = 1000          # points per proposal round (radfriendsregion.py:124)
+    members_class = ResidentMembers   # who answers the neighbour queries (tests: the CPU oracle)
 
     def __init__(self, members, maxdistance=None, metric='euclidean', nbootstraps=10,
                  verbose=False, device=0):
@@ -92,7 +94,7 @@ class RadFriendsRegion(object):
             raise NotImplementedError('only the euclidean metric runs natively '
                                       '(radfriendsregion.py:61)')
         self.members = members
-        self._resident = ResidentMembers(members, device=device)
+        self._resident = self.members_class(members, device=device)
         if maxdistance is None:
             maxdistance = self._resident.bootstrapped_maxdistance(nbootstraps)
         self.maxdistance = maxdistance

@@ -300,13 +300,29 @@ def make_multi_loglikelihood(x, y, noise_level=0.01, devices=None):
     """Build the callable of sample.py:101-108 over a resident copy of (x, y).
 
     Returns ``multi_loglikelihood(params, data_mask)`` with ``params = (A, mu, log_sig)``;
-    the attribute ``.dataset`` exposes the ResidentDataset and ``.batch(params_list,
-    data_mask)`` evaluates several parameter vectors in one pass.
+    the attribute ``.dataset`` exposes the ResidentDataset, ``.batch(params_list, data_mask)``
+    evaluates several parameter vectors in one pass, and ``.speculate`` / ``.last_draw`` are the
+    hook massivedatans_b200.hiermetriclearn uses to batch a constrained draw through the
+    sampler's lambda.
     """
     ds = ResidentDataset(x, y, devices=devices)
     p = numpy.empty((1, 3))
 
+    pending = []
+
+    def _points(params_list):
+        q = numpy.array(params_list, dtype=numpy.float64).reshape((-1, 3))
+        q[:, 2] = 10 ** q[:, 2]
+        return q
+
     def multi_loglikelihood(params, data_mask):
+        if pending:
+            # a batch announced by speculate(): the mask only arrives with this call
+            q, Lmins = pending.pop()
+            ds.begin_draw(data_mask, Lmins)
+            k, L, counts = ds.draw_batch(q, noise_level)
+            multi_loglikelihood.last_draw = (k, L, counts)
+            return L if k == 0 else None
         A, mu, log_sig_kms = params
         p[0, 0] = A
         p[0, 1] = mu
@@ -314,12 +330,23 @@ def make_multi_loglikelihood(x, y, noise_level=0.01, devices=None):
         return ds.loglike_batch(p, data_mask, noise_level)[0]
 
     def batch(params_list, data_mask):
-        q = numpy.array(params_list, dtype=numpy.float64).reshape((-1, 3))
-        q[:, 2] = 10 ** q[:, 2]
-        return ds.loglike_batch(q, data_mask, noise_level)
+        return ds.loglike_batch(_points(params_list), data_mask, noise_level)
+
+    def speculate(params_list, Lmins):
+        """Announce the next candidates of a constrained draw (hiermetriclearn.py:181-196) and
+        the thresholds they are tested against.  The NEXT ``multi_loglikelihood(params_list[0],
+        data_mask)`` call scores all of them in one pass with the accept test on the device and
+        leaves ``(k, L_k, counts)`` in ``.last_draw``: k = first candidate with
+        ``any(L > Lmins)`` (-1: none), L_k = its logL vector, counts = accepting data sets per
+        candidate.  That call returns L_0 only if k == 0 (no other logL vector leaves the
+        device), else None."""
+        del pending[:]
+        pending.append((_points(params_list), numpy.array(Lmins, dtype=numpy.float64)))
 
     multi_loglikelihood.dataset = ds
     multi_loglikelihood.batch = batch
+    multi_loglikelihood.speculate = speculate
+    multi_loglikelihood.last_draw = None
     return multi_loglikelihood
 
 
