@@ -22,7 +22,9 @@ through the likelihood callable itself: ``speculator.speculate(xs, Lmins)`` anno
 the next ``loglikelihood(xs[0])`` call carries the mask and runs it, ``speculator.last_draw``
 holds ``(k, L_k, counts)``.  ``massivedatans_b200.likelihood.make_multi_loglikelihood`` returns
 such a callable.  Without a speculator (or with ``batch_size=1``) every candidate is scored by
-its own call, as in the reference.
+its own call, as in the reference.  ``adaptive`` (default) starts every draw with one candidate
+and doubles the pass width after each fully rejected pass, so an easy draw costs what it costs
+in the reference and a long rejection chain of n candidates takes about log2(n) passes.
 
 Python-3 note: hiermetriclearn.py:53 compares ``maxdistance`` with
 ``prev_maxdistance = None``; here "no previous radius" skips the ``force_shrink`` branch.
@@ -39,7 +41,7 @@ UNIT_CUBE_CHANCE = 0.1           # hiermetriclearn.py:126
 class MetricLearningFriendsConstrainer(object):
     def __init__(self, metriclearner, rebuild_every=50, metric_rebuild_every=50, verbose=False,
                  keep_phantom_points=False, optimize_phantom_points=False, force_shrink=False,
-                 batch_size=16, speculator=None, region_class=RadFriendsRegion):
+                 batch_size=16, speculator=None, adaptive=True, region_class=RadFriendsRegion):
         if metriclearner not in ('none', 'simplescaling', 'truncatedscaling'):
             raise ValueError('unknown metriclearner %r' % (metriclearner,))
         self.iter_since_metric_rebuild = 0
@@ -58,6 +60,7 @@ class MetricLearningFriendsConstrainer(object):
         self.generator = None
         self.batch_size = max(1, int(batch_size))
         self.speculator = speculator
+        self.adaptive = bool(adaptive)
         self.region_class = region_class
         self._queue = []             # candidates of the current proposal round, not yet scored
         self.nbatches = 0            # likelihood passes issued
@@ -198,8 +201,12 @@ class MetricLearningFriendsConstrainer(object):
         rebuild, rebuild_metric = self._draw_constrained_prepare(
             Lmins, priortransform, loglikelihood, live_pointsu, ndim, **kwargs)
         speculative = self.speculator is not None and self.batch_size > 1
+        # adaptive: most draws are accepted at the first try, so the first pass scores one
+        # candidate; every fully rejected pass doubles the next one up to batch_size
+        width = 1 if self.adaptive else self.batch_size
         while True:
-            batch = self._peek(self.batch_size if speculative else 1)
+            batch = self._peek(min(width, self.batch_size) if speculative else 1)
+            width *= 2
             for u, _ in batch:
                 assert (u >= 0).all() and (u <= 1).all(), u
             xs = [priortransform(u) for u, _ in batch]

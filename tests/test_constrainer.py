@@ -112,13 +112,15 @@ class OracleLikelihood(object):
         return Ls[0] if k == 0 else None
 
 
-@pytest.mark.parametrize('tag,batch', [('a', 1), ('a', 16), ('b', 4), ('c', 1), ('c', 7)])
-def test_constrainer_reproduces_reference_draws_on_the_oracle(fixture, tag, batch):
+@pytest.mark.parametrize('tag,batch,adaptive', [('a', 1, False), ('a', 16, False), ('a', 16, True),
+                                                ('b', 4, False), ('c', 1, True), ('c', 7, False),
+                                                ('c', 8, True)])
+def test_constrainer_reproduces_reference_draws_on_the_oracle(fixture, tag, batch, adaptive):
     ndata, nlive, niter, seed_data, seed_run = fixture[tag + '_cfg']
     x, y, _ = synth.horns(int(ndata), seed=int(seed_data))
     like = OracleLikelihood(x, y)
     c = MetricLearningFriendsConstrainer(batch_size=batch, speculator=like if batch > 1 else None,
-                                         region_class=OracleRegion, **CONFIG[tag])
+                                         adaptive=adaptive, region_class=OracleRegion, **CONFIG[tag])
     res = run_draws(c, like, int(ndata), int(nlive), int(niter), int(seed_run))
     check(res, fixture, tag)
     assert c.region.maxdistance == float(fixture[tag + '_maxdistance'])
@@ -136,15 +138,16 @@ def test_constrainer_rejects_unknown_metric():
 
 # ------------------------------------------------------------------------- GPU: the product path
 @pytest.mark.gpu
-@pytest.mark.parametrize('tag,batch', [('a', 1), ('a', 16), ('b', 8), ('c', 16)])
-def test_constrainer_reproduces_reference_draws_on_the_device(fixture, tag, batch):
+@pytest.mark.parametrize('tag,batch,adaptive', [('a', 1, False), ('a', 16, False), ('a', 16, True),
+                                                ('b', 8, False), ('c', 16, True)])
+def test_constrainer_reproduces_reference_draws_on_the_device(fixture, tag, batch, adaptive):
     from massivedatans_b200 import _lib
     from massivedatans_b200.likelihood import make_multi_loglikelihood
     ndata, nlive, niter, seed_data, seed_run = fixture[tag + '_cfg']
     x, y, _ = synth.horns(int(ndata), seed=int(seed_data))
     like = make_multi_loglikelihood(x, y, synth.NOISE_LEVEL)
     c = MetricLearningFriendsConstrainer(batch_size=batch, speculator=like if batch > 1 else None,
-                                         **CONFIG[tag])
+                                         adaptive=adaptive, **CONFIG[tag])
     before = _lib.load().mdns_launch_count()
     res = run_draws(c, like, int(ndata), int(nlive), int(niter), int(seed_run))
     assert _lib.load().mdns_launch_count() > before
@@ -168,7 +171,7 @@ def test_speculation_at_scale_matches_one_by_one():
     runs = []
     for batch in (1, 16):
         c = MetricLearningFriendsConstrainer(batch_size=batch, speculator=like if batch > 1 else None,
-                                             **CONFIG['a'])
+                                             adaptive=False, **CONFIG['a'])
         runs.append((run_draws(c, like, ndata, nlive, niter, 9), c))
     (r1, c1), (r16, c16) = runs
     assert numpy.array_equal(r1['u'], r16['u'])

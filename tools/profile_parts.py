@@ -57,6 +57,23 @@ def main():
         q = neighbors.most_distant_nearest_neighbor(xx)
     print('most_distant_nearest_neighbor: %.3f ms (%.5f)'
           % (1e3 * (time.perf_counter() - t0) / args.reps, q))
+    # device-side candidate generation (ball draws + neighbour count + thinning in one kernel)
+    from massivedatans_b200.clustering.radfriendsregion import RadFriendsRegion
+    region = RadFriendsRegion(members=xx, maxdistance=r)
+    pts = region.generate_device(m, seed=1)
+    t0 = time.perf_counter()
+    for i in range(args.reps):
+        pts = region.generate_device(m, seed=1, first_proposal=(i + 1) * m)
+    t_gen = (time.perf_counter() - t0) / args.reps
+    print('generate_device n=%d proposals=%d: %.3f ms (accepted points to the host included), '
+          '%.3e proposals/s, %.3e pair tests/s, accepted fraction %.3f'
+          % (n, m, 1e3 * t_gen, m / t_gen, n * float(m) / t_gen, len(pts) / float(m)))
+    t0 = time.perf_counter()
+    numpy.random.seed(2)
+    host = [region._ball_round(1000, d) for _ in range(max(1, m // 1000))]
+    t_host = time.perf_counter() - t0
+    print('host-RNG ball rounds (numpy draws + device neighbour count), same number of proposals: '
+          '%.3f ms, accepted fraction %.3f' % (1e3 * t_host, sum(len(h) for h in host) / float(m)))
     # MUSE-type likelihood, cube wider than L2
     y, v, t = synth.muse(ndata=args.muse_ndata, nspec=3600)
     ds = ResidentDataset(None, y, variance=v)
