@@ -239,15 +239,28 @@ __global__ void __launch_bounds__(NB_THREADS) region_generate_kernel(
 	const double scale = r * pow(urad, 1.0 / D) / sqrt(norm2);
 #pragma unroll
 	for (int k = 0; k < D; ++k) y[k] = xs[(size_t)k * npad + centre] + y[k] * scale;
+	// The count only thins the proposals (no bit-exact contract with cneighbors.c here), so the
+	// squared distance uses fused multiply-adds: 2D instead of 3D-1 FP64 instructions per pair.
+	// Two chunks of 32 members are in flight per iteration, as in count_within_kernel.
 	int cnt = 0;
-	for (int base = 0; base < n; base += 32) {
-		const int i = base + lane;
-		const bool valid = i < n;
-		double x[D];
+	for (int base = 0; base < n; base += 64) {
+		const int i0 = base + lane, i1 = base + 32 + lane;
+		const bool valid0 = i0 < n, valid1 = i1 < n;
+		double x0[D], x1[D];
 #pragma unroll
-		for (int k = 0; k < D; ++k) x[k] = valid ? xs[(size_t)k * npad + i] : 0.0;
-		const double d = sqdist_reg<D>(x, y);
-		cnt += __popc(__ballot_sync(0xffffffffu, valid && d < T));
+		for (int k = 0; k < D; ++k) {
+			x0[k] = valid0 ? xs[(size_t)k * npad + i0] : 0.0;
+			x1[k] = valid1 ? xs[(size_t)k * npad + i1] : 0.0;
+		}
+		double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+		for (int k = 0; k < D; ++k) {
+			const double t0 = x0[k] - y[k], t1 = x1[k] - y[k];
+			d0 = __fma_rn(t0, t0, d0);
+			d1 = __fma_rn(t1, t1, d1);
+		}
+		cnt += __popc(__ballot_sync(0xffffffffu, valid0 && d0 < T));
+		cnt += __popc(__ballot_sync(0xffffffffu, valid1 && d1 < T));
 	}
 	if (lane == 0) {
 #pragma unroll
