@@ -104,6 +104,36 @@ int mdns_muse_eval_spectra(mdns_dataset *ds, const double *ypred, int K,
                            const uint8_t *mask, double *Lout);
 
 /*
+ * MUSE stellar-population model on the device (musefuse.py:222-284 `model`), so that a batch of
+ * K parameter points becomes K staged model spectra without a spectrum crossing PCIe.
+ *   grids[nZ][nages][nwave]  template grids, one [nages][nwave] array per metallicity
+ *                            (musefuse.py:176-185 `grid`), non-negative
+ *   Zs[nZ]                   metallicity nodes, increasing (musefuse.py:188)
+ *   ages[nages]              template ages in yr, increasing (musefuse.py:191)
+ *   model_wavelength[nwave]  template wavelengths, strictly increasing, same unit as
+ *                            `wavelength` (musefuse.py:206-207)
+ *   calzetti[nwave]          attenuation curve on the template grid (musefuse.py:208-217)
+ *   wavelength[nx]           data wavelength grid; nx = channels of the data set
+ *   norm_index               template channel the spectrum is normalised at (2050, :255)
+ * Everything is copied to every device of `ds`.
+ */
+typedef struct mdns_muse_model mdns_muse_model;
+int mdns_muse_model_create(mdns_dataset *ds, const double *grids, int nZ, const double *Zs,
+                           int nages, const double *ages, int nwave,
+                           const double *model_wavelength, const double *calzetti,
+                           const double *wavelength, int nx, int norm_index,
+                           mdns_muse_model **out);
+int mdns_muse_model_destroy(mdns_muse_model *m);
+/* params[K][5] = (Z, SFtau, sfage, z, EBV), the arguments of model() (SFtau in yr, i.e.
+ * 10**logSFtau, musefuse.py:524).  Builds the K spectra and stages them like
+ * mdns_stage_spectra; follow with mdns_set_mask + mdns_muse_launch + mdns_fetch.
+ * nonzero[K] (may be NULL): numpy.any(ypred) per spectrum, the guard of musefuse.py:528-530.
+ * MDNS_EINVAL if a metallicity lies below Zs[0] (the reference raises IndexError there). */
+int mdns_muse_model_stage(mdns_muse_model *m, const double *params, int K, int *nonzero);
+/* The K spectra of the last mdns_muse_model_stage, ypred_out[K][nx] (parity checks). */
+int mdns_muse_model_spectra(mdns_muse_model *m, double *ypred_out);
+
+/*
  * Staged interface (inputs resident in HBM; used for device-side timing and
  * by callers that keep the mask across many candidates, e.g. one
  * draw_constrained call, hiermetriclearn.py:173-211).

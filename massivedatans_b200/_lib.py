@@ -67,6 +67,11 @@ SIGNATURES = {
     'mdns_timer_start': (c_int, [_P]),
     'mdns_timer_stop': (c_int, [_P, POINTER(c_float)]),
     'mdns_set_tuning': (c_int, [_P, c_int, c_int, c_int, c_int]),
+    'mdns_muse_model_create': (c_int, [_P, _P, c_int, _P, c_int, _P, c_int, _P, _P, _P, c_int, c_int,
+                                       POINTER(_P)]),
+    'mdns_muse_model_destroy': (c_int, [_P]),
+    'mdns_muse_model_stage': (c_int, [_P, _P, c_int, _P]),
+    'mdns_muse_model_spectra': (c_int, [_P, _P]),
     'mdns_region_create': (c_int, [c_int, POINTER(c_void_p)]),
     'mdns_region_destroy': (c_int, [_P]),
     'mdns_region_set_members': (c_int, [_P, _P, c_int, c_int]),

@@ -388,6 +388,35 @@ int mdns_internal_threshold_buffer(mdns_dataset *ds, int shard, double **d_lmins
 	return MDNS_OK;
 }
 
+static int ensure_batch(mdns_dataset *ds, Shard &s, int K);
+
+// internal (muse_model.cu): the model-spectrum buffer of shard `shard` sized for K spectra
+// ([Kpad][pitch] doubles, padding zero), for a producer kernel on the shard's stream
+int mdns_internal_model_buffer(mdns_dataset *ds, int shard, int K, double **d_model, long long *pitch,
+                               int *nx)
+{
+	if (!ds || shard < 0 || shard >= (int)ds->shards.size() || K <= 0 || !d_model) return MDNS_EINVAL;
+	Shard &s = ds->shards[shard];
+	MDNS_CUDA(cudaSetDevice(s.device));
+	int rc = ensure_batch(ds, s, K);
+	if (rc != MDNS_OK) return rc;
+	*d_model = s.d_model;
+	if (pitch) *pitch = (long long)ds->pitch;
+	if (nx) *nx = ds->nx;
+	return MDNS_OK;
+}
+
+// internal (muse_model.cu): K spectra were written into every shard's model buffer by device
+// kernels on the shards' streams -- same state as after mdns_stage_spectra
+int mdns_internal_spectra_staged(mdns_dataset *ds, int K)
+{
+	if (!ds || K <= 0) return MDNS_EINVAL;
+	ds->K = K;
+	ds->staged = 2;
+	ds->launched = 0;
+	return MDNS_OK;
+}
+
 int mdns_dataset_destroy(mdns_dataset *ds)
 {
 	if (!ds) return MDNS_OK;

@@ -373,3 +373,134 @@ def make_muse_loglikelihood(y, noise_level, model, jitter=1e-5, devices=None):
     multi_loglikelihood_clike.dataset = ds
     multi_loglikelihood_clike.Lout = Lout
     return multi_loglikelihood_clike
+
+
+def calzetti(model_wavelength_nm):
+    """Calzetti attenuation curve on the template grid in nm (musefuse.py:208-217): host-side
+    table built once per model, like the reference's module-level ``calzetti_result``."""
+    w = numpy.asarray(model_wavelength_nm, dtype=numpy.float64)
+    k = numpy.zeros_like(w)
+    blue = w < 630
+    k[blue] = 2.659 * (-2.156 + 1.509e3 / w[blue] - 0.198e6 / w[blue] ** 2
+                       + 0.011e9 / w[blue] ** 3) + 4.05
+    red = w >= 630
+    k[red] = 2.659 * (-1.857 + 1.040e3 / w[red]) + 4.05
+    return k
+
+
+class DeviceMuseModel(object):
+    """``model(Z, SFtau, sfage, z, EBV)`` of musefuse.py:222-284 evaluated on the devices of a
+    ResidentDataset for batches of parameter points; the spectra are staged where
+    ``mdns_muse_launch`` reads them and never visit the host.
+
+    grids : [nZ, nages, nwave] template grids (musefuse.py:176-185, one file per metallicity)
+    Zs, ages, model_wavelength : their axes (musefuse.py:188,191,181/207); wavelengths in the unit
+        of ``wavelength``, the data grid (musefuse.py:82/206)
+    """
+
+    def __init__(self, dataset, grids, Zs, ages, model_wavelength, wavelength, calzetti_curve=None,
+                 norm_index=2050):
+        lib = _lib.load()
+        grids = numpy.ascontiguousarray(grids, dtype=numpy.float64)
+        if grids.ndim != 3:
+            raise ValueError('grids must be [nZ, nages, nwave]')
+        nZ, nages, nwave = grids.shape
+        Zs = numpy.ascontiguousarray(Zs, dtype=numpy.float64)
+        ages = numpy.ascontiguousarray(ages, dtype=numpy.float64)
+        mw = numpy.ascontiguousarray(model_wavelength, dtype=numpy.float64)
+        wl = numpy.ascontiguousarray(wavelength, dtype=numpy.float64)
+        if Zs.shape != (nZ,) or ages.shape != (nages,) or mw.shape != (nwave,):
+            raise ValueError('Zs, ages, model_wavelength must match the axes of grids')
+        if wl.shape != (dataset.nx,):
+            raise ValueError('wavelength must have one entry per channel of the data set')
+        if calzetti_curve is None:
+            calzetti_curve = calzetti(mw)
+        cz = numpy.ascontiguousarray(calzetti_curve, dtype=numpy.float64)
+        if cz.shape != (nwave,):
+            raise ValueError('calzetti_curve must have nwave entries')
+        handle = ctypes.c_void_p()
+        _lib.check(lib.mdns_muse_model_create(dataset._h, _addr(grids), nZ, _addr(Zs), nages,
+                                              _addr(ages), nwave, _addr(mw), _addr(cz), _addr(wl),
+                                              dataset.nx, int(norm_index), ctypes.byref(handle)),
+                   'mdns_muse_model_create')
+        self._lib = lib
+        self._h = handle
+        self._dataset = dataset
+        self.nx = dataset.nx
+        self._finalizer = weakref.finalize(self, lib.mdns_muse_model_destroy, handle)
+
+    def close(self):
+        self._finalizer()
+
+    def stage(self, params):
+        """params[K, 5] = (Z, SFtau, sfage, z, EBV); returns nonzero[K] (numpy.any per spectrum)."""
+        p = numpy.ascontiguousarray(params, dtype=numpy.float64).reshape((-1, 5))
+        self._last_K = len(p)
+        nonzero = numpy.zeros(len(p), dtype=numpy.int32)
+        _lib.check(self._lib.mdns_muse_model_stage(self._h, _addr(p), len(p), _addr(nonzero)),
+                   'mdns_muse_model_stage')
+        return nonzero != 0
+
+    def spectra(self):
+        """The spectra of the last ``stage`` call, [K, nx] (for checks; costs a download)."""
+        out = numpy.empty((self._last_K, self.nx))
+        _lib.check(self._lib.mdns_muse_model_spectra(self._h, _addr(out)), 'mdns_muse_model_spectra')
+        return out
+
+    def __call__(self, Z, SFtau, sfage, z, EBV):
+        """One model spectrum on the host, the reference's call signature (musefuse.py:222)."""
+        self.stage([[Z, SFtau, sfage, z, EBV]])
+        return self.spectra()[0]
+
+    def loglike_batch(self, params, data_mask, Lout):
+        """K parameter points -> ``Lout[K, ndata]`` as cmuselike.c writes it (masked entries),
+        model and likelihood on the device; returns nonzero[K]."""
+        p = numpy.ascontiguousarray(params, dtype=numpy.float64).reshape((-1, 5))
+        nonzero = self.stage(p)
+        ds = self._dataset
+        if ds.set_mask(data_mask) > 0:
+            ds.launch_muse()
+            _lib.check(self._lib.mdns_fetch(ds._h, _addr(Lout), len(p) * ds.ndata), 'mdns_fetch')
+        return nonzero
+
+
+def make_muse_loglikelihood_device(y, noise_level, grids, Zs, ages, model_wavelength, wavelength,
+                                   jitter=1e-5, devices=None, norm_index=2050):
+    """``multi_loglikelihood_clike`` of musefuse.py:520-535 with the model on the device too.
+
+    Returns ``multi_loglikelihood_clike(params, data_mask)``, params = (Z, logSFtau, SFage, z, EBV);
+    ``.batch(params_list, data_mask)`` scores several parameter vectors in one pass and returns
+    ``L[K, n_act]`` WITHOUT the jitter term (one draw per call in the reference; the caller adds
+    it where it wants the reference's stream); ``.model`` is the DeviceMuseModel.
+    """
+    ds = ResidentDataset(None, y, variance=noise_level, devices=devices)
+    model = DeviceMuseModel(ds, grids, Zs, ages, model_wavelength, wavelength, norm_index=norm_index)
+    Lout = numpy.zeros(ds.ndata)       # persistent, as the global at musefuse.py:519
+
+    def _points(params_list):
+        q = numpy.array(params_list, dtype=numpy.float64).reshape((-1, 5))
+        q[:, 1] = 10 ** q[:, 1]        # SFtau = 10**logSFtau, musefuse.py:524
+        return q
+
+    def multi_loglikelihood_clike(params, data_mask):
+        nonzero = model.loglike_batch(_points([params]), data_mask, Lout.reshape((1, -1)))
+        if not nonzero[0]:
+            # musefuse.py:528-530 -- give low probability to solutions with no stars
+            return numpy.ones(data_mask.sum()) * -1e100
+        res = Lout[data_mask]
+        if jitter:
+            res = res + numpy.random.normal(0, jitter, size=data_mask.sum())
+        return res
+
+    def batch(params_list, data_mask):
+        q = _points(params_list)
+        full = numpy.zeros((len(q), ds.ndata))
+        nonzero = model.loglike_batch(q, data_mask, full)
+        res = full[:, numpy.asarray(data_mask, dtype=bool)]
+        res[~nonzero, :] = -1e100
+        return res
+
+    multi_loglikelihood_clike.dataset = ds
+    multi_loglikelihood_clike.model = model
+    multi_loglikelihood_clike.batch = batch
+    return multi_loglikelihood_clike

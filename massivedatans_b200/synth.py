@@ -126,6 +126,51 @@ def muse(ndata=MUSE_NDATA, nspec=MUSE_NSPEC, seed=3):
     return y, v, template
 
 
+MUSE_ZS = numpy.log10([0.0001, 0.0004, 0.004, 0.008, 0.02, 0.05, 0.1])    # musefuse.py:188
+
+
+def muse_grids(nZ=7, nages=111, nwave=2400, seed=4):
+    """Synthetic stand-in for the stellar-population template grids musefuse.py:176-185 reads
+    from external BC03 text files (absent from the reference tree): per metallicity one
+    non-negative array [nages, nwave], a continuum that reddens with age plus absorption
+    features.  Returns (Zs[nZ], ages[nages] in yr (0 first, increasing), model_wavelength[nwave]
+    in Angstrom as in the files (musefuse.py:181, divided by 10 at :207), grids[nZ, nages, nwave]).
+    """
+    rg = numpy.random.default_rng(seed)
+    ages = numpy.concatenate(([0.0], numpy.logspace(5, numpy.log10(2e10), nages - 1)))
+    wl = numpy.linspace(2000.0, 11000.0, nwave)
+    t = (wl - wl[0]) / (wl[-1] - wl[0])
+    grids = numpy.empty((nZ, nages, nwave))
+    lines = rg.uniform(0.05, 0.95, size=12)
+    for iZ in range(nZ):
+        for a in range(nages):
+            red = a / float(nages)
+            cont = (1.2 - red) * numpy.exp(-3.0 * t * (1.0 - red)) + red * t ** (0.5 + 0.1 * iZ)
+            absorb = 1.0
+            for c in lines:
+                absorb = absorb - (0.1 + 0.05 * iZ) * red * numpy.exp(-0.5 * ((t - c) / 0.004) ** 2)
+            grids[iZ, a] = cont * absorb * (1.0 + 0.02 * rg.standard_normal(nwave)).clip(0.5) \
+                * 10.0 ** (-3.0 * red)
+    return MUSE_ZS[:nZ].copy(), ages, wl, grids
+
+
+def muse_wavelength(nspec=MUSE_NSPEC):
+    """Data wavelength grid in Angstrom (MUSE: 4750-9350 A; musefuse.py:82)."""
+    return 4750.0 + (9350.0 - 4750.0) / nspec * numpy.arange(nspec)
+
+
+def muse_parameter_points(K, seed=8, nZ=7):
+    """(Z, logSFtau, SFage, z, EBV) inside the prior of musefuse.py:329-346."""
+    rg = numpy.random.default_rng(seed)
+    p = numpy.empty((K, 5))
+    p[:, 0] = rg.uniform(MUSE_ZS[0], MUSE_ZS[nZ - 1] + 0.3, size=K)
+    p[:, 1] = rg.uniform(6.0, numpy.log10(4e9), size=K)
+    p[:, 2] = rg.uniform(0.05, 13.0, size=K)
+    p[:, 3] = rg.uniform(0.0, 0.9, size=K)
+    p[:, 4] = rg.uniform(0.0, 2.0, size=K)
+    return p
+
+
 def priortransform(cube):
     """sample.py:52-58 -- unit cube -> (A, mu, log_sig)."""
     cube = numpy.array(cube, dtype=float, copy=True)

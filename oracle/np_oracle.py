@@ -105,3 +105,35 @@ def subsets_labels(live_pointsp, data_mask, npoints):
         first.setdefault(comp[d], d)
         labels[d] = first[comp[d]]
     return labels
+
+
+def calzetti(model_wavelength_nm):
+    """musefuse.py:208-217 -- Calzetti attenuation curve k(lambda) on the template grid (nm)."""
+    w = numpy.asarray(model_wavelength_nm, dtype=float)
+    k = numpy.zeros_like(w)
+    blue = w < 630
+    k[blue] = 2.659 * (-2.156 + 1.509e3 / w[blue] - 0.198e6 / w[blue] ** 2
+                       + 0.011e9 / w[blue] ** 3) + 4.05
+    red = w >= 630
+    k[red] = 2.659 * (-1.857 + 1.040e3 / w[red]) + 4.05
+    return k
+
+
+def muse_model(Zs, ages, model_wavelength_nm, calz, grids, wavelength_nm, Z, SFtau, sfage, z, EBV,
+               norm_index=2050):
+    """musefuse.py:222-284 -- the stellar-population model spectrum on the data grid:
+    metallicity bin, delayed-exponential star-formation history over the template ages,
+    SFH-weighted template sum, normalisation at one template channel, Calzetti extinction at
+    rest frame, linear interpolation onto the redshifted data wavelengths."""
+    iZ = numpy.where(Zs <= Z)[-1][-1]
+    templates = grids[iZ]
+    t = sfage * 1.e9 - ages
+    t[t <= 0] = 0
+    SFtau = float(SFtau)
+    sfh = t / SFtau ** 2 * numpy.exp(-t / SFtau)
+    sfh /= sfh.max()
+    dage = ages[1:] - ages[:-1]
+    spec = numpy.sum(templates[:-1] * sfh[:-1].reshape((-1, 1)) * dage.reshape((-1, 1)), axis=0)
+    spec /= 1e-10 + spec[norm_index]
+    spec = spec * 10 ** (-2.5 * calz * EBV)
+    return numpy.interp(x=wavelength_nm / (1 + z), xp=model_wavelength_nm, fp=spec)
