@@ -27,13 +27,17 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 sys.path.insert(0, HERE)
 
 CASES = {
-    # tag: (ndata, nlive, niter, data seed, run seed, constructor arguments)
+    # tag: (ndata, nlive, niter, data seed, run seed, constructor arguments[, threshold rank])
     'a': (16, 40, 600, 21, 3, dict(metriclearner='truncatedscaling', force_shrink=True,
                                    rebuild_every=30, metric_rebuild_every=5)),
     'b': (6, 60, 100, 22, 4, dict(metriclearner='simplescaling', force_shrink=False,
                                   rebuild_every=1000, metric_rebuild_every=20)),
     'c': (10, 30, 400, 23, 5, dict(metriclearner='none', force_shrink=True,
                                   rebuild_every=8, metric_rebuild_every=3)),
+    # thresholds at the BEST live point of every data set: hundreds of tries per draw, the
+    # `ntoaccept > 200` metric rebuild inside the loop (hiermetriclearn.py:206-211)
+    'd': (4, 30, 24, 24, 6, dict(metriclearner='truncatedscaling', force_shrink=True,
+                                 rebuild_every=1000, metric_rebuild_every=20), -1),
 }
 
 
@@ -51,7 +55,9 @@ def main():
         from hiermetriclearn import MetricLearningFriendsConstrainer
         import clustering.neighbors as nb
         assert nb.bootstrapped_maxdistance is not None, 'reference cneighbors.so did not load'
-        for tag, (ndata, nlive, niter, seed_data, seed_run, kw) in CASES.items():
+        for tag, case in CASES.items():
+            ndata, nlive, niter, seed_data, seed_run, kw = case[:6]
+            rank = case[6] if len(case) > 6 else 0
             x, y, _ = synth.horns(ndata, seed=seed_data)
             ncalls = [0]
 
@@ -67,10 +73,11 @@ def main():
             c.prev_maxdistance = _NoPrevious()
             sink = io.StringIO()
             with contextlib.redirect_stdout(sink):
-                res = run_draws(c, multi_loglikelihood, ndata, nlive, niter, seed_run)
+                res = run_draws(c, multi_loglikelihood, ndata, nlive, niter, seed_run, rank=rank)
             for k, v in res.items():
                 out['%s_%s' % (tag, k)] = v
             out[tag + '_cfg'] = numpy.array([ndata, nlive, niter, seed_data, seed_run])
+            out[tag + '_rank'] = rank
             out[tag + '_ncalls'] = ncalls[0]
             out[tag + '_maxdistance'] = c.region.maxdistance
             print(tag, 'draws', niter, 'tries', res['ntoaccept'].sum(), 'max tries',

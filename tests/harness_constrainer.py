@@ -40,9 +40,12 @@ def group_mask(it, ndata, rs):
     return mask
 
 
-def run_draws(constrainer, multi_loglikelihood, ndata, nlive, niter, seed):
+def run_draws(constrainer, multi_loglikelihood, ndata, nlive, niter, seed, rank=0):
     """Returns dict(u[niter, 3], ntoaccept[niter], L[niter, ndata] (nan where not drawn for),
-    naccepted[niter]); `multi_loglikelihood(params, data_mask)` as sample.py:101-108."""
+    naccepted[niter]); `multi_loglikelihood(params, data_mask)` as sample.py:101-108.
+    `rank`: which live likelihood of every data set is the threshold -- 0 = the minimum (nested
+    sampling), -1 = the maximum (long rejection chains: exercises the in-loop rebuild triggers of
+    hiermetriclearn.py:200-211)."""
     numpy.random.seed(seed)
     rs = numpy.random.RandomState(seed + 1000)      # group choice: not part of the shared stream
     everyone = numpy.ones(ndata, dtype=bool)
@@ -60,7 +63,7 @@ def run_draws(constrainer, multi_loglikelihood, ndata, nlive, niter, seed):
         members = numpy.unique(live_p[:, mask])     # multi_nested_sampler.py:139-143
         live_u = numpy.array([pile[i] for i in members])
         worst = live_L.argmin(axis=0)
-        Lmins = live_L.min(axis=0)[mask]
+        Lmins = (live_L.min(axis=0) if rank == 0 else numpy.sort(live_L, axis=0)[rank])[mask]
         u, x, L, ntoaccept = constrainer.draw_constrained(
             Lmins=Lmins, priortransform=priortransform,
             loglikelihood=lambda p: multi_loglikelihood(p, mask),

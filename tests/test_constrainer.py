@@ -25,6 +25,9 @@ CONFIG = {      # constructor arguments of tests/golden/make_golden_constrainer.
     'b': dict(metriclearner='simplescaling', force_shrink=False, rebuild_every=1000,
               metric_rebuild_every=20),
     'c': dict(metriclearner='none', force_shrink=True, rebuild_every=8, metric_rebuild_every=3),
+    # thresholds at the best live point: up to 2926 tries per draw, in-loop metric rebuilds
+    'd': dict(metriclearner='truncatedscaling', force_shrink=True, rebuild_every=1000,
+              metric_rebuild_every=20),
 }
 
 
@@ -114,14 +117,16 @@ class OracleLikelihood(object):
 
 @pytest.mark.parametrize('tag,batch,adaptive', [('a', 1, False), ('a', 16, False), ('a', 16, True),
                                                 ('b', 4, False), ('c', 1, True), ('c', 7, False),
-                                                ('c', 8, True)])
+                                                ('c', 8, True), ('d', 1, False), ('d', 16, True),
+                                                ('d', 5, False)])
 def test_constrainer_reproduces_reference_draws_on_the_oracle(fixture, tag, batch, adaptive):
     ndata, nlive, niter, seed_data, seed_run = fixture[tag + '_cfg']
     x, y, _ = synth.horns(int(ndata), seed=int(seed_data))
     like = OracleLikelihood(x, y)
     c = MetricLearningFriendsConstrainer(batch_size=batch, speculator=like if batch > 1 else None,
                                          adaptive=adaptive, region_class=OracleRegion, **CONFIG[tag])
-    res = run_draws(c, like, int(ndata), int(nlive), int(niter), int(seed_run))
+    res = run_draws(c, like, int(ndata), int(nlive), int(niter), int(seed_run),
+                    rank=int(fixture[tag + '_rank']))
     check(res, fixture, tag)
     assert c.region.maxdistance == float(fixture[tag + '_maxdistance'])
     if batch == 1:
@@ -139,7 +144,8 @@ def test_constrainer_rejects_unknown_metric():
 # ------------------------------------------------------------------------- GPU: the product path
 @pytest.mark.gpu
 @pytest.mark.parametrize('tag,batch,adaptive', [('a', 1, False), ('a', 16, False), ('a', 16, True),
-                                                ('b', 8, False), ('c', 16, True)])
+                                                ('b', 8, False), ('c', 16, True), ('d', 16, True),
+                                                ('d', 16, False)])
 def test_constrainer_reproduces_reference_draws_on_the_device(fixture, tag, batch, adaptive):
     from massivedatans_b200 import _lib
     from massivedatans_b200.likelihood import make_multi_loglikelihood
@@ -149,7 +155,8 @@ def test_constrainer_reproduces_reference_draws_on_the_device(fixture, tag, batc
     c = MetricLearningFriendsConstrainer(batch_size=batch, speculator=like if batch > 1 else None,
                                          adaptive=adaptive, **CONFIG[tag])
     before = _lib.load().mdns_launch_count()
-    res = run_draws(c, like, int(ndata), int(nlive), int(niter), int(seed_run))
+    res = run_draws(c, like, int(ndata), int(nlive), int(niter), int(seed_run),
+                    rank=int(fixture[tag + '_rank']))
     assert _lib.load().mdns_launch_count() > before
     check(res, fixture, tag)
     assert c.region.maxdistance == float(fixture[tag + '_maxdistance'])
