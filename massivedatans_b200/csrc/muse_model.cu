@@ -11,6 +11,7 @@
 //   4. template /= 1e-10 + template[norm_index]                                      (:255)
 //   5. template *= 10**(-2.5 * calzetti * EBV)                                      (:258)
 //   6. linear interpolation onto wavelength/(1+z), clamped at the ends (numpy.interp) (:279)
+// Three launches per batch: weights (2), template sum (3), and 4-6 fused in the resampling kernel.
 // and the K spectra land in the data set's staged model buffer (what mdns_stage_spectra fills
 // from the host), so mdns_muse_launch follows without any spectrum crossing PCIe.
 //
@@ -38,14 +39,18 @@ namespace {
 
 constexpr int MM_THREADS = 128;
 
-// params[k] = (Z, SFtau, sfage, z, EBV); sfh[k][a] for a < nages (normalised to the maximum)
+// params[k] = (Z, SFtau, sfage, z, EBV, metallicity bin); sfh[k][a] for a < nages (normalised to
+// the maximum); also clears the candidate's "spectrum is not all zero" flag
+constexpr int MM_P = 6;
 __global__ void __launch_bounds__(MM_THREADS) muse_sfh_kernel(const double *__restrict__ params,
                                                               const double *__restrict__ ages, int nages,
-                                                              double *__restrict__ sfh)
+                                                              double *__restrict__ sfh,
+                                                              int *__restrict__ nonzero)
 {
 	__shared__ double red[MM_THREADS / 32];
 	const int k = blockIdx.x;
-	const double tau = params[k * 5 + 1], sfage = params[k * 5 + 2];
+	if (threadIdx.x == 0) nonzero[k] = 0;
+	const double tau = params[k * MM_P + 1], sfage = params[k * MM_P + 2];
 	const double tau2 = tau * tau;
 	const double start = sfage * 1.e9;
 	double best = -1.0;       // sfh >= 0; NaN entries are tracked separately (numpy's max returns NaN)
@@ -75,7 +80,7 @@ __global__ void __launch_bounds__(MM_THREADS) muse_sfh_kernel(const double *__re
 
 // tmpl[k][w] = sum_a (grid[iZ_k][a][w] * sfh[k][a]) * dage[a], a = 0 .. nages-2, in order
 __global__ void __launch_bounds__(MM_THREADS) muse_template_kernel(
-    const double *__restrict__ grids, const int *__restrict__ iZ, const double *__restrict__ sfh,
+    const double *__restrict__ grids, const double *__restrict__ params, const double *__restrict__ sfh,
     const double *__restrict__ dage, int nages, int nwave, double *__restrict__ tmpl)
 {
 	extern __shared__ double sm[];        // sfh[k][0..nages-2], dage[0..nages-2]
@@ -88,7 +93,7 @@ __global__ void __launch_bounds__(MM_THREADS) muse_template_kernel(
 	__syncthreads();
 	const int w = blockIdx.x * MM_THREADS + threadIdx.x;
 	if (w >= nwave) return;
-	const double *g = grids + (size_t)iZ[k] * nages * nwave + w;
+	const double *g = grids + (size_t)(int)params[k * MM_P + 5] * nages * nwave + w;
 	double acc = 0.0;
 	// four rows in flight per iteration; the additions stay in age order
 	int a = 0;
@@ -105,46 +110,34 @@ __global__ void __launch_bounds__(MM_THREADS) muse_template_kernel(
 	tmpl[(size_t)k * nwave + w] = acc;
 }
 
-// steps 4 and 5 in place; norms[k] = 1e-10 + tmpl[k][norm_index] was taken by muse_norm_kernel
-// before this kernel overwrites the channel
-__global__ void __launch_bounds__(MM_THREADS) muse_extinct_kernel(const double *__restrict__ params,
-                                                                  const double *__restrict__ calz,
-                                                                  const double *__restrict__ norms,
-                                                                  int nwave, double *__restrict__ tmpl)
+// steps 4-6: normalisation, extinction and numpy.interp(x = wavelength/(1+z), xp = model_wavelength,
+// fp = template) -> model[k][c].  The normalised, extincted template is only needed at the two
+// nodes around every output channel, so it is evaluated there (two pow per output channel, same
+// operations as a pass over the whole template: v/norm * 10**((-2.5*calz)*EBV)).
+__device__ __forceinline__ double muse_node(const double *__restrict__ raw, const double *__restrict__ calz,
+                                            int j, double norm, double ebv)
 {
-	const int k = blockIdx.y;
-	const int w = blockIdx.x * MM_THREADS + threadIdx.x;
-	if (w >= nwave) return;
-	const double ebv = params[k * 5 + 4];
-	const double v = tmpl[(size_t)k * nwave + w] / norms[k];
-	tmpl[(size_t)k * nwave + w] = v * pow(10.0, __dmul_rn(__dmul_rn(-2.5, calz[w]), ebv));
+	return (raw[j] / norm) * pow(10.0, __dmul_rn(__dmul_rn(-2.5, calz[j]), ebv));
 }
 
-__global__ void muse_norm_kernel(const double *__restrict__ tmpl, int nwave, int norm_index, int K,
-                                 double *__restrict__ norms, int *__restrict__ nonzero)
-{
-	const int k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k >= K) return;
-	norms[k] = 1e-10 + tmpl[(size_t)k * nwave + norm_index];
-	nonzero[k] = 0;
-}
-
-// step 6: numpy.interp(x = wavelength/(1+z), xp = model_wavelength, fp = tmpl[k]) -> model[k][c]
 __global__ void __launch_bounds__(MM_THREADS) muse_resample_kernel(
     const double *__restrict__ params, const double *__restrict__ wavelength, int nx,
-    const double *__restrict__ xp, int nwave, const double *__restrict__ tmpl,
-    double *__restrict__ model, long long mpitch, int *__restrict__ nonzero)
+    const double *__restrict__ xp, const double *__restrict__ calz, int nwave, int norm_index,
+    const double *__restrict__ tmpl, double *__restrict__ model, long long mpitch,
+    int *__restrict__ nonzero)
 {
 	const int k = blockIdx.y;
 	const int c = blockIdx.x * MM_THREADS + threadIdx.x;
 	if (c >= nx) return;
-	const double x = wavelength[c] / (1 + params[k * 5 + 3]);
-	const double *fp = tmpl + (size_t)k * nwave;
+	const double x = wavelength[c] / (1 + params[k * MM_P + 3]);
+	const double ebv = params[k * MM_P + 4];
+	const double *raw = tmpl + (size_t)k * nwave;
+	const double norm = 1e-10 + raw[norm_index];
 	double r;
 	if (x > xp[nwave - 1]) {
-		r = fp[nwave - 1];
+		r = muse_node(raw, calz, nwave - 1, norm, ebv);
 	} else if (x < xp[0]) {
-		r = fp[0];
+		r = muse_node(raw, calz, 0, norm, ebv);
 	} else if (x != x) {
 		r = x;
 	} else {
@@ -156,17 +149,17 @@ __global__ void __launch_bounds__(MM_THREADS) muse_resample_kernel(
 		}
 		int j = lo;
 		if (xp[hi] <= x) j = hi;
-		if (j == nwave - 1) {
-			r = fp[j];
-		} else if (xp[j] == x) {
-			r = fp[j];
+		const double fj = muse_node(raw, calz, j, norm, ebv);
+		if (j == nwave - 1 || xp[j] == x) {
+			r = fj;
 		} else {
-			const double slope = (fp[j + 1] - fp[j]) / (xp[j + 1] - xp[j]);
-			r = __dadd_rn(__dmul_rn(slope, x - xp[j]), fp[j]);
+			const double fj1 = muse_node(raw, calz, j + 1, norm, ebv);
+			const double slope = (fj1 - fj) / (xp[j + 1] - xp[j]);
+			r = __dadd_rn(__dmul_rn(slope, x - xp[j]), fj);
 			if (r != r) {
 				// numpy retries from the right node, then gives the common value
-				r = __dadd_rn(__dmul_rn(slope, x - xp[j + 1]), fp[j + 1]);
-				if (r != r && fp[j] == fp[j + 1]) r = fp[j];
+				r = __dadd_rn(__dmul_rn(slope, x - xp[j + 1]), fj1);
+				if (r != r && fj == fj1) r = fj;
 			}
 		}
 	}
@@ -178,8 +171,8 @@ struct MmDevice {
 	int device = 0;
 	double *grids = nullptr, *ages = nullptr, *dage = nullptr, *xp = nullptr, *calz = nullptr,
 	       *wavelength = nullptr;
-	double *params = nullptr, *sfh = nullptr, *tmpl = nullptr, *norms = nullptr;
-	int *iZ = nullptr, *nonzero = nullptr;
+	double *params = nullptr, *sfh = nullptr, *tmpl = nullptr;
+	int *nonzero = nullptr;
 	int cap_K = 0;
 };
 
@@ -205,8 +198,6 @@ static void mm_free(MmDevice &d)
 	cudaFree(d.params);
 	cudaFree(d.sfh);
 	cudaFree(d.tmpl);
-	cudaFree(d.norms);
-	cudaFree(d.iZ);
 	cudaFree(d.nonzero);
 }
 
@@ -224,18 +215,14 @@ static int mm_reserve(mdns_muse_model *m, MmDevice &d, int K)
 	cudaFree(d.params);
 	cudaFree(d.sfh);
 	cudaFree(d.tmpl);
-	cudaFree(d.norms);
-	cudaFree(d.iZ);
 	cudaFree(d.nonzero);
-	d.params = d.sfh = d.tmpl = d.norms = nullptr;
-	d.iZ = d.nonzero = nullptr;
+	d.params = d.sfh = d.tmpl = nullptr;
+	d.nonzero = nullptr;
 	d.cap_K = 0;
 	const int cap = K + K / 2 + 4;
-	MDNS_CUDA(cudaMalloc((void **)&d.params, (size_t)cap * 5 * sizeof(double)));
+	MDNS_CUDA(cudaMalloc((void **)&d.params, (size_t)cap * MM_P * sizeof(double)));
 	MDNS_CUDA(cudaMalloc((void **)&d.sfh, (size_t)cap * m->nages * sizeof(double)));
 	MDNS_CUDA(cudaMalloc((void **)&d.tmpl, (size_t)cap * m->nwave * sizeof(double)));
-	MDNS_CUDA(cudaMalloc((void **)&d.norms, (size_t)cap * sizeof(double)));
-	MDNS_CUDA(cudaMalloc((void **)&d.iZ, (size_t)cap * sizeof(int)));
 	MDNS_CUDA(cudaMalloc((void **)&d.nonzero, (size_t)cap * sizeof(int)));
 	d.cap_K = cap;
 	return MDNS_OK;
@@ -314,7 +301,8 @@ int mdns_muse_model_stage(mdns_muse_model *m, const double *params, int K, int *
 		set_error("mdns_muse_model_stage: need model, params[K][5], K > 0");
 		return MDNS_EINVAL;
 	}
-	std::vector<int> iZ(K);
+	// one upload per shard: the five model arguments and the metallicity bin of every point
+	std::vector<double> packed((size_t)K * MM_P);
 	for (int k = 0; k < K; ++k) {
 		const double Z = params[k * 5];
 		int j = -1;
@@ -326,7 +314,8 @@ int mdns_muse_model_stage(mdns_muse_model *m, const double *params, int K, int *
 			          m->Zs[0]);
 			return MDNS_EINVAL;
 		}
-		iZ[k] = j;
+		for (int q = 0; q < 5; ++q) packed[(size_t)k * MM_P + q] = params[k * 5 + q];
+		packed[(size_t)k * MM_P + 5] = (double)j;
 	}
 	const size_t smem = (size_t)2 * (m->nages - 1) * sizeof(double);
 	if (smem > 48 * 1024) {
@@ -344,22 +333,16 @@ int mdns_muse_model_stage(mdns_muse_model *m, const double *params, int K, int *
 		cudaStream_t st = (cudaStream_t)vst;
 		rc = mm_reserve(m, d, K);
 		if (rc != MDNS_OK) return rc;
-		MDNS_CUDA(cudaMemcpyAsync(d.params, params, (size_t)K * 5 * sizeof(double),
+		MDNS_CUDA(cudaMemcpyAsync(d.params, packed.data(), packed.size() * sizeof(double),
 		                          cudaMemcpyHostToDevice, st));
-		MDNS_CUDA(cudaMemcpyAsync(d.iZ, iZ.data(), (size_t)K * sizeof(int), cudaMemcpyHostToDevice, st));
-		muse_sfh_kernel<<<K, MM_THREADS, 0, st>>>(d.params, d.ages, m->nages, d.sfh);
+		muse_sfh_kernel<<<K, MM_THREADS, 0, st>>>(d.params, d.ages, m->nages, d.sfh, d.nonzero);
 		MDNS_LAUNCHED_HELPER("muse_sfh_kernel");
 		muse_template_kernel<<<dim3(ceil_div(m->nwave, MM_THREADS), K), MM_THREADS, smem, st>>>(
-		    d.grids, d.iZ, d.sfh, d.dage, m->nages, m->nwave, d.tmpl);
+		    d.grids, d.params, d.sfh, d.dage, m->nages, m->nwave, d.tmpl);
 		MDNS_LAUNCHED("muse_template_kernel");
-		muse_norm_kernel<<<ceil_div(K, 64), 64, 0, st>>>(d.tmpl, m->nwave, m->norm_index, K, d.norms,
-		                                                  d.nonzero);
-		MDNS_LAUNCHED_HELPER("muse_norm_kernel");
-		muse_extinct_kernel<<<dim3(ceil_div(m->nwave, MM_THREADS), K), MM_THREADS, 0, st>>>(
-		    d.params, d.calz, d.norms, m->nwave, d.tmpl);
-		MDNS_LAUNCHED_HELPER("muse_extinct_kernel");
 		muse_resample_kernel<<<dim3(ceil_div(m->nx, MM_THREADS), K), MM_THREADS, 0, st>>>(
-		    d.params, d.wavelength, m->nx, d.xp, m->nwave, d.tmpl, d_model, pitch, d.nonzero);
+		    d.params, d.wavelength, m->nx, d.xp, d.calz, m->nwave, m->norm_index, d.tmpl, d_model,
+		    pitch, d.nonzero);
 		MDNS_LAUNCHED_HELPER("muse_resample_kernel");
 		if (s == 0 && nonzero) {
 			MDNS_CUDA(cudaMemcpyAsync(nonzero, d.nonzero, (size_t)K * sizeof(int),

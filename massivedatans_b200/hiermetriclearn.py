@@ -187,6 +187,9 @@ class MetricLearningFriendsConstrainer(object):
         if self.speculator is not None and len(batch) > 1:
             self.speculator.speculate(xs, Lmins)
             loglikelihood(xs[0])
+            if self.speculator.last_draw is None:
+                raise RuntimeError('the speculator did not see the announced batch: '
+                                   '`loglikelihood` must call the callable given as `speculator`')
             k, L, _ = self.speculator.last_draw
             return k, L
         for k, x in enumerate(xs):

@@ -316,14 +316,17 @@ def make_multi_loglikelihood(x, y, noise_level=0.01, devices=None):
         return q
 
     def multi_loglikelihood(params, data_mask):
+        A, mu, log_sig_kms = params
         if pending:
             # a batch announced by speculate(): the mask only arrives with this call
             q, Lmins = pending.pop()
-            ds.begin_draw(data_mask, Lmins)
-            k, L, counts = ds.draw_batch(q, noise_level)
-            multi_loglikelihood.last_draw = (k, L, counts)
-            return L if k == 0 else None
-        A, mu, log_sig_kms = params
+            if q[0, 0] == A and q[0, 1] == mu and q[0, 2] == 10 ** log_sig_kms:
+                ds.begin_draw(data_mask, Lmins)
+                k, L, counts = ds.draw_batch(q, noise_level)
+                multi_loglikelihood.last_draw = (k, L, counts)
+                return L if k == 0 else None
+            # some other caller came in between: the announcement is void
+            multi_loglikelihood.last_draw = None
         p[0, 0] = A
         p[0, 1] = mu
         p[0, 2] = 10 ** log_sig_kms
@@ -341,6 +344,7 @@ def make_multi_loglikelihood(x, y, noise_level=0.01, devices=None):
         candidate.  That call returns L_0 only if k == 0 (no other logL vector leaves the
         device), else None."""
         del pending[:]
+        multi_loglikelihood.last_draw = None
         pending.append((_points(params_list), numpy.array(Lmins, dtype=numpy.float64)))
 
     multi_loglikelihood.dataset = ds
@@ -427,6 +431,7 @@ class DeviceMuseModel(object):
         self._h = handle
         self._dataset = dataset
         self.nx = dataset.nx
+        self._last_K = 0
         self._finalizer = weakref.finalize(self, lib.mdns_muse_model_destroy, handle)
 
     def close(self):
@@ -443,6 +448,8 @@ class DeviceMuseModel(object):
 
     def spectra(self):
         """The spectra of the last ``stage`` call, [K, nx] (for checks; costs a download)."""
+        if self._last_K <= 0:
+            raise RuntimeError('no spectra staged yet: call stage(params) first')
         out = numpy.empty((self._last_K, self.nx))
         _lib.check(self._lib.mdns_muse_model_spectra(self._h, _addr(out)), 'mdns_muse_model_spectra')
         return out

@@ -147,6 +147,27 @@ def test_callable_with_guard_jitter_and_batch(fixture):
 
 
 @pytest.mark.gpu
+def test_model_on_a_sharded_cube(fixture):
+    # two shards (on one device if the box has a single GPU): every shard builds the spectra
+    # for its own pass
+    from oracle import port
+    from massivedatans_b200 import _lib
+    from massivedatans_b200.likelihood import make_muse_loglikelihood_device
+    ndata = 257
+    y, v, _ = synth.muse(ndata=ndata, nspec=fixture['nspec'])
+    devices = [0, 1] if _lib.load().mdns_device_count() >= 2 else [0, 0]
+    f = make_muse_loglikelihood_device(y, v, fixture['grids'], fixture['Zs'], fixture['ages'],
+                                       fixture['model_wavelength'], fixture['wavelength'],
+                                       jitter=0, devices=devices)
+    mask = synth.masks(ndata)['half']
+    params = synth.muse_parameter_points(5, seed=12)
+    L = f.batch(params, mask)
+    for k, spec in enumerate(oracle_spectra(fixture, params)):
+        assert rel(L[k], port.cmuselike(y, v, spec, mask)[mask]) < 1e-9
+    assert rel(f(params[3], mask), L[3]) < 1e-14
+
+
+@pytest.mark.gpu
 def test_model_argument_errors(fixture):
     from massivedatans_b200 import _lib
     from massivedatans_b200.likelihood import DeviceMuseModel
