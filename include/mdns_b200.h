@@ -280,6 +280,16 @@ int mdns_region_generate(mdns_region *rg, double maxdistance, uint64_t seed, uin
                          int nproposals, double *points_out, int64_t capacity, int *n_out);
 int mdns_region_is_within(mdns_region *rg, double maxdistance, const double *y,
                           int *result);
+/* Per-axis "SupFriends" distance, clustering/neighbors.py:22-73 (find_maxdistance).
+ * neighbors.py:24-25: nearest_out[i] = index of the member nearest to member i (euclidean,
+ * i itself excluded).  Needs >= 2 members. */
+int mdns_region_nearest_index(mdns_region *rg, int *nearest_out);
+/* neighbors.py:40-43: covered_out[q] = 1 if some member ref[r] lies inside the per-axis box
+ * maxdistance[ndim] around member query[q] (|x_qk - x_rk| < maxdistance[k] for every axis k).
+ * The sequential box growth of neighbors.py:44-58 stays with the caller, which only has to
+ * visit the members reported uncovered. */
+int mdns_region_axis_covered(mdns_region *rg, const double *maxdistance, const int *query, int nq,
+                             const int *ref, int nr, uint8_t *covered_out);
 /* cneighbors.c:125-179: chosen[n][nboot] float64 0/1 (round index fastest). */
 int mdns_region_bootstrapped_maxdistance(mdns_region *rg, const double *chosen,
                                          int nboot, double *result);

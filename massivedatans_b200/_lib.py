@@ -78,6 +78,8 @@ SIGNATURES = {
     'mdns_region_count_within': (c_int, [_P, c_double, _P, c_int, _P, c_int]),
     'mdns_region_generate': (c_int, [_P, c_double, ctypes.c_uint64, ctypes.c_uint64, c_int, _P, c_int64,
                                      POINTER(c_int)]),
+    'mdns_region_nearest_index': (c_int, [_P, _P]),
+    'mdns_region_axis_covered': (c_int, [_P, _P, _P, c_int, _P, c_int, _P]),
     'mdns_region_is_within': (c_int, [_P, c_double, _P, POINTER(c_int)]),
     'mdns_region_bootstrapped_maxdistance': (c_int, [_P, _P, c_int, POINTER(c_double)]),
     'mdns_region_most_distant_nearest_neighbor': (c_int, [_P, POINTER(c_double)]),

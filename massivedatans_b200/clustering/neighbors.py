@@ -95,42 +95,62 @@ def find_rdistance(u, verbose=False, nbootstraps=15, metric='euclidean'):
     return bootstrapped_maxdistance(u, nbootstraps)
 
 
-# --- per-axis "SupFriends" distance (neighbors.py:22-73): host logic, same RNG use ---------
+# --- per-axis "SupFriends" distance (neighbors.py:22-73) ------------------------------------
+# The O(n^2) parts run on the device over members uploaded once per call: the nearest other
+# member of every member (neighbors.py:24-25) and, per bootstrap round, which un-chosen members
+# already have a chosen member inside the per-axis box (neighbors.py:40-43).  The box only ever
+# grows within a round, so a member the device reports covered stays covered; the host walks
+# the uncovered ones in the reference's order, re-checks them against the grown box and applies
+# the reference's growth step (neighbors.py:44-58).  numpy.random is consumed exactly as in the
+# reference (one `choice` per round).
 
-def initial_maxdistance_guess(u):
-    """neighbors.py:22-29: per-axis |delta| to each point's nearest neighbour, maximised."""
+def _resident(u):
+    from .radfriendsregion import ResidentMembers
+    return ResidentMembers(u)
+
+
+def initial_maxdistance_guess(u, _members=None):
+    """neighbors.py:22-29: per axis, the largest |delta| between a point and its nearest
+    neighbour."""
+    u = _f64(u, 2)
+    members = _members if _members is not None else _resident(u)
+    nearest = members.nearest_index()
+    return numpy.abs(u[nearest, :] - u).max(axis=0)
+
+
+def update_maxdistance(u, ibootstrap, maxdistance, verbose=False, _members=None):
+    """neighbors.py:31-62: one bootstrap round -- every point left out of the resample must have
+    a resampled point inside the box; where none has, the box grows towards the point whose
+    clipped offsets have the smallest log-volume (the reference's choice, neighbors.py:47-55)."""
     u = _f64(u, 2)
     n = len(u)
-    d2 = ((u[:, None, :] - u[None, :, :]) ** 2).sum(axis=2)
-    numpy.fill_diagonal(d2, numpy.inf)
-    nearest = d2.argmin(axis=1)
-    return numpy.abs(u[nearest, :] - u[numpy.arange(n), :]).max(axis=0)
-
-
-def update_maxdistance(u, ibootstrap, maxdistance, verbose=False):
-    """neighbors.py:31-62: one bootstrap round of the per-axis box half-widths."""
-    n, ndim = u.shape
+    members = _members if _members is not None else _resident(u)
     choice = list(set(numpy.random.choice(numpy.arange(n), size=n)))
-    notchosen = set(range(n)) - set(choice)
-    for i in notchosen:
-        dists = numpy.abs(u[i, :] - u[choice, :])
-        close = numpy.all(dists < maxdistance.reshape((1, -1)), axis=1)
-        if not close.any():
-            suggest = numpy.where(maxdistance > dists, dists, maxdistance)
-            increase = numpy.log(suggest).sum(axis=1) - numpy.log(maxdistance).sum()
-            nearest = numpy.argmin(increase)
-            if verbose:
-                print(ibootstrap, 'nearest:', u[i], u[nearest], increase[nearest])
-            maxdistance = numpy.where(dists[nearest] > maxdistance, dists[nearest], maxdistance)
-            if verbose:
-                print(ibootstrap, 'extending:', maxdistance)
+    left_out = list(set(range(n)) - set(choice))       # the reference's iteration order
+    covered = members.axis_covered(maxdistance, left_out, choice)
+    for i, done in zip(left_out, covered):
+        if done:
+            continue
+        offsets = numpy.abs(u[i, :] - u[choice, :])
+        if numpy.all(offsets < maxdistance.reshape((1, -1)), axis=1).any():
+            continue                                   # an earlier growth of this round got it
+        clipped = numpy.where(maxdistance > offsets, offsets, maxdistance)
+        cost = numpy.log(clipped).sum(axis=1) - numpy.log(maxdistance).sum()
+        towards = numpy.argmin(cost)
+        if verbose:
+            print(ibootstrap, 'nearest:', u[i], u[towards], cost[towards])
+        maxdistance = numpy.where(offsets[towards] > maxdistance, offsets[towards], maxdistance)
+        if verbose:
+            print(ibootstrap, 'extending:', maxdistance)
     return maxdistance
 
 
 def find_maxdistance(u, verbose=False, nbootstraps=15):
     """neighbors.py:64-73."""
     u = _f64(u, 2)
-    maxdistance = initial_maxdistance_guess(u)
+    members = _resident(u)
+    maxdistance = initial_maxdistance_guess(u, _members=members)
     for ibootstrap in range(nbootstraps):
-        maxdistance = update_maxdistance(u, ibootstrap, maxdistance, verbose=verbose)
+        maxdistance = update_maxdistance(u, ibootstrap, maxdistance, verbose=verbose,
+                                         _members=members)
     return maxdistance

@@ -60,6 +60,27 @@ class ResidentMembers(object):
                                                    ctypes.byref(res)), 'mdns_region_is_within')
         return res.value == 1
 
+    def nearest_index(self):
+        """Index of every member's nearest other member (clustering/neighbors.py:24-25)."""
+        out = numpy.empty(self.n, dtype=numpy.int32)
+        _lib.check(self._lib.mdns_region_nearest_index(self._h, out.ctypes.data),
+                   'mdns_region_nearest_index')
+        return out
+
+    def axis_covered(self, maxdistance, query, ref):
+        """For every listed member: is some member of `ref` inside the per-axis box
+        `maxdistance` around it (clustering/neighbors.py:40-43)."""
+        md = numpy.ascontiguousarray(maxdistance, dtype=numpy.float64)
+        if md.shape != (self.ndim,):
+            raise ValueError('maxdistance must have one entry per axis')
+        q = numpy.ascontiguousarray(query, dtype=numpy.int32)
+        r = numpy.ascontiguousarray(ref, dtype=numpy.int32)
+        out = numpy.zeros(len(q), dtype=numpy.uint8)
+        _lib.check(self._lib.mdns_region_axis_covered(self._h, md.ctypes.data, q.ctypes.data, len(q),
+                                                      r.ctypes.data, len(r), out.ctypes.data),
+                   'mdns_region_axis_covered')
+        return out != 0
+
     def generate(self, maxdistance, nproposals, seed, first_proposal=0):
         """``nproposals`` ball draws fused with the neighbour count on the device; returns the
         accepted points [k, ndim] (uniform in the union of balls), in proposal order."""

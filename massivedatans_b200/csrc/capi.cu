@@ -1503,6 +1503,72 @@ int mdns_region_generate(mdns_region *rg, double maxdistance, uint64_t seed, uin
 	return MDNS_OK;
 }
 
+int mdns_region_nearest_index(mdns_region *rg, int *nearest_out)
+{
+	if (!rg || !nearest_out) {
+		set_error("mdns_region_nearest_index: need rg and nearest_out[n]");
+		return MDNS_EINVAL;
+	}
+	if (rg->ndim == 0 || rg->n < 2) {
+		set_error("nearest neighbours need at least two members");
+		return MDNS_ESTATE;
+	}
+	MDNS_CUDA(cudaSetDevice(rg->device));
+	int rc = grow(&rg->d_qidx, &rg->q_cap, (size_t)rg->n, false);
+	if (rc != MDNS_OK) return rc;
+	rc = launch_nn_index(rg->d_xs, rg->n, rg->npad, rg->ndim, rg->d_qidx, rg->stream);
+	if (rc != MDNS_OK) return rc;
+	MDNS_CUDA(cudaMemcpyAsync(nearest_out, rg->d_qidx, (size_t)rg->n * sizeof(int),
+	                          cudaMemcpyDeviceToHost, rg->stream));
+	MDNS_CUDA(cudaStreamSynchronize(rg->stream));
+	return MDNS_OK;
+}
+
+int mdns_region_axis_covered(mdns_region *rg, const double *maxdistance, const int *query, int nq,
+                             const int *ref, int nr, uint8_t *covered_out)
+{
+	if (!rg || !maxdistance || nq < 0 || nr < 0 || (nq > 0 && (!query || !covered_out)) ||
+	    (nr > 0 && !ref)) {
+		set_error("mdns_region_axis_covered: need rg, maxdistance[ndim], query[nq], ref[nr], covered_out[nq]");
+		return MDNS_EINVAL;
+	}
+	if (rg->ndim == 0) {
+		set_error("region has no members: call mdns_region_set_members first");
+		return MDNS_ESTATE;
+	}
+	for (int q = 0; q < nq; ++q)
+		if (query[q] < 0 || query[q] >= rg->n) {
+			set_error("query index %d out of range (%d members)", query[q], rg->n);
+			return MDNS_EINVAL;
+		}
+	for (int r = 0; r < nr; ++r)
+		if (ref[r] < 0 || ref[r] >= rg->n) {
+			set_error("reference index %d out of range (%d members)", ref[r], rg->n);
+			return MDNS_EINVAL;
+		}
+	if (nq == 0) return MDNS_OK;
+	MDNS_CUDA(cudaSetDevice(rg->device));
+	int rc = grow(&rg->d_qidx, &rg->q_cap, (size_t)nq, false);
+	if (rc == MDNS_OK) rc = grow(&rg->d_ridx, &rg->r_cap, (size_t)(nr > 0 ? nr : 1), false);
+	if (rc == MDNS_OK) rc = grow(&rg->d_yy, &rg->yy_cap, (size_t)rg->ndim, false);
+	if (rc == MDNS_OK) rc = grow(&rg->d_gen_keep, &rg->gen_keep_cap, (size_t)nq, false);
+	if (rc != MDNS_OK) return rc;
+	MDNS_CUDA(cudaMemcpyAsync(rg->d_qidx, query, (size_t)nq * sizeof(int), cudaMemcpyHostToDevice,
+	                          rg->stream));
+	if (nr > 0)
+		MDNS_CUDA(cudaMemcpyAsync(rg->d_ridx, ref, (size_t)nr * sizeof(int), cudaMemcpyHostToDevice,
+		                          rg->stream));
+	MDNS_CUDA(cudaMemcpyAsync(rg->d_yy, maxdistance, (size_t)rg->ndim * sizeof(double),
+	                          cudaMemcpyHostToDevice, rg->stream));
+	rc = launch_axis_covered(rg->d_xs, rg->npad, rg->ndim, rg->d_yy, rg->d_qidx, nq, rg->d_ridx, nr,
+	                         rg->d_gen_keep, rg->stream);
+	if (rc != MDNS_OK) return rc;
+	MDNS_CUDA(cudaMemcpyAsync(covered_out, rg->d_gen_keep, (size_t)nq, cudaMemcpyDeviceToHost,
+	                          rg->stream));
+	MDNS_CUDA(cudaStreamSynchronize(rg->stream));
+	return MDNS_OK;
+}
+
 int mdns_region_is_within(mdns_region *rg, double maxdistance, const double *y, int *result)
 {
 	if (!rg || !y || !result) {

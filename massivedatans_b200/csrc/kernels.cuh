@@ -128,6 +128,11 @@ int launch_region_generate(const double *xs, int n, int npad, int ndim, double r
                            uint8_t *keep, int *nnear, cudaStream_t st);
 int launch_gather_points(const double *points, int ndim, const int *idx, int n, double *out,
                          cudaStream_t st);
+// per-axis SupFriends distance (neighbors.py:22-73): nearest other member of every member; and
+// "is some listed reference member inside the per-axis box md around the listed query member"
+int launch_nn_index(const double *xs, int n, int npad, int ndim, int *nearest, cudaStream_t st);
+int launch_axis_covered(const double *xs, int npad, int ndim, const double *md, const int *query,
+                        int nq, const int *ref, int nr, uint8_t *covered, cudaStream_t st);
 int launch_within_single(const double *xs, int n, int npad, int ndim, const double *y, double T,
                          int *flag, cudaStream_t st);
 // chosen[n][nboot] doubles -> per round: query list (un-chosen i) and reference list (chosen j).

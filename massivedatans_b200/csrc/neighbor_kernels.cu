@@ -318,6 +318,97 @@ int launch_gather_points(const double *points, int ndim, const int *idx, int n, 
 	return MDNS_OK;
 }
 
+// ------------------------------------------- per-axis ("SupFriends") distance ---
+// clustering/neighbors.py:22-73.  Two data-parallel pieces; the sequential growth of the per-axis
+// box (neighbors.py:44-58) stays on the host, which only visits the uncovered points.
+
+// neighbors.py:24-25: index of every member's nearest other member (euclidean; the reference
+// sorts the cdist row and takes the second entry).  One warp per member, generic in the
+// dimension; ties go to the smaller index.
+__global__ void __launch_bounds__(NB_THREADS) nn_index_kernel(const double *__restrict__ xs, int n,
+                                                              int npad, int ndim,
+                                                              int *__restrict__ nearest)
+{
+	const int lane = threadIdx.x & 31;
+	const long long i = ((long long)blockIdx.x * NB_THREADS + threadIdx.x) >> 5;
+	if (i >= n) return;
+	double best = __longlong_as_double(0x7ff0000000000000LL);   // +inf
+	int arg = -1;
+	for (int base = 0; base < n; base += 32) {
+		const int j = base + lane;
+		if (j < n && j != i) {
+			double t = __dsub_rn(xs[j], xs[i]);
+			double d = __dmul_rn(t, t);
+			for (int k = 1; k < ndim; ++k) {
+				t = __dsub_rn(xs[(size_t)k * npad + j], xs[(size_t)k * npad + i]);
+				d = __dadd_rn(d, __dmul_rn(t, t));
+			}
+			if (d < best) {       // j increases within a lane: the first minimum is kept
+				best = d;
+				arg = j;
+			}
+		}
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+		const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+		if (oa >= 0 && (arg < 0 || ob < best || (ob == best && oa < arg))) {
+			best = ob;
+			arg = oa;
+		}
+	}
+	if (lane == 0) nearest[i] = arg;
+}
+
+// neighbors.py:40-43: covered[q] = any listed reference member j with |x_qk - x_jk| < md_k on
+// every axis k.  One warp per listed query, ballot early exit.
+__global__ void __launch_bounds__(NB_THREADS) axis_covered_kernel(
+    const double *__restrict__ xs, int npad, int ndim, const double *__restrict__ md,
+    const int *__restrict__ query, int nq, const int *__restrict__ ref, int nr,
+    uint8_t *__restrict__ covered)
+{
+	const int lane = threadIdx.x & 31;
+	const long long q = ((long long)blockIdx.x * NB_THREADS + threadIdx.x) >> 5;
+	if (q >= nq) return;
+	const int i = query[q];
+	bool found = false;
+	for (int base = 0; base < nr; base += 32) {
+		const int r = base + lane;
+		bool close = r < nr;
+		if (close) {
+			const int j = ref[r];
+			for (int k = 0; k < ndim; ++k) {
+				const double dist = fabs(__dsub_rn(xs[(size_t)k * npad + i], xs[(size_t)k * npad + j]));
+				close = close && dist < md[k];
+			}
+		}
+		if (__ballot_sync(0xffffffffu, close) != 0u) {
+			found = true;
+			break;
+		}
+	}
+	if (lane == 0) covered[q] = found ? 1 : 0;
+}
+
+int launch_nn_index(const double *xs, int n, int npad, int ndim, int *nearest, cudaStream_t st)
+{
+	if (n <= 0) return MDNS_OK;
+	nn_index_kernel<<<ceil_div(n, NB_THREADS / 32), NB_THREADS, 0, st>>>(xs, n, npad, ndim, nearest);
+	MDNS_LAUNCHED("nn_index_kernel");
+	return MDNS_OK;
+}
+
+int launch_axis_covered(const double *xs, int npad, int ndim, const double *md, const int *query,
+                        int nq, const int *ref, int nr, uint8_t *covered, cudaStream_t st)
+{
+	if (nq <= 0) return MDNS_OK;
+	axis_covered_kernel<<<ceil_div(nq, NB_THREADS / 32), NB_THREADS, 0, st>>>(xs, npad, ndim, md, query,
+	                                                                        nq, ref, nr, covered);
+	MDNS_LAUNCHED("axis_covered_kernel");
+	return MDNS_OK;
+}
+
 // ------------------------------------------------------- single-point test ---
 // cneighbors.c:77-92: members are spread over the whole grid; any hit raises the flag.
 __global__ void __launch_bounds__(NB_THREADS) within_single_kernel(const double *__restrict__ xs,

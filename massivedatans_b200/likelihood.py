@@ -312,15 +312,18 @@ def make_multi_loglikelihood(x, y, noise_level=0.01, devices=None):
 
     def _points(params_list):
         q = numpy.array(params_list, dtype=numpy.float64).reshape((-1, 3))
-        q[:, 2] = 10 ** q[:, 2]
+        for k in range(len(q)):
+            # scalar power per point, as sample.py:103 computes it (numpy's vectorised pow may
+            # round differently from the scalar one)
+            q[k, 2] = 10 ** q[k, 2]
         return q
 
     def multi_loglikelihood(params, data_mask):
         A, mu, log_sig_kms = params
         if pending:
             # a batch announced by speculate(): the mask only arrives with this call
-            q, Lmins = pending.pop()
-            if q[0, 0] == A and q[0, 1] == mu and q[0, 2] == 10 ** log_sig_kms:
+            first, q, Lmins = pending.pop()
+            if first[0] == A and first[1] == mu and first[2] == log_sig_kms:
                 ds.begin_draw(data_mask, Lmins)
                 k, L, counts = ds.draw_batch(q, noise_level)
                 multi_loglikelihood.last_draw = (k, L, counts)
@@ -345,7 +348,8 @@ def make_multi_loglikelihood(x, y, noise_level=0.01, devices=None):
         device), else None."""
         del pending[:]
         multi_loglikelihood.last_draw = None
-        pending.append((_points(params_list), numpy.array(Lmins, dtype=numpy.float64)))
+        first = numpy.array(params_list[0], dtype=numpy.float64)
+        pending.append((first, _points(params_list), numpy.array(Lmins, dtype=numpy.float64)))
 
     multi_loglikelihood.dataset = ds
     multi_loglikelihood.batch = batch
@@ -486,7 +490,8 @@ def make_muse_loglikelihood_device(y, noise_level, grids, Zs, ages, model_wavele
 
     def _points(params_list):
         q = numpy.array(params_list, dtype=numpy.float64).reshape((-1, 5))
-        q[:, 1] = 10 ** q[:, 1]        # SFtau = 10**logSFtau, musefuse.py:524
+        for k in range(len(q)):
+            q[k, 1] = 10 ** q[k, 1]    # SFtau = 10**logSFtau, a scalar power as at musefuse.py:524
         return q
 
     def multi_loglikelihood_clike(params, data_mask):

@@ -137,3 +137,35 @@ def muse_model(Zs, ages, model_wavelength_nm, calz, grids, wavelength_nm, Z, SFt
     spec /= 1e-10 + spec[norm_index]
     spec = spec * 10 ** (-2.5 * calz * EBV)
     return numpy.interp(x=wavelength_nm / (1 + z), xp=model_wavelength_nm, fp=spec)
+
+
+def initial_maxdistance_guess(u):
+    """clustering/neighbors.py:22-29 -- per axis, the largest |delta| between a point and its
+    nearest neighbour (second entry of the sorted cdist row)."""
+    dist = scipy.spatial.distance.cdist(u, u)
+    nearest = numpy.array([dist[i, :].argsort()[1] for i in range(len(u))])
+    return numpy.abs(u[nearest, :] - u).max(axis=0)
+
+
+def update_maxdistance(u, maxdistance):
+    """clustering/neighbors.py:31-62 -- one bootstrap round of the per-axis box (draws one
+    numpy.random.choice like the reference)."""
+    n = len(u)
+    choice = list(set(numpy.random.choice(numpy.arange(n), size=n)))
+    for i in set(range(n)) - set(choice):
+        offsets = numpy.abs(u[i, :] - u[choice, :])
+        if numpy.all(offsets < maxdistance.reshape((1, -1)), axis=1).any():
+            continue
+        clipped = numpy.where(maxdistance > offsets, offsets, maxdistance)
+        cost = numpy.log(clipped).sum(axis=1) - numpy.log(maxdistance).sum()
+        towards = numpy.argmin(cost)
+        maxdistance = numpy.where(offsets[towards] > maxdistance, offsets[towards], maxdistance)
+    return maxdistance
+
+
+def find_maxdistance(u, nbootstraps=15):
+    """clustering/neighbors.py:64-73."""
+    maxdistance = initial_maxdistance_guess(u)
+    for _ in range(nbootstraps):
+        maxdistance = update_maxdistance(u, maxdistance)
+    return maxdistance
