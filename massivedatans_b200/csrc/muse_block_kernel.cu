@@ -15,8 +15,7 @@
 //     pass and come from L1/L2 through the read-only path.  Longer rows (NF = 0) re-read
 //     the slot from shared memory in both passes;
 //   * block-wide FP64 reductions: warp butterfly + fixed-order sum of the warp partials,
-//     so the result does not depend on scheduling; candidates go in blocks of 16 between two
-//     group barriers (all first passes, barrier, all second passes, barrier);
+//     so the result does not depend on scheduling;
 //   * G = 2: the CTA is split into two groups of 256 threads that work on alternate data sets
 //     of the CTA's list with their own named barriers.  With one data set at a time the two
 //     passes and their two block-wide reductions form a latency chain of ~1.8 us per row, longer
@@ -33,13 +32,38 @@ namespace mdns {
 constexpr int MB_THREADS = 512;
 constexpr int MB_WARPS = MB_THREADS / 32;
 constexpr int MB_STAGES = 3;
-constexpr int MB_KB = 16;         // candidates per barrier pair (multiple of every KT)
 constexpr size_t MB_SMEM_LIMIT = 220 * 1024;
 
 // named barrier of one thread group (barrier 0 is __syncthreads)
 __device__ __forceinline__ void group_sync(int group, int nthreads)
 {
 	asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(nthreads) : "memory");
+}
+
+// sum over the TG threads of one group; `red` is one of the group's two alternating buffers
+template <int N, int NCOL, int TG>
+__device__ __forceinline__ void group_sum(double (&v)[N], double (*red)[MB_WARPS][NCOL], int group,
+                                          int gtid)
+{
+	constexpr int GW = TG / 32;
+	const int warp = gtid >> 5, lane = gtid & 31;
+#pragma unroll
+	for (int i = 0; i < N; ++i) {
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) v[i] += shfl_xor_f64(v[i], o);
+	}
+	if (lane == 0) {
+#pragma unroll
+		for (int i = 0; i < N; ++i) (*red)[warp][i] = v[i];
+	}
+	group_sync(group, TG);
+#pragma unroll
+	for (int i = 0; i < N; ++i) {
+		double s = 0.0;
+#pragma unroll
+		for (int w = 0; w < GW; ++w) s += (*red)[w][i];
+		v[i] = s;
+	}
 }
 
 template <int KT, int NF, int G>
@@ -50,8 +74,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) muse_block_kernel(const LikeArg
 	constexpr int PERIOD = (G == 1 || MB_STAGES % 2 == 0) ? MB_STAGES : 2 * MB_STAGES;
 	static_assert(G == 1 || G == 2, "one or two data sets in flight");
 	__shared__ uint64_t full_bar[G][MB_STAGES];
-	__shared__ double red1[G][MB_KB][MB_WARPS / G][2];    // per-warp partials of (s1, s2) per candidate
-	__shared__ double red2[G][MB_KB][MB_WARPS / G];       // and of chi
+	__shared__ double red[G][2][MB_WARPS][2 * KT];
 	const int nfrag = (a.nx + 1) >> 1;
 	const int mfp = a.mpitch >> 1;
 	const uint32_t row_bytes = (uint32_t)a.pitch * 8u;
@@ -86,6 +109,7 @@ __global__ void __launch_bounds__(MB_THREADS, 1) muse_block_kernel(const LikeArg
 	}
 
 	const double2 *model = reinterpret_cast<const double2 *>(a.model);
+	int flip = 0;
 	for (long long it = group; it < nmine; it += G) {
 		const int slot = (int)(it % MB_STAGES);
 		const long long r = (long long)blockIdx.x + it * gridDim.x;
@@ -117,101 +141,65 @@ __global__ void __launch_bounds__(MB_THREADS, 1) muse_block_kernel(const LikeArg
 		}
 		const int niter = NF > 0 ? NF : (nfrag + TG - 1) / TG;
 
-		// Candidates in blocks of MB_KB: pass 1 for the whole block (KT at a time out of the
-		// registers), ONE group barrier, pass 2 for the whole block, ONE barrier, results.  The
-		// partial sums go warp butterfly -> per-warp slots in shared memory -> fixed-order sum
-		// over the warps, exactly as a block-wide reduction per KT candidates would do it (same
-		// bits), but the number of barriers per data set does not grow with the batch (two per 16
-		// candidates instead of two per KT).  Measured: no change at K = 4 (0.88 ms on the
-		// 40 000 x 3600 cube either way) -- batches are bounded by the model spectra, which every
-		// row pair streams again from L2 in both passes (K x 28.8 KB x 2 per data set), not by
-		// the barriers.
-		const int warp = gtid >> 5, lane = gtid & 31;
-		constexpr int GW = TG / 32;
-		for (int kb = 0; kb < a.K; kb += MB_KB) {
-			const int kn = a.K - kb < MB_KB ? a.K - kb : MB_KB;
+		// Batches (K > KT): every KT candidates cost two passes over the row's registers, two
+		// block-wide reductions and 2 x KT model spectra streamed from L1/L2.  Tried: all first
+		// passes of 16 candidates, one barrier, all second passes, one barrier (same bits) --
+		// no faster (K = 4 on the 40 000 x 3600 cube 0.88 vs 0.84 ms): batches are bounded by
+		// re-streaming the model spectra from L2 for every row pair (K x 28.8 KB x 2 passes,
+		// ~11 TB/s), not by the barriers, and this order lets pass 2 find its spectra in L1.
+		for (int k0 = 0; k0 < a.K; k0 += KT) {
 			// ---- pass 1: s1 = sum y*m*w, s2 = sum m*m*w (cmuselike.c:51-56)
-			for (int k0 = 0; k0 < kn; k0 += KT) {
-				double acc[2 * KT];
+			double acc[2 * KT];
 #pragma unroll
-				for (int i = 0; i < 2 * KT; ++i) acc[i] = 0.0;
+			for (int i = 0; i < 2 * KT; ++i) acc[i] = 0.0;
 #pragma unroll
-				for (int i = 0; i < niter; ++i) {
-					const int f = gtid + i * TG;
-					if (f < nfrag) {
-						const double2 y = NF > 0 ? ry[NF > 0 ? i : 0] : sy[f];
-						const double2 w = NF > 0 ? rw[NF > 0 ? i : 0] : sw[f];
-#pragma unroll
-						for (int k = 0; k < KT; ++k) {
-							const double2 m = __ldg(model + (size_t)(kb + k0 + k) * mfp + f);
-							const double t0 = m.x * w.x, t1 = m.y * w.y;
-							acc[2 * k] = fma(y.x, t0, acc[2 * k]);
-							acc[2 * k] = fma(y.y, t1, acc[2 * k]);
-							acc[2 * k + 1] = fma(m.x, t0, acc[2 * k + 1]);
-							acc[2 * k + 1] = fma(m.y, t1, acc[2 * k + 1]);
-						}
-					}
-				}
-#pragma unroll
-				for (int i = 0; i < 2 * KT; ++i) {
-#pragma unroll
-					for (int o = 16; o > 0; o >>= 1) acc[i] += shfl_xor_f64(acc[i], o);
-				}
-				if (lane == 0) {
+			for (int i = 0; i < niter; ++i) {
+				const int f = gtid + i * TG;
+				if (f < nfrag) {
+					const double2 y = NF > 0 ? ry[NF > 0 ? i : 0] : sy[f];
+					const double2 w = NF > 0 ? rw[NF > 0 ? i : 0] : sw[f];
 #pragma unroll
 					for (int k = 0; k < KT; ++k) {
-						red1[group][k0 + k][warp][0] = acc[2 * k];
-						red1[group][k0 + k][warp][1] = acc[2 * k + 1];
+						const double2 m = __ldg(model + (size_t)(k0 + k) * mfp + f);
+						const double t0 = m.x * w.x, t1 = m.y * w.y;
+						acc[2 * k] = fma(y.x, t0, acc[2 * k]);
+						acc[2 * k] = fma(y.y, t1, acc[2 * k]);
+						acc[2 * k + 1] = fma(m.x, t0, acc[2 * k + 1]);
+						acc[2 * k + 1] = fma(m.y, t1, acc[2 * k + 1]);
 					}
 				}
 			}
-			group_sync(group, TG);
+			group_sum<2 * KT, 2 * KT, TG>(acc, &red[group][flip], group, gtid);
+			flip ^= 1;
+			double s[KT];
+#pragma unroll
+			for (int k = 0; k < KT; ++k) s[k] = acc[2 * k] / (acc[2 * k + 1] + 1e-10);
 			// ---- pass 2: chi = sum (y - s*m)^2 * w (cmuselike.c:58-61)
-			for (int k0 = 0; k0 < kn; k0 += KT) {
-				double s[KT], chi[KT];
+			double chi[KT];
 #pragma unroll
-				for (int k = 0; k < KT; ++k) {
-					double s1 = 0.0, s2 = 0.0;
+			for (int k = 0; k < KT; ++k) chi[k] = 0.0;
 #pragma unroll
-					for (int w = 0; w < GW; ++w) {
-						s1 += red1[group][k0 + k][w][0];
-						s2 += red1[group][k0 + k][w][1];
+			for (int i = 0; i < niter; ++i) {
+				const int f = gtid + i * TG;
+				if (f < nfrag) {
+					const double2 y = NF > 0 ? ry[NF > 0 ? i : 0] : sy[f];
+					const double2 w = NF > 0 ? rw[NF > 0 ? i : 0] : sw[f];
+#pragma unroll
+					for (int k = 0; k < KT; ++k) {
+						const double2 m = __ldg(model + (size_t)(k0 + k) * mfp + f);
+						const double r0 = fma(-s[k], m.x, y.x);
+						const double r1 = fma(-s[k], m.y, y.y);
+						chi[k] = fma(r0 * r0, w.x, chi[k]);
+						chi[k] = fma(r1 * r1, w.y, chi[k]);
 					}
-					s[k] = s1 / (s2 + 1e-10);
-					chi[k] = 0.0;
-				}
-#pragma unroll
-				for (int i = 0; i < niter; ++i) {
-					const int f = gtid + i * TG;
-					if (f < nfrag) {
-						const double2 y = NF > 0 ? ry[NF > 0 ? i : 0] : sy[f];
-						const double2 w = NF > 0 ? rw[NF > 0 ? i : 0] : sw[f];
-#pragma unroll
-						for (int k = 0; k < KT; ++k) {
-							const double2 m = __ldg(model + (size_t)(kb + k0 + k) * mfp + f);
-							const double r0 = fma(-s[k], m.x, y.x);
-							const double r1 = fma(-s[k], m.y, y.y);
-							chi[k] = fma(r0 * r0, w.x, chi[k]);
-							chi[k] = fma(r1 * r1, w.y, chi[k]);
-						}
-					}
-				}
-#pragma unroll
-				for (int k = 0; k < KT; ++k) {
-#pragma unroll
-					for (int o = 16; o > 0; o >>= 1) chi[k] += shfl_xor_f64(chi[k], o);
-				}
-				if (lane == 0) {
-#pragma unroll
-					for (int k = 0; k < KT; ++k) red2[group][k0 + k][warp] = chi[k];
 				}
 			}
-			group_sync(group, TG);
-			if (gtid < kn) {
-				double chi = 0.0;
+			group_sum<KT, 2 * KT, TG>(chi, &red[group][flip], group, gtid);
+			flip ^= 1;
+			if (gtid == 0) {
 #pragma unroll
-				for (int w = 0; w < GW; ++w) chi += red2[group][gtid][w];
-				a.out[(long long)(kb + gtid) * a.out_stride + row] = -0.5 * chi;
+				for (int k = 0; k < KT; ++k)
+					if (k0 + k < a.K) a.out[(long long)(k0 + k) * a.out_stride + row] = -0.5 * chi[k];
 			}
 		}
 		if (NF == 0) {
