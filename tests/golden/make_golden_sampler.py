@@ -164,8 +164,21 @@ def main():
     logZerr = numpy.asarray(results['logZerr'], dtype=float)
     # analytic no-signal value for orientation (plotevidences.py:17)
     null = (-0.5 * (y / noise_level) ** 2).sum(axis=0)
+    # posterior moments per data set from the weighted samples, with the weights
+    # plotposterior.py:21-27 uses (logwidth + L, normalised); x = (A, mu, log10 sig)
+    u, xs, L, w, mask = [numpy.asarray(a, dtype=float) for a in zip(*results['weights'])]
+    lw = w + L                                      # [nsamples, ndata]
+    lw[~numpy.isfinite(lw)] = -numpy.inf
+    lw -= lw.max(axis=0)
+    p = numpy.exp(lw)
+    p /= p.sum(axis=0)
+    feat = xs.copy()                                # [nsamples, ndata, 3]
+    feat[:, :, 0] = numpy.log10(numpy.where(feat[:, :, 0] > 0, feat[:, :, 0], 1.0))
+    post_mean = (p[:, :, None] * feat).sum(axis=0)
+    post_std = numpy.sqrt((p[:, :, None] * (feat - post_mean) ** 2).sum(axis=0))
+    post_ess = 1.0 / (p ** 2).sum(axis=0)
     out = os.path.join(HERE, 'sampler_run.npz')
-    numpy.savez(out, ndata=NDATA, nlive=NLIVE, seed_data=SEED_DATA, seed_run=SEED_RUN,
+    numpy.savez(out, post_mean=post_mean, post_std=post_std, post_ess=post_ess, ndata=NDATA, nlive=NLIVE, seed_data=SEED_DATA, seed_run=SEED_RUN,
                 logZ=logZ, logZerr=logZerr, ndraws=int(sampler.ndraws),
                 niterations=int(results['niterations']), null_logZ=null,
                 information=numpy.asarray(results['information'], dtype=float))
@@ -174,6 +187,7 @@ def main():
         print('data set %2d  logZ %10.3f +- %.3f   (null %10.3f, line height %.4f)'
               % (d, logZ[d], logZerr[d], null[d], truth['height_narrow'][d]))
     print('ndraws', sampler.ndraws, 'niterations', results['niterations'])
+    print('posterior mu mean', post_mean[:, 1].round(2), 'std', post_std[:, 1].round(2), 'ess', post_ess.round(0))
 
 
 if __name__ == '__main__':

@@ -138,6 +138,7 @@ def run(backend, ndata, nlive=100, niter=600, batch=8, rebuild_every=25, seed=1,
     region = None
     pending = numpy.zeros((0, ndim))
     trace = []
+    dead_u, dead_logw = [], []
     for it in range(niter):
         worst = live_L.argmin(axis=0)
         Lmin = live_L[worst, numpy.arange(ndata)]
@@ -189,6 +190,10 @@ def run(backend, ndata, nlive=100, niter=600, batch=8, rebuild_every=25, seed=1,
                     + numpy.where(numpy.isfinite(logZ), numpy.exp(logZ - logZnew) * (H + logZ), 0.0)
                     - logZnew)
         H, logZ = Hnew, logZnew
+        # weighted posterior samples: the dead point of every data set with logwidth + L
+        # (multi_nested_integrator.py:118, plotposterior.py:21)
+        dead_u.append(numpy.array([pile_u[i] for i in live_idx[worst, numpy.arange(ndata)]]))
+        dead_logw.append(wi)
         for d in range(ndata):
             idx, Ld = shelves[d].pop(0)
             live_idx[worst[d], d] = idx
@@ -201,5 +206,17 @@ def run(backend, ndata, nlive=100, niter=600, batch=8, rebuild_every=25, seed=1,
     rest = logw + Lmax + numpy.log(numpy.exp(live_L - Lmax).sum(axis=0))
     logZ = numpy.logaddexp(logZ, rest)
     H = numpy.maximum(H, 0.0)
-    return dict(logZ=logZ, logZerr=numpy.sqrt(H / nlive), H=H, ndraws=ndraws, nbatches=nbatches,
+    # posterior moments per data set in (log10 A, mu, log10 sig), dead points + live remainder
+    # (multi_nested_integrator.py:163-170 appends the live points as the tail)
+    live_u = numpy.array([[pile_u[i] for i in live_idx[:, d]] for d in range(ndata)])  # [ndata, nlive, ndim]
+    samples_u = numpy.concatenate([numpy.array(dead_u), live_u.transpose((1, 0, 2))], axis=0)
+    samples_lw = numpy.concatenate([numpy.array(dead_logw), logw + live_L], axis=0)     # [ns, ndata]
+    feat = priortransform(samples_u.reshape((-1, ndim))).reshape(samples_u.shape)
+    feat[:, :, 0] = numpy.log10(feat[:, :, 0])
+    p = numpy.exp(samples_lw - samples_lw.max(axis=0))
+    p /= p.sum(axis=0)
+    post_mean = (p[:, :, None] * feat).sum(axis=0)
+    post_std = numpy.sqrt((p[:, :, None] * (feat - post_mean) ** 2).sum(axis=0))
+    post_ess = 1.0 / (p ** 2).sum(axis=0)
+    return dict(post_mean=post_mean, post_std=post_std, post_ess=post_ess, logZ=logZ, logZerr=numpy.sqrt(H / nlive), H=H, ndraws=ndraws, nbatches=nbatches,
                 trace=trace, remainder_fraction=numpy.exp(rest - logZ))

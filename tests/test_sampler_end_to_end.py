@@ -1,5 +1,5 @@
-"""End-to-end check of the north star's last correctness clause: evidences of a fixed-seed
-nested-sampling run agree with the reference within nested-sampling noise.
+"""End-to-end check of the north star's last correctness clause: evidences and posteriors of a
+fixed-seed nested-sampling run agree with the reference within nested-sampling noise.
 
 The reference side is tests/golden/sampler_run.npz: the REFERENCE's own sampler stack
 (multi_nested_integrator + MultiNestedSampler + MetricLearningFriendsConstrainer + RadFriends)
@@ -38,6 +38,20 @@ def _check_against_reference(run, g):
     # both must see the lines: evidence far above the no-signal value where the line is strong
     strong = g['null_logZ'] < g['logZ'] - 50
     assert strong.any() and (run['logZ'][strong] > g['null_logZ'][strong] + 50).all()
+    # posteriors: weighted means of (log10 A, mu, log10 sig) per data set agree within the
+    # Monte-Carlo error of the two weighted samples (std / sqrt(effective sample size) each;
+    # weights as plotposterior.py:21-27), and where the line position is well constrained
+    # (std < 5 nm in the reference run) the two runs put it at the same wavelength
+    err = numpy.sqrt(g['post_std'] ** 2 / g['post_ess'][:, None]
+                     + run['post_std'] ** 2 / run['post_ess'][:, None])
+    zp = (run['post_mean'] - g['post_mean']) / err
+    assert numpy.isfinite(zp).all()
+    assert numpy.abs(zp).max() < 5.0, zp
+    assert numpy.sqrt((zp ** 2).mean()) < 2.0, zp
+    sharp = g['post_std'][:, 1] < 5.0
+    assert sharp.sum() >= 5
+    assert numpy.abs(run['post_mean'][sharp, 1] - g['post_mean'][sharp, 1]).max() < 3.0
+    assert (run['post_std'][sharp, 1] < 10.0).all()
 
 
 def test_harness_on_oracle_matches_reference_sampler_evidences(golden):
@@ -57,6 +71,8 @@ def test_gpu_run_reproduces_oracle_run_draw_by_draw(golden):
     assert [t[2] for t in got['trace']] == [t[2] for t in want['trace']]
     assert numpy.allclose(got['logZ'], want['logZ'], rtol=1e-9, atol=0)
     assert numpy.allclose(got['H'], want['H'], rtol=1e-6, atol=1e-9)
+    assert numpy.allclose(got['post_mean'], want['post_mean'], rtol=1e-9, atol=1e-12)
+    assert numpy.allclose(got['post_std'], want['post_std'], rtol=1e-6, atol=1e-12)
 
 
 @pytest.mark.gpu
