@@ -53,7 +53,7 @@ class Timed(object):
             self.n += 1
 
 
-def run(constrainer, like, init_L, pile0, ndata, nlive, ndraws, seed):
+def run(constrainer, like, init_L, pile0, ndata, nlive, ndraws, seed, groups='cycle', rank=0):
     """The loop of tests/harness_constrainer.py::run_draws with vectorised bookkeeping and a
     timer around draw_constrained."""
     numpy.random.seed(seed)
@@ -65,10 +65,17 @@ def run(constrainer, like, init_L, pile0, ndata, nlive, ndraws, seed):
     cols = numpy.arange(ndata)
     us, tries, per_draw = [], [], []
     for it in range(ndraws):
-        mask = group_mask(it, ndata, rs)
+        if groups == 'single':
+            mask = numpy.zeros(ndata, dtype=bool)
+            mask[rs.randint(ndata)] = True
+        else:
+            mask = group_mask(it, ndata, rs)
         members = numpy.unique(live_p[:, mask])
         live_u = numpy.array([pile[i] for i in members])
-        Lmins = live_L[worst, cols][mask]
+        if rank == 0:
+            Lmins = live_L[worst, cols][mask]
+        else:
+            Lmins = numpy.sort(live_L[:, mask], axis=0)[rank]
         t0 = time.perf_counter()
         u, x, L, n = constrainer.draw_constrained(
             Lmins=Lmins, priortransform=priortransform,
@@ -93,6 +100,12 @@ def main():
     ap.add_argument('--cpu-draws', type=int, default=40)
     ap.add_argument('--batch', type=int, default=16)
     ap.add_argument('--seed', type=int, default=1)
+    ap.add_argument('--groups', choices=('cycle', 'single'), default='cycle',
+                    help='cycle: all, all, random half, single data set; single: focussed draws '
+                         'for one data set at a time (the late-stage regime of the sampler)')
+    ap.add_argument('--rank', type=int, default=0,
+                    help='which live likelihood is the threshold: 0 = minimum (nested sampling), '
+                         '-1 = maximum (long rejection chains)')
     ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'constrainer.json'))
     args = ap.parse_args()
     N, nlive = args.ndata, args.nlive
@@ -105,7 +118,9 @@ def main():
     init_L = numpy.array(like.batch([priortransform(u) for u in pile0], numpy.ones(N, dtype=bool)))
     t_init = time.perf_counter() - t0
     res = {'ndata': N, 'nlive': nlive, 'nx': int(y.shape[0]), 'draws': args.draws,
-           'constrainer': CONSTRAINER, 'groups': 'all, all, random half, single data set (cyclic)',
+           'constrainer': CONSTRAINER, 'threshold_rank': args.rank,
+           'groups': 'all, all, random half, single data set (cyclic)' if args.groups == 'cycle'
+           else 'one data set per draw',
            'initial_population_gpu_s': t_init}
     lib = _lib.load()
     arms, pers = {}, {}
@@ -115,7 +130,8 @@ def main():
         c = MetricLearningFriendsConstrainer(batch_size=batch, speculator=like if batch > 1 else None,
                                              adaptive=adaptive, **CONSTRAINER)
         l0 = lib.mdns_launch_count()
-        us, tries, per = run(c, tl, init_L, pile0, N, nlive, args.draws, args.seed)
+        us, tries, per = run(c, tl, init_L, pile0, N, nlive, args.draws, args.seed, args.groups,
+                             args.rank)
         arms[name] = (us, tries)
         pers[name] = per
         res[name] = {'batch': batch, 'draw_s_total': float(per.sum()), 'ms_per_draw': 1e3 * float(per.mean()),
@@ -164,7 +180,8 @@ def main():
 
         tl = Timed(ref_like)
         c = MetricLearningFriendsConstrainer(batch_size=1, region_class=RefRegion, **CONSTRAINER)
-        us, tries, per = run(c, tl, init_L, pile0, N, nlive, args.cpu_draws, args.seed)
+        us, tries, per = run(c, tl, init_L, pile0, N, nlive, args.cpu_draws, args.seed, args.groups,
+                             args.rank)
         n = args.cpu_draws
         same = numpy.array_equal(us, arms['gpu_one_by_one'][0][:n]) and \
             numpy.array_equal(tries, arms['gpu_one_by_one'][1][:n])
