@@ -210,8 +210,8 @@ class MetricLearningFriendsConstrainer(object):
         while True:
             batch = self._peek(min(width, self.batch_size) if speculative else 1)
             width *= 2
-            for u, _ in batch:
-                assert (u >= 0).all() and (u <= 1).all(), u
+            cube = numpy.array([u for u, _ in batch])
+            assert (cube >= 0).all() and (cube <= 1).all(), cube       # hiermetriclearn.py:182
             xs = [priortransform(u) for u, _ in batch]
             k, L = self._score(batch, xs, Lmins, loglikelihood)
             # replay the reference's per-candidate bookkeeping (hiermetriclearn.py:181-211) up
