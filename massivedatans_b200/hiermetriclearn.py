@@ -22,7 +22,9 @@ through the likelihood callable itself: ``speculator.speculate(xs, Lmins)`` anno
 the next ``loglikelihood(xs[0])`` call carries the mask and runs it, ``speculator.last_draw``
 holds ``(k, L_k, counts)``.  ``massivedatans_b200.likelihood.make_multi_loglikelihood`` returns
 such a callable.  Without a speculator (or with ``batch_size=1``) every candidate is scored by
-its own call, as in the reference.  ``adaptive`` (default) starts every draw with one candidate
+its own call, as in the reference.  ``device_proposals=m`` (off by default) switches the proposal
+rounds to the fused device generator, m proposals per round: statistically equivalent draws, not
+the reference's random stream.  ``adaptive`` (default) starts every draw with one candidate
 and doubles the pass width after each fully rejected pass, so an easy draw costs what it costs
 in the reference and a long rejection chain of n candidates takes about log2(n) passes.
 
@@ -41,7 +43,8 @@ UNIT_CUBE_CHANCE = 0.1           # hiermetriclearn.py:126
 class MetricLearningFriendsConstrainer(object):
     def __init__(self, metriclearner, rebuild_every=50, metric_rebuild_every=50, verbose=False,
                  keep_phantom_points=False, optimize_phantom_points=False, force_shrink=False,
-                 batch_size=16, speculator=None, adaptive=True, region_class=RadFriendsRegion):
+                 batch_size=16, speculator=None, adaptive=True, device_proposals=0,
+                 region_class=RadFriendsRegion):
         if metriclearner not in ('none', 'simplescaling', 'truncatedscaling'):
             raise ValueError('unknown metriclearner %r' % (metriclearner,))
         self.iter_since_metric_rebuild = 0
@@ -61,6 +64,7 @@ class MetricLearningFriendsConstrainer(object):
         self.batch_size = max(1, int(batch_size))
         self.speculator = speculator
         self.adaptive = bool(adaptive)
+        self.device_proposals = int(device_proposals)    # proposals per device round, 0 = host RNG
         self.region_class = region_class
         self._queue = []             # candidates of the current proposal round, not yet scored
         self.nbatches = 0            # likelihood passes issued
@@ -123,6 +127,23 @@ class MetricLearningFriendsConstrainer(object):
         per round: ``(us[k, ndim], proposals spent since the previous non-empty round)``.  The
         reference yields the rows of each array one at a time, the first carrying the count."""
         spent = 0
+        if self.device_proposals > 0:
+            # statistical mode (SURVEY.md 8(f) rank 3): the ball draws, the neighbour count and
+            # the 1/count thinning happen in one kernel (RadFriendsRegion.generate_device); only
+            # the accepted points come back.  Same distribution (uniform in the region), not
+            # numpy's random stream: one numpy draw per region seeds the device stream, so a run
+            # is still reproducible from the numpy seed, but it is not the reference's run.
+            seed = int(numpy.random.randint(0, 2 ** 31 - 1))
+            first = 0
+            while True:
+                ws = self.region.generate_device(self.device_proposals, seed, first_proposal=first)
+                first += self.device_proposals
+                spent += self.device_proposals
+                us = self.metric.untransform(ws)
+                inside = numpy.logical_and(us < 1, us > 0).all(axis=1)
+                if inside.any():
+                    yield us[inside, :], spent
+                    spent = 0
         while True:
             if ndim < 40:
                 for ws, n in self.region.generate(UNIT_CUBE_DRAWS):

@@ -186,3 +186,40 @@ def test_speculation_at_scale_matches_one_by_one():
     assert numpy.array_equal(r1['naccepted'], r16['naccepted'])
     assert numpy.allclose(r1['L'], r16['L'], rtol=1e-10, atol=0, equal_nan=True)
     assert c16.nbatches <= c1.nbatches
+
+
+@pytest.mark.gpu
+def test_device_proposals_are_a_statistically_equivalent_generator(fixture):
+    # proposals from the fused device generator (not numpy's stream): every draw is still a valid
+    # constrained draw, and the run needs about as many tries as the reference's run
+    from massivedatans_b200.likelihood import make_multi_loglikelihood
+    tag = 'a'
+    ndata, nlive, niter, seed_data, seed_run = fixture[tag + '_cfg']
+    x, y, _ = synth.horns(int(ndata), seed=int(seed_data))
+    like = make_multi_loglikelihood(x, y, synth.NOISE_LEVEL)
+    c = MetricLearningFriendsConstrainer(batch_size=16, speculator=like, device_proposals=4096,
+                                         **CONFIG[tag])
+    res = run_draws(c, like, int(ndata), int(nlive), int(niter), int(seed_run))
+    assert ((res['u'] > 0) & (res['u'] < 1)).all()
+    assert (res['naccepted'] >= 1).all()                   # run_draws asserts L > Lmins somewhere
+    assert not numpy.array_equal(res['u'], fixture[tag + '_u'])        # a different stream
+    want = fixture[tag + '_ntoaccept']
+    # same efficiency.  The number of tries is heavy-tailed (up to ~100 for the single-data-set
+    # groups) and runs diverge after the first draw; six host-RNG runs of this configuration
+    # with seeds 3..8 (oracle backend) gave mean tries 2.85 .. 4.44, first-try share 0.34 .. 0.46
+    # and share within four tries 0.745 .. 0.862 (the fixture's run: 3.95, 0.34, 0.745)
+    tries = res['ntoaccept']
+    assert 2.3 < tries.mean() < 5.5, tries.mean()
+    assert 0.28 < (tries <= 1).mean() < 0.54, (tries <= 1).mean()
+    assert 0.68 < (tries <= 4).mean() < 0.92, (tries <= 4).mean()
+    assert want.mean() > 0
+    # and the same typical likelihood gain per draw (the accepted points sit in the same shells)
+    gain = numpy.nanmedian(res['L'], axis=1)
+    gain_ref = numpy.nanmedian(fixture[tag + '_L'], axis=1)
+    assert abs(numpy.median(gain[-100:]) - numpy.median(gain_ref[-100:])) < \
+        0.5 * numpy.std(gain_ref[-100:]) + 1.0
+    # reproducible from the numpy seed
+    c2 = MetricLearningFriendsConstrainer(batch_size=16, speculator=like, device_proposals=4096,
+                                          **CONFIG[tag])
+    res2 = run_draws(c2, like, int(ndata), int(nlive), int(niter), int(seed_run))
+    assert numpy.array_equal(res['u'], res2['u'])

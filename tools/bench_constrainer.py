@@ -124,11 +124,15 @@ def main():
            'initial_population_gpu_s': t_init}
     lib = _lib.load()
     arms, pers = {}, {}
-    for name, batch, adaptive in (('gpu_one_by_one', 1, False), ('gpu_speculative', args.batch, False),
-                                  ('gpu_speculative_adaptive', args.batch, True)):
+    for name, batch, adaptive, devprop in (('gpu_one_by_one', 1, False, 0),
+                                           ('gpu_speculative', args.batch, False, 0),
+                                           ('gpu_speculative_adaptive', args.batch, True, 0),
+                                           # statistical mode: proposals from the fused device
+                                           # generator (not numpy's stream -> different draws)
+                                           ('gpu_speculative_device_proposals', 4 * args.batch, True, 8192)):
         tl = Timed(like)
         c = MetricLearningFriendsConstrainer(batch_size=batch, speculator=like if batch > 1 else None,
-                                             adaptive=adaptive, **CONSTRAINER)
+                                             adaptive=adaptive, device_proposals=devprop, **CONSTRAINER)
         l0 = lib.mdns_launch_count()
         us, tries, per = run(c, tl, init_L, pile0, N, nlive, args.draws, args.seed, args.groups,
                              args.rank)
