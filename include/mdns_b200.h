@@ -167,6 +167,14 @@ int mdns_set_thresholds(mdns_dataset *ds, const double *Lmins);
 int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const double *Lmins,
                             int *accept_counts, int *first_k, double *Lout,
                             int64_t lout_capacity);
+/* One call per speculative pass of a constrained draw: mdns_set_mask (a repeated mask is
+ * recognised), mdns_set_thresholds (skipped when a short Lmins equals the staged one),
+ * mdns_stage_params and mdns_clike_first_accept.  *n_act_out = active data sets; Lout must hold
+ * that many doubles. */
+int mdns_clike_draw_pass(mdns_dataset *ds, const uint8_t *mask, const double *Lmins,
+                         const double *params, int K, double noise, double scale,
+                         int *accept_counts, int *first_k, double *Lout, int64_t lout_capacity,
+                         int *n_act_out);
 /* The same decision, returning only what the sampler consumes (multi_nested_sampler.py:482-485
  * pushes the new point onto the shelves of the data sets with Lj[j] > Lmins[j]): idx_out[0..n)
  * = positions j (in the compacted active order, increasing) of the data sets the first accepted

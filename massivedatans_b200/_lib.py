@@ -44,6 +44,8 @@ SIGNATURES = {
     'mdns_set_thresholds': (c_int, [_P, _P]),
     'mdns_clike_first_accept': (c_int, [_P, c_double, c_double, _P, _P, POINTER(c_int), _P,
                                         c_int64]),
+    'mdns_clike_draw_pass': (c_int, [_P, _P, _P, _P, c_int, c_double, c_double, _P, POINTER(c_int), _P,
+                                     c_int64, POINTER(c_int)]),
     'mdns_clike_first_accept_sparse': (c_int, [_P, c_double, c_double, _P, _P, POINTER(c_int), _P, _P,
                                                c_int64, POINTER(c_int)]),
     'mdns_clike_accept_counts': (c_int, [_P, c_double, c_double, _P, _P]),

@@ -127,6 +127,7 @@ struct mdns_dataset {
 	Tuning tuning;
 	int64_t resident_bytes = 0;
 	bool thresholds_staged = false;   // d_lmins holds thresholds aligned with the current mask
+	std::vector<double> host_lmins;   // copy of the staged thresholds when short (mdns_clike_draw_pass)
 	double single[3] = {0, 0, 0};     // the candidate of a K = 1 batch, passed by value
 	double xp_tol = 1e-10;        // relative error bound enforced by the expanded form
 	long long xp_redo_total = 0;  // rows recomputed in the direct form so far
@@ -384,6 +385,7 @@ int mdns_internal_threshold_buffer(mdns_dataset *ds, int shard, double **d_lmins
 	int rc = grow(&s.d_lmins, &s.lmins_cap, (size_t)s.n, false);
 	if (rc != MDNS_OK) return rc;
 	*d_lmins = s.d_lmins;
+	ds->host_lmins.clear();           // written by a device kernel: no host copy to compare with
 	if (shard == (int)ds->shards.size() - 1) ds->thresholds_staged = true;
 	return MDNS_OK;
 }
@@ -530,6 +532,10 @@ int mdns_set_mask(mdns_dataset *ds, const uint8_t *mask, int *n_act_out)
 // Accept thresholds of the active data sets (the `Lmins` of draw_constrained,
 // hiermetriclearn.py:173: constant while candidates are tried), aligned with the compacted
 // active order of the current mask.  Stays resident until the next mdns_set_mask.
+// thresholds of at most this many active data sets are compared with the staged ones before
+// they are uploaded again (mdns_clike_draw_pass)
+static constexpr int DRAW_PASS_COMPARE_MAX = 8192;
+
 int mdns_set_thresholds(mdns_dataset *ds, const double *Lmins)
 {
 	if (!ds || !Lmins) {
@@ -554,6 +560,10 @@ int mdns_set_thresholds(mdns_dataset *ds, const double *Lmins)
 		MDNS_CUDA(cudaStreamSynchronize(s.stream));
 	}
 	ds->thresholds_staged = true;
+	if (ds->n_act_total <= DRAW_PASS_COMPARE_MAX)
+		ds->host_lmins.assign(Lmins, Lmins + ds->n_act_total);
+	else
+		ds->host_lmins.clear();
 	return MDNS_OK;
 }
 
@@ -957,6 +967,34 @@ int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const 
 		off += s.n_act;
 	}
 	return mdns_sync(ds);
+}
+
+int mdns_clike_draw_pass(mdns_dataset *ds, const uint8_t *mask, const double *Lmins,
+                         const double *params, int K, double noise, double scale,
+                         int *accept_counts, int *first_k, double *Lout, int64_t lout_capacity,
+                         int *n_act_out)
+{
+	if (!ds || !Lmins || !params || !first_k || !Lout || K <= 0) {
+		set_error("mdns_clike_draw_pass: need ds, Lmins, params, first_k, Lout, K > 0");
+		return MDNS_EINVAL;
+	}
+	int n_act = 0;
+	int rc = mdns_set_mask(ds, mask, &n_act);       // returns at once for a repeated mask
+	if (rc != MDNS_OK) return rc;
+	if (n_act_out) *n_act_out = n_act;
+	*first_k = -1;
+	if (accept_counts)
+		for (int k = 0; k < K; ++k) accept_counts[k] = 0;
+	if (n_act == 0) return MDNS_OK;
+	// the thresholds stay the same while the candidates of one constrained draw are tried
+	// (hiermetriclearn.py:173-211): short vectors are compared with the staged copy instead of
+	// being uploaded (and synchronised on) again
+	const bool same = ds->thresholds_staged && ds->host_lmins.size() == (size_t)n_act &&
+	                  memcmp(Lmins, ds->host_lmins.data(), (size_t)n_act * sizeof(double)) == 0;
+	if (!same && (rc = mdns_set_thresholds(ds, Lmins)) != MDNS_OK) return rc;
+	if ((rc = mdns_stage_params(ds, params, K)) != MDNS_OK) return rc;
+	return mdns_clike_first_accept(ds, noise, scale, nullptr, accept_counts, first_k, Lout,
+	                               lout_capacity);
 }
 
 // Two-step form for one process per GPU (torchrun): every rank counts the accepting data sets

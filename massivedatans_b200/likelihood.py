@@ -236,6 +236,35 @@ class ResidentDataset(object):
             return -1, None, counts
         return first.value, out, counts
 
+    def draw_pass(self, data_mask, Lmins, params, noise, scale=-0.5):
+        """``begin_draw`` + ``draw_batch`` in one native call (one speculative pass of a
+        constrained draw): a repeated mask and repeated short thresholds are recognised and not
+        uploaded again.  Returns ``(k, L, counts)`` like ``draw_batch``."""
+        p = numpy.ascontiguousarray(params, dtype=numpy.float64).reshape((-1, 3))
+        K = len(p)
+        counts = numpy.zeros(K, dtype=numpy.int32)
+        if data_mask is None:
+            m, n_act = None, self.ndata
+        else:
+            m = self._mask(data_mask)
+            n_act = int(numpy.count_nonzero(m))
+        Lmins = numpy.ascontiguousarray(Lmins, dtype=numpy.float64)
+        if Lmins.shape != (n_act,):
+            raise ValueError('Lmins must have one entry per active data set')
+        self._draw_n_act = n_act
+        if n_act == 0:
+            self.set_mask(m)
+            return -1, None, counts
+        out = _pool.empty(n_act)
+        first = ctypes.c_int(-1)
+        _lib.check(self._lib.mdns_clike_draw_pass(self._h, _addr(m), _addr(Lmins), _addr(p), K, noise,
+                                                  scale, _addr(counts), ctypes.byref(first),
+                                                  _addr(out), out.size, None),
+                   'mdns_clike_draw_pass')
+        if first.value < 0:
+            return -1, None, counts
+        return first.value, out, counts
+
     def draw_counts(self, params, noise, scale=-0.5):
         """First step of the two-step form (one process per GPU): score the next K candidates of
         the draw started with ``begin_draw`` and return the accept counts of THIS process's data
@@ -325,8 +354,7 @@ def make_multi_loglikelihood(x, y, noise_level=0.01, devices=None):
             # a batch announced by speculate(): the mask only arrives with this call
             first, q, Lmins = pending.pop()
             if first[0] == A and first[1] == mu and first[2] == log_sig_kms:
-                ds.begin_draw(data_mask, Lmins)
-                k, L, counts = ds.draw_batch(q, noise_level)
+                k, L, counts = ds.draw_pass(data_mask, Lmins, q, noise_level)
                 multi_loglikelihood.last_draw = (k, L, counts)
                 return L if k == 0 else None
             # some other caller came in between: the announcement is void

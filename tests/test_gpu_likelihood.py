@@ -474,6 +474,48 @@ def test_first_accepted_matches_one_at_a_time_loop(oracle_port, N):
         ds.draw_batch(pts, synth.NOISE_LEVEL)       # thresholds do not survive a new mask
 
 
+def test_draw_pass_is_begin_draw_plus_draw_batch(oracle_port):
+    # one native call per speculative pass; repeated masks / short thresholds are recognised and
+    # not uploaded again -- the answers must not depend on what was recognised
+    N = 3000
+    x, y, _ = synth.horns(N, legacy=False, seed=10)
+    ds = ResidentDataset(x, y)
+    pts = synth.parameter_points(7, seed=6)
+    masks = synth.masks(N)
+    masks['single'] = numpy.arange(N) == 1234
+    for name in ('half', 'single', 'sparse', 'all', 'none', 'single'):
+        m = masks[name]
+        n_act = int(m.sum())
+        if n_act == 0:
+            k, L, counts = ds.draw_pass(m, numpy.zeros(0), pts, synth.NOISE_LEVEL)
+            assert k == -1 and L is None and (counts == 0).all()
+            continue
+        Ls = ds.loglike_batch(pts, m, synth.NOISE_LEVEL).copy()
+        first3 = Ls[:3].max(axis=0)
+        variants = [first3 + 1e-6 * numpy.abs(first3),      # candidates 0..2 rejected everywhere
+                    Ls.min(axis=0) - 1.0,                    # everything accepts
+                    Ls.max(axis=0) + 1.0]                    # nothing accepts
+        for Lmins in variants + variants[:1]:                # ... and back to the first again
+            want_counts = (Ls > Lmins).sum(axis=1)
+            want_first = int(numpy.argmax(want_counts > 0)) if (want_counts > 0).any() else -1
+            for repeat in range(2):                          # second time: nothing is uploaded
+                k, L, counts = ds.draw_pass(m, Lmins.copy(), pts, synth.NOISE_LEVEL)
+                assert k == want_first, (name, repeat)
+                assert numpy.array_equal(counts, want_counts)
+                if k >= 0:
+                    assert numpy.array_equal(L, Ls[k])
+                else:
+                    assert L is None
+            ds.begin_draw(m, Lmins)
+            k2, L2, c2 = ds.draw_batch(pts, synth.NOISE_LEVEL)
+            assert k2 == want_first and numpy.array_equal(c2, want_counts)
+        # same thresholds, other candidates
+        k, L, counts = ds.draw_pass(m, variants[0], pts[3:], synth.NOISE_LEVEL)
+        assert numpy.array_equal(counts, (Ls[3:] > variants[0]).sum(axis=1))
+    with pytest.raises(ValueError):
+        ds.draw_pass(masks['half'], numpy.zeros(3), pts, synth.NOISE_LEVEL)
+
+
 def test_legacy_like_symbol_accumulates(oracle_port):
     # the reference's own argtypes (sample.py:85-96) on the drop-in veneer
     import os
