@@ -159,7 +159,9 @@ int mdns_clike_launch_fetch(mdns_dataset *ds, double noise, double scale, double
  * the accept test on the device.  Lmins[n_act] is aligned with the compacted active order.
  * accept_counts[K] (may be NULL) = data sets with scale*chi2 > Lmins per candidate;
  * *first_k = first candidate with a non-zero count, or -1; its logL vector is copied to Lout
- * (untouched when none accepts).  Only K ints and one vector cross PCIe. */
+ * (contents unspecified when none accepts).  Only K ints and one vector cross PCIe.  The accept
+ * test runs inside the likelihood kernels and the choice of first_k on the device; large vectors
+ * are downloaded in row chunks overlapped with the scoring of the next chunk. */
 /* Thresholds may also be staged once per constrained draw (they are constant while candidates
  * are tried, hiermetriclearn.py:173-211): mdns_set_thresholds after mdns_set_mask, then
  * mdns_clike_first_accept with Lmins = NULL for every batch of candidates. */
@@ -192,9 +194,45 @@ int mdns_clike_accept_counts(mdns_dataset *ds, double noise, double scale, const
 int mdns_fetch_candidate(mdns_dataset *ds, int k, double *Lout, int64_t lout_capacity);
 int mdns_fetch(mdns_dataset *ds, double *Lout, int64_t lout_capacity);
 int mdns_sync(mdns_dataset *ds);
+/* Experiment knob: the dense first-accept pass scores the active data sets in row chunks and
+ * downloads the (speculatively) selected candidate's rows of a finished chunk while the next one
+ * is scored; 0 = automatic, 1 = one chunk, up to 8. */
+int mdns_set_draw_chunks(mdns_dataset *ds, int nchunks);
+
+/* ---- one process per GPU: the exchange step ---------- */
+/*
+ * Data sets are independent (clike.c:68-74), so ranks never exchange data.  The one global
+ * decision of the path is `numpy.any(L > Lmins)` (hiermetriclearn.py:193): with a communicator
+ * attached, mdns_clike_first_accept[_sparse] / mdns_clike_draw_pass add the K per-candidate accept
+ * counts up over the ranks with ncclAllReduce on the data set's stream (NVLink / NVSwitch) before
+ * the first accepted candidate is chosen on the device -- every rank returns the same first_k and
+ * the GLOBAL counts, and its own slice of the logL vector.  Every rank must make the same calls
+ * (also ranks whose mask leaves them no active data set).  NCCL is bound with dlopen when the
+ * first of these functions is called; nothing else in the library needs it.
+ *   unique_id  MDNS_UNIQUE_ID_BYTES bytes from ncclGetUniqueId, created by one rank and handed to
+ *              the others by the caller (massivedatans_b200.sharding does it over TCP)
+ *   init       collective (ncclCommInitRank); the data set must live on ONE device
+ */
+#define MDNS_UNIQUE_ID_BYTES 128
+int mdns_comm_unique_id(void *id_out);
+int mdns_comm_init(mdns_dataset *ds, const void *id, int nranks, int rank);
+int mdns_comm_destroy(mdns_dataset *ds);
+int mdns_comm_info(const mdns_dataset *ds, int *nranks, int *rank);
+/* values[n] (host, n <= 1024) := sum (op 0) or max (op 1) over the ranks; doubles as a barrier.
+ * No communicator: values unchanged. */
+int mdns_comm_allreduce(mdns_dataset *ds, double *values, int n, int op);
+/* Device-consumer exchange: every rank contributes the logL vector of candidate k of its last
+ * clike launch (n_act entries); afterwards every rank holds all of them in rank order on its
+ * device and, if Lall != NULL, compacted in Lall (n_per_rank[r] entries of rank r; may be NULL).
+ * ncclAllGather on the data set's stream. */
+int mdns_comm_allgather_candidate(mdns_dataset *ds, int k, double *Lall, int64_t capacity,
+                                  int *n_per_rank);
 /* CUDA-event stopwatch on the data set's own streams (max over shards). */
 int mdns_timer_start(mdns_dataset *ds);
 int mdns_timer_stop(mdns_dataset *ds, float *elapsed_ms);
+/* Measurement aid: evict the L2 by overwriting a 256 MB scratch buffer on every shard's stream
+ * (between timed iterations of problems that fit in the 126 MB L2). */
+int mdns_flush_l2(mdns_dataset *ds);
 /* Kernel-variant override for experiments: lanes per data set (0 = auto),
  * fragments in flight per lane (0 = auto), candidates per pass (0 = auto),
  * data sets per lane group (0 = auto; > 1 selects the register-blocked kernel). */
@@ -269,6 +307,9 @@ typedef struct mdns_region mdns_region;
 /* A region owns the resident member set (live-point union, metric space). */
 int mdns_region_create(int device, mdns_region **out);
 int mdns_region_destroy(mdns_region *rg);
+/* CUDA-event stopwatch on the region's stream (measurement aid). */
+int mdns_region_timer_start(mdns_region *rg);
+int mdns_region_timer_stop(mdns_region *rg, float *elapsed_ms);
 /* xx[n][ndim] row-major (neighbors.py:100 argtype); upload once per region
  * (radfriendsregion.py:59-70 builds one region from `members`). */
 int mdns_region_set_members(mdns_region *rg, const double *xx, int n, int ndim);

@@ -66,8 +66,18 @@ SIGNATURES = {
     'mdns_livetable_replace_points': (c_int, [_P, _P, _P]),
     'mdns_livetable_subsets': (c_int, [_P, _P, c_int64, _P, POINTER(c_int), POINTER(c_int)]),
     'mdns_sync': (c_int, [_P]),
+    'mdns_set_draw_chunks': (c_int, [_P, c_int]),
+    'mdns_comm_unique_id': (c_int, [_P]),
+    'mdns_comm_init': (c_int, [_P, _P, c_int, c_int]),
+    'mdns_comm_destroy': (c_int, [_P]),
+    'mdns_comm_info': (c_int, [_P, POINTER(c_int), POINTER(c_int)]),
+    'mdns_comm_allreduce': (c_int, [_P, _P, c_int, c_int]),
+    'mdns_comm_allgather_candidate': (c_int, [_P, c_int, _P, c_int64, _P]),
     'mdns_timer_start': (c_int, [_P]),
     'mdns_timer_stop': (c_int, [_P, POINTER(c_float)]),
+    'mdns_flush_l2': (c_int, [_P]),
+    'mdns_region_timer_start': (c_int, [_P]),
+    'mdns_region_timer_stop': (c_int, [_P, POINTER(c_float)]),
     'mdns_set_tuning': (c_int, [_P, c_int, c_int, c_int, c_int]),
     'mdns_muse_model_create': (c_int, [_P, _P, c_int, _P, c_int, _P, c_int, _P, _P, _P, c_int, c_int,
                                        POINTER(_P)]),

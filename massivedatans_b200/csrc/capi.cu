@@ -11,6 +11,7 @@
 
 #include "hostutil.h"
 #include "kernels.cuh"
+#include "nccl_dl.h"
 
 namespace mdns {
 
@@ -80,6 +81,23 @@ struct Shard {
 	double *syy = nullptr;        // expanded form: sum of squares of every resident row
 	double *d_smm = nullptr;      // and of every staged model spectrum
 	size_t smm_cap = 0;
+	// the accept decision on the device: [first, count, redo, -, counts[K]] per block, one block
+	// per row chunk of a pass (kernels.cuh SEL_*); h_sel is its pinned copy
+	int *d_sel = nullptr, *h_sel = nullptr;
+	size_t sel_cap = 0, h_sel_cap = 0;
+	int *d_snap = nullptr;        // per-chunk snapshots of the running counts
+	size_t snap_cap = 0;
+	double *d_pick = nullptr;     // logL vector of the selected candidate
+	size_t pick_cap = 0;
+	cudaEvent_t ev_pick[8] = {nullptr};
+	unsigned char *d_flush = nullptr;   // measurement aid: written to evict the L2 (mdns_flush_l2)
+	double *d_ws = nullptr;       // stream-K partial sums of rows_dmma_kernel
+	int *d_tickets = nullptr;     // and its per-tile tickets (self-clearing)
+	// MUSE expanded form: y/v rows, their tensor maps, sum y^2/v per row, squared spectra, raw sums
+	double *YW = nullptr, *swyy = nullptr, *d_model2 = nullptr, *d_s1 = nullptr, *d_s2 = nullptr;
+	size_t model2_cap = 0, s12_cap = 0;
+	alignas(64) unsigned char tmap256_w[128];
+	alignas(64) unsigned char tmap_gather_w[128];
 	int *d_redo = nullptr;        // counters of the expanded kernel's direct-form fix-ups
 	int *d_redo_list = nullptr;   // and the rows to fix up in the current pass
 	bool counters_clear = false;  // per-pass counters already reset by the model kernel
@@ -131,6 +149,10 @@ struct mdns_dataset {
 	double single[3] = {0, 0, 0};     // the candidate of a K = 1 batch, passed by value
 	double xp_tol = 1e-10;        // relative error bound enforced by the expanded form
 	long long xp_redo_total = 0;  // rows recomputed in the direct form so far
+	// one process per GPU: the communicator of the exchange step (NCCL, bound at run time)
+	ncclComm_t comm = nullptr;
+	int comm_nranks = 1, comm_rank = 0;
+	int draw_chunks = 0;          // row chunks of the dense first-accept pass (0 = automatic)
 };
 
 static void shard_free(Shard &s)
@@ -157,6 +179,20 @@ static void shard_free(Shard &s)
 	cudaFree(s.d_smm);
 	cudaFree(s.d_redo);
 	cudaFree(s.d_redo_list);
+	cudaFree(s.d_sel);
+	cudaFree(s.d_snap);
+	cudaFree(s.d_pick);
+	cudaFree(s.d_ws);
+	cudaFree(s.d_flush);
+	cudaFree(s.d_tickets);
+	cudaFree(s.YW);
+	cudaFree(s.swyy);
+	cudaFree(s.d_model2);
+	cudaFree(s.d_s1);
+	cudaFree(s.d_s2);
+	if (s.h_sel) cudaFreeHost(s.h_sel);
+	for (auto &e : s.ev_pick)
+		if (e) cudaEventDestroy(e);
 	if (s.graph) cudaGraphExecDestroy(s.graph);
 	if (s.h_stage) cudaFreeHost(s.h_stage);
 	if (s.ev0) cudaEventDestroy(s.ev0);
@@ -299,6 +335,8 @@ int mdns_dataset_create(const double *x, const double *yy, const double *vv, int
 		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking);
 		for (auto &ev : s.ev_chunk)
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+		for (auto &ev : s.ev_pick)
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
 		if (e == cudaSuccess) e = cudaEventCreate(&s.ev0);
 		if (e == cudaSuccess) e = cudaEventCreate(&s.ev1);
 		if (e != cudaSuccess) {
@@ -329,6 +367,19 @@ int mdns_dataset_create(const double *x, const double *yy, const double *vv, int
 			ds->resident_bytes += (int64_t)s.n * 8;
 		}
 		ds->resident_bytes += (int64_t)s.n * ds->pitch * 8 * (vv ? 2 : 1);
+		{
+			// stream-K workspace of the tensor-path kernel: two partial tiles per resident CTA and
+			// one ticket per (matrix, tile)
+			const size_t wsd = rows_dmma_workspace_doubles(s.sm_count);
+			const size_t ntk = (size_t)2 * ceil_div(s.n, 256) + 2;
+			e = cudaMalloc((void **)&s.d_ws, wsd * sizeof(double));
+			if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_tickets, ntk * sizeof(int));
+			if (e == cudaSuccess) e = cudaMemsetAsync(s.d_tickets, 0, ntk * sizeof(int), s.stream);
+			if (e != cudaSuccess) {
+				set_error("device %d allocation failed: %s", s.device, cudaGetErrorString(e));
+				return fail(MDNS_ENOMEM);
+			}
+		}
 		const size_t mask_bytes = round_up(s.n, 16) + 16;
 		e = cudaMalloc((void **)&s.d_mask, mask_bytes);
 		if (e == cudaSuccess) e = cudaMemset(s.d_mask, 0, mask_bytes);
@@ -422,6 +473,7 @@ int mdns_internal_spectra_staged(mdns_dataset *ds, int K)
 int mdns_dataset_destroy(mdns_dataset *ds)
 {
 	if (!ds) return MDNS_OK;
+	mdns_comm_destroy(ds);
 	for (auto &s : ds->shards) shard_free(s);
 	delete ds;
 	return MDNS_OK;
@@ -496,6 +548,11 @@ int mdns_set_mask(mdns_dataset *ds, const uint8_t *mask, int *n_act_out)
 		if (n_act_out) *n_act_out = ds->n_act_total;
 		return MDNS_OK;
 	}
+	// from here on the per-shard state changes: forget the old mask first, so that a failure half
+	// way cannot leave the shortcut above believing in a mask some shards no longer hold
+	ds->host_mask.clear();
+	ds->thresholds_staged = false;
+	ds->launched = 0;
 	int total = 0;
 	bool all = true;
 	for (auto &s : ds->shards) {
@@ -518,13 +575,8 @@ int mdns_set_mask(mdns_dataset *ds, const uint8_t *mask, int *n_act_out)
 		all = all && s.all_active;
 		total += s.n_act;
 	}
-	if (mask && !all)
-		ds->host_mask.assign(mask, mask + ds->ndata);
-	else
-		ds->host_mask.clear();
+	if (mask && !all) ds->host_mask.assign(mask, mask + ds->ndata);
 	ds->n_act_total = total;
-	ds->launched = 0;
-	ds->thresholds_staged = false;    // thresholds are aligned with the compacted active order
 	if (n_act_out) *n_act_out = total;
 	return MDNS_OK;
 }
@@ -661,6 +713,8 @@ static void fill_args(const mdns_dataset *ds, const Shard &s, LikeArgs &a)
 	a.xp_counters_clear = s.counters_clear;
 	// error bound of the three sequential FP64 sums relative to Syy+Smm, over the tolerance
 	a.xp_guard = (2.0 * ds->nx + 4.0) * 1.1102230246251565e-16 / ds->xp_tol;
+	a.ws = s.d_ws;
+	a.tickets = s.d_tickets;
 }
 
 // may this launch take the expanded form? (mirrors the automatic choice of launch_clike)
@@ -730,8 +784,11 @@ static int xp_feedback(mdns_dataset *ds)
 	return MDNS_OK;
 }
 
-// chi-square of the active rows [r0, r0+nc) of one shard
-static int clike_rows(mdns_dataset *ds, Shard &s, double noise, double scale, int r0, int nc)
+// chi-square of the active rows [r0, r0+nc) of one shard.  accept: also count, per candidate,
+// the rows whose value exceeds the staged threshold (into s.d_counts, which the caller zeroed) --
+// inside the likelihood kernel where it can, else with accept_count_kernel over the rows just written.
+static int clike_rows(mdns_dataset *ds, Shard &s, double noise, double scale, int r0, int nc,
+                      bool accept = false)
 {
 	LikeArgs a;
 	fill_args(ds, s, a);
@@ -745,8 +802,17 @@ static int clike_rows(mdns_dataset *ds, Shard &s, double noise, double scale, in
 		a.active += r0;
 	else
 		a.Y += (size_t)r0 * ds->pitch;
+	if (accept) {
+		a.lmins = s.d_lmins + r0;
+		a.counts = s.d_counts;
+	}
+	int fused = 0;
+	int rc = launch_clike(a, ds->tuning, s.sm_count, s.stream, &fused);
 	s.counters_clear = false;     // the reset by the model kernel covers one launch only
-	return launch_clike(a, ds->tuning, s.sm_count, s.stream);
+	if (rc == MDNS_OK && accept && !fused)
+		rc = launch_accept_count(s.d_out + r0, s.n_act, nc, ds->K, s.d_lmins + r0, s.d_counts, s.stream,
+		                         false);
+	return rc;
 }
 
 int mdns_clike_launch(mdns_dataset *ds, double noise, double scale)
@@ -883,49 +949,245 @@ int mdns_clike_launch_fetch(mdns_dataset *ds, double noise, double scale, double
 	return xp_feedback(ds);
 }
 
-// Speculative batch of the constrained draw (hiermetriclearn.py:181-196): the K staged
-// candidates are scored in one pass; accept_counts[k] receives the number of active data sets
-// with scale*chi2 > Lmins; the logL vector of the FIRST candidate with a non-zero count (the
-// one the reference's one-at-a-time loop would have returned) is copied to Lout.  Only
-// K ints + one vector cross PCIe instead of K vectors.
-// Common part of the first-accept calls: score the staged candidates, count the accepting data
-// sets of every candidate on the device, find the first candidate with a non-zero count.
-// shard_counts[shard] = accepting data sets of that candidate on the shard.
-static int first_accept_core(mdns_dataset *ds, const char *who, double noise, double scale,
-                             const double *Lmins, int *accept_counts, int *first_k,
-                             std::vector<int> &shard_counts)
+// ---------------------------------------------------------------- accept passes ----
+// Speculative batch of the constrained draw (hiermetriclearn.py:181-196: one candidate at a time
+// until `numpy.any(L > Lmins)`): the K staged candidates are scored in one pass, the accept test
+// runs inside the likelihood kernels (per-candidate counts of accepting data sets), and the
+// decision -- the first candidate with a non-zero count, the one the reference's loop would have
+// returned -- is taken ON THE DEVICE, so that the fetch of its logL vector is enqueued behind it
+// without a host round trip.  One process per GPU: the K counts are summed over the ranks with
+// ncclAllReduce on the shard's stream before the decision (the one exchange step of the sharded
+// path).  Only K ints + one vector (or its accepting entries) cross PCIe.
+
+static int nccl_check(ncclResult_t r, const NcclApi *api, const char *what)
+{
+	if (r == ncclSuccess) return MDNS_OK;
+	set_error("%s failed: %s", what, api->GetErrorString(r));
+	return MDNS_ECUDA;
+}
+
+static int accept_check(mdns_dataset *ds, const char *who, const double *Lmins)
 {
 	int rc = clike_check(ds, who);
 	if (rc != MDNS_OK) return rc;
-	if (Lmins) {
-		if ((rc = mdns_set_thresholds(ds, Lmins)) != MDNS_OK) return rc;
-	} else if (!ds->thresholds_staged) {
-		set_error("%s: no thresholds (pass Lmins or call mdns_set_thresholds after mdns_set_mask)",
-		          who);
+	if (Lmins) return mdns_set_thresholds(ds, Lmins);
+	if (!ds->thresholds_staged) {
+		set_error("%s: no thresholds (pass Lmins or call mdns_set_thresholds after mdns_set_mask)", who);
 		return MDNS_ESTATE;
 	}
+	return MDNS_OK;
+}
+
+static int accept_buffers(mdns_dataset *ds, Shard &s, int nblocks, bool pick)
+{
+	const int Kpad = (int)round_up(ds->K, KT_MAX);
+	const size_t block = SEL_COUNTS + Kpad;
+	int rc = grow(&s.d_counts, &s.counts_cap, (size_t)Kpad, false);
+	if (rc == MDNS_OK) rc = grow(&s.d_sel, &s.sel_cap, block * nblocks, false);
+	if (rc == MDNS_OK) rc = grow(&s.d_snap, &s.snap_cap, (size_t)Kpad * nblocks, false);
+	if (rc == MDNS_OK && pick) rc = grow(&s.d_pick, &s.pick_cap, (size_t)(s.n_act > 0 ? s.n_act : 1), false);
+	if (rc != MDNS_OK) return rc;
+	if (block * nblocks > s.h_sel_cap) {
+		if (s.h_sel) MDNS_CUDA(cudaFreeHost(s.h_sel));
+		s.h_sel = nullptr;
+		s.h_sel_cap = 0;
+		const size_t cap = block * nblocks * 2;
+		MDNS_CUDA(cudaHostAlloc((void **)&s.h_sel, cap * sizeof(int), cudaHostAllocPortable));
+		s.h_sel_cap = cap;
+	}
+	return MDNS_OK;
+}
+
+// feedback of the expanded form from the counter that came down with the decision block
+static int xp_feedback_value(mdns_dataset *ds, Shard &s, int redo)
+{
+	if (redo <= 0 || !xp_candidate(ds, s)) return MDNS_OK;
+	MDNS_CUDA(cudaMemsetAsync(s.d_redo, 0, sizeof(int), s.stream));
+	ds->xp_redo_total += redo;
+	const long long passes = ceil_div(ds->K, 8);
+	if ((long long)redo * 50 > (long long)s.n_act * passes) ds->tuning.allow_expanded = false;
+	return MDNS_OK;
+}
+
+// rows per chunk of the overlapped dense pass: the download of the selected candidate's rows of
+// chunk c runs on the copy stream while chunk c+1 is scored
+static int accept_chunks(const mdns_dataset *ds, const Shard &s)
+{
+	if (ds->draw_chunks > 0) return std::min(ds->draw_chunks, 8);
+	const long long bytes = (long long)s.n_act * 8;
+	if (bytes < (2 << 20)) return 1;
+	int nchunk = (int)std::min<long long>(8, bytes / (1 << 20));
+	while (nchunk > 1 && s.n_act / nchunk < 65536) --nchunk;
+	return nchunk;
+}
+
+enum AcceptWant { WANT_COUNTS = 0, WANT_DENSE = 1, WANT_SPARSE = 2 };
+static constexpr int SPARSE_EAGER = 16384;   // accepting entries downloaded with the decision
+
+// One shard (one process per GPU, with or without a communicator).
+static int accept_pass_single(mdns_dataset *ds, double noise, double scale, AcceptWant want,
+                              int *accept_counts, int *first_k, double *Lout, int32_t *idx_out,
+                              double *val_out, int64_t capacity, int *n_out)
+{
+	Shard &s = ds->shards[0];
 	const int K = ds->K;
-	const size_t nsh = ds->shards.size();
-	std::vector<int> total(K, 0), part(K * nsh, 0);
-	for (auto &s : ds->shards) {
-		MDNS_CUDA(cudaSetDevice(s.device));
-		if (s.n_act > 0) {
-			if ((rc = grow(&s.d_counts, &s.counts_cap, (size_t)K, false)) != MDNS_OK) return rc;
-			if ((rc = clike_model(ds, s)) != MDNS_OK) return rc;
-			if ((rc = clike_rows(ds, s, noise, scale, 0, s.n_act)) != MDNS_OK) return rc;
-			if ((rc = launch_accept_count(s.d_out, s.n_act, s.n_act, K, s.d_lmins, s.d_counts,
-			                              s.stream)) != MDNS_OK)
-				return rc;
+	const int Kpad = (int)round_up(K, KT_MAX);
+	const size_t block = SEL_COUNTS + Kpad;
+	const NcclApi *nccl = nullptr;
+	if (ds->comm && !(nccl = nccl_api())) return MDNS_ECUDA;
+	MDNS_CUDA(cudaSetDevice(s.device));
+	const int nchunk = (want == WANT_DENSE && s.n_act > 0) ? accept_chunks(ds, s) : 1;
+	int rc = accept_buffers(ds, s, nchunk + 1, want == WANT_DENSE);
+	if (rc != MDNS_OK) return rc;
+	MDNS_CUDA(cudaMemsetAsync(s.d_counts, 0, (size_t)Kpad * sizeof(int), s.stream));
+	int *sel_final = s.d_sel + block * nchunk;        // the decision of the whole pass
+	if (s.n_act > 0 && (rc = clike_model(ds, s)) != MDNS_OK) return rc;
+	const int per = (int)round_up(ceil_div(std::max(s.n_act, 1), nchunk), 256);
+	int used_chunks = 0;
+	for (int r0 = 0, c = 0; r0 < s.n_act; r0 += per, ++c) {
+		const int nc = std::min(per, s.n_act - r0);
+		if ((rc = clike_rows(ds, s, noise, scale, r0, nc, true)) != MDNS_OK) return rc;
+		++used_chunks;
+		if (nchunk == 1) break;
+		// speculative pick of this chunk: the first candidate accepted by THIS process's rows so
+		// far -- the final (global) decision can only be an earlier candidate, checked below
+		MDNS_CUDA(cudaMemcpyAsync(s.d_snap + (size_t)c * Kpad, s.d_counts, (size_t)K * sizeof(int),
+		                          cudaMemcpyDeviceToDevice, s.stream));
+		MDNS_CUDA(cudaEventRecord(s.ev_pick[c], s.stream));
+		MDNS_CUDA(cudaStreamWaitEvent(s.copy_stream, s.ev_pick[c], 0));
+		int *sel_c = s.d_sel + block * c;
+		if ((rc = launch_select_first(s.d_snap + (size_t)c * Kpad, K, nullptr, sel_c, s.copy_stream)) != MDNS_OK)
+			return rc;
+		if ((rc = launch_gather_selected(s.d_out, s.n_act, r0, nc, sel_c, s.d_pick, s.copy_stream)) != MDNS_OK)
+			return rc;
+		MDNS_CUDA(cudaMemcpyAsync(Lout + r0, s.d_pick + r0, (size_t)nc * sizeof(double),
+		                          cudaMemcpyDeviceToHost, s.copy_stream));
+	}
+	// the exchange step: K integers summed over the ranks, on the stream, before the decision
+	if (ds->comm &&
+	    (rc = nccl_check(nccl->AllReduce(s.d_counts, s.d_counts, (size_t)K, ncclInt32, ncclSum, ds->comm,
+	                                     s.stream),
+	                     nccl, "ncclAllReduce of the accept counts")) != MDNS_OK)
+		return rc;
+	if ((rc = launch_select_first(s.d_counts, K, xp_candidate(ds, s) ? s.d_redo : nullptr, sel_final,
+	                              s.stream)) != MDNS_OK)
+		return rc;
+	int eager = 0;
+	if (s.n_act > 0 && want == WANT_DENSE && nchunk == 1) {
+		if ((rc = launch_gather_selected(s.d_out, s.n_act, 0, s.n_act, sel_final, s.d_pick, s.stream)) != MDNS_OK)
+			return rc;
+		MDNS_CUDA(cudaMemcpyAsync(Lout, s.d_pick, (size_t)s.n_act * sizeof(double),
+		                          cudaMemcpyDeviceToHost, s.stream));
+	} else if (s.n_act > 0 && want == WANT_SPARSE) {
+		const size_t fbytes = round_up(s.n_act, 16) + 16;
+		if ((rc = grow(&s.d_flags, &s.flags_cap, fbytes, true)) != MDNS_OK) return rc;
+		if ((rc = grow(&s.d_acc_idx, &s.acc_idx_cap, (size_t)s.n_act, false)) != MDNS_OK) return rc;
+		if ((rc = grow(&s.d_acc_val, &s.acc_val_cap, (size_t)s.n_act, false)) != MDNS_OK) return rc;
+		if (!s.d_nacc) MDNS_CUDA(cudaMalloc((void **)&s.d_nacc, sizeof(int)));
+		if ((rc = launch_selected_flags(s.d_out, s.n_act, s.n_act, sel_final, s.d_lmins, s.d_flags,
+		                                s.stream)) != MDNS_OK)
+			return rc;
+		if ((rc = launch_compact_mask(s.d_flags, s.n_act, s.d_scratch, s.d_acc_idx, s.d_nacc, s.stream)) != MDNS_OK)
+			return rc;
+		if ((rc = launch_gather_selected_values(s.d_out, s.n_act, sel_final, s.d_acc_idx, s.d_nacc,
+		                                        s.n_act, s.d_acc_val, s.stream)) != MDNS_OK)
+			return rc;
+		// the first entries travel with the decision; the rest (if any) after it is known
+		eager = (int)std::min<int64_t>(std::min(s.n_act, SPARSE_EAGER), capacity);
+		if (eager > 0) {
+			MDNS_CUDA(cudaMemcpyAsync(idx_out, s.d_acc_idx, (size_t)eager * sizeof(int),
+			                          cudaMemcpyDeviceToHost, s.stream));
+			MDNS_CUDA(cudaMemcpyAsync(val_out, s.d_acc_val, (size_t)eager * sizeof(double),
+			                          cudaMemcpyDeviceToHost, s.stream));
 		}
 	}
-	for (size_t i = 0; i < nsh; ++i) {
-		Shard &s = ds->shards[i];
+	// decision blocks -> pinned host memory.  The chunk blocks were written on the copy stream.
+	if (nchunk > 1) {
+		MDNS_CUDA(cudaMemcpyAsync(s.h_sel, s.d_sel, block * used_chunks * sizeof(int),
+		                          cudaMemcpyDeviceToHost, s.copy_stream));
+		MDNS_CUDA(cudaStreamSynchronize(s.copy_stream));
+	}
+	MDNS_CUDA(cudaMemcpyAsync(s.h_sel + block * nchunk, sel_final, block * sizeof(int),
+	                          cudaMemcpyDeviceToHost, s.stream));
+	MDNS_CUDA(cudaStreamSynchronize(s.stream));
+	ds->launched = 1;
+	const int *hf = s.h_sel + block * nchunk;
+	const int first = hf[SEL_FIRST];
+	*first_k = first;
+	if (accept_counts)
+		for (int k = 0; k < K; ++k) accept_counts[k] = hf[SEL_COUNTS + k];
+	if ((rc = xp_feedback_value(ds, s, hf[SEL_REDO])) != MDNS_OK) return rc;
+	if (first < 0 || s.n_act == 0) return MDNS_OK;
+	if (want == WANT_DENSE && nchunk > 1) {
+		// chunks whose speculative pick was a later candidate than the final decision: fetch again
+		bool again = false;
+		for (int r0 = 0, c = 0; r0 < s.n_act; r0 += per, ++c) {
+			if (s.h_sel[block * c + SEL_FIRST] == first) continue;
+			const int nc = std::min(per, s.n_act - r0);
+			if ((rc = launch_gather_selected(s.d_out, s.n_act, r0, nc, sel_final, s.d_pick, s.stream)) != MDNS_OK)
+				return rc;
+			MDNS_CUDA(cudaMemcpyAsync(Lout + r0, s.d_pick + r0, (size_t)nc * sizeof(double),
+			                          cudaMemcpyDeviceToHost, s.stream));
+			again = true;
+		}
+		if (again) MDNS_CUDA(cudaStreamSynchronize(s.stream));
+	}
+	if (want == WANT_SPARSE) {
+		// the candidate's count is the global one under a communicator; this process's share is
+		// the length of its own compacted list
+		int mine = hf[SEL_COUNT];
+		if (ds->comm) {
+			MDNS_CUDA(cudaMemcpyAsync(&mine, s.d_nacc, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+			MDNS_CUDA(cudaStreamSynchronize(s.stream));
+		}
+		if (mine > capacity) {
+			set_error("the accepted candidate is accepted for %d data sets, the output holds %lld", mine,
+			          (long long)capacity);
+			return MDNS_EINVAL;
+		}
+		if (mine > eager) {
+			MDNS_CUDA(cudaMemcpyAsync(idx_out + eager, s.d_acc_idx + eager, (size_t)(mine - eager) * sizeof(int),
+			                          cudaMemcpyDeviceToHost, s.stream));
+			MDNS_CUDA(cudaMemcpyAsync(val_out + eager, s.d_acc_val + eager,
+			                          (size_t)(mine - eager) * sizeof(double), cudaMemcpyDeviceToHost,
+			                          s.stream));
+			MDNS_CUDA(cudaStreamSynchronize(s.stream));
+		}
+		*n_out = mine;
+	}
+	return MDNS_OK;
+}
+
+// Several shards driven by one process (devices = [0..N-1], what the reference's single Python
+// process uses): every shard counts on its device, the host adds the K counts up.
+// shard_counts[shard] = accepting data sets of the first accepted candidate on that shard.
+static int accept_pass_multi(mdns_dataset *ds, double noise, double scale, int *accept_counts,
+                             int *first_k, std::vector<int> &shard_counts)
+{
+	int rc;
+	const int K = ds->K;
+	const int Kpad = (int)round_up(K, KT_MAX);
+	const size_t nsh = ds->shards.size();
+	std::vector<int> total(K, 0);
+	for (auto &s : ds->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		if (s.n_act == 0) continue;
+		if ((rc = accept_buffers(ds, s, 1, false)) != MDNS_OK) return rc;
+		MDNS_CUDA(cudaMemsetAsync(s.d_counts, 0, (size_t)Kpad * sizeof(int), s.stream));
+		if ((rc = clike_model(ds, s)) != MDNS_OK) return rc;
+		if ((rc = clike_rows(ds, s, noise, scale, 0, s.n_act, true)) != MDNS_OK) return rc;
+		if ((rc = launch_select_first(s.d_counts, K, xp_candidate(ds, s) ? s.d_redo : nullptr, s.d_sel,
+		                              s.stream)) != MDNS_OK)
+			return rc;
+		MDNS_CUDA(cudaMemcpyAsync(s.h_sel, s.d_sel, (SEL_COUNTS + (size_t)K) * sizeof(int),
+		                          cudaMemcpyDeviceToHost, s.stream));
+	}
+	for (auto &s : ds->shards) {
 		if (s.n_act == 0) continue;
 		MDNS_CUDA(cudaSetDevice(s.device));
-		MDNS_CUDA(cudaMemcpyAsync(part.data() + i * K, s.d_counts, (size_t)K * sizeof(int),
-		                          cudaMemcpyDeviceToHost, s.stream));
 		MDNS_CUDA(cudaStreamSynchronize(s.stream));
-		for (int k = 0; k < K; ++k) total[k] += part[i * K + k];
+		for (int k = 0; k < K; ++k) total[k] += s.h_sel[SEL_COUNTS + k];
+		if ((rc = xp_feedback_value(ds, s, s.h_sel[SEL_REDO])) != MDNS_OK) return rc;
 	}
 	ds->launched = 1;
 	int first = -1;
@@ -936,8 +1198,9 @@ static int first_accept_core(mdns_dataset *ds, const char *who, double noise, do
 	*first_k = first;
 	shard_counts.assign(nsh, 0);
 	if (first >= 0)
-		for (size_t i = 0; i < nsh; ++i) shard_counts[i] = part[i * K + first];
-	return xp_feedback(ds);
+		for (size_t i = 0; i < nsh; ++i)
+			if (ds->shards[i].n_act > 0) shard_counts[i] = ds->shards[i].h_sel[SEL_COUNTS + first];
+	return MDNS_OK;
 }
 
 int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const double *Lmins,
@@ -947,13 +1210,17 @@ int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const 
 		set_error("mdns_clike_first_accept: need ds, first_k and Lout");
 		return MDNS_EINVAL;
 	}
+	int rc = accept_check(ds, "mdns_clike_first_accept", Lmins);
+	if (rc != MDNS_OK) return rc;
 	if (lout_capacity < ds->n_act_total) {
 		set_error("Lout holds %lld doubles, %d needed", (long long)lout_capacity, ds->n_act_total);
 		return MDNS_EINVAL;
 	}
+	if (ds->shards.size() == 1)
+		return accept_pass_single(ds, noise, scale, WANT_DENSE, accept_counts, first_k, Lout, nullptr,
+		                          nullptr, 0, nullptr);
 	std::vector<int> shard_counts;
-	int rc = first_accept_core(ds, "mdns_clike_first_accept", noise, scale, Lmins, accept_counts,
-	                           first_k, shard_counts);
+	rc = accept_pass_multi(ds, noise, scale, accept_counts, first_k, shard_counts);
 	if (rc != MDNS_OK || *first_k < 0) return rc;
 	const int first = *first_k;
 	long long off = 0;
@@ -985,7 +1252,7 @@ int mdns_clike_draw_pass(mdns_dataset *ds, const uint8_t *mask, const double *Lm
 	*first_k = -1;
 	if (accept_counts)
 		for (int k = 0; k < K; ++k) accept_counts[k] = 0;
-	if (n_act == 0) return MDNS_OK;
+	if (n_act == 0 && !ds->comm) return MDNS_OK;
 	// the thresholds stay the same while the candidates of one constrained draw are tried
 	// (hiermetriclearn.py:173-211): short vectors are compared with the staged copy instead of
 	// being uploaded (and synchronised on) again
@@ -997,10 +1264,9 @@ int mdns_clike_draw_pass(mdns_dataset *ds, const uint8_t *mask, const double *Lm
 	                               lout_capacity);
 }
 
-// Two-step form for one process per GPU (torchrun): every rank counts the accepting data sets
-// of its own shard; the ranks add their K counts up (the one exchange step of the sharded path:
-// an all-reduce of K integers) and then fetch the logL vector of the globally first accepted
-// candidate from their shard.
+// Two-step form for callers that run the exchange themselves (e.g. a host-side all-reduce between
+// processes without a communicator): accept counts of THIS process's data sets, then the logL
+// vector of candidate k of the same launch.
 int mdns_clike_accept_counts(mdns_dataset *ds, double noise, double scale, const double *Lmins,
                              int *accept_counts)
 {
@@ -1008,10 +1274,19 @@ int mdns_clike_accept_counts(mdns_dataset *ds, double noise, double scale, const
 		set_error("mdns_clike_accept_counts: need ds and accept_counts");
 		return MDNS_EINVAL;
 	}
+	int rc = accept_check(ds, "mdns_clike_accept_counts", Lmins);
+	if (rc != MDNS_OK) return rc;
 	int first = -1;
+	if (ds->shards.size() == 1 && !ds->comm)
+		return accept_pass_single(ds, noise, scale, WANT_COUNTS, accept_counts, &first, nullptr, nullptr,
+		                          nullptr, 0, nullptr);
+	if (ds->comm) {
+		set_error("mdns_clike_accept_counts: the data set has a communicator, the exchange is built "
+		          "into mdns_clike_first_accept");
+		return MDNS_ESTATE;
+	}
 	std::vector<int> shard_counts;
-	return first_accept_core(ds, "mdns_clike_accept_counts", noise, scale, Lmins, accept_counts,
-	                         &first, shard_counts);
+	return accept_pass_multi(ds, noise, scale, accept_counts, &first, shard_counts);
 }
 
 int mdns_fetch_candidate(mdns_dataset *ds, int k, double *Lout, int64_t lout_capacity)
@@ -1037,7 +1312,7 @@ int mdns_fetch_candidate(mdns_dataset *ds, int k, double *Lout, int64_t lout_cap
 	return mdns_sync(ds);
 }
 
-// The same, returning only what multi_nested_sampler.py:482-485 consumes: the data sets the
+// The same decision, returning only what multi_nested_sampler.py:482-485 consumes: the data sets the
 // first accepted candidate is accepted for (positions in the compacted active order,
 // increasing) and their logL.  A stable device compaction keeps the order; only
 // 12 bytes per accepting data set cross PCIe.
@@ -1050,9 +1325,13 @@ int mdns_clike_first_accept_sparse(mdns_dataset *ds, double noise, double scale,
 		return MDNS_EINVAL;
 	}
 	*n_out = 0;
+	int rc = accept_check(ds, "mdns_clike_first_accept_sparse", Lmins);
+	if (rc != MDNS_OK) return rc;
+	if (ds->shards.size() == 1)
+		return accept_pass_single(ds, noise, scale, WANT_SPARSE, accept_counts, first_k, nullptr, idx_out,
+		                          val_out, capacity, n_out);
 	std::vector<int> shard_counts;
-	int rc = first_accept_core(ds, "mdns_clike_first_accept_sparse", noise, scale, Lmins,
-	                           accept_counts, first_k, shard_counts);
+	rc = accept_pass_multi(ds, noise, scale, accept_counts, first_k, shard_counts);
 	if (rc != MDNS_OK || *first_k < 0) return rc;
 	const int first = *first_k;
 	long long n_total = 0;
@@ -1099,6 +1378,184 @@ int mdns_clike_first_accept_sparse(mdns_dataset *ds, double noise, double scale,
 		off += ds->shards[i].n_act;
 	}
 	*n_out = (int)n_total;
+	return MDNS_OK;
+}
+
+// ------------------------------------------------------- one process per GPU: exchange ----
+// The communicator lives with the data set: its collectives run on the shard's stream, ordered
+// with the kernels that produce what they move.
+int mdns_comm_unique_id(void *id_out)
+{
+	if (!id_out) {
+		set_error("mdns_comm_unique_id: id_out is null");
+		return MDNS_EINVAL;
+	}
+	const NcclApi *nccl = nccl_api();
+	if (!nccl) return MDNS_ECUDA;
+	static_assert(sizeof(ncclUniqueId) == MDNS_UNIQUE_ID_BYTES, "ncclUniqueId size");
+	ncclUniqueId id;
+	int rc = nccl_check(nccl->GetUniqueId(&id), nccl, "ncclGetUniqueId");
+	if (rc != MDNS_OK) return rc;
+	memcpy(id_out, &id, sizeof id);
+	return MDNS_OK;
+}
+
+int mdns_comm_init(mdns_dataset *ds, const void *id, int nranks, int rank)
+{
+	if (!ds || !id || nranks < 1 || rank < 0 || rank >= nranks) {
+		set_error("mdns_comm_init: need ds, id, 0 <= rank < nranks");
+		return MDNS_EINVAL;
+	}
+	if (ds->shards.size() != 1) {
+		set_error("mdns_comm_init: one process per GPU -- the data set must live on one device");
+		return MDNS_ESTATE;
+	}
+	if (ds->comm) {
+		set_error("mdns_comm_init: the data set already has a communicator");
+		return MDNS_ESTATE;
+	}
+	const NcclApi *nccl = nccl_api();
+	if (!nccl) return MDNS_ECUDA;
+	MDNS_CUDA(cudaSetDevice(ds->shards[0].device));
+	ncclUniqueId uid;
+	memcpy(&uid, id, sizeof uid);
+	ncclComm_t comm = nullptr;
+	int rc = nccl_check(nccl->CommInitRank(&comm, nranks, uid, rank), nccl, "ncclCommInitRank");
+	if (rc != MDNS_OK) return rc;
+	ds->comm = comm;
+	ds->comm_nranks = nranks;
+	ds->comm_rank = rank;
+	return MDNS_OK;
+}
+
+int mdns_comm_destroy(mdns_dataset *ds)
+{
+	if (!ds || !ds->comm) return MDNS_OK;
+	const NcclApi *nccl = nccl_api();
+	if (!nccl) return MDNS_ECUDA;
+	cudaSetDevice(ds->shards[0].device);
+	cudaStreamSynchronize(ds->shards[0].stream);
+	nccl->CommDestroy(ds->comm);
+	ds->comm = nullptr;
+	ds->comm_nranks = 1;
+	ds->comm_rank = 0;
+	return MDNS_OK;
+}
+
+int mdns_comm_info(const mdns_dataset *ds, int *nranks, int *rank)
+{
+	if (!ds) {
+		set_error("null data set");
+		return MDNS_EINVAL;
+	}
+	if (nranks) *nranks = ds->comm ? ds->comm_nranks : 1;
+	if (rank) *rank = ds->comm ? ds->comm_rank : 0;
+	return MDNS_OK;
+}
+
+// values[n] (host) := sum (op 0) or max (op 1) over the ranks; a barrier as a side effect.
+// Without a communicator the values stay as they are.
+int mdns_comm_allreduce(mdns_dataset *ds, double *values, int n, int op)
+{
+	if (!ds || !values || n <= 0 || n > 1024 || (op != 0 && op != 1)) {
+		set_error("mdns_comm_allreduce: need ds, values, 0 < n <= 1024, op 0 (sum) or 1 (max)");
+		return MDNS_EINVAL;
+	}
+	if (!ds->comm) return MDNS_OK;
+	const NcclApi *nccl = nccl_api();
+	if (!nccl) return MDNS_ECUDA;
+	Shard &s = ds->shards[0];
+	MDNS_CUDA(cudaSetDevice(s.device));
+	int rc = grow(&s.d_pick, &s.pick_cap, (size_t)std::max(n, s.n_act), false);
+	if (rc != MDNS_OK) return rc;
+	MDNS_CUDA(cudaMemcpyAsync(s.d_pick, values, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+	rc = nccl_check(nccl->AllReduce(s.d_pick, s.d_pick, (size_t)n, ncclFloat64, op ? ncclMax : ncclSum,
+	                                ds->comm, s.stream),
+	                nccl, "ncclAllReduce");
+	if (rc != MDNS_OK) return rc;
+	MDNS_CUDA(cudaMemcpyAsync(values, s.d_pick, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+	MDNS_CUDA(cudaStreamSynchronize(s.stream));
+	return MDNS_OK;
+}
+
+// The device-consumer exchange of SURVEY section 8(e): every rank contributes the logL vector of
+// candidate k of its last clike launch; after the call every rank holds all of them, in rank order,
+// in a device buffer ([nranks][nmax], nmax = largest n_act) and -- if Lall is given -- compacted on
+// the host (n_per_rank[r] entries of rank r after those of the ranks before it).
+int mdns_comm_allgather_candidate(mdns_dataset *ds, int k, double *Lall, int64_t capacity,
+                                  int *n_per_rank)
+{
+	if (!ds || ds->launched != 1 || k < 0 || k >= ds->K) {
+		set_error("mdns_comm_allgather_candidate: need a clike launch and 0 <= k < K");
+		return ds ? MDNS_ESTATE : MDNS_EINVAL;
+	}
+	if (ds->shards.size() != 1) {
+		set_error("mdns_comm_allgather_candidate: one process per GPU only");
+		return MDNS_ESTATE;
+	}
+	Shard &s = ds->shards[0];
+	const int nr = ds->comm ? ds->comm_nranks : 1;
+	const NcclApi *nccl = nullptr;
+	if (ds->comm && !(nccl = nccl_api())) return MDNS_ECUDA;
+	MDNS_CUDA(cudaSetDevice(s.device));
+	int rc = accept_buffers(ds, s, nr + 1, true);
+	if (rc != MDNS_OK) return rc;
+	// the ranks' n_act (ints through the decision block buffer)
+	std::vector<int> nper(nr, s.n_act);
+	if (ds->comm) {
+		MDNS_CUDA(cudaMemcpyAsync(s.d_sel + ds->comm_rank, &s.n_act, sizeof(int), cudaMemcpyHostToDevice,
+		                          s.stream));
+		rc = nccl_check(nccl->AllGather(s.d_sel + ds->comm_rank, s.d_sel, 1, ncclInt32, ds->comm, s.stream),
+		                nccl, "ncclAllGather of the active counts");
+		if (rc != MDNS_OK) return rc;
+		MDNS_CUDA(cudaMemcpyAsync(nper.data(), s.d_sel, (size_t)nr * sizeof(int), cudaMemcpyDeviceToHost,
+		                          s.stream));
+		MDNS_CUDA(cudaStreamSynchronize(s.stream));
+	}
+	int nmax = 1;
+	long long total = 0;
+	for (int r = 0; r < nr; ++r) {
+		nmax = std::max(nmax, nper[r]);
+		total += nper[r];
+	}
+	if (n_per_rank)
+		for (int r = 0; r < nr; ++r) n_per_rank[r] = nper[r];
+	if (Lall && capacity < total) {
+		set_error("Lall holds %lld doubles, %lld needed", (long long)capacity, total);
+		return MDNS_EINVAL;
+	}
+	// gather buffer [nr][nmax]: this rank's slot is filled in place, the collective does the rest
+	if ((rc = grow(&s.d_s1, &s.s12_cap, (size_t)nr * nmax, false)) != MDNS_OK) return rc;
+	double *mine = s.d_s1 + (size_t)(ds->comm ? ds->comm_rank : 0) * nmax;
+	if (s.n_act > 0)
+		MDNS_CUDA(cudaMemcpyAsync(mine, s.d_out + (size_t)k * s.n_act, (size_t)s.n_act * sizeof(double),
+		                          cudaMemcpyDeviceToDevice, s.stream));
+	if (ds->comm) {
+		rc = nccl_check(nccl->AllGather(mine, s.d_s1, (size_t)nmax, ncclFloat64, ds->comm, s.stream), nccl,
+		                "ncclAllGather of the candidate's logL");
+		if (rc != MDNS_OK) return rc;
+	}
+	if (Lall) {
+		long long off = 0;
+		for (int r = 0; r < nr; ++r) {
+			if (nper[r] > 0)
+				MDNS_CUDA(cudaMemcpyAsync(Lall + off, s.d_s1 + (size_t)r * nmax, (size_t)nper[r] * sizeof(double),
+				                          cudaMemcpyDeviceToHost, s.stream));
+			off += nper[r];
+		}
+	}
+	MDNS_CUDA(cudaStreamSynchronize(s.stream));
+	return MDNS_OK;
+}
+
+// experiment knob: row chunks of the overlapped dense first-accept pass (0 = automatic, 1 = none)
+int mdns_set_draw_chunks(mdns_dataset *ds, int nchunks)
+{
+	if (!ds || nchunks < 0 || nchunks > 8) {
+		set_error("mdns_set_draw_chunks: need ds and 0 <= nchunks <= 8");
+		return MDNS_EINVAL;
+	}
+	ds->draw_chunks = nchunks;
 	return MDNS_OK;
 }
 
@@ -1214,6 +1671,23 @@ int mdns_fetch(mdns_dataset *ds, double *Lout, int64_t lout_capacity)
 			for (int i = 0; i < s.n; ++i)
 				if (m[i]) dst[i] = src[i];
 		}
+	}
+	return MDNS_OK;
+}
+
+// Measurement aid (B200_PROFILING.md: flush the L2 between timed iterations when the inputs fit
+// in it): overwrite a 256 MB scratch buffer on every shard's stream.
+int mdns_flush_l2(mdns_dataset *ds)
+{
+	if (!ds) {
+		set_error("null data set");
+		return MDNS_EINVAL;
+	}
+	const size_t bytes = (size_t)256 << 20;
+	for (auto &s : ds->shards) {
+		MDNS_CUDA(cudaSetDevice(s.device));
+		if (!s.d_flush) MDNS_CUDA(cudaMalloc((void **)&s.d_flush, bytes));
+		MDNS_CUDA(cudaMemsetAsync(s.d_flush, 0x5a, bytes, s.stream));
 	}
 	return MDNS_OK;
 }
@@ -1338,6 +1812,7 @@ struct mdns_region {
 	size_t rcounts_cap = 0;
 	double *d_result = nullptr;       // 1 double
 	int *d_flag = nullptr;            // 1 int
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // stopwatch on the region's stream
 	// device-side candidate generation
 	double *d_gen_points = nullptr, *d_gen_out = nullptr;
 	uint8_t *d_gen_keep = nullptr;
@@ -1406,8 +1881,37 @@ int mdns_region_destroy(mdns_region *rg)
 	cudaFree(rg->d_gen_idx);
 	cudaFree(rg->d_gen_scratch);
 	cudaFree(rg->d_gen_count);
+	if (rg->ev0) cudaEventDestroy(rg->ev0);
+	if (rg->ev1) cudaEventDestroy(rg->ev1);
 	if (rg->stream) cudaStreamDestroy(rg->stream);
 	delete rg;
+	return MDNS_OK;
+}
+
+// CUDA-event stopwatch on the region's stream (measurement aid, like mdns_timer_*).
+int mdns_region_timer_start(mdns_region *rg)
+{
+	if (!rg) {
+		set_error("null region");
+		return MDNS_EINVAL;
+	}
+	MDNS_CUDA(cudaSetDevice(rg->device));
+	if (!rg->ev0) MDNS_CUDA(cudaEventCreate(&rg->ev0));
+	if (!rg->ev1) MDNS_CUDA(cudaEventCreate(&rg->ev1));
+	MDNS_CUDA(cudaEventRecord(rg->ev0, rg->stream));
+	return MDNS_OK;
+}
+
+int mdns_region_timer_stop(mdns_region *rg, float *elapsed_ms)
+{
+	if (!rg || !elapsed_ms || !rg->ev0 || !rg->ev1) {
+		set_error("mdns_region_timer_stop: need rg, elapsed_ms and a started timer");
+		return MDNS_EINVAL;
+	}
+	MDNS_CUDA(cudaSetDevice(rg->device));
+	MDNS_CUDA(cudaEventRecord(rg->ev1, rg->stream));
+	MDNS_CUDA(cudaEventSynchronize(rg->ev1));
+	MDNS_CUDA(cudaEventElapsedTime(elapsed_ms, rg->ev0, rg->ev1));
 	return MDNS_OK;
 }
 

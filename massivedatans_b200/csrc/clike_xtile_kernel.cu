@@ -85,7 +85,12 @@ __global__ void __launch_bounds__(256) xtile_fixup_kernel(const LikeArgs a, cons
 			}
 #pragma unroll
 			for (int o = 16; o > 0; o >>= 1) s += shfl_xor_f64(s, o);
-			if (lane == 0) a.out[(long long)(k0 + k) * a.out_stride + gr] = s * inv;
+			if (lane == 0) {
+				const double val = s * inv;
+				if (a.out) a.out[(long long)(k0 + k) * a.out_stride + gr] = val;
+				// the fused accept test of rows_dmma_kernel skipped this pair
+				if (a.lmins && a.counts && val > a.lmins[gr]) atomicAdd(a.counts + k0 + k, 1);
+			}
 		}
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.xp_redo, n);

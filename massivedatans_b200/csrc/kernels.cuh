@@ -40,7 +40,7 @@ int launch_compact_mask(const uint8_t *mask, int n, int *scratch, int *active, i
                         cudaStream_t st);
 
 struct LikeArgs {
-	const double *Y;      // rows
+	const double *Y = nullptr;      // rows
 	const double *W;      // inverse-variance rows (muse) or nullptr
 	long long pitch;      // doubles
 	int nx;
@@ -70,6 +70,19 @@ struct LikeArgs {
 	                      // [1 + pass] list length of each pass of the current launch
 	int *xp_list;         // rows (within the launch) to recompute, capacity = rows of the shard
 	bool xp_counters_clear;  // the per-pass counters were already reset by the model kernel
+	// accept test fused into the likelihood epilogues (hiermetriclearn.py:193 `L > Lmins`):
+	// counts[k] += number of rows of this launch whose value exceeds lmins[row]
+	const double *lmins = nullptr;   // [n_rows], aligned with the launch's (compacted) rows
+	int *counts = nullptr;           // [Kpad] device counters (zeroed by the caller)
+	// stream-K partial sums of rows_dmma_kernel: workspace slots and one ticket per tile
+	double *ws = nullptr;
+	int *tickets = nullptr;
+	// second (rows, batch) pair of the raw contraction (MUSE: 1/v rows against squared spectra)
+	const void *tmap256_b = nullptr;
+	const void *tmap_gather_b = nullptr;
+	const double *model_b = nullptr;
+	double *out_b = nullptr;
+	const double *swyy = nullptr;    // MUSE expanded form: resident sum of y^2/v per row
 };
 
 struct Tuning {
@@ -84,11 +97,22 @@ struct Tuning {
 	int rows = 0;    // data sets per lane group in the block kernel: 1, 2, 4 (0 = auto)
 };
 
-int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t st);
+// *accept_fused (may be null): set to 1 when the chosen kernel applied a.lmins / a.counts itself
+int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t st,
+                 int *accept_fused = nullptr);
 int launch_muse(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t st);
 // counts[k] = #{r : L[k*stride + r] > lmins[r]}  (hiermetriclearn.py:193 on the device)
 int launch_accept_count(const double *L, long long stride, int n, int K, const double *lmins,
-                        int *counts, cudaStream_t st);
+                        int *counts, cudaStream_t st, bool zero = true);
+// the accept decision on the device (see likelihood_kernels.cu): layout of the `sel` block
+constexpr int SEL_FIRST = 0, SEL_COUNT = 1, SEL_REDO = 2, SEL_COUNTS = 4;
+int launch_select_first(const int *counts, int K, const int *redo, int *sel, cudaStream_t st);
+int launch_gather_selected(const double *L, long long stride, int r0, int n, const int *sel,
+                           double *out, cudaStream_t st);
+int launch_selected_flags(const double *L, long long stride, int n, const int *sel,
+                          const double *lmins, uint8_t *flags, cudaStream_t st);
+int launch_gather_selected_values(const double *L, long long stride, const int *sel, const int *idx,
+                                  const int *n_dev, int n_max, double *out, cudaStream_t st);
 // sparse accept: flags[r] = L[r] > lmins[r]; out[i] = L[idx[i]]
 int launch_accept_flags(const double *L, int n, const double *lmins, uint8_t *flags, cudaStream_t st);
 int launch_gather_values(const double *L, const int *idx, int n, double *out, cudaStream_t st);
@@ -109,6 +133,12 @@ bool dmma_fits(const LikeArgs &a, int kt, int stages);
 int launch_clike_dmma(const LikeArgs &a, int kt, int stages, int sm_count, cudaStream_t st);
 int launch_clike_xtile(const LikeArgs &a, int kt, int lane_rows, int stages, int sm_count,
                        cudaStream_t st);
+// stream-K contraction on the FP64 tensor path (rows_dmma_kernel.cu): the clike epilogue with the
+// fused accept test, or (raw) the contraction(s) themselves for the MUSE expanded form
+bool rows_dmma_fits(const LikeArgs &a, int kt, int stages);
+size_t rows_dmma_workspace_doubles(int sm_count);
+int launch_rows_dmma(const LikeArgs &a, int kt, int stages, bool raw, int nmat, int sm_count,
+                     cudaStream_t st);
 // out[r] = sum_j rows[r*pitch + j]^2 (rows: resident data sets or padded model spectra)
 int launch_row_sumsq(const double *rows, long long n_rows, long long pitch, int nx, double *out,
                      cudaStream_t st);

@@ -330,6 +330,12 @@ __global__ void __launch_bounds__(LK_THREADS) clike_rows_kernel(const LikeArgs a
 	const double inv = a.scale / a.noise2;
 	if (!IM) mbar_wait(&bar, 0);
 
+	// fused accept test (hiermetriclearn.py:193): accepting data sets per candidate, counted per
+	// warp with a ballot and flushed with one atomic per (warp, candidate) at the end
+	int acnt[KT];
+#pragma unroll
+	for (int k = 0; k < KT; ++k) acnt[k] = 0;
+
 	for (long long rb = (long long)blockIdx.x * RPC + warp * G; rb < a.n_rows;
 	     rb += (long long)gridDim.x * RPC) {
 		const long long r = rb + g;
@@ -337,6 +343,7 @@ __global__ void __launch_bounds__(LK_THREADS) clike_rows_kernel(const LikeArgs a
 		double acc0[KT], acc1[KT];
 #pragma unroll
 		for (int k = 0; k < KT; ++k) acc0[k] = acc1[k] = 0.0;
+		const double lm = (valid && a.lmins) ? __ldg(a.lmins + r) : 0.0;
 		if (valid) {
 			const long long row = a.active ? (long long)a.active[r] : r;
 			const double2 *p = reinterpret_cast<const double2 *>(a.Y + row * a.pitch);
@@ -369,9 +376,16 @@ __global__ void __launch_bounds__(LK_THREADS) clike_rows_kernel(const LikeArgs a
 			double s = acc0[k] + acc1[k];
 #pragma unroll
 			for (int o = L / 2; o > 0; o >>= 1) s += shfl_xor_f64(s, o);
-			if (valid && gl == 0 && k0 + k < a.K)
-				a.out[(long long)(k0 + k) * a.out_stride + r] = s * inv;
+			const bool mine = valid && gl == 0 && k0 + k < a.K;
+			const double val = s * inv;
+			if (mine && a.out) a.out[(long long)(k0 + k) * a.out_stride + r] = val;
+			if (a.counts) acnt[k] += __popc(__ballot_sync(0xffffffffu, mine && val > lm));
 		}
+	}
+	if (a.counts && lane == 0) {
+#pragma unroll
+		for (int k = 0; k < KT; ++k)
+			if (acnt[k]) atomicAdd(a.counts + k0 + k, acnt[k]);
 	}
 }
 
@@ -423,6 +437,8 @@ __global__ void __launch_bounds__(LK_THREADS, 2) clike_block_kernel(const LikeAr
 	const int k0 = blockIdx.y * KT;
 	const int mfp = a.mpitch >> 1;
 	const int nfrag = (a.nx + 1) >> 1;
+	__shared__ int s_cnt[KT];
+	if (threadIdx.x < KT) s_cnt[threadIdx.x] = 0;
 	stage_model_tma<KT>(sm, &bar, a.model, a.mpitch, k0);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -430,6 +446,7 @@ __global__ void __launch_bounds__(LK_THREADS, 2) clike_block_kernel(const LikeAr
 	const int nchunks = (nfrag + L * U - 1) / (L * U);
 	const double inv = a.scale / a.noise2;
 	mbar_wait(&bar, 0);
+	int acnt = 0, my_k = 0;      // fused accept test: this lane's candidate and its count
 
 	for (long long rb = (long long)blockIdx.x * RPC + (warp * G + g) * R; rb - g * R < a.n_rows;
 	     rb += (long long)gridDim.x * RPC) {
@@ -482,9 +499,19 @@ __global__ void __launch_bounds__(LK_THREADS, 2) clike_block_kernel(const LikeAr
 			GroupReduce<KT, L / 2>::run(acc[r], gl, kidx);
 			// after the transposing steps the lanes whose low bits are zero own a total
 			const bool owner = (gl & (L / OWNERS - 1)) == 0;
-			if (owner && rb + r < a.n_rows && k0 + kidx < a.K)
-				a.out[(long long)(k0 + kidx) * a.out_stride + rb + r] = acc[r][0] * inv;
+			if (owner && rb + r < a.n_rows && k0 + kidx < a.K) {
+				const double val = acc[r][0] * inv;
+				if (a.out) a.out[(long long)(k0 + kidx) * a.out_stride + rb + r] = val;
+				if (a.lmins && val > __ldg(a.lmins + rb + r)) ++acnt;
+				my_k = kidx;
+			}
 		}
+	}
+	if (a.counts) {
+		if (acnt) atomicAdd(&s_cnt[my_k], acnt);
+		__syncthreads();
+		if (threadIdx.x < KT && s_cnt[threadIdx.x])
+			atomicAdd(a.counts + k0 + threadIdx.x, s_cnt[threadIdx.x]);
 	}
 }
 
@@ -603,8 +630,20 @@ static int pick_ktile(int K, int mpitch, int requested)
 	return kt;
 }
 
-int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t st)
+// the stream-K tensor-path kernel when its workspace is there, else round 1's whole-tile kernel
+static int launch_dmma_auto(const LikeArgs &a, int kt, int stages, int sm_count, cudaStream_t st,
+                            int *accept_fused)
 {
+	if (rows_dmma_fits(a, kt, stages)) {
+		if (accept_fused) *accept_fused = 1;
+		return launch_rows_dmma(a, kt, stages, false, 1, sm_count, st);
+	}
+	return launch_clike_dmma(a, kt, stages, sm_count, st);
+}
+
+int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t st, int *accept_fused)
+{
+	if (accept_fused) *accept_fused = 0;
 	if (a.n_rows <= 0 || a.K <= 0) return MDNS_OK;
 	const int nfrag = (a.nx + 1) >> 1;
 	int L = t.lanes;
@@ -616,7 +655,9 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		int stages = ((t.rows >= 2 && t.rows <= 4) || (t.rows >= 12 && t.rows <= 14)) ? t.rows : 3;
 		while (kt > 8 && !dmma_fits(a, kt, stages)) kt >>= 1;
 		if (!dmma_fits(a, kt, stages)) stages = 2;
-		return launch_clike_dmma(a, kt, stages, sm_count, st);
+		// unroll = 1 selects round 1's whole-tile kernel (A/B measurements)
+		if (t.unroll == 1) return launch_clike_dmma(a, kt, stages, sm_count, st);
+		return launch_dmma_auto(a, kt, stages, sm_count, st, accept_fused);
 	}
 	if (L == 2 && !a.active) {
 		// expanded form, register-blocked over data sets (all-active rows only)
@@ -648,15 +689,15 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		// (two producer warps).  Measured, 5e5 active of 1e6 data sets: K=8 0.152 ms (block kernel
 		// 0.180), K=16 0.173 ms (0.358), K=32 0.43 ms (0.71); up to 4 candidates the block kernel
 		// wins (K=4 0.141 ms).
-		if (a.K >= 32 && dmma_fits(a, 32, 3)) return launch_clike_dmma(a, 32, 3, sm_count, st);
-		if (a.K >= 16 && dmma_fits(a, 16, 13)) return launch_clike_dmma(a, 16, 13, sm_count, st);
-		if (dmma_fits(a, 8, 13)) return launch_clike_dmma(a, 8, 13, sm_count, st);
+		if (a.K >= 32 && dmma_fits(a, 32, 3)) return launch_dmma_auto(a, 32, 3, sm_count, st, accept_fused);
+		if (a.K >= 16 && dmma_fits(a, 16, 13)) return launch_dmma_auto(a, 16, 13, sm_count, st, accept_fused);
+		if (dmma_fits(a, 8, 13)) return launch_dmma_auto(a, 8, 13, sm_count, st, accept_fused);
 	}
 	if (L == 1 || L == 2 || L == 3) {
 		// tile kernel requested but not applicable (masked rows): automatic choice
 		Tuning d;
 		d.allow_expanded = t.allow_expanded;
-		return launch_clike(a, d, sm_count, st);
+		return launch_clike(a, d, sm_count, st, accept_fused);
 	}
 	if (L == 0 && t.unroll == 0 && t.ktile == 0 && t.rows == 0 && !a.active && a.K >= XP_MIN_K &&
 	    a.n_rows >= 32768) {
@@ -669,9 +710,9 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 			// 0.277).  Stage counts + 10 select the 16-warp shape.  From K = 3 on a pass of 8
 			// (padded) candidates on the tensor path beats the lanes-across-channels kernels
 			// (K=4: 0.266 ms vs 0.289 ms block kernel).
-			if (a.K >= 32 && dmma_fits(a, 32, 3)) return launch_clike_dmma(a, 32, 3, sm_count, st);
-			if (a.K >= 16 && dmma_fits(a, 16, 13)) return launch_clike_dmma(a, 16, 13, sm_count, st);
-			if (dmma_fits(a, 8, 14)) return launch_clike_dmma(a, 8, 14, sm_count, st);
+			if (a.K >= 32 && dmma_fits(a, 32, 3)) return launch_dmma_auto(a, 32, 3, sm_count, st, accept_fused);
+			if (a.K >= 16 && dmma_fits(a, 16, 13)) return launch_dmma_auto(a, 16, 13, sm_count, st, accept_fused);
+			if (dmma_fits(a, 8, 14)) return launch_dmma_auto(a, 8, 14, sm_count, st, accept_fused);
 			const int xkt = a.K >= 16 && xtile_fits(a, 16, 2) ? 16 : 8;
 			if (xtile_fits(a, xkt, 2)) return launch_clike_xtile(a, xkt, 2, 2, sm_count, st);
 		}
@@ -691,7 +732,7 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 	if ((size_t)kt * a.mpitch * 8 > 200 * 1024) {
 		// spectra too long for a whole model row in shared memory: the tensor-path kernel
 		// streams the model in 16-channel slices beside the data, whatever the channel count
-		if (t.allow_expanded && dmma_fits(a, 8, 3)) return launch_clike_dmma(a, 8, 3, sm_count, st);
+		if (t.allow_expanded && dmma_fits(a, 8, 3)) return launch_dmma_auto(a, 8, 3, sm_count, st, accept_fused);
 		set_error("model spectrum of %d channels does not fit in shared memory", a.nx);
 		return MDNS_EINVAL;
 	}
@@ -703,8 +744,10 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		int bu = t.unroll;
 		if (rows == 4 && bu != 1 && bu != 2) bu = 2;
 		if (rows == 2 && bu != 2 && bu != 4) bu = 4;
+		if (accept_fused) *accept_fused = 1;
 		return launch_clike_block(a, rows, bu, kt, sm_count, st);
 	}
+	if (accept_fused) *accept_fused = 1;
 	return L == 8 ? launch_clike_u<8>(a, U, kt, sm_count, st)
 	              : launch_clike_u<32>(a, U, kt, sm_count, st);
 }
@@ -741,13 +784,117 @@ __global__ void __launch_bounds__(256) accept_count_kernel(const double *__restr
 }
 
 int launch_accept_count(const double *L, long long stride, int n, int K, const double *lmins,
-                        int *counts, cudaStream_t st)
+                        int *counts, cudaStream_t st, bool zero)
 {
 	if (K <= 0) return MDNS_OK;
-	MDNS_CUDA(cudaMemsetAsync(counts, 0, (size_t)K * sizeof(int), st));
+	if (zero) MDNS_CUDA(cudaMemsetAsync(counts, 0, (size_t)K * sizeof(int), st));
 	if (n <= 0) return MDNS_OK;
 	accept_count_kernel<<<dim3(ceil_div(n, AC_ROWS), K), 256, 0, st>>>(L, stride, n, lmins, counts);
 	MDNS_LAUNCHED("accept_count_kernel");
+	return MDNS_OK;
+}
+
+// ---- the decision on the device: no host round trip between the counts and the fetch ----
+// sel[0] = first candidate with a non-zero count (the one the reference's one-at-a-time loop stops
+// at, hiermetriclearn.py:181-196) or -1; sel[1] = its count; sel[2] = rows recomputed in the direct
+// form so far (host feedback of the expanded form); sel[3] = spare; sel[4 + k] = counts[k].
+__global__ void select_first_kernel(const int *__restrict__ counts, int K,
+                                    const int *__restrict__ redo, int *__restrict__ sel)
+{
+	__shared__ int s_first;
+	if (threadIdx.x == 0) s_first = 0x7fffffff;
+	__syncthreads();
+	for (int k = threadIdx.x; k < K; k += blockDim.x) {
+		const int c = counts[k];
+		sel[SEL_COUNTS + k] = c;
+		if (c > 0) atomicMin(&s_first, k);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const int f = s_first == 0x7fffffff ? -1 : s_first;
+		sel[0] = f;
+		sel[1] = f >= 0 ? counts[f] : 0;
+		sel[2] = redo ? redo[0] : 0;
+		sel[3] = 0;
+	}
+}
+
+int launch_select_first(const int *counts, int K, const int *redo, int *sel, cudaStream_t st)
+{
+	select_first_kernel<<<1, 128, 0, st>>>(counts, K, redo, sel);
+	MDNS_LAUNCHED_HELPER("select_first_kernel");
+	return MDNS_OK;
+}
+
+// out[r] = L[sel[0]][r0 + r], r < n: the logL vector of the selected candidate (nothing if none)
+__global__ void __launch_bounds__(256) gather_selected_kernel(const double *__restrict__ L,
+                                                              long long stride, int r0, int n,
+                                                              const int *__restrict__ sel,
+                                                              double *__restrict__ out)
+{
+	const int f = sel[0];
+	if (f < 0) return;
+	const double *row = L + (long long)f * stride + r0;
+	for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) out[r0 + i] = row[i];
+}
+
+int launch_gather_selected(const double *L, long long stride, int r0, int n, const int *sel,
+                           double *out, cudaStream_t st)
+{
+	if (n <= 0) return MDNS_OK;
+	int blocks = ceil_div(n, 256 * 4);
+	if (blocks > 148 * 8) blocks = 148 * 8;
+	gather_selected_kernel<<<blocks, 256, 0, st>>>(L, stride, r0, n, sel, out);
+	MDNS_LAUNCHED_HELPER("gather_selected_kernel");
+	return MDNS_OK;
+}
+
+// sparse form: flags[r] = L[sel[0]][r] > lmins[r] (all zero if no candidate was selected); the
+// tail up to the next multiple of 16 bytes is cleared for the compaction
+__global__ void __launch_bounds__(256) selected_flags_kernel(const double *__restrict__ L,
+                                                             long long stride, int n,
+                                                             const int *__restrict__ sel,
+                                                             const double *__restrict__ lmins,
+                                                             uint8_t *__restrict__ flags)
+{
+	const int i = blockIdx.x * 256 + threadIdx.x;
+	const int npad = (n + 15) / 16 * 16;
+	const int f = sel[0];
+	if (i < npad) flags[i] = (f >= 0 && i < n && L[(long long)f * stride + i] > lmins[i]) ? 1 : 0;
+}
+
+int launch_selected_flags(const double *L, long long stride, int n, const int *sel,
+                          const double *lmins, uint8_t *flags, cudaStream_t st)
+{
+	if (n <= 0) return MDNS_OK;
+	selected_flags_kernel<<<ceil_div((n + 15) / 16 * 16, 256), 256, 0, st>>>(L, stride, n, sel, lmins, flags);
+	MDNS_LAUNCHED_HELPER("selected_flags_kernel");
+	return MDNS_OK;
+}
+
+// out[i] = L[sel[0]][idx[i]], i < *n_dev
+__global__ void __launch_bounds__(256) gather_selected_values_kernel(const double *__restrict__ L,
+                                                                     long long stride,
+                                                                     const int *__restrict__ sel,
+                                                                     const int *__restrict__ idx,
+                                                                     const int *__restrict__ n_dev,
+                                                                     double *__restrict__ out)
+{
+	const int f = sel[0];
+	if (f < 0) return;
+	const int n = *n_dev;
+	const double *row = L + (long long)f * stride;
+	for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) out[i] = row[idx[i]];
+}
+
+int launch_gather_selected_values(const double *L, long long stride, const int *sel, const int *idx,
+                                  const int *n_dev, int n_max, double *out, cudaStream_t st)
+{
+	if (n_max <= 0) return MDNS_OK;
+	int blocks = ceil_div(n_max, 256 * 4);
+	if (blocks > 148 * 4) blocks = 148 * 4;
+	gather_selected_values_kernel<<<blocks, 256, 0, st>>>(L, stride, sel, idx, n_dev, out);
+	MDNS_LAUNCHED_HELPER("gather_selected_values_kernel");
 	return MDNS_OK;
 }
 

@@ -97,10 +97,49 @@ class ResidentDataset(object):
         self._lib = lib
         self._h = handle
         self.has_variance = variance is not None
+        self._draw_n_act = None         # active data sets of the draw in progress (begin_draw)
+        self._comm = False
         self._finalizer = weakref.finalize(self, lib.mdns_dataset_destroy, handle)
 
     def close(self):
         self._finalizer()
+
+    # -- one process per GPU -------------------------------------------------
+    def comm_unique_id(self):
+        """128 bytes identifying a new communicator (rank 0 creates, the others receive it:
+        sharding.exchange_unique_id)."""
+        buf = ctypes.create_string_buffer(128)
+        _lib.check(self._lib.mdns_comm_unique_id(buf), 'mdns_comm_unique_id')
+        return buf.raw
+
+    def init_comm(self, unique_id, nranks, rank):
+        """Attach the communicator of the exchange step (collective: every rank calls it).  From
+        then on draw_batch / draw_batch_sparse / draw_pass / first_accepted return the GLOBAL
+        decision: accept counts summed over the ranks by ncclAllReduce on the device."""
+        uid = ctypes.create_string_buffer(bytes(unique_id), 128)
+        _lib.check(self._lib.mdns_comm_init(self._h, uid, int(nranks), int(rank)), 'mdns_comm_init')
+        self._comm = True
+
+    def comm_allreduce(self, values, op='sum'):
+        """Sum / max of a few host doubles over the ranks (doubles as a barrier)."""
+        v = numpy.ascontiguousarray(values, dtype=numpy.float64).copy()
+        _lib.check(self._lib.mdns_comm_allreduce(self._h, _addr(v), v.size, 1 if op == 'max' else 0),
+                   'mdns_comm_allreduce')
+        return v
+
+    def allgather_candidate(self, k, nranks):
+        """logL vectors of candidate k of the last launch of every rank -> (L_all, n_per_rank)."""
+        nper = numpy.zeros(int(nranks), dtype=numpy.int32)
+        _lib.check(self._lib.mdns_comm_allgather_candidate(self._h, int(k), None, 0, _addr(nper)),
+                   'mdns_comm_allgather_candidate')
+        out = _pool.empty(int(nper.sum()))
+        _lib.check(self._lib.mdns_comm_allgather_candidate(self._h, int(k), _addr(out), out.size,
+                                                           _addr(nper)),
+                   'mdns_comm_allgather_candidate')
+        return out, nper
+
+    def set_draw_chunks(self, nchunks=0):
+        _lib.check(self._lib.mdns_set_draw_chunks(self._h, int(nchunks)), 'mdns_set_draw_chunks')
 
     # -- staged interface ----------------------------------------------------
     def set_mask(self, data_mask):
@@ -109,7 +148,14 @@ class ResidentDataset(object):
             data_mask = self._mask(data_mask)
         _lib.check(self._lib.mdns_set_mask(self._h, _addr(data_mask), ctypes.byref(n)),
                    'mdns_set_mask')
+        self._draw_n_act = None         # thresholds of a draw in progress no longer apply
         return n.value
+
+    def _draw_state(self):
+        if self._draw_n_act is None:
+            raise RuntimeError('no constrained draw in progress: call begin_draw(data_mask, Lmins) '
+                               '(or draw_pass) before draw_batch / draw_counts / fetch_candidate')
+        return self._draw_n_act
 
     def _mask(self, data_mask):
         m = numpy.ascontiguousarray(data_mask)
@@ -149,6 +195,9 @@ class ResidentDataset(object):
         ms = ctypes.c_float()
         _lib.check(self._lib.mdns_timer_stop(self._h, ctypes.byref(ms)), 'mdns_timer_stop')
         return ms.value
+
+    def flush_l2(self):
+        _lib.check(self._lib.mdns_flush_l2(self._h), 'mdns_flush_l2')
 
     def set_tuning(self, lanes=0, unroll=0, ktile=0, rows=0):
         _lib.check(self._lib.mdns_set_tuning(self._h, lanes, unroll, ktile, rows),
@@ -194,7 +243,7 @@ class ResidentDataset(object):
         if Lmins.shape != (n_act,):
             raise ValueError('Lmins must have one entry per active data set')
         counts = numpy.zeros(K, dtype=numpy.int32)
-        if n_act == 0:
+        if n_act == 0 and not self._comm:
             return -1, None, counts
         out = _pool.empty(n_act)
         first = ctypes.c_int(-1)
@@ -213,8 +262,9 @@ class ResidentDataset(object):
         Lmins = numpy.ascontiguousarray(Lmins, dtype=numpy.float64)
         if Lmins.shape != (n_act,):
             raise ValueError('Lmins must have one entry per active data set')
-        if n_act > 0:
-            _lib.check(self._lib.mdns_set_thresholds(self._h, _addr(Lmins)), 'mdns_set_thresholds')
+        if n_act == 0:
+            Lmins = numpy.zeros(1)      # nothing to compare with; keeps the call sequence uniform
+        _lib.check(self._lib.mdns_set_thresholds(self._h, _addr(Lmins)), 'mdns_set_thresholds')
         self._draw_n_act = n_act
         return n_act
 
@@ -222,10 +272,10 @@ class ResidentDataset(object):
         """Score the next K candidates of the draw started with ``begin_draw``; returns
         ``(k, L, counts)`` like ``first_accepted``.  Per call only the K parameter points go to
         the device and K counts plus at most one logL vector come back."""
+        n_act = self._draw_state()
         K = self.stage_params(params)
-        n_act = self._draw_n_act
         counts = numpy.zeros(K, dtype=numpy.int32)
-        if n_act == 0:
+        if n_act == 0 and not self._comm:
             return -1, None, counts
         out = _pool.empty(n_act)
         first = ctypes.c_int(-1)
@@ -251,9 +301,9 @@ class ResidentDataset(object):
         Lmins = numpy.ascontiguousarray(Lmins, dtype=numpy.float64)
         if Lmins.shape != (n_act,):
             raise ValueError('Lmins must have one entry per active data set')
-        self._draw_n_act = n_act
-        if n_act == 0:
+        if n_act == 0 and not self._comm:
             self.set_mask(m)
+            self._draw_n_act = 0
             return -1, None, counts
         out = _pool.empty(n_act)
         first = ctypes.c_int(-1)
@@ -261,6 +311,7 @@ class ResidentDataset(object):
                                                   scale, _addr(counts), ctypes.byref(first),
                                                   _addr(out), out.size, None),
                    'mdns_clike_draw_pass')
+        self._draw_n_act = n_act
         if first.value < 0:
             return -1, None, counts
         return first.value, out, counts
@@ -269,16 +320,17 @@ class ResidentDataset(object):
         """First step of the two-step form (one process per GPU): score the next K candidates of
         the draw started with ``begin_draw`` and return the accept counts of THIS process's data
         sets; see ``sharding.global_first_accepted`` for the exchange."""
+        n_act = self._draw_state()
         K = self.stage_params(params)
         counts = numpy.zeros(K, dtype=numpy.int32)
-        if self._draw_n_act > 0:
+        if n_act > 0:
             _lib.check(self._lib.mdns_clike_accept_counts(self._h, noise, scale, None, _addr(counts)),
                        'mdns_clike_accept_counts')
         return counts
 
     def fetch_candidate(self, k):
         """Second step: the logL vector of candidate k of the launch behind ``draw_counts``."""
-        out = _pool.empty(self._draw_n_act)
+        out = _pool.empty(self._draw_state())
         if self._draw_n_act > 0:
             _lib.check(self._lib.mdns_fetch_candidate(self._h, int(k), _addr(out), out.size),
                        'mdns_fetch_candidate')
@@ -289,13 +341,13 @@ class ResidentDataset(object):
         (multi_nested_sampler.py:482-485): ``(k, j, Lj, counts)`` with ``j`` the positions (in the
         compacted active order, increasing) of the data sets candidate ``k`` is accepted for and
         ``Lj`` their logL; ``(-1, None, None, counts)`` if no candidate is accepted."""
+        n_act = self._draw_state()
         K = self.stage_params(params)
-        n_act = self._draw_n_act
         counts = numpy.zeros(K, dtype=numpy.int32)
-        if n_act == 0:
+        if n_act == 0 and not self._comm:
             return -1, None, None, counts
-        idx = numpy.empty(n_act, dtype=numpy.int32)
-        val = _pool.empty(n_act)
+        idx = numpy.empty(max(n_act, 1), dtype=numpy.int32)
+        val = _pool.empty(max(n_act, 1))
         first = ctypes.c_int(-1)
         n = ctypes.c_int(0)
         _lib.check(self._lib.mdns_clike_first_accept_sparse(

@@ -98,7 +98,14 @@ def _worker_accept(rank, world, port, N, out_path):
     Lmins[0] = full[4, 0] - 1e-3
     i0, n = sharding.shard_ranges(N, world)[rank]
     local = (full[:, i0:i0 + n] > Lmins[i0:i0 + n]).sum(axis=1)      # what draw_counts returns
-    k, total = sharding.global_first_accepted(local)
+    import torch
+
+    def allreduce_sum(v):          # the exchange run by the caller: gloo on the host
+        t = torch.as_tensor(numpy.asarray(v, dtype=numpy.int64))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.numpy()
+
+    k, total = sharding.global_first_accepted(local, allreduce_sum)
     want_total = (full > Lmins).sum(axis=1)
     assert numpy.array_equal(total, want_total)
     assert k == sharding.first_accepted_from_counts(want_total)
@@ -116,3 +123,51 @@ def test_two_rank_first_accept_needs_the_count_exchange(tmp_path, oracle_port):
     # the globally first accepted candidate is not the one rank 0 would have picked alone
     assert k_global <= k_rank0 or k_rank0 == -1
     assert k_global >= 0
+
+
+def _worker_rendezvous(rank, world, port, out_dir):
+    # the hand-over of the NCCL id (sharding.exchange_unique_id): plain TCP, no framework
+    made = []
+
+    def make_id():
+        made.append(1)
+        return bytes(range(128))
+
+    uid = sharding.exchange_unique_id(make_id, rank, world, addr='127.0.0.1', port=port, timeout=60)
+    assert (len(made) == 1) == (rank == 0)
+    with open(os.path.join(out_dir, 'uid%d' % rank), 'wb') as f:
+        f.write(uid)
+
+
+@pytest.mark.timeout(120)
+def test_unique_id_rendezvous_over_tcp(tmp_path):
+    import torch.multiprocessing as mp
+    world = 3
+    mp.spawn(_worker_rendezvous, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(str(tmp_path / ('uid%d' % r)), 'rb').read() == bytes(range(128))
+
+
+def test_dist_env_and_decision_rule(monkeypatch):
+    monkeypatch.setenv('RANK', '3')
+    monkeypatch.setenv('WORLD_SIZE', '8')
+    monkeypatch.setenv('LOCAL_RANK', '3')
+    assert sharding.dist_env() == (3, 8, 3)
+    assert sharding.global_first_accepted([0, 0, 2, 1]) == (2, pytest.approx([0, 0, 2, 1]))
+    assert sharding.global_first_accepted([0, 0], lambda v: v + numpy.array([0, 5]))[0] == 1
+    assert sharding.first_accepted_from_counts([0, 0, 0]) == -1
+
+
+def test_package_does_not_import_torch():
+    # north star: the shim and its Python surface carry no PyTorch dependency
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = ('import sys; import massivedatans_b200, massivedatans_b200.sharding, '
+            'massivedatans_b200.likelihood, massivedatans_b200.livepoints, '
+            'massivedatans_b200.hiermetriclearn, massivedatans_b200.clustering.neighbors, '
+            'massivedatans_b200.clustering.radfriendsregion; '
+            'assert "torch" not in sys.modules, "torch was imported"')
+    subprocess.check_call([sys.executable, '-c', code], cwd=ROOT)
+    src = open(os.path.join(ROOT, 'massivedatans_b200', 'sharding.py')).read()
+    assert 'import torch' not in src

@@ -1,0 +1,127 @@
+#!/usr/bin/env python
+"""Round-2 A/B: stream-K tensor-path kernel (rows_dmma_kernel) against round 1's whole-tile kernel
+(clike_dmma_kernel), device-timed, plus the accept passes end to end.
+
+    python tools/r2_ab.py [--out gpurun_out/r2_ab.json]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from massivedatans_b200 import _lib, synth  # noqa: E402
+from massivedatans_b200.likelihood import ResidentDataset  # noqa: E402
+
+PEAK = 6529.7
+
+
+def algo_bytes(n, nx, K):
+    return n * nx * 8 + K * nx * 8 + K * n * 8 + n
+
+
+def timed(ds, reps):
+    for _ in range(3):
+        ds.launch_clike(0.01, -0.5)
+    ds.sync()
+    ds.timer_start()
+    for _ in range(reps):
+        ds.launch_clike(0.01, -0.5)
+    return ds.timer_stop() / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'r2_ab.json'))
+    args = ap.parse_args()
+    lib = _lib.load()
+    res = {'kernel_ab': [], 'accept': []}
+    shapes = [(1000000, 200, 'horns'), (125000, 1000, 'realistic'), (500000, 1000, 'realistic')]
+    for n, nx, kind in shapes:
+        if kind == 'horns':
+            x, y, _ = synth.horns(n, nx=nx, legacy=False, seed=1000)
+        else:
+            x, y, _ = synth.realistic(n, nx=nx)
+        ds = ResidentDataset(x, y)
+        ds.set_mask(None)
+        for K in (4, 8, 16, 32, 64):
+            pts = synth.parameter_points(K, seed=7)
+            ds.stage_params(pts)
+            row = {'n': n, 'nx': nx, 'K': K}
+            for name, tun in (('auto', (0, 0, 0, 0)), ('old', (3, 1, 0, 0))):
+                ds.set_tuning(*tun)
+                t = timed(ds, 30 if K <= 16 else 10)
+                gbs = algo_bytes(n, nx, K) / (t * 1e-3) / 1e9
+                row[name] = {'ms': t, 'frac': gbs / PEAK, 'kernel': lib.mdns_last_kernel().decode()}
+            ds.set_tuning(0, 0, 0, 0)
+            # parity of the two kernels against each other on a sample
+            out_new = numpy.empty((K, n))
+            ds.launch_clike(0.01, -0.5)
+            ds.fetch(out_new)
+            ds.set_tuning(3, 1, 0, 0)
+            out_old = numpy.empty((K, n))
+            ds.launch_clike(0.01, -0.5)
+            ds.fetch(out_old)
+            ds.set_tuning(0, 0, 0, 0)
+            row['max_rel_new_vs_old'] = float(numpy.max(numpy.abs(out_new - out_old) / numpy.abs(out_old)))
+            res['kernel_ab'].append(row)
+            print(row, flush=True)
+        if kind == 'horns':
+            # accept passes end to end: dense (chunk-overlapped), one chunk, sparse
+            K = 16
+            pts = synth.parameter_points(K, seed=7)
+            L = ds.loglike_batch(pts, None, 0.01).copy()
+            wins = numpy.bincount(numpy.argmax(L, axis=0), minlength=K)
+            order = numpy.argsort(wins, kind='stable')
+            pts_fa, L_fa = numpy.ascontiguousarray(pts[order]), L[order]
+            Lmins = numpy.max(L_fa[:K - 1], axis=0)
+            for label, chunks in (('dense_auto', 0), ('dense_1chunk', 1), ('dense_4', 4), ('dense_8', 8)):
+                ds.set_draw_chunks(chunks)
+                ds.begin_draw(None, Lmins)
+                for _ in range(3):
+                    k, Lk, c = ds.draw_batch(pts_fa, 0.01)
+                t0 = time.perf_counter()
+                for _ in range(50):
+                    k, Lk, c = ds.draw_batch(pts_fa, 0.01)
+                dt = (time.perf_counter() - t0) / 50
+                ok = bool(k == K - 1 and numpy.array_equal(Lk, L_fa[K - 1]) and
+                          numpy.array_equal(c, (L_fa > Lmins).sum(axis=1)))
+                res['accept'].append({'mode': label, 'ms': 1e3 * dt, 'ok': ok, 'k': int(k)})
+                print(res['accept'][-1], flush=True)
+            ds.set_draw_chunks(0)
+            margin = L_fa[K - 1] - Lmins
+            Lmins_s = Lmins + max(float(numpy.quantile(margin, 0.99)), 0.0)
+            ds.begin_draw(None, Lmins_s)
+            for _ in range(3):
+                ks, js, Ljs, cs = ds.draw_batch_sparse(pts_fa, 0.01)
+            t0 = time.perf_counter()
+            for _ in range(50):
+                ks, js, Ljs, cs = ds.draw_batch_sparse(pts_fa, 0.01)
+            dt = (time.perf_counter() - t0) / 50
+            want_j = numpy.nonzero(L_fa[K - 1] > Lmins_s)[0]
+            ok = bool(ks == K - 1 and numpy.array_equal(js, want_j) and
+                      numpy.array_equal(Ljs, L_fa[K - 1][want_j]))
+            res['accept'].append({'mode': 'sparse', 'ms': 1e3 * dt, 'ok': ok, 'n': int(len(want_j))})
+            print(res['accept'][-1], flush=True)
+            # a guess that turns out wrong: candidate 3 accepted only for the LAST data set
+            Lm = numpy.max(L_fa, axis=0) + 1.0
+            Lm[n - 1] = L_fa[3, n - 1] - 1e-6
+            Lm[0] = L_fa[5, 0] - 1e-6
+            ds.begin_draw(None, Lm)
+            k, Lk, c = ds.draw_batch(pts_fa, 0.01)
+            ok = bool(k == 3 and numpy.array_equal(Lk, L_fa[3]))
+            res['accept'].append({'mode': 'late_decision', 'ok': ok, 'k': int(k)})
+            print(res['accept'][-1], flush=True)
+        ds.close()
+        del ds, y
+    with open(args.out, 'w') as f:
+        json.dump(res, f, indent=1)
+
+
+if __name__ == '__main__':
+    main()
