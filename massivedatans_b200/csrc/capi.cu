@@ -119,6 +119,34 @@ struct Shard {
 			       xp_tol == o.xp_tol && model == o.model && out == o.out && in == o.in && smm == o.smm;
 		}
 	} graph_key;
+	// accept passes (accept_enqueue) as CUDA graphs: a few of them, because the caller's result
+	// buffer is part of what a graph was captured with and callers rotate between buffers
+	struct AcceptKey {
+		int K = -1, staged = 0, n_act = -1, all_active = 0;
+		int lanes = 0, unroll = 0, ktile = 0, rows = 0, allow_expanded = 0;
+		int want = 0, nchunk = 0, eager = 0;
+		double noise = 0, scale = 0, xp_tol = 0;
+		const void *comm = nullptr;
+		const void *ptrs[16] = {nullptr};
+		bool operator==(const AcceptKey &o) const
+		{
+			return K == o.K && staged == o.staged && n_act == o.n_act && all_active == o.all_active &&
+			       lanes == o.lanes && unroll == o.unroll && ktile == o.ktile && rows == o.rows &&
+			       allow_expanded == o.allow_expanded && want == o.want && nchunk == o.nchunk &&
+			       eager == o.eager && noise == o.noise && scale == o.scale && xp_tol == o.xp_tol &&
+			       comm == o.comm && memcmp(ptrs, o.ptrs, sizeof ptrs) == 0;
+		}
+	};
+	struct AcceptGraph {
+		AcceptKey key;
+		cudaGraphExec_t exec = nullptr;
+		long long launches = 0;
+		const char *kernel = "";
+		unsigned long long used = 0;
+	};
+	static constexpr int NAGRAPH = 4;
+	AcceptGraph agraphs[NAGRAPH];
+	unsigned long long agraph_clock = 0;
 	int n_act = 0;
 	bool all_active = true;
 	alignas(64) unsigned char tmap[128];      // CUtensorMaps of Y (tile kernel), 128-row boxes
@@ -194,6 +222,8 @@ static void shard_free(Shard &s)
 	for (auto &e : s.ev_pick)
 		if (e) cudaEventDestroy(e);
 	if (s.graph) cudaGraphExecDestroy(s.graph);
+	for (auto &g : s.agraphs)
+		if (g.exec) cudaGraphExecDestroy(g.exec);
 	if (s.h_stage) cudaFreeHost(s.h_stage);
 	if (s.ev0) cudaEventDestroy(s.ev0);
 	if (s.ev1) cudaEventDestroy(s.ev1);
@@ -1024,6 +1054,92 @@ static int accept_chunks(const mdns_dataset *ds, const Shard &s)
 enum AcceptWant { WANT_COUNTS = 0, WANT_DENSE = 1, WANT_SPARSE = 2 };
 static constexpr int SPARSE_EAGER = 16384;   // accepting entries downloaded with the decision
 
+// Everything one accept pass enqueues on the shard's two streams (no host synchronisation inside:
+// the sequence can be captured into a CUDA graph).  Buffers must have been grown before.
+struct AcceptPlan {
+	AcceptWant want;
+	int nchunk, per, eager;
+	double noise, scale;
+	double *Lout;
+	int32_t *idx_out;
+	double *val_out;
+};
+
+static int accept_enqueue(mdns_dataset *ds, Shard &s, const AcceptPlan &p, const NcclApi *nccl)
+{
+	const int K = ds->K;
+	const int Kpad = (int)round_up(K, KT_MAX);
+	const size_t block = SEL_COUNTS + Kpad;
+	int rc;
+	MDNS_CUDA(cudaMemsetAsync(s.d_counts, 0, (size_t)Kpad * sizeof(int), s.stream));
+	int *sel_final = s.d_sel + block * p.nchunk;        // the decision of the whole pass
+	if (s.n_act > 0 && (rc = clike_model(ds, s)) != MDNS_OK) return rc;
+	int used_chunks = 0;
+	for (int r0 = 0, c = 0; r0 < s.n_act; r0 += p.per, ++c) {
+		const int nc = std::min(p.per, s.n_act - r0);
+		if ((rc = clike_rows(ds, s, p.noise, p.scale, r0, nc, true)) != MDNS_OK) return rc;
+		++used_chunks;
+		if (p.nchunk == 1) break;
+		// speculative pick of this chunk: the first candidate accepted by THIS process's rows so
+		// far -- the final (global) decision can only be an earlier candidate, checked afterwards
+		MDNS_CUDA(cudaMemcpyAsync(s.d_snap + (size_t)c * Kpad, s.d_counts, (size_t)K * sizeof(int),
+		                          cudaMemcpyDeviceToDevice, s.stream));
+		MDNS_CUDA(cudaEventRecord(s.ev_pick[c], s.stream));
+		MDNS_CUDA(cudaStreamWaitEvent(s.copy_stream, s.ev_pick[c], 0));
+		int *sel_c = s.d_sel + block * c;
+		if ((rc = launch_select_first(s.d_snap + (size_t)c * Kpad, K, nullptr, sel_c, s.copy_stream)) != MDNS_OK)
+			return rc;
+		if ((rc = launch_gather_selected(s.d_out, s.n_act, r0, nc, sel_c, s.d_pick, s.copy_stream)) != MDNS_OK)
+			return rc;
+		MDNS_CUDA(cudaMemcpyAsync(p.Lout + r0, s.d_pick + r0, (size_t)nc * sizeof(double),
+		                          cudaMemcpyDeviceToHost, s.copy_stream));
+	}
+	// the exchange step: K integers summed over the ranks, on the stream, before the decision
+	if (ds->comm &&
+	    (rc = nccl_check(nccl->AllReduce(s.d_counts, s.d_counts, (size_t)K, ncclInt32, ncclSum, ds->comm,
+	                                     s.stream),
+	                     nccl, "ncclAllReduce of the accept counts")) != MDNS_OK)
+		return rc;
+	if ((rc = launch_select_first(s.d_counts, K, xp_candidate(ds, s) ? s.d_redo : nullptr, sel_final,
+	                              s.stream)) != MDNS_OK)
+		return rc;
+	if (s.n_act > 0 && p.want == WANT_DENSE && p.nchunk == 1) {
+		if ((rc = launch_gather_selected(s.d_out, s.n_act, 0, s.n_act, sel_final, s.d_pick, s.stream)) != MDNS_OK)
+			return rc;
+		MDNS_CUDA(cudaMemcpyAsync(p.Lout, s.d_pick, (size_t)s.n_act * sizeof(double),
+		                          cudaMemcpyDeviceToHost, s.stream));
+	} else if (s.n_act > 0 && p.want == WANT_SPARSE) {
+		if ((rc = launch_selected_flags(s.d_out, s.n_act, s.n_act, sel_final, s.d_lmins, s.d_flags,
+		                                s.stream)) != MDNS_OK)
+			return rc;
+		if ((rc = launch_compact_mask(s.d_flags, s.n_act, s.d_scratch, s.d_acc_idx, s.d_nacc, s.stream)) != MDNS_OK)
+			return rc;
+		if ((rc = launch_gather_selected_values(s.d_out, s.n_act, sel_final, s.d_acc_idx, s.d_nacc,
+		                                        s.n_act, s.d_acc_val, s.stream)) != MDNS_OK)
+			return rc;
+		// the length of this process's list rides in the spare slot of the decision block
+		MDNS_CUDA(cudaMemcpyAsync(sel_final + 3, s.d_nacc, sizeof(int), cudaMemcpyDeviceToDevice, s.stream));
+		// the first entries travel with the decision; the rest (if any) after it is known
+		if (p.eager > 0) {
+			MDNS_CUDA(cudaMemcpyAsync(p.idx_out, s.d_acc_idx, (size_t)p.eager * sizeof(int),
+			                          cudaMemcpyDeviceToHost, s.stream));
+			MDNS_CUDA(cudaMemcpyAsync(p.val_out, s.d_acc_val, (size_t)p.eager * sizeof(double),
+			                          cudaMemcpyDeviceToHost, s.stream));
+		}
+	}
+	// decision blocks -> pinned host memory; the chunk blocks were written on the copy stream,
+	// which then joins the main stream again
+	if (p.nchunk > 1 && used_chunks > 0) {
+		MDNS_CUDA(cudaMemcpyAsync(s.h_sel, s.d_sel, block * used_chunks * sizeof(int),
+		                          cudaMemcpyDeviceToHost, s.copy_stream));
+		MDNS_CUDA(cudaEventRecord(s.ev_pick[7], s.copy_stream));
+		MDNS_CUDA(cudaStreamWaitEvent(s.stream, s.ev_pick[7], 0));
+	}
+	MDNS_CUDA(cudaMemcpyAsync(s.h_sel + block * p.nchunk, sel_final, block * sizeof(int),
+	                          cudaMemcpyDeviceToHost, s.stream));
+	return MDNS_OK;
+}
+
 // One shard (one process per GPU, with or without a communicator).
 static int accept_pass_single(mdns_dataset *ds, double noise, double scale, AcceptWant want,
                               int *accept_counts, int *first_k, double *Lout, int32_t *idx_out,
@@ -1036,94 +1152,112 @@ static int accept_pass_single(mdns_dataset *ds, double noise, double scale, Acce
 	const NcclApi *nccl = nullptr;
 	if (ds->comm && !(nccl = nccl_api())) return MDNS_ECUDA;
 	MDNS_CUDA(cudaSetDevice(s.device));
-	const int nchunk = (want == WANT_DENSE && s.n_act > 0) ? accept_chunks(ds, s) : 1;
-	int rc = accept_buffers(ds, s, nchunk + 1, want == WANT_DENSE);
+	AcceptPlan p;
+	p.want = want;
+	p.noise = noise;
+	p.scale = scale;
+	p.Lout = Lout;
+	p.idx_out = idx_out;
+	p.val_out = val_out;
+	p.nchunk = (want == WANT_DENSE && s.n_act > 0) ? std::min(accept_chunks(ds, s), 7) : 1;
+	p.per = (int)round_up(ceil_div(std::max(s.n_act, 1), p.nchunk), 256);
+	p.eager = want == WANT_SPARSE ? (int)std::min<int64_t>(std::min(s.n_act, SPARSE_EAGER), capacity) : 0;
+	int rc = accept_buffers(ds, s, p.nchunk + 1, want == WANT_DENSE);
 	if (rc != MDNS_OK) return rc;
-	MDNS_CUDA(cudaMemsetAsync(s.d_counts, 0, (size_t)Kpad * sizeof(int), s.stream));
-	int *sel_final = s.d_sel + block * nchunk;        // the decision of the whole pass
-	if (s.n_act > 0 && (rc = clike_model(ds, s)) != MDNS_OK) return rc;
-	const int per = (int)round_up(ceil_div(std::max(s.n_act, 1), nchunk), 256);
-	int used_chunks = 0;
-	for (int r0 = 0, c = 0; r0 < s.n_act; r0 += per, ++c) {
-		const int nc = std::min(per, s.n_act - r0);
-		if ((rc = clike_rows(ds, s, noise, scale, r0, nc, true)) != MDNS_OK) return rc;
-		++used_chunks;
-		if (nchunk == 1) break;
-		// speculative pick of this chunk: the first candidate accepted by THIS process's rows so
-		// far -- the final (global) decision can only be an earlier candidate, checked below
-		MDNS_CUDA(cudaMemcpyAsync(s.d_snap + (size_t)c * Kpad, s.d_counts, (size_t)K * sizeof(int),
-		                          cudaMemcpyDeviceToDevice, s.stream));
-		MDNS_CUDA(cudaEventRecord(s.ev_pick[c], s.stream));
-		MDNS_CUDA(cudaStreamWaitEvent(s.copy_stream, s.ev_pick[c], 0));
-		int *sel_c = s.d_sel + block * c;
-		if ((rc = launch_select_first(s.d_snap + (size_t)c * Kpad, K, nullptr, sel_c, s.copy_stream)) != MDNS_OK)
-			return rc;
-		if ((rc = launch_gather_selected(s.d_out, s.n_act, r0, nc, sel_c, s.d_pick, s.copy_stream)) != MDNS_OK)
-			return rc;
-		MDNS_CUDA(cudaMemcpyAsync(Lout + r0, s.d_pick + r0, (size_t)nc * sizeof(double),
-		                          cudaMemcpyDeviceToHost, s.copy_stream));
-	}
-	// the exchange step: K integers summed over the ranks, on the stream, before the decision
-	if (ds->comm &&
-	    (rc = nccl_check(nccl->AllReduce(s.d_counts, s.d_counts, (size_t)K, ncclInt32, ncclSum, ds->comm,
-	                                     s.stream),
-	                     nccl, "ncclAllReduce of the accept counts")) != MDNS_OK)
-		return rc;
-	if ((rc = launch_select_first(s.d_counts, K, xp_candidate(ds, s) ? s.d_redo : nullptr, sel_final,
-	                              s.stream)) != MDNS_OK)
-		return rc;
-	int eager = 0;
-	if (s.n_act > 0 && want == WANT_DENSE && nchunk == 1) {
-		if ((rc = launch_gather_selected(s.d_out, s.n_act, 0, s.n_act, sel_final, s.d_pick, s.stream)) != MDNS_OK)
-			return rc;
-		MDNS_CUDA(cudaMemcpyAsync(Lout, s.d_pick, (size_t)s.n_act * sizeof(double),
-		                          cudaMemcpyDeviceToHost, s.stream));
-	} else if (s.n_act > 0 && want == WANT_SPARSE) {
+	if (want == WANT_SPARSE && s.n_act > 0) {
 		const size_t fbytes = round_up(s.n_act, 16) + 16;
 		if ((rc = grow(&s.d_flags, &s.flags_cap, fbytes, true)) != MDNS_OK) return rc;
 		if ((rc = grow(&s.d_acc_idx, &s.acc_idx_cap, (size_t)s.n_act, false)) != MDNS_OK) return rc;
 		if ((rc = grow(&s.d_acc_val, &s.acc_val_cap, (size_t)s.n_act, false)) != MDNS_OK) return rc;
 		if (!s.d_nacc) MDNS_CUDA(cudaMalloc((void **)&s.d_nacc, sizeof(int)));
-		if ((rc = launch_selected_flags(s.d_out, s.n_act, s.n_act, sel_final, s.d_lmins, s.d_flags,
-		                                s.stream)) != MDNS_OK)
-			return rc;
-		if ((rc = launch_compact_mask(s.d_flags, s.n_act, s.d_scratch, s.d_acc_idx, s.d_nacc, s.stream)) != MDNS_OK)
-			return rc;
-		if ((rc = launch_gather_selected_values(s.d_out, s.n_act, sel_final, s.d_acc_idx, s.d_nacc,
-		                                        s.n_act, s.d_acc_val, s.stream)) != MDNS_OK)
-			return rc;
-		// the first entries travel with the decision; the rest (if any) after it is known
-		eager = (int)std::min<int64_t>(std::min(s.n_act, SPARSE_EAGER), capacity);
-		if (eager > 0) {
-			MDNS_CUDA(cudaMemcpyAsync(idx_out, s.d_acc_idx, (size_t)eager * sizeof(int),
-			                          cudaMemcpyDeviceToHost, s.stream));
-			MDNS_CUDA(cudaMemcpyAsync(val_out, s.d_acc_val, (size_t)eager * sizeof(double),
-			                          cudaMemcpyDeviceToHost, s.stream));
+	}
+	static const bool use_graph = []() {
+		const char *e = getenv("MDNS_NO_GRAPH");
+		return !(e && *e && *e != '0');
+	}();
+	if (!use_graph || inline_single(ds)) {      // (a by-value candidate is a kernel argument)
+		if ((rc = accept_enqueue(ds, s, p, nccl)) != MDNS_OK) return rc;
+	} else {
+		// the pass as a CUDA graph, replayed while nothing it was captured with has changed
+		Shard::AcceptKey key;
+		key.K = K;
+		key.staged = ds->staged;
+		key.n_act = s.n_act;
+		key.all_active = s.all_active ? 1 : 0;
+		key.lanes = ds->tuning.lanes;
+		key.unroll = ds->tuning.unroll;
+		key.ktile = ds->tuning.ktile;
+		key.rows = ds->tuning.rows;
+		key.allow_expanded = ds->tuning.allow_expanded ? 1 : 0;
+		key.want = (int)want;
+		key.nchunk = p.nchunk;
+		key.eager = p.eager;
+		key.noise = noise;
+		key.scale = scale;
+		key.xp_tol = ds->xp_tol;
+		key.comm = ds->comm;
+		const void *ptrs[] = {s.d_model, s.d_out, s.d_in, s.d_smm, s.d_counts, s.d_sel, s.d_snap, s.d_pick,
+		                      s.d_lmins, s.d_flags, s.d_acc_idx, s.d_acc_val, s.h_sel, Lout, idx_out, val_out};
+		static_assert(sizeof ptrs == sizeof key.ptrs, "graph key");
+		memcpy(key.ptrs, ptrs, sizeof ptrs);
+		Shard::AcceptGraph *hit = nullptr, *victim = nullptr;
+		for (auto &g : s.agraphs)
+			if (g.exec && key == g.key) hit = &g;
+		for (auto &g : s.agraphs)        // an empty slot, else the least recently used one
+			if (!victim || (victim->exec && (!g.exec || g.used < victim->used))) victim = &g;
+		if (!hit) {
+			if (victim->exec) {
+				cudaGraphExecDestroy(victim->exec);
+				victim->exec = nullptr;
+			}
+			const long long before = g_launches.load();
+			MDNS_CUDA(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+			rc = accept_enqueue(ds, s, p, nccl);
+			cudaGraph_t g = nullptr;
+			const cudaError_t e = cudaStreamEndCapture(s.stream, &g);
+			if (rc != MDNS_OK) {
+				if (g) cudaGraphDestroy(g);
+				cudaGetLastError();
+				return rc;
+			}
+			if (e != cudaSuccess || !g) {
+				set_error("stream capture of the accept pass failed: %s", cudaGetErrorString(e));
+				return MDNS_ECUDA;
+			}
+			const cudaError_t ei = cudaGraphInstantiate(&victim->exec, g, 0);
+			cudaGraphDestroy(g);
+			if (ei != cudaSuccess) {
+				victim->exec = nullptr;
+				set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+				return MDNS_ECUDA;
+			}
+			victim->key = key;
+			victim->launches = g_launches.load() - before;   // counted once at capture
+			victim->kernel = g_last_kernel.load();
+			hit = victim;
+		} else {
+			g_launches.fetch_add(hit->launches, std::memory_order_relaxed);
+			g_last_kernel.store(hit->kernel, std::memory_order_relaxed);
 		}
+		hit->used = ++s.agraph_clock;
+		MDNS_CUDA(cudaGraphLaunch(hit->exec, s.stream));
 	}
-	// decision blocks -> pinned host memory.  The chunk blocks were written on the copy stream.
-	if (nchunk > 1) {
-		MDNS_CUDA(cudaMemcpyAsync(s.h_sel, s.d_sel, block * used_chunks * sizeof(int),
-		                          cudaMemcpyDeviceToHost, s.copy_stream));
-		MDNS_CUDA(cudaStreamSynchronize(s.copy_stream));
-	}
-	MDNS_CUDA(cudaMemcpyAsync(s.h_sel + block * nchunk, sel_final, block * sizeof(int),
-	                          cudaMemcpyDeviceToHost, s.stream));
 	MDNS_CUDA(cudaStreamSynchronize(s.stream));
 	ds->launched = 1;
-	const int *hf = s.h_sel + block * nchunk;
+	const int *hf = s.h_sel + block * p.nchunk;
 	const int first = hf[SEL_FIRST];
 	*first_k = first;
 	if (accept_counts)
 		for (int k = 0; k < K; ++k) accept_counts[k] = hf[SEL_COUNTS + k];
 	if ((rc = xp_feedback_value(ds, s, hf[SEL_REDO])) != MDNS_OK) return rc;
 	if (first < 0 || s.n_act == 0) return MDNS_OK;
-	if (want == WANT_DENSE && nchunk > 1) {
+	if (want == WANT_DENSE && p.nchunk > 1) {
 		// chunks whose speculative pick was a later candidate than the final decision: fetch again
 		bool again = false;
-		for (int r0 = 0, c = 0; r0 < s.n_act; r0 += per, ++c) {
+		for (int r0 = 0, c = 0; r0 < s.n_act; r0 += p.per, ++c) {
 			if (s.h_sel[block * c + SEL_FIRST] == first) continue;
-			const int nc = std::min(per, s.n_act - r0);
+			const int nc = std::min(p.per, s.n_act - r0);
+			int *sel_final = s.d_sel + block * p.nchunk;
 			if ((rc = launch_gather_selected(s.d_out, s.n_act, r0, nc, sel_final, s.d_pick, s.stream)) != MDNS_OK)
 				return rc;
 			MDNS_CUDA(cudaMemcpyAsync(Lout + r0, s.d_pick + r0, (size_t)nc * sizeof(double),
@@ -1133,23 +1267,18 @@ static int accept_pass_single(mdns_dataset *ds, double noise, double scale, Acce
 		if (again) MDNS_CUDA(cudaStreamSynchronize(s.stream));
 	}
 	if (want == WANT_SPARSE) {
-		// the candidate's count is the global one under a communicator; this process's share is
-		// the length of its own compacted list
-		int mine = hf[SEL_COUNT];
-		if (ds->comm) {
-			MDNS_CUDA(cudaMemcpyAsync(&mine, s.d_nacc, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-			MDNS_CUDA(cudaStreamSynchronize(s.stream));
-		}
+		// (under a communicator the candidate's count is the global one; hf[3] is this process's)
+		const int mine = hf[3];
 		if (mine > capacity) {
 			set_error("the accepted candidate is accepted for %d data sets, the output holds %lld", mine,
 			          (long long)capacity);
 			return MDNS_EINVAL;
 		}
-		if (mine > eager) {
-			MDNS_CUDA(cudaMemcpyAsync(idx_out + eager, s.d_acc_idx + eager, (size_t)(mine - eager) * sizeof(int),
-			                          cudaMemcpyDeviceToHost, s.stream));
-			MDNS_CUDA(cudaMemcpyAsync(val_out + eager, s.d_acc_val + eager,
-			                          (size_t)(mine - eager) * sizeof(double), cudaMemcpyDeviceToHost,
+		if (mine > p.eager) {
+			MDNS_CUDA(cudaMemcpyAsync(idx_out + p.eager, s.d_acc_idx + p.eager,
+			                          (size_t)(mine - p.eager) * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+			MDNS_CUDA(cudaMemcpyAsync(val_out + p.eager, s.d_acc_val + p.eager,
+			                          (size_t)(mine - p.eager) * sizeof(double), cudaMemcpyDeviceToHost,
 			                          s.stream));
 			MDNS_CUDA(cudaStreamSynchronize(s.stream));
 		}

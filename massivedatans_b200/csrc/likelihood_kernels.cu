@@ -634,6 +634,7 @@ static int pick_ktile(int K, int mpitch, int requested)
 static int launch_dmma_auto(const LikeArgs &a, int kt, int stages, int sm_count, cudaStream_t st,
                             int *accept_fused)
 {
+	if (kt == 16 && stages == 13) stages = 3;     // 8 consumer warps x 32 data sets (see rows_dmma_fits)
 	if (rows_dmma_fits(a, kt, stages)) {
 		if (accept_fused) *accept_fused = 1;
 		return launch_rows_dmma(a, kt, stages, false, 1, sm_count, st);

@@ -69,15 +69,108 @@ __device__ __forceinline__ void rd_dmma(double &c0, double &c1, double a, double
 	             : "d"(a), "d"(b));
 }
 
-// the stream-K schedule: T units over G CTAs
+// The schedule.  VT = nmat * ntiles virtual tiles of nch chunks each, G CTAs.
+//   bulk       CTA b takes the whole tiles b, b + G, b + 2G, ... of the first `waves` full waves
+//              (neighbouring CTAs stream neighbouring rows, as the round-1 kernel did);
+//   remainder  the last VT - waves*G tiles (between G and 2G-1 of them when VT >= G) are cut
+//              into G equal unit ranges: CTA b owns units [b*T/G, (b+1)*T/G) of the T = rem*nch.
 struct RdSched {
-	long long T;       // units = virtual tiles * chunks
+	long long T;       // units of the remainder
 	int G;             // CTAs
 	int nch;           // chunks per tile
+	int waves;         // whole-tile rounds before the remainder
 	__device__ __forceinline__ long long begin(int b) const { return (long long)b * T / G; }
 	// the CTA whose range holds unit u
 	__device__ __forceinline__ int owner(long long u) const { return (int)(((u + 1) * G - 1) / T); }
 };
+
+__device__ __forceinline__ RdSched rd_schedule(int nmat, int ntiles, int nch, int G)
+{
+	RdSched sc;
+	const int VT = nmat * ntiles;
+	sc.G = G;
+	sc.nch = nch;
+	sc.waves = VT / G > 1 ? VT / G - 1 : 0;
+	sc.T = (long long)(VT - sc.waves * G) * nch;
+	return sc;
+}
+
+// what a CTA keeps of its schedule (shared memory: the hot loop has no registers to spare)
+struct RdMine {
+	long long u0, u1;      // unit range within the remainder
+	int waves;             // whole tiles before it
+	int lv_first, nseg;    // first remainder tile touched (remainder-local) and how many
+};
+
+// segment `seg` of this CTA: virtual tile, chunk range, and whether it is a cut tile
+__device__ __forceinline__ void rd_segment(const RdMine &m, int seg, int G, int nch, int &vt, int &cs,
+                                           int &ce)
+{
+	if (seg < m.waves) {
+		vt = blockIdx.x + seg * G;
+		cs = 0;
+		ce = nch;
+		return;
+	}
+	const int lv = m.lv_first + (seg - m.waves);
+	const long long ub = (long long)lv * nch;
+	cs = (int)((m.u0 > ub ? m.u0 : ub) - ub);
+	ce = (int)((m.u1 < ub + nch ? m.u1 : ub + nch) - ub);
+	vt = m.waves * G + lv;
+}
+
+// ---- epilogue of the expanded chi-square, specialised on what the tile needs ------------------
+// FULL: every row of the tile and every candidate of the pass is valid (no predicates);
+// COUNT: fused accept test into the packed per-lane counters cntp[nc] (two 16-bit counts);
+// STORE: the logL matrix is wanted.
+template <int NC, int MR, bool GATHER, bool FULL, bool COUNT, bool STORE>
+__device__ __forceinline__ void rd_epilogue_clike(const double (&acc)[MR][NC][2], const LikeArgs &a,
+                                                  const double *s_smm, int tile, int warp, int pr, int t,
+                                                  int kp0, int kp1, int k0, int kt_valid, int pass,
+                                                  double inv, unsigned (&cntp)[NC])
+{
+	unsigned redo_mask = 0;
+#pragma unroll
+	for (int mr = 0; mr < MR; ++mr) {
+		const long long gr = (long long)tile * RD_ROWS + warp * (8 * MR) + mr * 8 + pr;
+		const bool live = FULL || gr < a.n_rows;
+		const double syy = !live ? 0.0 : GATHER ? __ldg(a.syy + a.active[gr]) : __ldg(a.syy + a.row0 + gr);
+		double lm = 0.0;
+		if (COUNT) lm = live ? __ldg(a.lmins + gr) : __longlong_as_double(0x7ff0000000000000LL);
+		double *o0 = nullptr, *o1 = nullptr;
+		if (STORE) {
+			o0 = a.out + (long long)(k0 + kp0) * a.out_stride + gr;
+			o1 = a.out + (long long)(k0 + kp1) * a.out_stride + gr;
+		}
+		bool redo = false;
+#pragma unroll
+		for (int nc = 0; nc < NC; ++nc) {
+#pragma unroll
+			for (int i = 0; i < 2; ++i) {
+				const int kp = i ? kp1 : kp0;
+				const double smm = s_smm[nc * 8 + kp];
+				const double chi = syy + fma(-2.0, acc[mr][nc][i], smm);
+				const bool ok = chi >= a.xp_guard * (syy + smm);   // false for NaN too
+				const bool valid = FULL || (live && nc * 8 + kp < kt_valid);
+				const double val = chi * inv;
+				if (STORE && valid && ok) (i ? o1 : o0)[(long long)nc * 8 * a.out_stride] = val;
+				if (COUNT && valid && ok && val > lm) cntp[nc] += 1u << (16 * i);
+				redo = redo || (valid && !ok);
+			}
+		}
+		if (redo) redo_mask |= 1u << mr;
+	}
+	// the four lanes of a group share the data set: list it once
+	redo_mask |= __shfl_xor_sync(0xffffffffu, redo_mask, 1);
+	redo_mask |= __shfl_xor_sync(0xffffffffu, redo_mask, 2);
+	if (redo_mask && t == 0) {
+#pragma unroll
+		for (int mr = 0; mr < MR; ++mr)
+			if (redo_mask & (1u << mr))
+				a.xp_list[atomicAdd(a.xp_redo + 1 + pass, 1)] =
+				    (int)((long long)tile * RD_ROWS + warp * (8 * MR) + mr * 8 + pr);
+	}
+}
 
 template <int NC, int STAGES, int MR, bool GATHER, int EPI>
 __global__ void __launch_bounds__(RD_ROWS / (8 * MR) * 32 + (GATHER ? 64 : 32)) rows_dmma_kernel(
@@ -90,23 +183,28 @@ __global__ void __launch_bounds__(RD_ROWS / (8 * MR) * 32 + (GATHER ? 64 : 32)) 
 	constexpr int CTHREADS = WARPS * 32;
 	constexpr int MODEL_BYTES = KT * RD_BOX_CH * 8;
 	constexpr int STAGE_BYTES = RD_STAGE_BYTES + MODEL_BYTES;   // multiple of 1 KB
-	constexpr int NACC = MR * NC * 2;
 	extern __shared__ __align__(1024) unsigned char smem_raw[];
 	__shared__ uint64_t full_bar[STAGES], empty_bar[STAGES];
+	__shared__ double s_smm[KT];
 	__shared__ int s_counts[KT];
 	__shared__ int s_last;
+	__shared__ RdMine s_mine;
 	unsigned char *ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int ntiles = (a.n_rows + RD_ROWS - 1) / RD_ROWS;
-	RdSched sc;
-	sc.nch = ((int)a.pitch + RD_BOX_CH - 1) / RD_BOX_CH;
-	sc.T = (long long)nmat * ntiles * sc.nch;
-	sc.G = gridDim.x;
-	const long long u0 = sc.begin(blockIdx.x), u1 = sc.begin(blockIdx.x + 1);
-	const int vt_first = (int)(u0 / sc.nch), vt_last = (int)((u1 - 1) / sc.nch);
+	const int nch = ((int)a.pitch + RD_BOX_CH - 1) / RD_BOX_CH;
+	const int G = gridDim.x;
 
 	if (threadIdx.x == 0) {
+		const RdSched sc = rd_schedule(nmat, ntiles, nch, G);
+		RdMine m;
+		m.waves = sc.waves;
+		m.u0 = sc.begin(blockIdx.x);
+		m.u1 = sc.begin(blockIdx.x + 1);
+		m.lv_first = (int)(m.u0 / nch);
+		m.nseg = m.u1 > m.u0 ? (int)((m.u1 - 1) / nch) - m.lv_first + 1 : 0;
+		s_mine = m;
 #pragma unroll
 		for (int s = 0; s < STAGES; ++s) {
 			mbar_init(&full_bar[s], 1);
@@ -114,68 +212,68 @@ __global__ void __launch_bounds__(RD_ROWS / (8 * MR) * 32 + (GATHER ? 64 : 32)) 
 		}
 		mbar_fence_init();
 	}
-	if (threadIdx.x < KT) s_counts[threadIdx.x] = 0;
+	if (threadIdx.x < KT) {
+		s_counts[threadIdx.x] = 0;
+		s_smm[threadIdx.x] = EPI == EPI_CLIKE ? a.smm[k0 + threadIdx.x] : 0.0;
+	}
 	__syncthreads();
+	const int nseg = s_mine.waves + s_mine.nseg;
 
 	if (warp >= WARPS) {
 		// ===================== producer =====================
 		int it = 0;
-		if (u1 > u0) {
-			if (GATHER) {
-				const int pl = (warp - WARPS) * 32 + lane;     // 0..63: one group of four rows each
-				for (int vt = vt_first; vt <= vt_last; ++vt) {
-					const int mat = vt >= ntiles ? 1 : 0;
-					const int tile = vt - mat * ntiles;
-					const long long ub = (long long)vt * sc.nch;
-					const int cs = (int)((u0 > ub ? u0 : ub) - ub);
-					const int ce = (int)((u1 < ub + sc.nch ? u1 : ub + sc.nch) - ub);
-					const CUtensorMap *ta = mat ? &tmapA1 : &tmapA0;
-					const CUtensorMap *tb = mat ? &tmapB1 : &tmapB0;
-					int rows[4];
+		if (GATHER) {
+			const int pl = (warp - WARPS) * 32 + lane;     // 0..63: one group of four rows each
+			for (int seg = 0; seg < nseg; ++seg) {
+				int vt, cs, ce;
+				rd_segment(s_mine, seg, G, nch, vt, cs, ce);
+				const int mat = vt >= ntiles ? 1 : 0;
+				const int tile = vt - mat * ntiles;
+				const CUtensorMap *ta = mat ? &tmapA1 : &tmapA0;
+				const CUtensorMap *tb = mat ? &tmapB1 : &tmapB0;
+				int rows[4];
 #pragma unroll
-					for (int j = 0; j < 4; ++j) {
-						const long long r = (long long)tile * RD_ROWS + pl * 4 + j;
-						rows[j] = a.active[r < a.n_rows ? r : a.n_rows - 1];
-					}
-					for (int c = cs; c < ce; ++c, ++it) {
-						const int stage = it % STAGES;
-						const uint32_t round = (uint32_t)(it / STAGES);
-						unsigned char *dst = ring + (size_t)stage * STAGE_BYTES;
-						if (pl == 0) {
-							mbar_wait(&empty_bar[stage], (round & 1u) ^ 1u);
-							mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-							rd_tma_load_2d(dst + RD_STAGE_BYTES, tb, c * RD_BOX_CH, k0, &full_bar[stage]);
-						}
-						__syncwarp();
-						asm volatile("bar.sync 1, 64;" ::: "memory");
-						rd_tma_gather4(dst + pl * 512, ta, c * RD_BOX_CH, rows[0], rows[1], rows[2],
-						               rows[3], &full_bar[stage]);
-					}
+				for (int j = 0; j < 4; ++j) {
+					const long long r = (long long)tile * RD_ROWS + pl * 4 + j;
+					rows[j] = a.active[r < a.n_rows ? r : a.n_rows - 1];
 				}
-			} else if (lane == 0) {
-				for (int vt = vt_first; vt <= vt_last; ++vt) {
-					const int mat = vt >= ntiles ? 1 : 0;
-					const int tile = vt - mat * ntiles;
-					const long long ub = (long long)vt * sc.nch;
-					const int cs = (int)((u0 > ub ? u0 : ub) - ub);
-					const int ce = (int)((u1 < ub + sc.nch ? u1 : ub + sc.nch) - ub);
-					const CUtensorMap *ta = mat ? &tmapA1 : &tmapA0;
-					const CUtensorMap *tb = mat ? &tmapB1 : &tmapB0;
-					const int r0 = a.row0 + tile * RD_ROWS;
-					for (int c = cs; c < ce; ++c, ++it) {
-						const int stage = it % STAGES;
-						const uint32_t round = (uint32_t)(it / STAGES);
+				for (int c = cs; c < ce; ++c, ++it) {
+					const int stage = it % STAGES;
+					const uint32_t round = (uint32_t)(it / STAGES);
+					unsigned char *dst = ring + (size_t)stage * STAGE_BYTES;
+					if (pl == 0) {
 						mbar_wait(&empty_bar[stage], (round & 1u) ^ 1u);
-						// out-of-bounds parts of a box are zero-filled and still counted
 						mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-						unsigned char *dst = ring + (size_t)stage * STAGE_BYTES;
-						rd_tma_load_2d(dst, ta, c * RD_BOX_CH, r0, &full_bar[stage]);
 						rd_tma_load_2d(dst + RD_STAGE_BYTES, tb, c * RD_BOX_CH, k0, &full_bar[stage]);
 					}
+					__syncwarp();
+					asm volatile("bar.sync 1, 64;" ::: "memory");
+					rd_tma_gather4(dst + pl * 512, ta, c * RD_BOX_CH, rows[0], rows[1], rows[2],
+					               rows[3], &full_bar[stage]);
+				}
+			}
+		} else if (lane == 0) {
+			for (int seg = 0; seg < nseg; ++seg) {
+				int vt, cs, ce;
+				rd_segment(s_mine, seg, G, nch, vt, cs, ce);
+				const int mat = vt >= ntiles ? 1 : 0;
+				const int tile = vt - mat * ntiles;
+				const CUtensorMap *ta = mat ? &tmapA1 : &tmapA0;
+				const CUtensorMap *tb = mat ? &tmapB1 : &tmapB0;
+				const int r0 = a.row0 + tile * RD_ROWS;
+				for (int c = cs; c < ce; ++c, ++it) {
+					const int stage = it % STAGES;
+					const uint32_t round = (uint32_t)(it / STAGES);
+					mbar_wait(&empty_bar[stage], (round & 1u) ^ 1u);
+					// out-of-bounds parts of a box are zero-filled and still counted
+					mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+					unsigned char *dst = ring + (size_t)stage * STAGE_BYTES;
+					rd_tma_load_2d(dst, ta, c * RD_BOX_CH, r0, &full_bar[stage]);
+					rd_tma_load_2d(dst + RD_STAGE_BYTES, tb, c * RD_BOX_CH, k0, &full_bar[stage]);
 				}
 			}
 		}
-	} else if (u1 > u0) {
+	} else {
 		// ===================== consumer warps =====================
 		const int g = lane >> 2, t = lane & 3;
 		const int pr = ((g & 3) << 1) | (g >> 2);      // physical row of logical row g
@@ -183,17 +281,19 @@ __global__ void __launch_bounds__(RD_ROWS / (8 * MR) * 32 + (GATHER ? 64 : 32)) 
 		const int a_row_off = (warp * (8 * MR) + pr) * 128 + (t & 1) * 8;
 		const int a_chunk = t >> 1;
 		const int b_row_off = RD_STAGE_BYTES + pr * 128 + (t & 1) * 8;
+		// logical columns 2t, 2t+1 of a candidate tile -> physical candidates (same permutation)
+		const int kp0 = (((2 * t) & 3) << 1) | ((2 * t) >> 2);
+		const int kp1 = (((2 * t + 1) & 3) << 1) | ((2 * t + 1) >> 2);
 		const double inv = a.scale / a.noise2;
-		int cnt[NC][2];
+		unsigned cntp[NC];
 #pragma unroll
-		for (int nc = 0; nc < NC; ++nc) cnt[nc][0] = cnt[nc][1] = 0;
+		for (int nc = 0; nc < NC; ++nc) cntp[nc] = 0;
 		int it = 0;
-		for (int vt = vt_first; vt <= vt_last; ++vt) {
+		for (int seg = 0; seg < nseg; ++seg) {
+			int vt, cs, ce;
+			rd_segment(s_mine, seg, G, nch, vt, cs, ce);
 			const int mat = vt >= ntiles ? 1 : 0;
 			const int tile = vt - mat * ntiles;
-			const long long ub = (long long)vt * sc.nch;
-			const int cs = (int)((u0 > ub ? u0 : ub) - ub);
-			const int ce = (int)((u1 < ub + sc.nch ? u1 : ub + sc.nch) - ub);
 			double acc[MR][NC][2];
 #pragma unroll
 			for (int mr = 0; mr < MR; ++mr)
@@ -223,10 +323,11 @@ __global__ void __launch_bounds__(RD_ROWS / (8 * MR) * 32 + (GATHER ? 64 : 32)) 
 				__syncwarp();
 				if (lane == 0) rd_mbar_arrive(&empty_bar[stage]);
 			}
-			if (cs != 0 || ce != sc.nch) {
+			if (cs != 0 || ce != nch) {
 				// a cut tile: park this CTA's partial sums; the last of the tile's CTAs to get here
 				// adds all of them up in CTA order and carries on to the epilogue
-				double *slot = a.ws + (size_t)(blockIdx.x * 2 + (vt == vt_first ? 0 : 1)) * (RD_ROWS * KT);
+				const int lv = vt - s_mine.waves * G;        // remainder-local tile
+				double *slot = a.ws + (size_t)(blockIdx.x * 2 + (seg == s_mine.waves ? 0 : 1)) * (RD_ROWS * KT);
 #pragma unroll
 				for (int mr = 0; mr < MR; ++mr)
 #pragma unroll
@@ -236,9 +337,18 @@ __global__ void __launch_bounds__(RD_ROWS / (8 * MR) * 32 + (GATHER ? 64 : 32)) 
 							__stcg(slot + ((mr * NC + nc) * 2 + i) * CTHREADS + tid, acc[mr][nc][i]);
 				__threadfence();
 				asm volatile("bar.sync 2, %0;" ::"n"(CTHREADS) : "memory");
+				const RdSched sc = rd_schedule(nmat, ntiles, nch, G);
+				const long long ub = (long long)lv * nch;
+				const int b_first = sc.owner(ub), b_last = sc.owner(ub + nch - 1);
 				if (tid == 0) {
-					const int b_first = sc.owner(ub), b_last = sc.owner(ub + sc.nch - 1);
+					// release / acquire through ONE thread, as a grid barrier does it: the fence after
+					// the CTA barrier is cumulative over the other threads' stores, the one after the
+					// atomic orders the reads of the other CTAs' slots behind it.  (Fences by the
+					// storing threads alone, before the barrier, let a few rows of a slot arrive late
+					// on the B200: the finalising CTA then saw the previous launch's values.)
+					__threadfence();
 					const int old = atomicAdd(a.tickets + vt, 1);
+					__threadfence();
 					const int last = old == b_last - b_first ? 1 : 0;
 					if (last) a.tickets[vt] = 0;      // ready for the next launch
 					s_last = last;
@@ -250,9 +360,8 @@ __global__ void __launch_bounds__(RD_ROWS / (8 * MR) * 32 + (GATHER ? 64 : 32)) 
 				for (int mr = 0; mr < MR; ++mr)
 #pragma unroll
 					for (int nc = 0; nc < NC; ++nc) acc[mr][nc][0] = acc[mr][nc][1] = 0.0;
-				const int b_first = sc.owner(ub), b_last = sc.owner(ub + sc.nch - 1);
 				for (int bb = b_first; bb <= b_last; ++bb) {
-					const int first_of_bb = (int)(sc.begin(bb) / sc.nch) == vt ? 0 : 1;
+					const int first_of_bb = (int)(sc.begin(bb) / nch) == lv ? 0 : 1;
 					const double *src = a.ws + (size_t)(bb * 2 + first_of_bb) * (RD_ROWS * KT);
 #pragma unroll
 					for (int mr = 0; mr < MR; ++mr)
@@ -264,69 +373,53 @@ __global__ void __launch_bounds__(RD_ROWS / (8 * MR) * 32 + (GATHER ? 64 : 32)) 
 				}
 			}
 			// ---- epilogue: lane holds S[row(g)][2t + {0,1}] of every (row tile, candidate tile)
+			if (EPI == EPI_RAW) {
+				double *outp = mat ? a.out_b : a.out;
 #pragma unroll
-			for (int mr = 0; mr < MR; ++mr) {
-				const long long gr = (long long)tile * RD_ROWS + warp * (8 * MR) + mr * 8 + pr;
-				const bool live = gr < a.n_rows;
-				if (EPI == EPI_RAW) {
-					double *outp = mat ? a.out_b : a.out;
+				for (int mr = 0; mr < MR; ++mr) {
+					const long long gr = (long long)tile * RD_ROWS + warp * (8 * MR) + mr * 8 + pr;
+					const bool live = gr < a.n_rows;
 #pragma unroll
 					for (int nc = 0; nc < NC; ++nc)
 #pragma unroll
 						for (int i = 0; i < 2; ++i) {
-							const int col = 2 * t + i;
-							const int k = nc * 8 + (((col & 3) << 1) | (col >> 2));
+							const int k = nc * 8 + (i ? kp1 : kp0);
 							if (live && k < kt_valid)
 								outp[(long long)(k0 + k) * a.out_stride + gr] = acc[mr][nc][i];
 						}
-					continue;
 				}
-				const double syy = !live ? 0.0
-				                   : GATHER ? __ldg(a.syy + a.active[gr])
-				                            : __ldg(a.syy + a.row0 + gr);
-				const double lm = (live && a.lmins) ? __ldg(a.lmins + gr) : 0.0;
-				bool redo = false;
+				continue;
+			}
+			const bool full = kt_valid == KT && (long long)(tile + 1) * RD_ROWS <= a.n_rows;
+#define RD_EPI(FULL, COUNT, STORE)                                                                       \
+	rd_epilogue_clike<NC, MR, GATHER, FULL, COUNT, STORE>(acc, a, s_smm, tile, warp, pr, t, kp0, kp1, k0, \
+	                                                      kt_valid, pass, inv, cntp)
+			if (a.counts) {
+				if (a.out) {
+					if (full) RD_EPI(true, true, true); else RD_EPI(false, true, true);
+				} else {
+					if (full) RD_EPI(true, true, false); else RD_EPI(false, true, false);
+				}
+				// the packed counters hold 16 bits: flush long before they can overflow
+				if ((seg & 2047) == 2047) {
 #pragma unroll
-				for (int nc = 0; nc < NC; ++nc) {
-#pragma unroll
-					for (int i = 0; i < 2; ++i) {
-						const int col = 2 * t + i;      // logical column -> physical candidate
-						const int k = nc * 8 + (((col & 3) << 1) | (col >> 2));
-						const double smm = __ldg(a.smm + k0 + k);
-						const double chi = syy + fma(-2.0, acc[mr][nc][i], smm);
-						const bool ok = chi >= a.xp_guard * (syy + smm);   // false for NaN too
-						if (live && k < kt_valid) {
-							if (ok) {
-								const double val = chi * inv;
-								if (a.out) a.out[(long long)(k0 + k) * a.out_stride + gr] = val;
-								if (a.lmins && val > lm) ++cnt[nc][i];
-							} else {
-								redo = true;
-							}
-						}
+					for (int nc = 0; nc < NC; ++nc) {
+						if (cntp[nc] & 0xffffu) atomicAdd(&s_counts[nc * 8 + kp0], (int)(cntp[nc] & 0xffffu));
+						if (cntp[nc] >> 16) atomicAdd(&s_counts[nc * 8 + kp1], (int)(cntp[nc] >> 16));
+						cntp[nc] = 0;
 					}
 				}
-				// the four lanes of a group share the data set: list it once
-				int flag = redo ? 1 : 0;
-				flag |= __shfl_xor_sync(0xffffffffu, flag, 1);
-				flag |= __shfl_xor_sync(0xffffffffu, flag, 2);
-				if (flag && t == 0) a.xp_list[atomicAdd(a.xp_redo + 1 + pass, 1)] = (int)gr;
+			} else {
+				if (full) RD_EPI(true, false, true); else RD_EPI(false, false, true);
 			}
+#undef RD_EPI
 		}
 		if (EPI == EPI_CLIKE && a.counts) {
-			// lanes with equal t hold the same candidates: add over g, then one shared atomic each
 #pragma unroll
-			for (int nc = 0; nc < NC; ++nc)
-#pragma unroll
-				for (int i = 0; i < 2; ++i) {
-					int c = cnt[nc][i];
-					c += __shfl_xor_sync(0xffffffffu, c, 4);
-					c += __shfl_xor_sync(0xffffffffu, c, 8);
-					c += __shfl_xor_sync(0xffffffffu, c, 16);
-					const int col = 2 * t + i;
-					const int k = nc * 8 + (((col & 3) << 1) | (col >> 2));
-					if (g == 0 && c) atomicAdd(&s_counts[k], c);
-				}
+			for (int nc = 0; nc < NC; ++nc) {
+				if (cntp[nc] & 0xffffu) atomicAdd(&s_counts[nc * 8 + kp0], (int)(cntp[nc] & 0xffffu));
+				if (cntp[nc] >> 16) atomicAdd(&s_counts[nc * 8 + kp1], (int)(cntp[nc] >> 16));
+			}
 		}
 	}
 	if (EPI == EPI_CLIKE && a.counts) {
@@ -414,7 +507,10 @@ static int launch_rd_inst(const LikeArgs &a, int nmat, int sm_count, cudaStream_
 
 bool rows_dmma_fits(const LikeArgs &a, int kt, int stages)
 {
-	static const int shapes[][2] = {{8, 3}, {8, 13}, {8, 14}, {16, 3}, {16, 13}, {32, 3}, {32, 2}};
+	// (16 candidates with 16 consumer warps is not instantiated: it needs a 56-register cap to keep
+	// two CTAs per SM, spills under it, was no faster than 8 warps x 32 data sets -- and gave wrong
+	// sums in a few rows of a cut tile about once in four launches on the B200, the only shape to)
+	static const int shapes[][2] = {{8, 3}, {8, 13}, {8, 14}, {16, 3}, {32, 3}, {32, 2}};
 	bool known = false;
 	for (auto &sh : shapes) known = known || (sh[0] == kt && sh[1] == stages);
 	if (!known) return false;
@@ -446,7 +542,6 @@ int launch_rows_dmma(const LikeArgs &a, int kt, int stages, bool raw, int nmat, 
 	MDNS_RD(8, 3, 2)
 	MDNS_RD(8, 4, 2)
 	MDNS_RD(16, 3, 4)
-	MDNS_RD(16, 3, 2)
 	MDNS_RD(32, 3, 4)
 	MDNS_RD(32, 2, 4)
 #undef MDNS_RD

@@ -153,7 +153,7 @@ class ResidentDataset(object):
 
     def _draw_state(self):
         if self._draw_n_act is None:
-            raise RuntimeError('no constrained draw in progress: call begin_draw(data_mask, Lmins) '
+            raise _lib.MdnsError('no constrained draw in progress: call begin_draw(data_mask, Lmins) '
                                '(or draw_pass) before draw_batch / draw_counts / fetch_candidate')
         return self._draw_n_act
 

@@ -9,6 +9,11 @@ import ctypes
 import numpy
 import pytest
 
+# the FP64 tensor-path kernels: stream-K (round 2) and whole-tile (round 1, kept for the shapes
+# only it is instantiated for)
+TENSOR = (b'rows_dmma_kernel', b'clike_dmma_kernel')
+TENSOR_GATHER = (b'rows_dmma_kernel(gather)', b'clike_dmma_kernel(gather)')
+
 from conftest import rel_err
 from massivedatans_b200 import _lib, synth
 from massivedatans_b200.likelihood import (ResidentDataset, make_multi_loglikelihood,
@@ -182,7 +187,7 @@ def test_clike_expanded_tensor_path_variants(oracle_port, ktile, stages, N, nx, 
     ds.set_tuning(3, 0, ktile, stages)
     pts = synth.parameter_points(K, seed=N + 3)
     got = ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0)
-    assert _lib.load().mdns_last_kernel() == b'clike_dmma_kernel'
+    assert _lib.load().mdns_last_kernel() in TENSOR
     allm = numpy.ones(N, dtype=bool)
     for k in sorted(set((0, 1, 7, 8, K // 2, K - 2, K - 1)) & set(range(K))):
         p = pts[k]
@@ -206,7 +211,7 @@ def test_clike_expanded_tensor_path_masked_gather(oracle_port, ktile, stages, N,
         if name == 'all' or not m.any():
             continue
         got = ds.loglike_batch(pts, m, synth.NOISE_LEVEL, scale=1.0)
-        assert _lib.load().mdns_last_kernel() == b'clike_dmma_kernel(gather)'
+        assert _lib.load().mdns_last_kernel() in TENSOR_GATHER
         assert got.shape == (K, int(m.sum()))
         for k in sorted(set((0, 7, 8, K // 2, K - 1))):
             p = pts[k]
@@ -225,13 +230,13 @@ def test_clike_masked_batches_automatic_choice(oracle_port):
     m = synth.masks(N)['half']
     pts = synth.parameter_points(20, seed=9)
     got = ds.loglike_batch(pts, m, synth.NOISE_LEVEL)
-    assert lib.mdns_last_kernel() == b'clike_dmma_kernel(gather)'
+    assert lib.mdns_last_kernel() in TENSOR_GATHER
     for k in (0, 15, 16, 19):
         p = pts[k]
         want = -0.5 * oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, m)
         assert rel_err(got[k], want) < TOL_XP
     mid = ds.loglike_batch(pts[:8], m, synth.NOISE_LEVEL)
-    assert lib.mdns_last_kernel() == b'clike_dmma_kernel(gather)'
+    assert lib.mdns_last_kernel() in TENSOR_GATHER
     assert rel_err(mid, got[:8]) < TOL_XP
     small = ds.loglike_batch(pts[:4], m, synth.NOISE_LEVEL)
     assert lib.mdns_last_kernel() in (b'clike_block_kernel', b'clike_rows_kernel')
@@ -254,16 +259,16 @@ def test_clike_expanded_form_automatic_choice(oracle_port):
     lib = _lib.load()
     pts = synth.parameter_points(35, seed=2)
     got = ds.loglike_batch(pts, None, synth.NOISE_LEVEL)
-    assert lib.mdns_last_kernel() == b'clike_dmma_kernel'
+    assert lib.mdns_last_kernel() in TENSOR
     allm = numpy.ones(N, dtype=bool)
     for k in (0, 7, 8, 31, 32, 34):
         p = pts[k]
         want = -0.5 * oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, allm)
         assert rel_err(got[k], want) < TOL_XP
     ds.loglike_batch(pts[:2], None, synth.NOISE_LEVEL)
-    assert lib.mdns_last_kernel() not in (b'clike_xtile_kernel', b'clike_dmma_kernel')
+    assert lib.mdns_last_kernel() not in (b'clike_xtile_kernel',) + TENSOR
     ds.loglike_batch(pts, synth.masks(N)['half'], synth.NOISE_LEVEL)
-    assert lib.mdns_last_kernel() not in (b'clike_xtile_kernel', b'clike_dmma_kernel')
+    assert lib.mdns_last_kernel() not in (b'clike_xtile_kernel',) + TENSOR
     ds.set_expanded(False)
     got = ds.loglike_batch(pts[:9], None, synth.NOISE_LEVEL)
     assert lib.mdns_last_kernel() == b'clike_tile_kernel'
@@ -275,7 +280,8 @@ def test_clike_expanded_form_automatic_choice(oracle_port):
 
 @pytest.mark.parametrize('tuning,kernel', [((2, 2, 8, 3), b'clike_xtile_kernel'),
                                            ((3, 0, 8, 2), b'clike_dmma_kernel'),
-                                           ((3, 0, 8, 13), b'clike_dmma_kernel')])
+                                           ((3, 0, 8, 3), b'rows_dmma_kernel'),
+                                           ((3, 0, 8, 13), b'rows_dmma_kernel')])
 def test_clike_expanded_form_cancellation_guard(oracle_port, tuning, kernel):
     # data that the candidate fits to ~1e-7 of its amplitude: Syy, Sym and Smm agree to 14
     # digits and their combination would be rounding noise.  Those (data set, candidate) pairs
@@ -307,7 +313,7 @@ def test_clike_expanded_form_cancellation_guard(oracle_port, tuning, kernel):
     assert not enabled
     ds.set_tuning(0, 0, 0, 0)
     again = ds.loglike_spectra(spectra, None, synth.NOISE_LEVEL, scale=1.0)
-    assert _lib.load().mdns_last_kernel() not in (b'clike_xtile_kernel', b'clike_dmma_kernel')
+    assert _lib.load().mdns_last_kernel() not in (b'clike_xtile_kernel',) + TENSOR
     assert rel_err(again, got) < TOL_XP
 
 
@@ -322,7 +328,7 @@ def test_clike_very_long_spectra(oracle_port, K):
     for name in ('all', 'half'):
         m = synth.masks(N)[name]
         got = ds.loglike_batch(pts, m, synth.NOISE_LEVEL, scale=1.0)
-        assert _lib.load().mdns_last_kernel().startswith(b'clike_dmma_kernel')
+        assert _lib.load().mdns_last_kernel() in TENSOR + TENSOR_GATHER
         for k in range(K):
             p = pts[k]
             want = oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, m)
@@ -704,7 +710,7 @@ def test_clike_full_size_properties():
     pts = synth.parameter_points(16, seed=3)
     pts[5, 0] = 0.0                                    # a candidate without a line
     full = ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0).copy()
-    assert lib.mdns_last_kernel() == b'clike_dmma_kernel'
+    assert lib.mdns_last_kernel() in TENSOR
     # (1) chi2(A=0) = sum (y/noise)^2 (plotevidences.py:17), numpy column sums in blocks
     want = numpy.empty(N)
     for lo in range(0, N, 100000):

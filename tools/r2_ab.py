@@ -26,13 +26,20 @@ def algo_bytes(n, nx, K):
 
 
 def timed(ds, reps):
-    for _ in range(3):
-        ds.launch_clike(0.01, -0.5)
-    ds.sync()
+    # warm up for >= 30 ms (clocks), then the best of three timed loops
     ds.timer_start()
-    for _ in range(reps):
+    for _ in range(10):
         ds.launch_clike(0.01, -0.5)
-    return ds.timer_stop() / reps
+    t10 = ds.timer_stop()
+    for _ in range(int(30.0 / max(t10 / 10, 1e-3))):
+        ds.launch_clike(0.01, -0.5)
+    best = 1e30
+    for _ in range(3):
+        ds.timer_start()
+        for _ in range(reps):
+            ds.launch_clike(0.01, -0.5)
+        best = min(best, ds.timer_stop() / reps)
+    return best
 
 
 def main():
@@ -41,7 +48,7 @@ def main():
     args = ap.parse_args()
     lib = _lib.load()
     res = {'kernel_ab': [], 'accept': []}
-    shapes = [(1000000, 200, 'horns'), (125000, 1000, 'realistic'), (500000, 1000, 'realistic')]
+    shapes = [(1000000, 200, 'horns')] if os.environ.get('AB_QUICK') else [(1000000, 200, 'horns'), (125000, 1000, 'realistic'), (500000, 1000, 'realistic')]
     for n, nx, kind in shapes:
         if kind == 'horns':
             x, y, _ = synth.horns(n, nx=nx, legacy=False, seed=1000)
@@ -49,11 +56,12 @@ def main():
             x, y, _ = synth.realistic(n, nx=nx)
         ds = ResidentDataset(x, y)
         ds.set_mask(None)
-        for K in (4, 8, 16, 32, 64):
+        for K in ((16,) if os.environ.get('AB_QUICK') else (4, 8, 16, 32, 64)):
             pts = synth.parameter_points(K, seed=7)
             ds.stage_params(pts)
             row = {'n': n, 'nx': nx, 'K': K}
-            for name, tun in (('auto', (0, 0, 0, 0)), ('old', (3, 1, 0, 0))):
+            for name, tun in (('old0', (3, 1, 0, 0)), ('auto', (0, 0, 0, 0)), ('old', (3, 1, 0, 0)), ('auto2', (0, 0, 0, 0)),
+                              ('mr4', (3, 0, min(K, 32) if K >= 8 else 8, 3))):
                 ds.set_tuning(*tun)
                 t = timed(ds, 30 if K <= 16 else 10)
                 gbs = algo_bytes(n, nx, K) / (t * 1e-3) / 1e9
@@ -79,7 +87,13 @@ def main():
             wins = numpy.bincount(numpy.argmax(L, axis=0), minlength=K)
             order = numpy.argsort(wins, kind='stable')
             pts_fa, L_fa = numpy.ascontiguousarray(pts[order]), L[order]
-            Lmins = numpy.max(L_fa[:K - 1], axis=0)
+            # thresholds half way between the best and the second best candidate where the last
+            # candidate wins, out of reach elsewhere: decisions do not hinge on the last bits
+            # (the summation order of a value depends on the launch geometry)
+            srt = numpy.sort(L_fa, axis=0)
+            top, second = srt[-1], srt[-2]
+            sure = (numpy.argmax(L_fa, axis=0) == K - 1) & (top - second > 1e-6 * numpy.abs(top))
+            Lmins = numpy.where(sure, 0.5 * (top + second), top + 1e-6 * numpy.abs(top) + 1e-6)
             for label, chunks in (('dense_auto', 0), ('dense_1chunk', 1), ('dense_4', 4), ('dense_8', 8)):
                 ds.set_draw_chunks(chunks)
                 ds.begin_draw(None, Lmins)
@@ -89,13 +103,16 @@ def main():
                 for _ in range(50):
                     k, Lk, c = ds.draw_batch(pts_fa, 0.01)
                 dt = (time.perf_counter() - t0) / 50
-                ok = bool(k == K - 1 and numpy.array_equal(Lk, L_fa[K - 1]) and
+                ok = bool(k == K - 1 and numpy.allclose(Lk, L_fa[K - 1], rtol=1e-12, atol=0) and
                           numpy.array_equal(c, (L_fa > Lmins).sum(axis=1)))
-                res['accept'].append({'mode': label, 'ms': 1e3 * dt, 'ok': ok, 'k': int(k)})
+                res['accept'].append({'mode': label, 'ms': 1e3 * dt, 'ok': ok, 'k': int(k),
+                                      'L_rel': float(numpy.max(numpy.abs(Lk - L_fa[K - 1]) / numpy.abs(L_fa[K - 1]))),
+                                      'counts_diff': (c - (L_fa > Lmins).sum(axis=1)).tolist()})
                 print(res['accept'][-1], flush=True)
             ds.set_draw_chunks(0)
-            margin = L_fa[K - 1] - Lmins
-            Lmins_s = Lmins + max(float(numpy.quantile(margin, 0.99)), 0.0)
+            margin = numpy.where(sure, L_fa[K - 1] - Lmins, -1.0)
+            cut = float(numpy.quantile(margin[sure], 0.98))
+            Lmins_s = numpy.where(margin > cut * 1.01, Lmins, numpy.where(margin < cut * 0.99, top + 1e-6 * numpy.abs(top) + 1e-6, top + 1.0))
             ds.begin_draw(None, Lmins_s)
             for _ in range(3):
                 ks, js, Ljs, cs = ds.draw_batch_sparse(pts_fa, 0.01)
@@ -105,16 +122,17 @@ def main():
             dt = (time.perf_counter() - t0) / 50
             want_j = numpy.nonzero(L_fa[K - 1] > Lmins_s)[0]
             ok = bool(ks == K - 1 and numpy.array_equal(js, want_j) and
-                      numpy.array_equal(Ljs, L_fa[K - 1][want_j]))
+                      numpy.allclose(Ljs, L_fa[K - 1][want_j], rtol=1e-12, atol=0))
             res['accept'].append({'mode': 'sparse', 'ms': 1e3 * dt, 'ok': ok, 'n': int(len(want_j))})
             print(res['accept'][-1], flush=True)
             # a guess that turns out wrong: candidate 3 accepted only for the LAST data set
             Lm = numpy.max(L_fa, axis=0) + 1.0
-            Lm[n - 1] = L_fa[3, n - 1] - 1e-6
-            Lm[0] = L_fa[5, 0] - 1e-6
+            Lm[n - 1] = L_fa[3, n - 1] - 1e-6 * abs(L_fa[3, n - 1])
+            Lm[0] = L_fa[5, 0] - 1e-6 * abs(L_fa[5, 0])
             ds.begin_draw(None, Lm)
             k, Lk, c = ds.draw_batch(pts_fa, 0.01)
-            ok = bool(k == 3 and numpy.array_equal(Lk, L_fa[3]))
+            want_k = int(numpy.nonzero((L_fa > Lm).any(axis=1))[0][0])
+            ok = bool(k == want_k and numpy.allclose(Lk, L_fa[want_k], rtol=1e-12, atol=0))
             res['accept'].append({'mode': 'late_decision', 'ok': ok, 'k': int(k)})
             print(res['accept'][-1], flush=True)
         ds.close()
