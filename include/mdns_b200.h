@@ -186,9 +186,10 @@ int mdns_clike_draw_pass(mdns_dataset *ds, const uint8_t *mask, const double *Lm
 int mdns_clike_first_accept_sparse(mdns_dataset *ds, double noise, double scale, const double *Lmins,
                                    int *accept_counts, int *first_k, int32_t *idx_out,
                                    double *val_out, int64_t capacity, int *n_out);
-/* Two-step form for one process per GPU: accept_counts[K] of this process's data sets (to be
- * summed over the processes: an all-reduce of K integers is the only exchange of the sharded
- * path), then the logL vector of candidate k of the same launch. */
+/* Two-step form: accept_counts[K] alone (of this process's data sets; summed over the ranks when
+ * a communicator is attached, see mdns_comm_init), then -- if wanted -- the logL vector of any
+ * candidate k of the same launch.  For callers whose consumer lives on the device (the live-point
+ * table) or that run the exchange between processes themselves. */
 int mdns_clike_accept_counts(mdns_dataset *ds, double noise, double scale, const double *Lmins,
                              int *accept_counts);
 int mdns_fetch_candidate(mdns_dataset *ds, int k, double *Lout, int64_t lout_capacity);

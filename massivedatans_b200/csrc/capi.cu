@@ -1406,14 +1406,9 @@ int mdns_clike_accept_counts(mdns_dataset *ds, double noise, double scale, const
 	int rc = accept_check(ds, "mdns_clike_accept_counts", Lmins);
 	if (rc != MDNS_OK) return rc;
 	int first = -1;
-	if (ds->shards.size() == 1 && !ds->comm)
+	if (ds->shards.size() == 1)     // (with a communicator attached these are the GLOBAL counts)
 		return accept_pass_single(ds, noise, scale, WANT_COUNTS, accept_counts, &first, nullptr, nullptr,
 		                          nullptr, 0, nullptr);
-	if (ds->comm) {
-		set_error("mdns_clike_accept_counts: the data set has a communicator, the exchange is built "
-		          "into mdns_clike_first_accept");
-		return MDNS_ESTATE;
-	}
 	std::vector<int> shard_counts;
 	return accept_pass_multi(ds, noise, scale, accept_counts, &first, shard_counts);
 }

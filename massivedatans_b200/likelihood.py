@@ -98,6 +98,7 @@ class ResidentDataset(object):
         self._h = handle
         self.has_variance = variance is not None
         self._draw_n_act = None         # active data sets of the draw in progress (begin_draw)
+        self._draw_mask = None          # and a copy of its mask (None = all)
         self._comm = False
         self._finalizer = weakref.finalize(self, lib.mdns_dataset_destroy, handle)
 
@@ -148,8 +149,17 @@ class ResidentDataset(object):
             data_mask = self._mask(data_mask)
         _lib.check(self._lib.mdns_set_mask(self._h, _addr(data_mask), ctypes.byref(n)),
                    'mdns_set_mask')
-        self._draw_n_act = None         # thresholds of a draw in progress no longer apply
+        # the thresholds of a draw in progress are aligned with ITS mask (the shim keeps them when
+        # the same mask comes again, mdns_set_mask); any other mask ends the draw
+        if self._draw_n_act is not None and not self._same_as_draw_mask(data_mask):
+            self._draw_n_act = None
         return n.value
+
+    def _same_as_draw_mask(self, data_mask):
+        dm = self._draw_mask
+        if data_mask is None or dm is None:
+            return data_mask is None and dm is None
+        return numpy.array_equal(data_mask, dm)
 
     def _draw_state(self):
         if self._draw_n_act is None:
@@ -266,6 +276,7 @@ class ResidentDataset(object):
             Lmins = numpy.zeros(1)      # nothing to compare with; keeps the call sequence uniform
         _lib.check(self._lib.mdns_set_thresholds(self._h, _addr(Lmins)), 'mdns_set_thresholds')
         self._draw_n_act = n_act
+        self._draw_mask = None if data_mask is None else numpy.array(data_mask, dtype=bool, copy=True)
         return n_act
 
     def draw_batch(self, params, noise, scale=-0.5):
@@ -304,6 +315,7 @@ class ResidentDataset(object):
         if n_act == 0 and not self._comm:
             self.set_mask(m)
             self._draw_n_act = 0
+            self._draw_mask = None if m is None else m.copy()
             return -1, None, counts
         out = _pool.empty(n_act)
         first = ctypes.c_int(-1)
@@ -312,18 +324,22 @@ class ResidentDataset(object):
                                                   _addr(out), out.size, None),
                    'mdns_clike_draw_pass')
         self._draw_n_act = n_act
+        if not self._same_as_draw_mask(m):
+            self._draw_mask = None if m is None else m.copy()
         if first.value < 0:
             return -1, None, counts
         return first.value, out, counts
 
     def draw_counts(self, params, noise, scale=-0.5):
-        """First step of the two-step form (one process per GPU): score the next K candidates of
-        the draw started with ``begin_draw`` and return the accept counts of THIS process's data
-        sets; see ``sharding.global_first_accepted`` for the exchange."""
+        """Counts only: score the next K candidates of the draw started with ``begin_draw`` and
+        return the accept counts -- of THIS process's data sets, or summed over the ranks when a
+        communicator is attached (``init_comm``).  The logL vectors stay on the device
+        (``fetch_candidate(k)`` downloads one; ``LiveTable`` consumes them in place).  Without a
+        communicator a caller may run the exchange itself: ``sharding.global_first_accepted``."""
         n_act = self._draw_state()
         K = self.stage_params(params)
         counts = numpy.zeros(K, dtype=numpy.int32)
-        if n_act > 0:
+        if n_act > 0 or self._comm:
             _lib.check(self._lib.mdns_clike_accept_counts(self._h, noise, scale, None, _addr(counts)),
                        'mdns_clike_accept_counts')
         return counts

@@ -74,6 +74,7 @@ class LiveTable(object):
         _lib.check(self._lib.mdns_livetable_stage_thresholds(self._h, self._dataset._h),
                    'mdns_livetable_stage_thresholds')
         self._dataset._draw_n_act = self.ndata
+        self._dataset._draw_mask = None
 
     def replace(self, rows, values):
         """live_pointsL[rows[d], d] = values[d] for every data set d with rows[d] >= 0."""

@@ -99,6 +99,45 @@ def realistic(N, nx=1000, seed=1):
     return x, y, dict(z=z)
 
 
+def realistic_fast(N, nx=1000, seed=1, threads=8, chunk=8192):
+    """The same spectra as `realistic` (same line parameters from the same RandomState) built
+    chunk by chunk on several host threads, directly in the channel-major orientation, with one
+    counter-based noise stream per chunk: 1e6 x 1000 (8 GB) in seconds instead of minutes.
+    Returns (x, y); the result does not depend on the number of threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    x = numpy.linspace(400, 800, nx)
+    rs = numpy.random.RandomState(seed)
+    z = rs.beta(2, 30, size=N) * 2
+    rest_wave = 440
+    width_broad = 10 ** rs.normal(3, 0.2, size=N) * rest_wave / 300000
+    width_narrow = 10 ** rs.normal(1, 0.2, size=N) * rest_wave / 300000
+    signal_level = 1. / (rs.power(1, size=N) * 100 + 2)
+    is_type1 = rs.uniform(size=N) < 0.5
+    height_broad = numpy.where(is_type1, 10 ** rs.normal(0, 0.2, size=N),
+                               10 ** rs.normal(-2, 0.2, size=N)) * signal_level
+    height_narrow = signal_level
+    y = numpy.empty((nx, N))
+    xc = x.reshape((-1, 1))
+
+    def work(lo):
+        hi = min(N, lo + chunk)
+        d = rest_wave - xc / (1. + z[lo:hi].reshape((1, -1)))          # mu - x/(1+z), [nx, chunk]
+        ym = numpy.exp(-0.5 * (d / width_broad[lo:hi]) ** 2)
+        ym *= height_broad[lo:hi]
+        t = numpy.exp(-0.5 * (d / width_narrow[lo:hi]) ** 2)
+        t *= height_narrow[lo:hi]
+        ym += t
+        rg = numpy.random.Generator(numpy.random.Philox(key=seed, counter=[0, 0, 0, lo]))
+        t = rg.standard_normal(size=ym.shape)
+        t *= NOISE_LEVEL
+        ym += t
+        y[:, lo:hi] = ym
+
+    with ThreadPoolExecutor(max(1, int(threads))) as pool:
+        list(pool.map(work, range(0, N, chunk)))
+    return x, y
+
+
 MUSE_NSPEC = 3600
 MUSE_NDATA = 4223
 MUSE_BANDS = ((1600, 1670), (1730, 1780), (1950, 2000), (2250, 2700), (2800, 3000))
