@@ -95,9 +95,10 @@ struct Shard {
 	int *d_tickets = nullptr;     // and its per-tile tickets (self-clearing)
 	// MUSE expanded form: y/v rows, their tensor maps, sum y^2/v per row, squared spectra, raw sums
 	double *YW = nullptr, *swyy = nullptr, *d_model2 = nullptr, *d_s1 = nullptr, *d_s2 = nullptr;
-	size_t model2_cap = 0, s12_cap = 0;
+	size_t model2_cap = 0, s12_cap = 0, s2_cap = 0;
 	alignas(64) unsigned char tmap256_w[128];
 	alignas(64) unsigned char tmap_gather_w[128];
+	bool has_muse_xp = false;     // resident y/v rows, Swyy and tensor maps of the expanded MUSE form
 	int *d_redo = nullptr;        // counters of the expanded kernel's direct-form fix-ups
 	int *d_redo_list = nullptr;   // and the rows to fix up in the current pass
 	bool counters_clear = false;  // per-pass counters already reset by the model kernel
@@ -181,6 +182,7 @@ struct mdns_dataset {
 	ncclComm_t comm = nullptr;
 	int comm_nranks = 1, comm_rank = 0;
 	int draw_chunks = 0;          // row chunks of the dense first-accept pass (0 = automatic)
+	bool muse_xp_last = false;    // the last mdns_muse_launch took the expanded form
 };
 
 static void shard_free(Shard &s)
@@ -381,6 +383,29 @@ int mdns_dataset_create(const double *x, const double *yy, const double *vv, int
 		               make_row_tensor_map(s.tmap_gather, s.Y, s.n, (long long)ds->pitch, 1) == MDNS_OK;
 		if (vv && (rc = upload_rows(s, vv, ndata, nx, ds->pitch, 1, &s.W)) != MDNS_OK)
 			return fail(rc);
+		if (vv) {
+			// expanded cmuselike form (muse_xp.cu): y/v rows, sum y^2/v per row, tensor maps of the
+			// two matrices the raw contraction streams
+			const size_t cbytes = (size_t)xtile_counter_capacity() * sizeof(int);
+			e = cudaMalloc((void **)&s.YW, (size_t)s.n * ds->pitch * sizeof(double));
+			if (e == cudaSuccess) e = cudaMalloc((void **)&s.swyy, (size_t)s.n * sizeof(double));
+			if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_redo, cbytes);
+			if (e == cudaSuccess) e = cudaMemsetAsync(s.d_redo, 0, cbytes, s.stream);
+			if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_redo_list, (size_t)s.n * sizeof(int));
+			if (e != cudaSuccess) {
+				set_error("device %d allocation failed: %s", s.device, cudaGetErrorString(e));
+				return fail(MDNS_ENOMEM);
+			}
+			if ((rc = launch_muse_prepare(s.Y, s.W, s.n, (long long)ds->pitch, nx, s.YW, s.swyy, s.stream)) !=
+			    MDNS_OK)
+				return fail(rc);
+			s.has_muse_xp =
+			    make_row_tensor_map(s.tmap256, s.YW, s.n, (long long)ds->pitch, 256) == MDNS_OK &&
+			    make_row_tensor_map(s.tmap256_w, s.W, s.n, (long long)ds->pitch, 256) == MDNS_OK &&
+			    make_row_tensor_map(s.tmap_gather, s.YW, s.n, (long long)ds->pitch, 1) == MDNS_OK &&
+			    make_row_tensor_map(s.tmap_gather_w, s.W, s.n, (long long)ds->pitch, 1) == MDNS_OK;
+			ds->resident_bytes += (int64_t)s.n * ds->pitch * 8 + (int64_t)s.n * 8;
+		}
 		if (s.has_tmap) {
 			// expanded form of the candidate-batch kernel: resident Syy per data set
 			e = cudaMalloc((void **)&s.syy, (size_t)s.n * sizeof(double));
@@ -1683,6 +1708,35 @@ int mdns_set_draw_chunks(mdns_dataset *ds, int nchunks)
 	return MDNS_OK;
 }
 
+// the kernels of one MUSE-type pass over one shard (capturable: no allocation, no synchronisation)
+static int muse_enqueue(mdns_dataset *ds, Shard &s, bool xp)
+{
+	const int K = ds->K;
+	LikeArgs a;
+	fill_args(ds, s, a);
+	a.noise2 = 1.0;
+	a.scale = 1.0;
+	a.out_stride = s.n;
+	if (!xp) return launch_muse(a, ds->tuning, s.sm_count, s.stream);
+	LikeArgs x = a;                  // the raw contraction: (y/v, m) -> S1, (1/v, m^2) -> S2
+	x.tmap256 = s.tmap256;
+	x.tmap256_b = s.tmap256_w;
+	x.tmap_gather = s.tmap_gather;
+	x.tmap_gather_b = s.tmap_gather_w;
+	x.out = s.d_s1;
+	x.out_b = s.d_s2;
+	x.out_stride = s.n_act;
+	int kt = ds->tuning.ktile;
+	if (kt != 8 && kt != 16 && kt != 32) kt = K > 16 ? 32 : K > 8 ? 16 : 8;
+	int stages = (ds->tuning.rows == 13 || ds->tuning.rows == 14 || ds->tuning.rows == 2) ? ds->tuning.rows : 3;
+	if (!rows_dmma_fits(x, kt, stages)) stages = 3;
+	int rc = launch_rows_dmma(x, kt, stages, true, 2, s.sm_count, s.stream);
+	if (rc != MDNS_OK) return rc;
+	a.swyy = s.swyy;
+	return launch_muse_xp_finalize(a, s.d_s1, s.d_s2, muse_xp_guard(ds->nx, ds->xp_tol), s.d_redo,
+	                               s.sm_count, s.stream);
+}
+
 int mdns_muse_launch(mdns_dataset *ds)
 {
 	if (!ds || ds->staged != 2) {
@@ -1693,17 +1747,104 @@ int mdns_muse_launch(mdns_dataset *ds)
 		set_error("data set has no variances: create it with vv");
 		return MDNS_ESTATE;
 	}
+	// batches of >= 3 spectra take the expanded form on the tensor path (tuning: lanes = 3 forces
+	// it from K = 1, lanes = 256 / 8 / 32 force the direct kernels)
+	const int K = ds->K;
+	const bool want_xp = ds->tuning.lanes == 3 ||
+	                     (ds->tuning.lanes == 0 && ds->tuning.allow_expanded && K >= MUSE_XP_MIN_K);
+	static const bool use_graph = []() {
+		const char *e = getenv("MDNS_NO_GRAPH");
+		return !(e && *e && *e != '0');
+	}();
+	ds->muse_xp_last = false;
 	for (auto &s : ds->shards) {
 		MDNS_CUDA(cudaSetDevice(s.device));
-		LikeArgs a;
-		fill_args(ds, s, a);
-		a.noise2 = 1.0;
-		a.scale = 1.0;
-		a.out_stride = s.n;
-		int rc = launch_muse(a, ds->tuning, s.sm_count, s.stream);
-		if (rc != MDNS_OK) return rc;
+		if (s.n_act == 0) continue;
+		const bool xp = want_xp && s.has_muse_xp;
+		int rc;
+		if (xp) {
+			const int Kpad = (int)round_up(K, KT_MAX);
+			rc = grow(&s.d_s1, &s.s12_cap, (size_t)Kpad * s.n_act, false);
+			if (rc == MDNS_OK) rc = grow(&s.d_s2, &s.s2_cap, (size_t)Kpad * s.n_act, false);
+			if (rc != MDNS_OK) return rc;
+			ds->muse_xp_last = true;
+		}
+		if (!use_graph) {
+			if ((rc = muse_enqueue(ds, s, xp)) != MDNS_OK) return rc;
+			continue;
+		}
+		Shard::GraphKey key;
+		key.K = K;
+		key.staged = xp ? 3 : 2;
+		key.n_act = s.n_act;
+		key.all_active = s.all_active ? 1 : 0;
+		key.lanes = ds->tuning.lanes;
+		key.unroll = ds->tuning.unroll;
+		key.ktile = ds->tuning.ktile;
+		key.rows = ds->tuning.rows;
+		key.allow_expanded = ds->tuning.allow_expanded ? 1 : 0;
+		key.xp_tol = ds->xp_tol;
+		key.model = s.d_model;
+		key.out = s.d_out;
+		key.in = s.d_s1;
+		key.smm = s.d_s2;
+		if (s.graph && key == s.graph_key) {
+			MDNS_CUDA(cudaGraphLaunch(s.graph, s.stream));
+			g_launches.fetch_add(s.graph_launches, std::memory_order_relaxed);
+			g_last_kernel.store(s.graph_kernel, std::memory_order_relaxed);
+			continue;
+		}
+		if (s.graph) {
+			cudaGraphExecDestroy(s.graph);
+			s.graph = nullptr;
+		}
+		const long long before = g_launches.load();
+		MDNS_CUDA(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+		rc = muse_enqueue(ds, s, xp);
+		cudaGraph_t g = nullptr;
+		const cudaError_t e = cudaStreamEndCapture(s.stream, &g);
+		if (rc != MDNS_OK) {
+			if (g) cudaGraphDestroy(g);
+			cudaGetLastError();
+			return rc;
+		}
+		if (e != cudaSuccess || !g) {
+			set_error("stream capture of the MUSE launch failed: %s", cudaGetErrorString(e));
+			return MDNS_ECUDA;
+		}
+		const cudaError_t ei = cudaGraphInstantiate(&s.graph, g, 0);
+		cudaGraphDestroy(g);
+		if (ei != cudaSuccess) {
+			s.graph = nullptr;
+			set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+			return MDNS_ECUDA;
+		}
+		s.graph_key = key;
+		s.graph_launches = g_launches.load() - before;
+		s.graph_kernel = g_last_kernel.load();
+		MDNS_CUDA(cudaGraphLaunch(s.graph, s.stream));
 	}
 	ds->launched = 2;
+	return MDNS_OK;
+}
+
+// After a synchronising call: rows the expanded MUSE form sent to the direct fix-up; data whose
+// candidates need it for more than 2 % of the rows goes back to the direct kernels.
+static int muse_xp_feedback(mdns_dataset *ds)
+{
+	if (!ds->muse_xp_last) return MDNS_OK;
+	for (auto &s : ds->shards) {
+		if (!s.has_muse_xp || s.n_act == 0) continue;
+		int redo = 0;
+		MDNS_CUDA(cudaSetDevice(s.device));
+		MDNS_CUDA(cudaMemcpyAsync(&redo, s.d_redo, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+		MDNS_CUDA(cudaStreamSynchronize(s.stream));
+		if (redo > 0) {
+			MDNS_CUDA(cudaMemsetAsync(s.d_redo, 0, sizeof(int), s.stream));
+			ds->xp_redo_total += redo;
+			if ((long long)redo * 50 > (long long)s.n_act) ds->tuning.allow_expanded = false;
+		}
+	}
 	return MDNS_OK;
 }
 
@@ -1785,6 +1926,7 @@ int mdns_fetch(mdns_dataset *ds, double *Lout, int64_t lout_capacity)
 		}
 	}
 	int rc = mdns_sync(ds);
+	if (rc == MDNS_OK) rc = muse_xp_feedback(ds);
 	if (rc != MDNS_OK) return rc;
 	for (auto &s : ds->shards) {
 		if (s.all_active || s.n_act == 0) continue;

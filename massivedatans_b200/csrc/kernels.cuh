@@ -15,6 +15,7 @@ namespace mdns {
 constexpr int ROW_ALIGN = 2;    // doubles (16 bytes)
 constexpr int XP_MIN_K = 3;     // smallest all-active batch that takes the expanded form by itself
 constexpr int XP_MIN_K_MASKED = 5;   // and the smallest masked one (gather4-fed tensor path)
+constexpr int MUSE_XP_MIN_K = 3; // smallest batch of spectra that takes the expanded cmuselike form
 constexpr int KT_MAX = 32;      // model buffers are padded to a multiple of this many candidates
 
 // in: channel-major chunk in[j*ld_in + c], j < nx, c < nb  (device staging)
@@ -139,6 +140,14 @@ bool rows_dmma_fits(const LikeArgs &a, int kt, int stages);
 size_t rows_dmma_workspace_doubles(int sm_count);
 int launch_rows_dmma(const LikeArgs &a, int kt, int stages, bool raw, int nmat, int sm_count,
                      cudaStream_t st);
+// cmuselike in expanded form (muse_xp.cu): resident y/v rows + sum y^2/v per row at upload; per
+// batch rows_dmma_kernel in raw mode (S1, S2; the second contraction squares the spectra on the
+// fly) and the finalize kernel (chi, guard, direct-form recomputation in place)
+int launch_muse_prepare(const double *Y, const double *W, long long n_rows, long long pitch, int nx,
+                        double *YW, double *swyy, cudaStream_t st);
+int launch_muse_xp_finalize(const LikeArgs &a, const double *S1, const double *S2, double guard,
+                            int *redo_total, int sm_count, cudaStream_t st);
+double muse_xp_guard(int nx, double tol);
 // out[r] = sum_j rows[r*pitch + j]^2 (rows: resident data sets or padded model spectra)
 int launch_row_sumsq(const double *rows, long long n_rows, long long pitch, int nx, double *out,
                      cudaStream_t st);

@@ -7,8 +7,9 @@
 //              with the cancellation guard + direct-form fix-up list of clike_xtile_kernel.cu and the
 //              accept test of hiermetriclearn.py:193 (`L > Lmins`) fused in: per-candidate counts of
 //              accepting data sets leave the kernel next to (or instead of) the logL matrix;
-//   EPI_RAW    S itself, for one or two (A, B) pairs in one launch: cmuselike.c:48-64 in expanded form
-//              needs S1 = (y/v) . m and S2 = (1/v) . m^2 (muse_xp_finalize_kernel turns them into chi2).
+//   EPI_RAW    S itself, for one or two row matrices in one launch, the second one contracted with
+//              the SQUARED batch: cmuselike.c:48-64 in expanded form needs S1 = (y/v) . m and
+//              S2 = (1/v) . m^2 (muse_xp_finalize_kernel turns them into chi2).
 //
 // Why stream-K.  The first tensor-path kernel (clike_dmma_kernel.cu, round 1) gave whole tiles to
 // CTAs round robin.  489 tiles on 296 resident CTAs (125 000 data sets x 1000 channels, one GPU's
@@ -36,6 +37,7 @@ constexpr int RD_ROWS = 256;                    // data sets per tile = rows of 
 constexpr int RD_BOX_CH = 16;                   // channels per box row = 128 bytes (swizzle span)
 constexpr int RD_STAGE_BYTES = RD_ROWS * RD_BOX_CH * 8;
 constexpr int EPI_CLIKE = 0, EPI_RAW = 1;
+constexpr int RD_BLOCK_CH = 64;                 // summation block of the raw contraction (channels)
 
 __device__ __forceinline__ void rd_mbar_arrive(uint64_t *bar)
 {
@@ -125,18 +127,22 @@ __device__ __forceinline__ void rd_segment(const RdMine &m, int seg, int G, int 
 // STORE: the logL matrix is wanted.
 template <int NC, int MR, bool GATHER, bool FULL, bool COUNT, bool STORE>
 __device__ __forceinline__ void rd_epilogue_clike(const double (&acc)[MR][NC][2], const LikeArgs &a,
-                                                  const double *s_smm, int tile, int warp, int pr, int t,
+                                                  const double *s_smm, const double *s_syy,
+                                                  const double *s_lm, int tile, int warp, int pr, int t,
                                                   int kp0, int kp1, int k0, int kt_valid, int pass,
                                                   double inv, unsigned (&cntp)[NC])
 {
 	unsigned redo_mask = 0;
 #pragma unroll
 	for (int mr = 0; mr < MR; ++mr) {
-		const long long gr = (long long)tile * RD_ROWS + warp * (8 * MR) + mr * 8 + pr;
+		const int lr = warp * (8 * MR) + mr * 8 + pr;            // row within the tile
+		const long long gr = (long long)tile * RD_ROWS + lr;
 		const bool live = FULL || gr < a.n_rows;
-		const double syy = !live ? 0.0 : GATHER ? __ldg(a.syy + a.active[gr]) : __ldg(a.syy + a.row0 + gr);
+		// Syy (and the threshold) of the tile's rows were prefetched into shared memory while the
+		// tile was being contracted (rd_prefetch_rows): no exposed load latency here
+		const double syy = live ? s_syy[lr] : 0.0;
 		double lm = 0.0;
-		if (COUNT) lm = live ? __ldg(a.lmins + gr) : __longlong_as_double(0x7ff0000000000000LL);
+		if (COUNT) lm = live ? s_lm[lr] : __longlong_as_double(0x7ff0000000000000LL);
 		double *o0 = nullptr, *o1 = nullptr;
 		if (STORE) {
 			o0 = a.out + (long long)(k0 + kp0) * a.out_stride + gr;
@@ -172,8 +178,35 @@ __device__ __forceinline__ void rd_epilogue_clike(const double (&acc)[MR][NC][2]
 	}
 }
 
+// Per-row epilogue inputs of a tile (Syy, accept threshold) fetched asynchronously into shared
+// memory (cp.async, no registers held across the contraction); every warp fetches and later
+// reads only its own rows, so a warp-level wait is all the synchronisation needed.
+__device__ __forceinline__ void rd_cp_async8(double *smem_dst, const double *gmem_src)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src)
+	             : "memory");
+}
+
+template <int MR, bool GATHER>
+__device__ __forceinline__ void rd_prefetch_rows(const LikeArgs &a, double *s_syy, double *s_lm, int tile,
+                                                 int warp, int pr, int t)
+{
+	if (t == 0) {
+#pragma unroll
+		for (int mr = 0; mr < MR; ++mr) {
+			const int lr = warp * (8 * MR) + mr * 8 + pr;
+			const long long gr = (long long)tile * RD_ROWS + lr;
+			if (gr < a.n_rows) {
+				rd_cp_async8(s_syy + lr, GATHER ? a.syy + a.active[gr] : a.syy + a.row0 + gr);
+				if (a.lmins) rd_cp_async8(s_lm + lr, a.lmins + gr);
+			}
+		}
+	}
+	asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 template <int NC, int STAGES, int MR, bool GATHER, int EPI>
-__global__ void __launch_bounds__(RD_ROWS / (8 * MR) * 32 + (GATHER ? 64 : 32)) rows_dmma_kernel(
+__global__ void __launch_bounds__(RD_ROWS / (8 * MR) * 32 + (GATHER ? 64 : 32), (NC == 2 && MR == 4) ? 2 : 1) rows_dmma_kernel(
     const __grid_constant__ CUtensorMap tmapA0, const __grid_constant__ CUtensorMap tmapA1,
     const __grid_constant__ CUtensorMap tmapB0, const __grid_constant__ CUtensorMap tmapB1,
     const LikeArgs a, const int k0, const int kt_valid, const int pass, const int nmat)
@@ -186,6 +219,7 @@ __global__ void __launch_bounds__(RD_ROWS / (8 * MR) * 32 + (GATHER ? 64 : 32)) 
 	extern __shared__ __align__(1024) unsigned char smem_raw[];
 	__shared__ uint64_t full_bar[STAGES], empty_bar[STAGES];
 	__shared__ double s_smm[KT];
+	__shared__ double s_syy[RD_ROWS], s_lm[RD_ROWS];
 	__shared__ int s_counts[KT];
 	__shared__ int s_last;
 	__shared__ RdMine s_mine;
@@ -299,6 +333,17 @@ __global__ void __launch_bounds__(RD_ROWS / (8 * MR) * 32 + (GATHER ? 64 : 32)) 
 			for (int mr = 0; mr < MR; ++mr)
 #pragma unroll
 				for (int nc = 0; nc < NC; ++nc) acc[mr][nc][0] = acc[mr][nc][1] = 0.0;
+			if (EPI == EPI_CLIKE) rd_prefetch_rows<MR, GATHER>(a, s_syy, s_lm, tile, warp, pr, t);
+			// raw contractions (long MUSE spectra) are summed in blocks of RD_BLOCK_CH channels: the
+			// rounding-error bound of a sum of C terms drops from ~C*u to ~(B + C/B)*u, which is
+			// what lets the expanded cmuselike form vouch for well-fitting candidates (muse_xp.cu)
+			double acc2[EPI == EPI_RAW ? MR : 1][EPI == EPI_RAW ? NC : 1][2];
+			if (EPI == EPI_RAW) {
+#pragma unroll
+				for (int mr = 0; mr < MR; ++mr)
+#pragma unroll
+					for (int nc = 0; nc < NC; ++nc) acc2[mr][nc][0] = acc2[mr][nc][1] = 0.0;
+			}
 			for (int c = cs; c < ce; ++c, ++it) {
 				const int stage = it % STAGES;
 				const uint32_t round = (uint32_t)(it / STAGES);
@@ -312,8 +357,11 @@ __global__ void __launch_bounds__(RD_ROWS / (8 * MR) * 32 + (GATHER ? 64 : 32)) 
 					for (int mr = 0; mr < MR; ++mr)
 						fa[mr] = *reinterpret_cast<const double *>(sbase + a_row_off + mr * 1024 + choff);
 #pragma unroll
-					for (int nc = 0; nc < NC; ++nc)
+					for (int nc = 0; nc < NC; ++nc) {
 						fb[nc] = *reinterpret_cast<const double *>(sbase + b_row_off + nc * 1024 + choff);
+						// second pair of the raw contraction: the SQUARED batch (cmuselike's sum m^2/v)
+						if (EPI == EPI_RAW && mat) fb[nc] *= fb[nc];
+					}
 #pragma unroll
 					for (int mr = 0; mr < MR; ++mr)
 #pragma unroll
@@ -322,6 +370,25 @@ __global__ void __launch_bounds__(RD_ROWS / (8 * MR) * 32 + (GATHER ? 64 : 32)) 
 				}
 				__syncwarp();
 				if (lane == 0) rd_mbar_arrive(&empty_bar[stage]);
+				if (EPI == EPI_RAW && ((c - cs) % (RD_BLOCK_CH / RD_BOX_CH)) == RD_BLOCK_CH / RD_BOX_CH - 1) {
+#pragma unroll
+					for (int mr = 0; mr < MR; ++mr)
+#pragma unroll
+						for (int nc = 0; nc < NC; ++nc)
+#pragma unroll
+							for (int i = 0; i < 2; ++i) {
+								acc2[mr][nc][i] += acc[mr][nc][i];
+								acc[mr][nc][i] = 0.0;
+							}
+				}
+			}
+			if (EPI == EPI_RAW) {
+#pragma unroll
+				for (int mr = 0; mr < MR; ++mr)
+#pragma unroll
+					for (int nc = 0; nc < NC; ++nc)
+#pragma unroll
+						for (int i = 0; i < 2; ++i) acc[mr][nc][i] += acc2[mr][nc][i];
 			}
 			if (cs != 0 || ce != nch) {
 				// a cut tile: park this CTA's partial sums; the last of the tile's CTAs to get here
@@ -391,9 +458,11 @@ __global__ void __launch_bounds__(RD_ROWS / (8 * MR) * 32 + (GATHER ? 64 : 32)) 
 				continue;
 			}
 			const bool full = kt_valid == KT && (long long)(tile + 1) * RD_ROWS <= a.n_rows;
+			asm volatile("cp.async.wait_all;" ::: "memory");
+			__syncwarp();
 #define RD_EPI(FULL, COUNT, STORE)                                                                       \
-	rd_epilogue_clike<NC, MR, GATHER, FULL, COUNT, STORE>(acc, a, s_smm, tile, warp, pr, t, kp0, kp1, k0, \
-	                                                      kt_valid, pass, inv, cntp)
+	rd_epilogue_clike<NC, MR, GATHER, FULL, COUNT, STORE>(acc, a, s_smm, s_syy, s_lm, tile, warp, pr, t, \
+	                                                      kp0, kp1, k0, kt_valid, pass, inv, cntp)
 			if (a.counts) {
 				if (a.out) {
 					if (full) RD_EPI(true, true, true); else RD_EPI(false, true, true);
@@ -472,15 +541,16 @@ static int launch_rd_inst(const LikeArgs &a, int nmat, int sm_count, cudaStream_
 	const long long kpad = (long long)round_up(a.K, KT_MAX);
 	int rc = make_row_tensor_map_box(&tb0, a.model, kpad, a.mpitch, KT);
 	if (rc != MDNS_OK) return rc;
-	rc = make_row_tensor_map_box(&tb1, nmat > 1 ? a.model_b : a.model, kpad, a.mpitch, KT);
-	if (rc != MDNS_OK) return rc;
+	tb1 = tb0;      // the second pair contracts with the same batch, squared on the fly
 	const int ntiles = ceil_div(a.n_rows, RD_ROWS);
 	const int nch = ceil_div(a.pitch, RD_BOX_CH);
 	const long long T = (long long)nmat * ntiles * nch;
-	// at least 8 chunks (256 KB of rows) per CTA on average
+	// at least 8 chunks (256 KB of rows) per CTA on average; problems too small to give every
+	// resident CTA 64 chunks run one CTA per SM (half as many partial tiles to exchange)
 	long long gx = (T + 7) / 8;
 	const long long resident = (long long)sm_count * occ;
 	if (gx > resident) gx = resident;
+	if (gx > sm_count && T / gx < 64) gx = T / 64 > sm_count ? T / 64 : sm_count;
 	if (gx < 1) gx = 1;
 	const int npass = ceil_div(a.K, KT);
 	if (EPI == EPI_CLIKE) {

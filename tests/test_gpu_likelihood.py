@@ -564,9 +564,17 @@ def test_muse_golden(golden):
     ypreds = numpy.array([synth.muse_template(nspec, phase=float(ph)) for ph in g['phases']])
     mask = g['mask']
     L = numpy.zeros((3, ndata))
+    ds.muse_loglike(ypreds, mask, L)                      # batch of 3: expanded form, tensor path
+    assert _lib.load().mdns_last_kernel().startswith(b'rows_dmma_kernel(raw')
+    assert rel_err(L[:, mask], g['Lout'][:, mask]) < TOL_XP
+    assert (L[:, ~mask] == 0).all()                       # cmuselike.c:49 -- untouched
+    ds.muse_loglike(ypreds, None, L)
+    assert rel_err(L, g['Lall']) < TOL_XP
+    ds.set_expanded(False)                                # the direct two-pass kernels
+    L = numpy.zeros((3, ndata))
     ds.muse_loglike(ypreds, mask, L)
     assert rel_err(L[:, mask], g['Lout'][:, mask]) < TOL
-    assert (L[:, ~mask] == 0).all()                       # cmuselike.c:49 -- untouched
+    assert (L[:, ~mask] == 0).all()
     ds.muse_loglike(ypreds, None, L)
     assert rel_err(L, g['Lall']) < TOL
     small = ResidentDataset(None, g['small_y'], variance=g['small_v'])
@@ -605,9 +613,14 @@ def test_muse_kernel_variants_and_batches(oracle_port, lanes, unroll, ktile, nda
     for mask in (numpy.ones(ndata, dtype=bool), rs.uniform(size=ndata) < 0.5):
         L = numpy.full((K, ndata), 3.0)
         ds.muse_loglike(ypreds, mask, L)
+        xp = _lib.load().mdns_last_kernel().startswith(b'rows_dmma_kernel(raw')
+        # automatic choice only: expanded form from K = 3 (spectra of two channels cancel so badly that
+        # the feedback switches it off again after the first pass)
+        assert not xp or lanes == 0
+        assert xp or lanes != 0 or nspec <= 2
         for k in range(K):
             want = oracle_port.cmuselike(y, v, ypreds[k], mask)
-            assert rel_err(L[k][mask], want[mask]) < TOL
+            assert rel_err(L[k][mask], want[mask]) < (TOL_XP if xp else TOL)
             assert (L[k][~mask] == 3.0).all()
 
 
@@ -629,6 +642,55 @@ def test_muse_block_kernel_many_rows_per_cta(oracle_port, groups, K):
     for k in range(K):
         want = oracle_port.cmuselike(y, v, ypreds[k], mask)
         assert rel_err(L[k][mask], want[mask]) < TOL
+
+
+@pytest.mark.parametrize('ndata,nspec,K', [(4223, 3600, 4), (4223, 3600, 16), (700, 360, 5), (50, 37, 3),
+                                           (9000, 1030, 37), (300, 8190, 9)])
+def test_muse_expanded_form_vs_oracle(oracle_port, ndata, nspec, K):
+    # cmuselike in expanded form: S1 = (y/v).m and S2 = (1/v).m^2 as two raw contractions on the
+    # FP64 tensor path (rows_dmma_kernel, stream-K over the channels), chi = Swyy - 2 s S1 + s^2 S2
+    y, v, t = synth.muse(ndata=ndata, nspec=nspec, seed=ndata + 7)
+    ds = ResidentDataset(None, y, variance=v)
+    ypreds = numpy.array([synth.muse_template(nspec, phase=0.05 + 0.11 * k) for k in range(K)])
+    rs = numpy.random.RandomState(ndata)
+    lib = _lib.load()
+    for mask in (numpy.ones(ndata, dtype=bool), rs.uniform(size=ndata) < 0.6):
+        L = numpy.full((K, ndata), 3.0)
+        for _ in range(2):                      # repeated launches: tickets and lists start clean
+            ds.muse_loglike(ypreds, mask, L)
+        assert lib.mdns_last_kernel().startswith(b'rows_dmma_kernel(raw')
+        for k in sorted(set((0, 1, K // 2, K - 1))):
+            want = oracle_port.cmuselike(y, v, ypreds[k], mask)
+            assert rel_err(L[k][mask], want[mask]) < 1e-9      # the contract; the guard enforces 1e-10
+            assert (L[k][~mask] == 3.0).all()
+    assert ds.expanded_stats()[0]
+
+
+def test_muse_expanded_form_cancellation_guard(oracle_port):
+    # a candidate that IS the template the cube was built from: chi is the noise alone, a few
+    # thousandths (and less) of Swyy.  The guard must send what it cannot vouch for to the direct
+    # fix-up, and data that needs it for more than 2 % of its rows switches the path off.
+    ndata, nspec, K = 3000, 3600, 4
+    y, v, t = synth.muse(ndata=ndata, nspec=nspec, seed=11)
+    y[:, ::7] = (t.reshape((-1, 1)) * numpy.linspace(100.0, 2000.0, len(y[0, ::7]))
+                 + numpy.random.RandomState(2).normal(size=(nspec, len(y[0, ::7]))) * numpy.sqrt(v[:, ::7]))
+    ds = ResidentDataset(None, y, variance=v)
+    ypreds = numpy.array([t] + [synth.muse_template(nspec, phase=0.2 * k) for k in range(1, K)])
+    mask = numpy.ones(ndata, dtype=bool)
+    L = numpy.zeros((K, ndata))
+    ds.muse_loglike(ypreds, mask, L)
+    assert _lib.load().mdns_last_kernel().startswith(b'rows_dmma_kernel(raw')
+    for k in range(K):
+        want = oracle_port.cmuselike(y, v, ypreds[k], mask)
+        assert rel_err(L[k], want) < 1e-9
+    enabled, redo = ds.expanded_stats()
+    assert redo >= ndata // 7 - 1            # the high signal-to-noise spectra were recomputed
+    assert not enabled                       # ... more than 2 % of the rows: direct kernels from now on
+    ds.muse_loglike(ypreds, mask, L)
+    assert _lib.load().mdns_last_kernel() == b'muse_block_kernel'
+    for k in range(K):
+        want = oracle_port.cmuselike(y, v, ypreds[k], mask)
+        assert rel_err(L[k], want) < TOL
 
 
 def test_muse_callable_matches_reference_wrapper(oracle_port):
