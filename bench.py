@@ -372,6 +372,9 @@ def run_ours(args):
         f = make_multi_loglikelihood(x, y, 0.01, devices=[device])
     ds = f.dataset
     if distributed:
+        # (NCCL prints its version banner to stdout at the first init when NCCL_DEBUG asks for it:
+        # rank 0's stdout carries the one JSON line and nothing else)
+        os.environ['NCCL_DEBUG'] = os.environ.get('MDNS_NCCL_DEBUG', 'WARN')
         sharding.init_comm_from_env(ds)
 
     def barrier():

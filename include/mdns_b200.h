@@ -67,6 +67,16 @@ typedef struct mdns_dataset mdns_dataset;
 int mdns_dataset_create(const double *x, const double *yy, const double *vv,
                         int ndata, int nx, const int *devices, int ndevices,
                         mdns_dataset **out);
+/*
+ * The same from files, without a host copy of the matrix (the loader half of sample.py:27-31,
+ * which reads the whole `y` into RAM: 8 GB at BASELINE configs[3]).  y_path / v_path: .npy files
+ * (numpy.save) holding the reference-layout matrix [nx][ndata], float64, C order; v_path may be
+ * NULL.  Column blocks are read with pread into a 64 MB pinned buffer, copied to the device and
+ * transposed there into the resident rows; every shard reads only its own columns.
+ * (The reference stores HDF5; h5py's `numpy.save(path, f['y'][()])` converts once.)
+ */
+int mdns_dataset_create_from_npy(const double *x, const char *y_path, const char *v_path,
+                                 const int *devices, int ndevices, mdns_dataset **out);
 int mdns_dataset_destroy(mdns_dataset *ds);
 int mdns_dataset_info(const mdns_dataset *ds, int *ndata, int *nx, int *nshards,
                       int64_t *resident_bytes);
@@ -364,8 +374,13 @@ double mdns_bootstrapped_maxdistance(const void *xx, int nsamples, int ndim,
 /*
  * One-shot likelihoods with the reference's exact C signatures (clike.c:34-40,
  * cmuselike.c:34-38).  The data matrix is made resident on first sight of
- * (pointer, shape) and re-used afterwards; a strided content fingerprint is
- * re-checked on every call and a changed matrix is uploaded again.
+ * (pointer, shape) and re-used afterwards.  The reference re-reads its arguments
+ * on every call (clike.c:72), so a cached matrix is re-validated on every call by
+ * hashing ALL of it (several host threads; ~25 ms per GB): any in-place edit is
+ * seen and the matrix is uploaded again.  At most two matrices stay resident
+ * (least recently used is dropped).  Callers that never modify a matrix in place
+ * can opt out of the full hash -- mdns_legacy_trust(1) or MDNS_LEGACY_TRUST=1:
+ * 256 probes only -- or, better, use the resident interface above.
  * mdns_clike_like accumulates into Lout as clike.c:72 does.
  */
 int mdns_clike_like(const void *x, const void *yy, int ndata, int nx, double A,
@@ -375,6 +390,10 @@ int mdns_cmuselike_like(const void *yy, const void *vv, const void *ypred,
                         const void *data_mask, int ndata, int nx, void *Lout);
 /* Drop every data set cached by the two functions above. */
 int mdns_legacy_reset(void);
+/* trust = 1: cached matrices are re-validated with 256 probes instead of a full hash (the caller
+ * vouches that they are not edited in place); 0: full hash (default); anything else: query.
+ * Returns the previous setting. */
+int mdns_legacy_trust(int trust);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,7 @@ SIGNATURES = {
     'mdns_host_alloc': (c_void_p, [c_int64]),
     'mdns_host_free': (c_int, [c_void_p]),
     'mdns_dataset_create': (c_int, [_P, _P, _P, c_int, c_int, _P, c_int, POINTER(c_void_p)]),
+    'mdns_dataset_create_from_npy': (c_int, [_P, c_char_p, c_char_p, _P, c_int, POINTER(c_void_p)]),
     'mdns_dataset_destroy': (c_int, [_P]),
     'mdns_dataset_info': (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int),
                                   POINTER(c_int64)]),
@@ -103,6 +104,7 @@ SIGNATURES = {
                                 _P, _P]),
     'mdns_cmuselike_like': (c_int, [_P, _P, _P, _P, c_int, c_int, _P]),
     'mdns_legacy_reset': (c_int, []),
+    'mdns_legacy_trust': (c_int, [c_int]),
 }
 
 _lib = None

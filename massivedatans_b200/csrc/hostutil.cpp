@@ -3,6 +3,8 @@
 
 #include <cmath>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 namespace mdns {
 
@@ -56,6 +58,52 @@ uint64_t fingerprint(const double *p, long long n)
 	mix(p[n - 1]);
 	mix((double)n);
 	return h;
+}
+
+// Content hash of a whole host array (every byte takes part): four independent multiply-rotate
+// lanes per thread, the array cut into one contiguous piece per thread, piece hashes combined in
+// order.  Memory-bandwidth bound: a 1.6 GB matrix takes a few tens of milliseconds on 8 threads.
+// Used by the legacy one-shot likelihood entry points, which must notice ANY in-place edit of a
+// matrix they hold a resident copy of (the reference re-reads its arguments on every call).
+static uint64_t hash_piece(const uint64_t *w, long long n)
+{
+	const uint64_t P1 = 0x9E3779B185EBCA87ULL, P2 = 0xC2B2AE3D27D4EB4FULL;
+	uint64_t a = P1, b = P2, c = P1 ^ P2, d = ~P1;
+	auto mix = [](uint64_t h, uint64_t v) {
+		h ^= v * 0xC2B2AE3D27D4EB4FULL;
+		h = (h << 31) | (h >> 33);
+		return h * 0x9E3779B185EBCA87ULL;
+	};
+	long long i = 0;
+	for (; i + 4 <= n; i += 4) {
+		a = mix(a, w[i]);
+		b = mix(b, w[i + 1]);
+		c = mix(c, w[i + 2]);
+		d = mix(d, w[i + 3]);
+	}
+	for (; i < n; ++i) a = mix(a, w[i]);
+	uint64_t h = mix(mix(mix(mix((uint64_t)n, a), b), c), d);
+	h ^= h >> 29;
+	h *= P2;
+	return h ^ (h >> 32);
+}
+
+uint64_t fingerprint_full(const double *p, long long n)
+{
+	if (n <= 0) return 0x51ED270B0F0F0F0FULL;
+	const uint64_t *w = reinterpret_cast<const uint64_t *>(p);   // doubles are 8-byte aligned
+	unsigned hw = std::thread::hardware_concurrency();
+	int nt = n < (1LL << 20) ? 1 : (int)(hw > 8 ? 8 : (hw ? hw : 1));
+	std::vector<uint64_t> part(nt, 0);
+	std::vector<std::thread> th;
+	const long long per = (n + nt - 1) / nt;
+	for (int t = 1; t < nt; ++t) {
+		const long long lo = t * per, hi = (t + 1) * per < n ? (t + 1) * per : n;
+		th.emplace_back([&part, w, lo, hi, t]() { part[t] = lo < hi ? hash_piece(w + lo, hi - lo) : 0; });
+	}
+	part[0] = hash_piece(w, per < n ? per : n);
+	for (auto &x : th) x.join();
+	return hash_piece(part.data(), nt);
 }
 
 }  // namespace mdns

@@ -148,6 +148,19 @@ int launch_muse_prepare(const double *Y, const double *W, long long n_rows, long
 int launch_muse_xp_finalize(const LikeArgs &a, const double *S1, const double *S2, double guard,
                             int *redo_total, int sm_count, cudaStream_t st);
 double muse_xp_guard(int nx, double tol);
+// the tcgen05 experiment (clike_i8_kernel.cu): cross term on the INT8 tensor path from 7-bit digit
+// planes of the FP64 operands (exact integer products, FP64 recombination)
+int i8_plane_pitch(int nx);
+long long i8_plane_rows(long long n);
+int i8_batch_rows(int K);
+int i8_digits();
+double i8_guard(int nx, double tol);
+int launch_i8_split(const double *rows, long long n_rows, long long pitch, int nx, int8_t *planes,
+                    long long plane_rows, int cp, double *scale, uint8_t *clear_flags, long long nflags,
+                    cudaStream_t st);
+int launch_clike_i8(const LikeArgs &a, const int8_t *planes_y, const double *scale_y, long long plane_rows_y,
+                    int8_t *planes_m, double *scale_m, uint8_t *flags, double tol, int sm_count,
+                    cudaStream_t st);
 // out[r] = sum_j rows[r*pitch + j]^2 (rows: resident data sets or padded model spectra)
 int launch_row_sumsq(const double *rows, long long n_rows, long long pitch, int nx, double *out,
                      cudaStream_t st);

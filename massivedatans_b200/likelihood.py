@@ -14,6 +14,7 @@ New, additive: ``ResidentDataset.loglike_batch`` scores K candidates in one pass
 """
 import ctypes
 import math
+import os
 import weakref
 
 import numpy
@@ -101,6 +102,41 @@ class ResidentDataset(object):
         self._draw_mask = None          # and a copy of its mask (None = all)
         self._comm = False
         self._finalizer = weakref.finalize(self, lib.mdns_dataset_destroy, handle)
+
+    @classmethod
+    def from_npy(cls, x, y_path, variance_path=None, devices=None):
+        """Data set made resident straight from .npy files holding the [nx, ndata] float64
+        matrices (numpy.save): the matrix never exists in host memory -- column blocks stream
+        through a 64 MB pinned buffer (sample.py:27-31 reads all of `y` into RAM instead)."""
+        lib = _lib.load()
+        _lib.require_device()
+        hdr = numpy.load(y_path, mmap_mode='r')
+        if hdr.ndim != 2 or hdr.dtype != numpy.float64:
+            raise ValueError('%s must hold a 2-d float64 array [nx, ndata]' % y_path)
+        nx, ndata = hdr.shape
+        del hdr
+        if x is not None:
+            x = numpy.ascontiguousarray(x, dtype=numpy.float64)
+            if x.shape != (nx,):
+                raise ValueError('x must have nx entries')
+        devs, ndev = None, 0
+        if devices is not None:
+            devs = numpy.ascontiguousarray(devices, dtype=numpy.int32)
+            ndev = len(devs)
+        handle = ctypes.c_void_p()
+        _lib.check(lib.mdns_dataset_create_from_npy(
+            _addr(x), os.fsencode(y_path), os.fsencode(variance_path) if variance_path else None,
+            _addr(devs), ndev, ctypes.byref(handle)), 'mdns_dataset_create_from_npy')
+        self = cls.__new__(cls)
+        self.nx, self.ndata = int(nx), int(ndata)
+        self._lib = lib
+        self._h = handle
+        self.has_variance = variance_path is not None
+        self._draw_n_act = None
+        self._draw_mask = None
+        self._comm = False
+        self._finalizer = weakref.finalize(self, lib.mdns_dataset_destroy, handle)
+        return self
 
     def close(self):
         self._finalizer()

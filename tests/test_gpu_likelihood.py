@@ -555,6 +555,81 @@ def test_legacy_like_symbol_accumulates(oracle_port):
     _lib.load().mdns_legacy_reset()
 
 
+@pytest.mark.parametrize('N,nx', [(5000, 200), (70001, 57)])
+def test_dataset_from_npy_file_is_the_same_resident_data(tmp_path, N, nx):
+    # the loader half of sample.py:27-31: the matrix goes file -> pinned block -> device, no host copy
+    x, y, _ = synth.horns(N, nx=nx, legacy=False, seed=N)
+    path = str(tmp_path / 'y.npy')
+    numpy.save(path, y)
+    a = ResidentDataset(x, y)
+    b = ResidentDataset.from_npy(x, path)
+    assert (b.nx, b.ndata) == (nx, N)
+    pts = synth.parameter_points(5, seed=1)
+    for mask in (None, synth.masks(N)['half']):
+        assert numpy.array_equal(a.loglike_batch(pts, mask, synth.NOISE_LEVEL),
+                                 b.loglike_batch(pts, mask, synth.NOISE_LEVEL))
+    # MUSE-type: data + variance files, two shards' worth of columns read separately
+    ym, vm, t = synth.muse(ndata=300, nspec=360)
+    numpy.save(str(tmp_path / 'ym.npy'), ym)
+    numpy.save(str(tmp_path / 'vm.npy'), vm)
+    c = ResidentDataset(None, ym, variance=vm)
+    d = ResidentDataset.from_npy(None, str(tmp_path / 'ym.npy'), str(tmp_path / 'vm.npy'))
+    allm = numpy.ones(300, dtype=bool)
+    La, Lb = numpy.zeros((1, 300)), numpy.zeros((1, 300))
+    c.muse_loglike(t, allm, La)
+    d.muse_loglike(t, allm, Lb)
+    assert numpy.array_equal(La, Lb)
+    with pytest.raises(_lib.MdnsError):
+        numpy.save(str(tmp_path / 'bad.npy'), y.astype(numpy.float32))
+        ResidentDataset.from_npy(x, str(tmp_path / 'bad.npy'))
+
+
+def test_legacy_like_sees_any_in_place_edit(oracle_port):
+    # round 1 re-validated a cached matrix with 256 strided probes: an edit between the probes
+    # was served stale.  The reference re-reads yy on every call (clike.c:72); the drop-in now
+    # hashes every byte by default, and keeps at most two matrices resident.
+    import os
+    lib = ctypes.CDLL(os.path.join(_lib.DROPIN_DIR, 'clike.so'))
+    lib.like.restype = ctypes.c_int
+    core = _lib.load()
+    core.mdns_legacy_reset()
+    assert core.mdns_legacy_trust(-1) == 0            # default: full hash
+    N, nx = 3000, 200
+    x, y, _ = synth.horns(N)
+    m = numpy.ones(N, dtype=bool)
+
+    def like(yy):
+        Lout = numpy.zeros(N)
+        assert lib.like(x.ctypes.data_as(ctypes.c_void_p), yy.ctypes.data_as(ctypes.c_void_p), N, nx,
+                        ctypes.c_double(0.5), ctypes.c_double(600.), ctypes.c_double(3.),
+                        ctypes.c_double(0.01), m.ctypes.data_as(ctypes.c_void_p),
+                        Lout.ctypes.data_as(ctypes.c_void_p)) == 0
+        return Lout
+
+    first = like(y)
+    assert rel_err(first, oracle_port.clike(x, y, 0.5, 600., 3., 0.01, m)) < TOL
+    step = (N * nx) // 256
+    cell = 5 * step + 1234                            # between two of the old probes
+    assert cell % step != 0 and cell != N * nx - 1
+    y.reshape(-1)[cell] += 0.25
+    second = like(y)
+    want = oracle_port.clike(x, y, 0.5, 600., 3., 0.01, m)
+    assert rel_err(second, want) < TOL and not numpy.array_equal(first, second)
+    # the opt-out: the caller vouches for immutability, the same edit now goes unnoticed
+    assert core.mdns_legacy_trust(1) == 0
+    y.reshape(-1)[cell] -= 0.25
+    stale = like(y)
+    assert numpy.array_equal(stale, second)
+    assert core.mdns_legacy_trust(0) == 1
+    assert rel_err(like(y), first) < TOL
+    # three matrices in turn: two stay resident, every answer is right
+    others = [synth.horns(N, seed=s)[1] for s in (5, 6)]
+    for _ in range(2):
+        for yy in [y] + others:
+            assert rel_err(like(yy), oracle_port.clike(x, yy, 0.5, 600., 3., 0.01, m)) < TOL
+    core.mdns_legacy_reset()
+
+
 # ------------------------------------------------------------------ MUSE ----
 def test_muse_golden(golden):
     g = golden('cmuselike')
