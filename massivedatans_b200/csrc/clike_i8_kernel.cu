@@ -21,12 +21,12 @@
 // guard keeps a result only if that bound is below the tolerance relative to chi2 and flags every
 // other data set for the direct-form fix-up, like the FP64 tensor path.
 //
-// Warp roles (one CTA per SM, 192 threads): warps 0-3 epilogue (TMEM lane quarters 0-3:
-// tcgen05.ld 32x32b, FP64 recombination, guard, accept test, logL stores), warp 4 TMA producer,
-// warp 5 TMEM allocation + MMA issue (one elected lane: tcgen05.mma.cta_group::1.kind::i8, operands
+// Warp roles (one CTA per SM, 320 threads): warps 0-7 epilogue (two per TMEM lane quarter:
+// tcgen05.ld 32x32b, exact 64-bit recombination, guard, logL stores), warp 8 TMA producer,
+// warp 9 TMEM allocation + MMA issue (one elected lane: tcgen05.mma.cta_group::1.kind::i8, operands
 // through 128-byte-swizzled K-major shared-memory descriptors, completion signalled with
 // tcgen05.commit on mbarriers).  Per 128-channel block the 7 candidate digit tiles (8 KB each) sit
-// in one of two B slots, the 7 data digit tiles (16 KB each) stream through a ring of 4 A slots.
+// in one of two B slots, the 7 data digit tiles (16 KB each) stream through a ring of 6 A slots.
 //
 // The digit planes of the resident rows are built once (1 byte per digit and channel: 7/8 of the
 // FP64 matrix, rows padded to 128 channels) and only when this path is asked for (tuning lanes = 5).
@@ -44,9 +44,10 @@ constexpr int I8_N = 64;                // candidates per tile (UMMA N)
 constexpr int I8_KB = 128;              // channels (bytes) per block = one 128-byte swizzle row
 constexpr int I8_A_BYTES = I8_M * I8_KB;    // 16 KB
 constexpr int I8_B_BYTES = I8_N * I8_KB;    // 8 KB
-constexpr int I8_A_SLOTS = 4;
+constexpr int I8_A_SLOTS = 6;
 constexpr int I8_B_SLOTS = 2;
-constexpr int I8_THREADS = 192;
+constexpr int I8_EPI_WARPS = 8;             // two per TMEM lane quarter: 32 of the 64 columns each
+constexpr int I8_THREADS = (I8_EPI_WARPS + 2) * 32;
 constexpr size_t I8_SMEM = (size_t)I8_A_SLOTS * I8_A_BYTES + (size_t)I8_B_SLOTS * I8_S * I8_B_BYTES + 1024;
 
 // ---- digit planes -----------------------------------------------------------------------------
@@ -127,6 +128,19 @@ __device__ __forceinline__ void i8_mma(uint32_t tmem_d, uint64_t desc_a, uint64_
 	    : "memory");
 }
 
+// the same with the accumulate flag known at compile time
+__device__ __forceinline__ void i8_mma_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc)
+{
+	asm volatile(
+	    "{\n\t"
+	    ".reg .pred p;\n\t"
+	    "setp.eq.b32 p, 0, 0;\n\t"
+	    "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%4, %4, %4, %4}, p;\n\t"
+	    "}\n" ::"r"(tmem_d),
+	    "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(0u)
+	    : "memory");
+}
+
 __device__ __forceinline__ void i8_commit(uint64_t *bar)
 {
 	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -159,6 +173,18 @@ __device__ __forceinline__ void i8_tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 	    : "memory");
 }
 
+__device__ __forceinline__ void i8_tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+	asm volatile(
+	    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+	    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+	    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+	      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+	      "=r"(r[15])
+	    : "r"(taddr)
+	    : "memory");
+}
+
 struct I8Args {
 	int n_rows, K, nct, nrt, nkb;
 	long long plane_rows_y;       // rows per digit plane of the data (multiple of 128)
@@ -168,6 +194,7 @@ struct I8Args {
 	long long out_stride;
 	uint8_t *flags;               // rows the guard could not vouch for
 	double guard, inv;
+	int dbg;                      // measurement knob (MDNS_I8_DBG): 1 = no recombination/stores, 2 = no TMEM reads either
 };
 
 __global__ void __launch_bounds__(I8_THREADS, 1) clike_i8_kernel(const __grid_constant__ CUtensorMap tmapY,
@@ -195,10 +222,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) clike_i8_kernel(const __grid_co
 			mbar_init(&empty_b[i], 1);
 		}
 		mbar_init(&tmem_full, 1);
-		mbar_init(&tmem_empty, 4);
+		mbar_init(&tmem_empty, I8_EPI_WARPS);
 		mbar_fence_init();
 	}
-	if (warp == 5) {
+	if (warp == I8_EPI_WARPS + 1) {
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
 		             "r"(512u)
 		             : "memory");
@@ -209,7 +236,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) clike_i8_kernel(const __grid_co
 	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 	const uint32_t tmem = s_tmem;
 
-	if (warp == 4) {
+	if (warp == I8_EPI_WARPS) {
 		// ===================== TMA producer =====================
 		if (lane == 0) {
 			int ia = 0, ib = 0;
@@ -232,7 +259,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) clike_i8_kernel(const __grid_co
 				}
 			}
 		}
-	} else if (warp == 5) {
+	} else if (warp == I8_EPI_WARPS + 1) {
 		// ===================== MMA issuer =====================
 		if (lane == 0) {
 			// instruction descriptor: D = S32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), both
@@ -246,19 +273,31 @@ __global__ void __launch_bounds__(I8_THREADS, 1) clike_i8_kernel(const __grid_co
 				for (int kb = 0; kb < a.nkb; ++kb, ++ib) {
 					const int sb = ib % I8_B_SLOTS;
 					mbar_wait(&full_b[sb], (ib / I8_B_SLOTS) & 1);
+					// descriptors differ only in the start-address field (bytes >> 4): everything below
+					// is additions of compile-time constants, the single issuing thread must not be
+					// the bottleneck (a first version built every descriptor from scratch: 125 cycles
+					// per MMA against a 32-cycle floor)
+					const uint64_t db0 = i8_smem_desc(smem_u32(smem_b + (size_t)sb * I8_S * I8_B_BYTES));
+#pragma unroll
 					for (int s = 0; s < I8_S; ++s, ++ia) {
 						const int sa = ia % I8_A_SLOTS;
 						mbar_wait(&full_a[sa], (ia / I8_A_SLOTS) & 1);
 						asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-						const uint32_t a_addr = smem_u32(smem_a + (size_t)sa * I8_A_BYTES);
+						const uint64_t da0 = i8_smem_desc(smem_u32(smem_a + (size_t)sa * I8_A_BYTES));
 						// digit s+1 of the data pairs with the digits t+1 <= P - (s+1) of the batch
-						for (int t = 0; t + s + 2 <= I8_P && t < I8_S; ++t) {
-							const uint32_t b_addr = smem_u32(smem_b + ((size_t)sb * I8_S + t) * I8_B_BYTES);
+#pragma unroll
+						for (int t = 0; t < I8_S; ++t) {
+							if (t + s + 2 > I8_P) continue;
 							const uint32_t d = tmem + (uint32_t)((s + t) * I8_N);     // accumulator p - 2
 #pragma unroll
-							for (int ks = 0; ks < I8_KB / 32; ++ks)
-								i8_mma(d, i8_smem_desc(a_addr + ks * 32), i8_smem_desc(b_addr + ks * 32), idesc,
-								       (kb | s | ks) != 0 ? 1u : 0u);
+							for (int ks = 0; ks < I8_KB / 32; ++ks) {
+								const uint64_t da = da0 + (uint64_t)(ks * 2);
+								const uint64_t db = db0 + (uint64_t)(t * (I8_B_BYTES >> 4) + ks * 2);
+								if (s == 0 && ks == 0)
+									i8_mma(d, da, db, idesc, kb != 0 ? 1u : 0u);
+								else
+									i8_mma_acc(d, da, db, idesc);
+							}
 						}
 						i8_commit(&empty_a[sa]);       // arrives when the MMAs above have read the slot
 					}
@@ -268,46 +307,65 @@ __global__ void __launch_bounds__(I8_THREADS, 1) clike_i8_kernel(const __grid_co
 			}
 		}
 	} else {
-		// ===================== epilogue warps 0..3 (TMEM lanes 32 warp .. 32 warp + 31) =====================
+		// ===================== epilogue warps 0..7 =====================
+		// warp w reads TMEM lanes 32 (w % 4) .. +31 (its rows) and the columns 32 (w / 4) .. +31 of
+		// every accumulator (its candidates).  The seven integer sums of a (row, candidate) pair are
+		// recombined exactly in two 64-bit integers (weights 2^-26 and 2^-54 relative to the digit
+		// scale) -- two int->double conversions per result instead of seven.
+		const int q = warp & 3, half = warp >> 2;
 		int it = 0;
 		for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
 			const int rt = tile / a.nct, ct = tile - rt * a.nct;
-			const long long row = (long long)rt * I8_M + warp * 32 + lane;
+			const long long row = (long long)rt * I8_M + q * 32 + lane;
 			const bool live = row < a.n_rows;
 			const double sy = live ? a.scale_y[row] : 0.0;
 			const double syy = live ? a.syy[row] : 0.0;
+			// this lane's candidate of the warp's 32: broadcast by shuffle when its column comes up
+			const int kmine = ct * I8_N + half * 32 + lane;
+			const double smm_l = kmine < a.K ? __ldg(a.smm + kmine) : 0.0;
+			const double sm_l = kmine < a.K ? __ldg(a.scale_m + kmine) : 0.0;
 			mbar_wait(&tmem_full, it & 1);
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 			bool redo = false;
+			if (a.dbg == 2) {
+				asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+				__syncwarp();
+				if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty)) : "memory");
+				continue;
+			}
 #pragma unroll 1
-			for (int h = 0; h < I8_N / 32; ++h) {
-				double acc[32];
+			for (int c16 = 0; c16 < 2; ++c16) {
+				uint32_t g[I8_NACC][16];
+				const uint32_t col0 = (uint32_t)(half * 32 + c16 * 16);
 #pragma unroll
-				for (int j = 0; j < 32; ++j) acc[j] = 0.0;
-#pragma unroll 1
-				for (int p = I8_P; p >= 2; --p) {             // smallest weights first
-					uint32_t r[32];
-					i8_tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)((p - 2) * I8_N + h * 32), r);
-					asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-					const double w = __longlong_as_double((long long)(1023 - (7 * p - 2)) << 52);   // 2^-(7p-2)
-#pragma unroll
-					for (int j = 0; j < 32; ++j) acc[j] = fma((double)(int)r[j], w, acc[j]);
-				}
-				if (h == I8_N / 32 - 1) {
-					// the accumulators are in registers: hand TMEM back to the MMA warp
+				for (int p = 0; p < I8_NACC; ++p)
+					i8_tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * I8_N) + col0, g[p]);
+				asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+				if (c16 == 1) {
+					// everything this warp needs is in registers: hand TMEM back to the MMA warp
 					asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 					__syncwarp();
-					if (lane == 0) {
-						asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty))
-						             : "memory");
-					}
+					if (lane == 0)
+						asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty)) : "memory");
+				}
+				if (a.dbg == 1) {
+					if ((g[0][0] ^ g[3][7] ^ g[6][15]) == 0x7fffffffu) redo = true;      // keep the loads alive
+					continue;
 				}
 #pragma unroll
-				for (int j = 0; j < 32; ++j) {
-					const int kl = h * 32 + j, k = ct * I8_N + kl;
+				for (int j = 0; j < 16; ++j) {
+					const int kl = half * 32 + c16 * 16 + j, k = ct * I8_N + kl;
+					// accumulators p = 0..6 carry the weights 2^-12, 2^-19, ..., 2^-54
+					const long long ihi = ((long long)(int)g[0][j] << 14) + ((long long)(int)g[1][j] << 7) + (int)g[2][j];
+					const long long ilo = ((long long)(int)g[3][j] << 21) + ((long long)(int)g[4][j] << 14) +
+					                      ((long long)(int)g[5][j] << 7) + (int)g[6][j];
+					const double s26 = __longlong_as_double((long long)(1023 - 26) << 52);
+					const double s54 = __longlong_as_double((long long)(1023 - 54) << 52);
+					const double dot = fma((double)ilo, s54, (double)ihi * s26);
+					const double smm = __shfl_sync(0xffffffffu, smm_l, c16 * 16 + j);
+					const double sm = __shfl_sync(0xffffffffu, sm_l, c16 * 16 + j);
 					if (k < a.K) {                              // uniform over the warp
-						const double smm = __ldg(a.smm + k);
-						const double sym = acc[j] * (sy * __ldg(a.scale_m + k));
+						const double sym = dot * (sy * sm);
 						const double chi = syy + fma(-2.0, sym, smm);
 						const bool ok = chi >= a.guard * (syy + smm);   // false for NaN too
 						if (live) {
@@ -324,7 +382,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) clike_i8_kernel(const __grid_co
 	}
 	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 	__syncthreads();
-	if (warp == 5) {
+	if (warp == I8_EPI_WARPS + 1) {
 		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 	}
 }
@@ -438,6 +496,10 @@ int launch_clike_i8(const LikeArgs &a, const int8_t *planes_y, const double *sca
 	g.flags = flags;
 	g.guard = i8_guard(a.nx, tol);
 	g.inv = a.scale / a.noise2;
+	{
+		const char *e = getenv("MDNS_I8_DBG");
+		g.dbg = e ? atoi(e) : 0;
+	}
 	MDNS_CUDA(cudaFuncSetAttribute(clike_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM));
 	long long gx = (long long)g.nrt * g.nct;
 	if (gx > sm_count) gx = sm_count;

@@ -555,6 +555,63 @@ def test_legacy_like_symbol_accumulates(oracle_port):
     _lib.load().mdns_legacy_reset()
 
 
+@pytest.mark.parametrize('N,nx,K', [(3000, 200, 64), (70000, 200, 37), (2049, 57, 64), (500, 1000, 130),
+                                    (129, 16, 5)])
+def test_clike_tcgen05_int8_split_operand_path(oracle_port, N, nx, K):
+    # the north star's tcgen05 experiment (tuning lanes = 5): cross term on the INT8 tensor path from
+    # 7-bit digit planes of the FP64 operands (exact integer products in TMEM, FP64 recombination).
+    # Stated tolerance: the guard keeps a result only if the a-priori bound of the dropped digits is
+    # below xp_tol (1e-10) relative to chi2; measured error on horns data ~1e-14.
+    x, y, _ = synth.horns(N, nx=nx, legacy=False, seed=N + 2)
+    ds = ResidentDataset(x, y)
+    ds.set_tuning(5, 0, 0, 0)
+    pts = synth.parameter_points(K, seed=N + 3)
+    got = ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0)
+    ds.stage_params(pts)
+    ds.set_mask(None)
+    ds.launch_clike(synth.NOISE_LEVEL, 1.0)
+    assert _lib.load().mdns_last_kernel() == b'clike_i8_kernel'
+    again = numpy.empty((K, N))
+    ds.fetch(again)
+    allm = numpy.ones(N, dtype=bool)
+    for k in sorted(set((0, 7, 8, K // 2, K - 1))):
+        p = pts[k]
+        want = oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, allm)
+        assert rel_err(again[k], want) < TOL_XP
+    # a masked batch is not this path's business: it falls back to the automatic choice
+    m = synth.masks(N)['half']
+    got = ds.loglike_batch(pts[:3], m, synth.NOISE_LEVEL, scale=1.0)
+    assert _lib.load().mdns_last_kernel() != b'clike_i8_kernel'
+    assert rel_err(got[1], oracle_port.clike(x, y, pts[1][0], pts[1][1], pts[1][2], synth.NOISE_LEVEL, m)) < TOL_XP
+
+
+def test_clike_tcgen05_int8_path_cancellation_guard(oracle_port):
+    # data that a candidate fits to 1e-7 of its amplitude: the dropped digits would be the whole
+    # residual; the guard must flag those data sets and the direct form must recompute them
+    N, nx, K = 4096, 200, 8
+    x = numpy.linspace(400, 800, nx)
+    rs = numpy.random.RandomState(5)
+    pts = synth.parameter_points(K, seed=3)
+    pts[:, 0] = 50.0
+    pts[:, 2] = rs.uniform(20, 60, size=K)
+    y = rs.normal(0, 1e-2, size=(nx, N))
+    fitted = numpy.arange(N) % 3 == 0
+    spectra = numpy.array([p[0] * numpy.exp(-0.5 * ((p[1] - x) / p[2]) ** 2) for p in pts])
+    for i in numpy.nonzero(fitted)[0]:
+        y[:, i] = spectra[i % K] + rs.normal(0, 1e-6, size=nx)
+    ds = ResidentDataset(x, y)
+    ds.set_tuning(5, 0, 0, 0)
+    ds.set_mask(None)
+    ds.stage_spectra(spectra)
+    ds.launch_clike(synth.NOISE_LEVEL, 1.0)
+    assert _lib.load().mdns_last_kernel() == b'clike_i8_kernel'
+    got = numpy.empty((K, N))
+    ds.fetch(got)
+    want = (((spectra[:, :, None] - y[None, :, :]) / synth.NOISE_LEVEL) ** 2).sum(axis=1)
+    assert rel_err(got, want) < 1e-9
+    assert rel_err(got[:, ~fitted], want[:, ~fitted]) < TOL_XP
+
+
 @pytest.mark.parametrize('N,nx', [(5000, 200), (70001, 57)])
 def test_dataset_from_npy_file_is_the_same_resident_data(tmp_path, N, nx):
     # the loader half of sample.py:27-31: the matrix goes file -> pinned block -> device, no host copy
