@@ -149,11 +149,15 @@ class RadFriendsRegion(object):
         us = numpy.random.uniform(self.lo, self.hi, size=(n, ndim))
         return us[self.are_inside(us), :]
 
-    def _ball_round(self, n, ndim):
-        centres = self.members[numpy.random.randint(0, len(self.members), n), :]
+    def _ball_round(self, n, ndim, members=None, maxdistance=None):
+        # centres and radius from what the generator captured when it was created
+        # (radfriendsregion.py:118-119); the neighbour count below uses the live member set (:167)
+        members = self.members if members is None else members
+        maxdistance = self.maxdistance if maxdistance is None else maxdistance
+        centres = members[numpy.random.randint(0, len(members), n), :]
         direction = numpy.random.normal(0, 1, size=(n, ndim))
         direction = direction / ((direction ** 2).sum(axis=1) ** 0.5).reshape((-1, 1))
-        radius = self.maxdistance * numpy.random.uniform(0, 1, size=(n, 1)) ** (1. / ndim)
+        radius = maxdistance * numpy.random.uniform(0, 1, size=(n, 1)) ** (1. / ndim)
         us = centres + direction * radius
         nnear = self.count_nearby_members(us)
         coin = numpy.random.uniform(size=len(us))
@@ -173,7 +177,8 @@ class RadFriendsRegion(object):
         radfriendsregion.py:117-182: alternating rounds of box draws (kept if inside the region)
         and ball draws (thinned by 1/number of members nearby)."""
         n = self.PROPOSALS
-        ndim = numpy.shape(self.members)[1]
+        members, maxdistance = self.members, self.maxdistance     # captured once, as the reference does
+        ndim = numpy.shape(members)[1]
         spent_total = 0
         spent = 0
         while nmax == 0 or spent_total < nmax:
@@ -185,7 +190,7 @@ class RadFriendsRegion(object):
                 spent = 0
             spent += n
             spent_total += n
-            us = self._ball_round(n, ndim)
+            us = self._ball_round(n, ndim, members, maxdistance)
             if len(us):
                 yield us, spent
                 spent = 0

@@ -5,7 +5,11 @@ signature and return value ``(u, x, L, ntoaccept)`` (hiermetriclearn.py:173-196)
 multi_nested_sampler.py:462-472 and cachedconstrainer.py:19-114 call it unchanged.  With the same
 numpy seed it reproduces the reference draw by draw: the proposals come from the same
 ``numpy.random`` calls in the same order (region: clustering/radfriendsregion.py here, a bit-exact
-mirror; metric: clustering/sdml.py), the neighbour tests are bit-exact device kernels.
+mirror; metric: clustering/sdml.py), the neighbour tests are bit-exact device kernels.  The one
+qualification: logL agrees with clike.c to rounding (1e-13 in the direct form, within the enforced
+1e-10 in the expanded forms that speculative batches of >= 3 candidates take), so an accept test
+``L > Lmins`` can come out differently only where |L - Lmins| is below that -- a tie that no
+seeded run in tests/golden/constrainer.npz (1124 draws, 22 000 tries) contains.
 
 What is new is *speculation*.  The reference scores one candidate per likelihood call and stops
 at the first with ``numpy.any(L > Lmins)`` (hiermetriclearn.py:181-196).  The candidates of one
