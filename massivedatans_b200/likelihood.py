@@ -195,7 +195,7 @@ class ResidentDataset(object):
         dm = self._draw_mask
         if data_mask is None or dm is None:
             return data_mask is None and dm is None
-        return numpy.array_equal(data_mask, dm)
+        return data_mask is dm or numpy.array_equal(data_mask, dm)
 
     def _draw_state(self):
         if self._draw_n_act is None:
@@ -360,8 +360,7 @@ class ResidentDataset(object):
                                                   _addr(out), out.size, None),
                    'mdns_clike_draw_pass')
         self._draw_n_act = n_act
-        if not self._same_as_draw_mask(m):
-            self._draw_mask = None if m is None else m.copy()
+        self._draw_mask = m          # (by reference: the shim itself compares the bytes on every pass)
         if first.value < 0:
             return -1, None, counts
         return first.value, out, counts

@@ -2,9 +2,9 @@
 """Compile the reference's Python modules to sourceless bytecode under oracle/_ref/pyref/
 (TEST INFRASTRUCTURE; runs only where /root/reference exists, the outputs travel to the GPU box
 like the compiled reference C).  No reference source is copied: the .pyc files are build
-products of the files where they lie, importable because they sit where `name.py` would
-(PEP 3147 legacy layout).  tests/test_reference_stack_gpu.py imports the reference's own
-sampler stack from there and runs it on the product path.
+products of the files where they lie (written as `name.bc`: snapshot tools tend to drop `*.pyc`),
+imported through the small finder in oracle/pyref_loader.py.  tests/test_reference_stack_gpu.py
+imports the reference's own sampler stack from there and runs it on the product path.
 
     python oracle/compile_pyref.py [/root/reference]
 """
@@ -31,7 +31,7 @@ def main():
         src = os.path.join(REF, rel)
         if not os.path.exists(src):
             continue
-        dst = os.path.join(OUT, rel[:-3] + '.pyc')
+        dst = os.path.join(OUT, rel[:-3] + '.bc')
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         try:
             py_compile.compile(src, cfile=dst, dfile=rel, doraise=True)

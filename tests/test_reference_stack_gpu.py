@@ -1,6 +1,6 @@
 """The REFERENCE's own sampler stack (multi_nested_integrator.py, multi_nested_sampler.py,
 cachedconstrainer.py, hiermetriclearn.py, clustering/*.py -- imported as bytecode compiled from
-the unmodified files, oracle/compile_pyref.py) running on the product path on a GPU:
+the unmodified files: oracle/compile_pyref.py, oracle/pyref_loader.py) running on the product path on a GPU:
 
 * its `clustering/neighbors.py` loads `cneighbors.so` from its own directory (neighbors.py:97-99):
   the file placed there is the zero-edit drop-in veneer massivedatans_b200/dropin/cneighbors.so,
@@ -32,7 +32,7 @@ PYREF = os.path.join(ROOT, 'oracle', '_ref', 'pyref')
 
 @pytest.mark.timeout(1500)
 def test_reference_sampler_stack_runs_on_the_shim(golden):
-    if not os.path.exists(os.path.join(PYREF, 'multi_nested_sampler.pyc')):
+    if not os.path.exists(os.path.join(PYREF, 'multi_nested_sampler.bc')):
         pytest.skip('reference bytecode not built (make -C oracle where /root/reference exists)')
     sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
     import make_golden_sampler as mg          # its stubs and settings; nothing of it touches /root/reference here
@@ -55,7 +55,8 @@ def test_reference_sampler_stack_runs_on_the_shim(golden):
 
     for name in [m for m in sys.modules if m == 'clustering' or m.startswith('clustering.')]:
         del sys.modules[name]               # the reference's package, not ours, under that name
-    sys.path.insert(0, PYREF)
+    from oracle import pyref_loader
+    finder = pyref_loader.install(PYREF)
     try:
         import cachedconstrainer
         from cachedconstrainer import (CachedConstrainer, MetricLearningFriendsConstrainer,
@@ -93,7 +94,7 @@ def test_reference_sampler_stack_runs_on_the_shim(golden):
             results = multi_nested_integrator(tolerance=0.5, multi_sampler=sampler,
                                               min_samples=0, max_samples=0)
     finally:
-        sys.path.remove(PYREF)
+        pyref_loader.uninstall(finder)
         for name in [m for m in sys.modules if m == 'clustering' or m.startswith('clustering.')]:
             del sys.modules[name]
     logZ = numpy.asarray(results['logZ'], dtype=float)
