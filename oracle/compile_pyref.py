@@ -15,11 +15,17 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = sys.argv[1] if len(sys.argv) > 1 else '/root/reference'
 OUT = os.path.join(HERE, '_ref', 'pyref')
-WANTED = ['multi_nested_integrator.py', 'multi_nested_sampler.py', 'cachedconstrainer.py',
-          'hiermetriclearn.py', 'elldrawer.py', 'friends.py', 'whitenedmcmc.py',
-          'clustering/__init__.py', 'clustering/neighbors.py', 'clustering/radfriendsregion.py',
-          'clustering/sdml.py', 'clustering/jarvispatrick.py', 'clustering/mst.py',
-          'clustering/metriclearning.py']
+
+
+def wanted():
+    """every module of the reference's root and of its clustering package"""
+    out = []
+    for sub in ('', 'clustering'):
+        d = os.path.join(REF, sub)
+        for name in sorted(os.listdir(d)):
+            if name.endswith('.py'):
+                out.append(os.path.join(sub, name) if sub else name)
+    return out
 
 
 def main():
@@ -27,7 +33,7 @@ def main():
         print('reference tree %s not present: keeping prebuilt %s (if any)' % (REF, OUT))
         return
     n = 0
-    for rel in WANTED:
+    for rel in wanted():
         src = os.path.join(REF, rel)
         if not os.path.exists(src):
             continue
