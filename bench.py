@@ -374,7 +374,9 @@ def run_ours(args):
     if distributed:
         # (NCCL prints its version banner to stdout at the first init when NCCL_DEBUG asks for it:
         # rank 0's stdout carries the one JSON line and nothing else)
-        os.environ['NCCL_DEBUG'] = os.environ.get('MDNS_NCCL_DEBUG', 'WARN')
+        os.environ.pop('NCCL_DEBUG', None)
+        if os.environ.get('MDNS_NCCL_DEBUG'):
+            os.environ['NCCL_DEBUG'] = os.environ['MDNS_NCCL_DEBUG']
         sharding.init_comm_from_env(ds)
 
     def barrier():

@@ -1014,7 +1014,7 @@ static int ensure_i8(mdns_dataset *ds, Shard &s)
 		MDNS_CUDA(cudaMalloc((void **)&s.i8_flags, (size_t)s.i8_rows));
 		MDNS_CUDA(cudaMemsetAsync(s.i8_flags, 0, (size_t)s.i8_rows, s.stream));
 		int rc = launch_i8_split(s.Y, s.n, (long long)ds->pitch, ds->nx, s.i8_y, s.i8_rows, cp, s.i8_sy,
-		                         nullptr, 0, s.stream);
+		                         nullptr, 0, nullptr, s.stream);
 		if (rc != MDNS_OK) return rc;
 		ds->resident_bytes += (int64_t)bytes;
 	}

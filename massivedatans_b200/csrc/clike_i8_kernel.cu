@@ -58,8 +58,10 @@ __global__ void __launch_bounds__(256) i8_split_kernel(const double *__restrict_
                                                        long long pitch, int nx, int8_t *__restrict__ planes,
                                                        long long plane_rows, int cp,
                                                        double *__restrict__ scale,
-                                                       uint8_t *__restrict__ clear_flags, long long nflags)
+                                                       uint8_t *__restrict__ clear_flags, long long nflags,
+                                                       int *__restrict__ zero_word)
 {
+	if (zero_word && blockIdx.x == 0 && threadIdx.x == 0) *zero_word = 0;
 	const int lane = threadIdx.x & 31;
 	const long long warps = (long long)gridDim.x * 8;
 	for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < n_rows; r += warps) {
@@ -93,13 +95,14 @@ __global__ void __launch_bounds__(256) i8_split_kernel(const double *__restrict_
 
 int launch_i8_split(const double *rows, long long n_rows, long long pitch, int nx, int8_t *planes,
                     long long plane_rows, int cp, double *scale, uint8_t *clear_flags, long long nflags,
-                    cudaStream_t st)
+                    int *zero_word, cudaStream_t st)
 {
 	long long blocks = (n_rows + 7) / 8;
+	if (clear_flags && blocks < 148 * 4) blocks = 148 * 4;      // enough threads to clear the flags quickly
 	if (blocks > 148 * 16) blocks = 148 * 16;
 	if (blocks < 1) blocks = 1;
 	i8_split_kernel<<<(unsigned)blocks, 256, 0, st>>>(rows, n_rows, pitch, nx, planes, plane_rows, cp, scale,
-	                                                   clear_flags, nflags);
+	                                                   clear_flags, nflags, zero_word);
 	MDNS_LAUNCHED_HELPER("i8_split_kernel");
 	return MDNS_OK;
 }
@@ -387,34 +390,25 @@ __global__ void __launch_bounds__(I8_THREADS, 1) clike_i8_kernel(const __grid_co
 	}
 }
 
-// direct-form recomputation of the flagged rows, all K candidates (one warp per (row, candidate))
-__global__ void __launch_bounds__(256) i8_fixup_kernel(const LikeArgs a, const uint8_t *__restrict__ flags,
-                                                       int *__restrict__ redo_total)
+// rows the guard flagged -> list (16 flags per thread, one 128-bit load); the direct-form
+// recomputation of the listed rows is xtile_fixup_kernel's, shared with the FP64 tensor path
+__global__ void __launch_bounds__(256) i8_collect_kernel(const uint8_t *__restrict__ flags, long long n_rows,
+                                                         int *__restrict__ list, int *__restrict__ list_len)
 {
-	const int lane = threadIdx.x & 31;
-	const long long warps = (long long)gridDim.x * 8;
-	const double inv = a.scale / a.noise2;
-	for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < a.n_rows; r += warps) {
-		if (!flags[r]) continue;
-		const double *y = a.Y + r * a.pitch;
-		for (int k = 0; k < a.K; ++k) {
-			const double *m = a.model + (size_t)k * a.mpitch;
-			double s = 0.0;
-			for (int j = lane; j < a.nx; j += 32) {
-				const double d = m[j] - y[j];
-				s = fma(d, d, s);
-			}
+	const long long base = ((long long)blockIdx.x * 256 + threadIdx.x) * 16;
+	if (base >= n_rows) return;
+	const uint4 w = *reinterpret_cast<const uint4 *>(flags + base);      // the buffer is padded to 128 rows
+	if ((w.x | w.y | w.z | w.w) == 0) return;
+	const uint32_t words[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-			for (int o = 16; o > 0; o >>= 1) s += shfl_xor_f64(s, o);
-			if (lane == 0) {
-				const double val = s * inv;
-				if (a.out) a.out[(long long)k * a.out_stride + r] = val;
-				if (a.lmins && a.counts && val > a.lmins[r]) atomicAdd(a.counts + k, 1);
-			}
-		}
-		if (lane == 0) atomicAdd(redo_total, 1);
-	}
+	for (int q = 0; q < 4; ++q)
+#pragma unroll
+		for (int b = 0; b < 4; ++b)
+			if (((words[q] >> (8 * b)) & 0xffu) && base + 4 * q + b < n_rows)
+				list[atomicAdd(list_len, 1)] = (int)(base + 4 * q + b);
 }
+
+int launch_xtile_fixup(const LikeArgs &a, int k0, int kv, int pass, int sm_count, cudaStream_t st);
 
 // ---- host side ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFnI8)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -474,7 +468,7 @@ int launch_clike_i8(const LikeArgs &a, const int8_t *planes_y, const double *sca
 	const int mrows = i8_batch_rows(a.K);
 	// digit planes of the staged batch (+ reset of the row flags)
 	int rc = launch_i8_split(a.model, mrows < (int)round_up(a.K, KT_MAX) ? mrows : (long long)round_up(a.K, KT_MAX),
-	                         a.mpitch, a.nx, planes_m, mrows, cp, scale_m, flags, a.n_rows, st);
+	                         a.mpitch, a.nx, planes_m, mrows, cp, scale_m, flags, a.n_rows, a.xp_redo + 1, st);
 	if (rc != MDNS_OK) return rc;
 	CUtensorMap ty, tm;
 	if ((rc = i8_tensor_map(&ty, planes_y, (long long)I8_S * plane_rows_y, cp, I8_M)) != MDNS_OK) return rc;
@@ -505,11 +499,14 @@ int launch_clike_i8(const LikeArgs &a, const int8_t *planes_y, const double *sca
 	if (gx > sm_count) gx = sm_count;
 	clike_i8_kernel<<<(unsigned)gx, I8_THREADS, I8_SMEM, st>>>(ty, tm, g);
 	MDNS_LAUNCHED("clike_i8_kernel");
+	// flagged rows -> list -> direct-form recomputation of all K candidates of those rows
+	i8_collect_kernel<<<ceil_div(ceil_div(a.n_rows, 16), 256), 256, 0, st>>>(flags, a.n_rows, a.xp_list,
+	                                                                         a.xp_redo + 1);
+	MDNS_LAUNCHED_HELPER("i8_collect_kernel");
 	LikeArgs f = a;
 	f.lmins = nullptr;
 	f.counts = nullptr;
-	i8_fixup_kernel<<<2 * sm_count, 256, 0, st>>>(f, flags, a.xp_redo);
-	MDNS_LAUNCHED_HELPER("i8_fixup_kernel");
+	if ((rc = launch_xtile_fixup(f, 0, a.K, 0, sm_count, st)) != MDNS_OK) return rc;
 	return MDNS_OK;
 }
 

@@ -157,7 +157,7 @@ int i8_digits();
 double i8_guard(int nx, double tol);
 int launch_i8_split(const double *rows, long long n_rows, long long pitch, int nx, int8_t *planes,
                     long long plane_rows, int cp, double *scale, uint8_t *clear_flags, long long nflags,
-                    cudaStream_t st);
+                    int *zero_word, cudaStream_t st);
 int launch_clike_i8(const LikeArgs &a, const int8_t *planes_y, const double *scale_y, long long plane_rows_y,
                     int8_t *planes_m, double *scale_m, uint8_t *flags, double tol, int sm_count,
                     cudaStream_t st);

@@ -20,6 +20,12 @@ KEYS = [
     'sm__throughput.avg.pct_of_peak_sustained_elapsed',
     'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
     'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+    'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active',
+    'sm__ops_path_tensor_src_fp64.avg.pct_of_peak_sustained_elapsed',
+    'sm__ops_path_tensor_src_int8.avg.pct_of_peak_sustained_elapsed',
+    'sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.avg.pct_of_peak_sustained_elapsed',
+    'smsp__inst_executed.sum',
     'sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active',
     'smsp__issue_active.avg.pct_of_peak_sustained_active',
     'sm__warps_active.avg.pct_of_peak_sustained_active',
