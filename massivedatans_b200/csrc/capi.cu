@@ -263,7 +263,9 @@ static int upload_rows(Shard &s, const MatrixSource &src, int ndata, int nx, siz
                        double **rows_out)
 {
 	double *rows = nullptr;
-	const size_t row_bytes = (size_t)s.n * pitch * sizeof(double);
+	// (one spare row, zero: slab_dmma_kernel reads the rows in pairs when the pitch is an odd
+	// multiple of 64 bytes, and an odd count leaves half a pair behind the last row)
+	const size_t row_bytes = ((size_t)s.n + 1) * pitch * sizeof(double);
 	MDNS_CUDA(cudaMalloc((void **)&rows, row_bytes));
 	MDNS_CUDA(cudaMemsetAsync(rows, 0, row_bytes, s.stream));
 	// staging chunk: at most ~256 MB (64 MB when read from a file), a multiple of 32 data sets
@@ -443,7 +445,7 @@ static int dataset_create_impl(const double *x, const MatrixSource &yy, const Ma
 		if (vv) {
 			// expanded cmuselike form (muse_xp.cu): y/v rows, sum y^2/v per row, tensor maps of the
 			// two matrices the raw contraction streams
-			const size_t cbytes = (size_t)xtile_counter_capacity() * sizeof(int);
+			const size_t cbytes = (size_t)(slab_counter_base() + slab_counter_count()) * sizeof(int);
 			e = cudaMalloc((void **)&s.YW, (size_t)s.n * ds->pitch * sizeof(double));
 			if (e == cudaSuccess) e = cudaMalloc((void **)&s.swyy, (size_t)s.n * sizeof(double));
 			if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_redo, cbytes);
@@ -466,7 +468,7 @@ static int dataset_create_impl(const double *x, const MatrixSource &yy, const Ma
 		if (s.has_tmap) {
 			// expanded form of the candidate-batch kernel: resident Syy per data set
 			e = cudaMalloc((void **)&s.syy, (size_t)s.n * sizeof(double));
-			const size_t cbytes = (size_t)xtile_counter_capacity() * sizeof(int);
+			const size_t cbytes = (size_t)(slab_counter_base() + slab_counter_count()) * sizeof(int);
 			if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_redo, cbytes);
 			if (e == cudaSuccess) e = cudaMemsetAsync(s.d_redo, 0, cbytes, s.stream);
 			if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_redo_list, (size_t)s.n * sizeof(int));
@@ -939,7 +941,7 @@ static bool xp_candidate(const mdns_dataset *ds, const Shard &s)
 		if (ds->tuning.lanes == 3) return true;
 		return ds->tuning.lanes == 0 && ds->K >= XP_MIN_K_MASKED && ds->tuning.allow_expanded;
 	}
-	if (ds->tuning.lanes == 2 || ds->tuning.lanes == 3 || ds->tuning.lanes == 5) return true;   // explicit request
+	if (ds->tuning.lanes == 2 || ds->tuning.lanes == 3 || ds->tuning.lanes == 5 || ds->tuning.lanes == 6) return true;   // explicit request
 	return ds->tuning.lanes == 0 && ds->K >= XP_MIN_K && ds->tuning.allow_expanded;
 }
 

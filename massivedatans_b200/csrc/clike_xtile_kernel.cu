@@ -41,6 +41,7 @@ constexpr int XT_ROWS = 256;                    // data sets per tile = rows of 
 constexpr int XT_BOX_CH = 16;                   // channels per box row = 128 bytes (swizzle span)
 constexpr int XT_STAGE_BYTES = XT_ROWS * XT_BOX_CH * 8;
 constexpr int XT_MAX_COUNTERS = 1024;           // ints behind a.xp_redo: total + one per pass
+constexpr int slab_counter_base_dev = 1024, slab_counter_count_dev = 512;   // = slab_dmma_kernel.cu
 #ifndef XT_UNROLL
 #define XT_UNROLL 2
 #endif
@@ -68,6 +69,9 @@ __device__ __forceinline__ void xt_tma_load_2d(void *smem_dst, const CUtensorMap
 __global__ void __launch_bounds__(256) xtile_fixup_kernel(const LikeArgs a, const int k0,
                                                           const int kt_valid, const int pass)
 {
+	// (slab_dmma_kernel hands out its slabs through a counter behind the list lengths: back to
+	// zero for the next launch of this pass)
+	if (blockIdx.x == 0 && threadIdx.x == 0 && pass < slab_counter_count_dev) a.xp_redo[slab_counter_base_dev + pass] = 0;
 	const int n = a.xp_redo[1 + pass];
 	if (n == 0) return;
 	const int lane = threadIdx.x & 31;

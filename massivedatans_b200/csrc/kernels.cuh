@@ -128,6 +128,14 @@ int launch_clike_tile(const LikeArgs &a, const void *tmap, int kt, int nbox, int
 // kt in {8, 16, 32}, lane_rows in {2, 4}, stages in {2, 3}
 bool xtile_fits(const LikeArgs &a, int kt, int stages);
 int xtile_counter_capacity();
+// per-warp slabs with the candidate batch resident in shared memory (slab_dmma_kernel.cu): short
+// spectra, all rows active; kt in {8, 16}, nslot in {2, 3}.  Its slab counters live behind the
+// fix-up counters: [slab_counter_base(), + slab_counter_count())
+bool slab_dmma_fits(const LikeArgs &a, int kt, int nslot);
+int launch_slab_dmma(const LikeArgs &a, int kt, int nslot, int sm_count, cudaStream_t st);
+long long slab_dmma_slabs(const LikeArgs &a);   // slabs this launch would be cut into
+int slab_counter_base();
+int slab_counter_count();
 // the same expanded form with the cross term on the FP64 tensor path (clike_dmma_kernel.cu);
 // kt in {8, 16, 32}, stages in {2, 3, 4}
 bool dmma_fits(const LikeArgs &a, int kt, int stages);

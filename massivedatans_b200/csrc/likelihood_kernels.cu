@@ -660,6 +660,18 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		if (t.unroll == 1) return launch_clike_dmma(a, kt, stages, sm_count, st);
 		return launch_dmma_auto(a, kt, stages, sm_count, st, accept_fused);
 	}
+	if (L == 6 && !a.active) {
+		// expanded form, per-warp slabs with the batch resident in shared memory (short spectra)
+		const int kt = t.ktile == 8 ? 8 : 16;
+		const int nslot = t.rows == 2 ? 2 : 3;
+		if (slab_dmma_fits(a, kt, nslot)) {
+			if (accept_fused) *accept_fused = 1;
+			return launch_slab_dmma(a, kt, nslot, sm_count, st);
+		}
+		Tuning d;
+		d.allow_expanded = t.allow_expanded;
+		return launch_clike(a, d, sm_count, st, accept_fused);
+	}
 	if (L == 2 && !a.active) {
 		// expanded form, register-blocked over data sets (all-active rows only)
 		int kt = t.ktile;
@@ -694,7 +706,7 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		if (a.K >= 16 && dmma_fits(a, 16, 13)) return launch_dmma_auto(a, 16, 13, sm_count, st, accept_fused);
 		if (dmma_fits(a, 8, 13)) return launch_dmma_auto(a, 8, 13, sm_count, st, accept_fused);
 	}
-	if (L == 1 || L == 2 || L == 3) {
+	if (L == 1 || L == 2 || L == 3 || L == 6) {
 		// tile kernel requested but not applicable (masked rows): automatic choice
 		Tuning d;
 		d.allow_expanded = t.allow_expanded;
@@ -712,6 +724,19 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 			// (padded) candidates on the tensor path beats the lanes-across-channels kernels
 			// (K=4: 0.266 ms vs 0.289 ms block kernel).
 			if (a.K >= 32 && dmma_fits(a, 32, 3)) return launch_dmma_auto(a, 32, 3, sm_count, st, accept_fused);
+			// 9..31 candidates on short spectra: per-warp slabs, batch resident in shared memory
+			// (slab_dmma_kernel.cu).  Same box, 1e6 x 200, K=16: 0.281-0.284 ms (0.93-0.94 of the
+			// roofline) against 0.305-0.314 for the stream-K kernel; 192 channels 0.262 vs 0.282;
+			// K=24 (two passes of 16) 0.554 vs 0.596.  Two slots per warp beat three (0.288); up to
+			// 8 candidates the stream-K kernel stays ahead (0.258 vs 0.268 ms)
+			// Every warp runs its slabs one box at a time, two copies in flight: per-warp speed is
+			// latency-bound and the machine only saturates with every warp busy for several
+			// slabs.  Below ~2 slabs per warp the stream-K kernel wins (1e5 x 200: 0.057 ms
+			// against 0.082), which is also what the row chunks of the dense accept pass are
+			if (a.K > 8 && slab_dmma_fits(a, 16, 2) && slab_dmma_slabs(a) >= 2LL * 16 * sm_count) {
+				if (accept_fused) *accept_fused = 1;
+				return launch_slab_dmma(a, 16, 2, sm_count, st);
+			}
 			if (a.K >= 16 && dmma_fits(a, 16, 13)) return launch_dmma_auto(a, 16, 13, sm_count, st, accept_fused);
 			if (dmma_fits(a, 8, 14)) return launch_dmma_auto(a, 8, 14, sm_count, st, accept_fused);
 			const int xkt = a.K >= 16 && xtile_fits(a, 16, 2) ? 16 : 8;

@@ -11,7 +11,7 @@ import pytest
 
 # the FP64 tensor-path kernels: stream-K (round 2) and whole-tile (round 1, kept for the shapes
 # only it is instantiated for)
-TENSOR = (b'rows_dmma_kernel', b'clike_dmma_kernel')
+TENSOR = (b'rows_dmma_kernel', b'clike_dmma_kernel', b'slab_dmma_kernel')
 TENSOR_GATHER = (b'rows_dmma_kernel(gather)', b'clike_dmma_kernel(gather)')
 
 from conftest import rel_err
@@ -199,6 +199,64 @@ def test_clike_expanded_tensor_path_variants(oracle_port, ktile, stages, N, nx, 
     assert rel_err(got, fma_form) < TOL_XP
 
 
+@pytest.mark.parametrize('ktile,nslot', [(16, 3), (16, 2), (8, 3), (8, 2)])
+@pytest.mark.parametrize('N,nx,K', [
+    (70001, 200, 16),     # pitch 200 = 8 mod 16: rows read in line-aligned PAIRS, odd count
+    (64, 200, 16),        # exactly one slab of pairs
+    (33, 200, 3),         # one slab, half empty; 3 of 8/16 candidates valid
+    (1, 200, 16),
+    (4097, 192, 20),      # aligned pitch: single rows; two passes of 16, three of 8
+    (5000, 199, 9),       # odd channel count: pitch 200, channel 199 is padding
+    (3000, 57, 17),       # pitch 58: misaligned single rows, last box 10 channels
+    (3000, 40, 16),       # pitch 40: pairs with S = 2 (five boxes per pair)
+    (2000, 52, 8),        # pitch 52: last box 4 channels (k-steps of pure padding skipped)
+    (300000, 72, 16),     # many slabs per warp: the slab counter hands out > 2 per warp
+])
+def test_clike_slab_tensor_kernel(oracle_port, ktile, nslot, N, nx, K):
+    # per-warp slabs, candidate batch resident in shared memory (lanes = 6): short spectra
+    x, y, _ = synth.horns(N, nx=nx, legacy=False, seed=N + 12)
+    ds = ResidentDataset(x, y)
+    ds.set_tuning(6, 0, ktile, nslot)
+    pts = synth.parameter_points(K, seed=N + 13)
+    lib = _lib.load()
+    allm = numpy.ones(N, dtype=bool)
+    got = None
+    # (spectra shorter than the ring is deep fall back to the automatic choice)
+    pitch = nx + (nx & 1)
+    slab = pitch >= 16 * nslot
+    for rep in range(3):          # the slab counter must come back at zero after every launch
+        g = numpy.array(ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0))
+        assert (lib.mdns_last_kernel() == b'slab_dmma_kernel') == slab
+        assert got is None or numpy.array_equal(g, got)
+        got = g
+    for k in sorted(set((0, 1, 7, 8, K // 2, K - 2, K - 1)) & set(range(K))):
+        p = pts[k]
+        want = oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, allm)
+        assert rel_err(got[k], want) < TOL_XP, k
+    assert ds.expanded_stats() == (True, 0)
+    # the stream-K kernel sums the same channels in the same order
+    ds.set_tuning(3, 0, 16 if ktile == 16 else 8, 3)
+    ref = numpy.array(ds.loglike_batch(pts, None, synth.NOISE_LEVEL, scale=1.0))
+    assert lib.mdns_last_kernel() in TENSOR
+    assert rel_err(got, ref) < 1e-13
+    # fused accept test: counts and first accepted candidate against numpy on the same matrix
+    ds.set_tuning(6, 0, ktile, nslot)
+    L = -0.5 * got
+    srt = numpy.sort(L, axis=0)
+    Lmins = srt[-1] + 1.0 + numpy.abs(srt[-1])
+    pick = numpy.arange(N) % 7 == 3
+    if K > 1 and pick.any():
+        Lmins[pick] = 0.5 * (srt[-1][pick] + srt[-2][pick])
+    k, Lk, counts = ds.first_accepted(pts, None, Lmins, synth.NOISE_LEVEL)
+    want_counts = (L > Lmins).sum(axis=1)
+    assert numpy.array_equal(counts, want_counts)
+    if want_counts.any():
+        want_k = int(numpy.nonzero(want_counts)[0][0])
+        assert k == want_k and rel_err(Lk, L[want_k]) < 1e-13
+    else:
+        assert k == -1
+
+
 @pytest.mark.parametrize('ktile,stages', [(8, 2), (8, 14), (16, 3), (16, 13), (32, 3), (32, 12)])
 @pytest.mark.parametrize('N,nx,K', [(700, 203, 9), (70000, 200, 37), (2049, 57, 20)])
 def test_clike_expanded_tensor_path_masked_gather(oracle_port, ktile, stages, N, nx, K):
@@ -281,7 +339,9 @@ def test_clike_expanded_form_automatic_choice(oracle_port):
 @pytest.mark.parametrize('tuning,kernel', [((2, 2, 8, 3), b'clike_xtile_kernel'),
                                            ((3, 0, 8, 2), b'clike_dmma_kernel'),
                                            ((3, 0, 8, 3), b'rows_dmma_kernel'),
-                                           ((3, 0, 8, 13), b'rows_dmma_kernel')])
+                                           ((3, 0, 8, 13), b'rows_dmma_kernel'),
+                                           ((6, 0, 8, 3), b'slab_dmma_kernel'),
+                                           ((6, 0, 16, 2), b'slab_dmma_kernel')])
 def test_clike_expanded_form_cancellation_guard(oracle_port, tuning, kernel):
     # data that the candidate fits to ~1e-7 of its amplitude: Syy, Sym and Smm agree to 14
     # digits and their combination would be rounding noise.  Those (data set, candidate) pairs
@@ -313,7 +373,7 @@ def test_clike_expanded_form_cancellation_guard(oracle_port, tuning, kernel):
     assert not enabled
     ds.set_tuning(0, 0, 0, 0)
     again = ds.loglike_spectra(spectra, None, synth.NOISE_LEVEL, scale=1.0)
-    assert _lib.load().mdns_last_kernel() not in (b'clike_xtile_kernel',) + TENSOR
+    assert _lib.load().mdns_last_kernel() not in (b'clike_xtile_kernel', b'slab_dmma_kernel') + TENSOR
     assert rel_err(again, got) < TOL_XP
 
 
