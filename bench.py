@@ -507,6 +507,12 @@ def run_ours(args):
         fa_s, (k_acc, L_acc, counts) = timed(lambda: ds.draw_batch(pts_fa, 0.01))
         ok = bool(k_acc == want_k and numpy.array_equal(counts, want_counts) and
                   (k_acc < 0 or numpy.allclose(L_acc, L_fa[k_acc], rtol=1e-12, atol=0)))
+        # the common outcome of a speculative batch in a long rejection chain: nothing accepted,
+        # nothing but the counts comes back
+        ds.begin_draw(mask, out_of_reach)
+        rej_s, (k_rej, _, c_rej) = timed(lambda: ds.draw_batch(pts_fa, 0.01))
+        ok = ok and bool(k_rej == -1 and not numpy.any(c_rej))
+        ds.begin_draw(mask, Lmins)
         # counts only: the consumer is on the device (live-point table)
         dc_s, dcounts = timed(lambda: ds.draw_counts(pts_fa, 0.01))
         ok = ok and bool(numpy.array_equal(dcounts, want_counts))
@@ -536,7 +542,12 @@ def run_ours(args):
                            if distributed else 'single process: none'),
               'api': 'ResidentDataset.begin_draw(data_mask, Lmins) once, then '
                      'draw_batch(params, noise) per step (accept test fused into the likelihood '
-                     'kernel, decision on the device, download overlapped in row chunks)',
+                     'kernel, decision on the device; the rows of the accepted candidate are '
+                     'fetched only once a chunk decision names one, overlapped with the next chunk)',
+              'none_accepted': {'value': evals_per_step_all * args.steps / rej_s, 'unit': UNIT,
+                                'ms_per_step': 1e3 * rej_s / args.steps,
+                                'd2h_bytes_per_step': K * 4 * nsh,
+                                'note': 'same call, thresholds out of reach: every candidate rejected'},
               'sparse': {'value': evals_per_step_all * args.steps / fs_s, 'unit': UNIT,
                          'ms_per_step': 1e3 * fs_s / args.steps,
                          'accepting_data_sets': int(len(want_j)), 'matches_full_matrix': sparse_ok,

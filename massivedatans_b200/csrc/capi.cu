@@ -1268,18 +1268,21 @@ static int xp_feedback_value(mdns_dataset *ds, Shard &s, int redo)
 	return MDNS_OK;
 }
 
-// rows per chunk of the overlapped dense pass: the download of the selected candidate's rows of
-// chunk c runs on the copy stream while chunk c+1 is scored
+// Row chunks of the dense pass.  The accept counts so far are downloaded as soon as a chunk has
+// been scored; the host watches for them and, if they name a candidate ("first candidate accepted
+// by this process's rows so far"), starts the download of that candidate's rows of the chunk
+// while the next chunk is being scored -- and downloads NOTHING while no candidate has been accepted, which is
+// what most speculative passes of a long rejection chain end with.
 static int accept_chunks(const mdns_dataset *ds, const Shard &s)
 {
-	if (ds->draw_chunks > 0) return std::min(ds->draw_chunks, 8);
-	// measured at 1e6 data sets x 200 channels, K = 16 (8 MB vector): 1 chunk 0.50 ms, 4 chunks
-	// 0.46 ms, 8 chunks 0.53 ms end to end -- every chunk is a launch with its own stream-K tail
-	const long long bytes = (long long)s.n_act * 8;
-	if (bytes < (4 << 20)) return 1;
-	int nchunk = (int)std::min<long long>(4, bytes / (2 << 20));
-	while (nchunk > 1 && s.n_act / nchunk < 131072) --nchunk;
-	return nchunk;
+	if (ds->draw_chunks > 0) return std::min(ds->draw_chunks, 7);
+	// Measured at 1e6 data sets x 200 channels, K = 16 (tools/r2_chunks.py): one launch 0.473 ms
+	// when a candidate is accepted and 0.320 ms when none is; two halves 0.458 / 0.370 ms, four
+	// chunks 0.505 / 0.455 ms -- every extra launch of the tensor-path kernels costs more (ramp,
+	// tail) than the overlap of half a download returns, and most passes of a rejection chain
+	// accept nothing.  One launch unless asked otherwise.
+	(void)s;
+	return 1;
 }
 
 enum AcceptWant { WANT_COUNTS = 0, WANT_DENSE = 1, WANT_SPARSE = 2 };
@@ -1305,25 +1308,24 @@ static int accept_enqueue(mdns_dataset *ds, Shard &s, const AcceptPlan &p, const
 	MDNS_CUDA(cudaMemsetAsync(s.d_counts, 0, (size_t)Kpad * sizeof(int), s.stream));
 	int *sel_final = s.d_sel + block * p.nchunk;        // the decision of the whole pass
 	if (s.n_act > 0 && (rc = clike_model(ds, s)) != MDNS_OK) return rc;
-	int used_chunks = 0;
+	bool forked = false;
 	for (int r0 = 0, c = 0; r0 < s.n_act; r0 += p.per, ++c) {
 		const int nc = std::min(p.per, s.n_act - r0);
 		if ((rc = clike_rows(ds, s, p.noise, p.scale, r0, nc, true)) != MDNS_OK) return rc;
-		++used_chunks;
 		if (p.nchunk == 1) break;
 		// speculative pick of this chunk: the first candidate accepted by THIS process's rows so
-		// far -- the final (global) decision can only be an earlier candidate, checked afterwards
+		// far -- the final (global) decision can only be an earlier candidate, checked afterwards.
+		// (The last chunk needs none: the final decision follows at once.)
+		if (r0 + p.per >= s.n_act) break;
 		MDNS_CUDA(cudaMemcpyAsync(s.d_snap + (size_t)c * Kpad, s.d_counts, (size_t)K * sizeof(int),
 		                          cudaMemcpyDeviceToDevice, s.stream));
 		MDNS_CUDA(cudaEventRecord(s.ev_pick[c], s.stream));
 		MDNS_CUDA(cudaStreamWaitEvent(s.copy_stream, s.ev_pick[c], 0));
-		int *sel_c = s.d_sel + block * c;
-		if ((rc = launch_select_first(s.d_snap + (size_t)c * Kpad, K, nullptr, sel_c, s.copy_stream)) != MDNS_OK)
-			return rc;
-		if ((rc = launch_gather_selected(s.d_out, s.n_act, r0, nc, sel_c, s.d_pick, s.copy_stream)) != MDNS_OK)
-			return rc;
-		MDNS_CUDA(cudaMemcpyAsync(p.Lout + r0, s.d_pick + r0, (size_t)nc * sizeof(double),
-		                          cudaMemcpyDeviceToHost, s.copy_stream));
+		// (the snapshot goes down as it is and the host picks: a kernel on the side branch would
+		// wait for the next chunk to END -- slab_dmma_kernel leaves no register for anyone else)
+		MDNS_CUDA(cudaMemcpyAsync(s.h_sel + block * c + SEL_COUNTS, s.d_snap + (size_t)c * Kpad,
+		                          (size_t)K * sizeof(int), cudaMemcpyDeviceToHost, s.copy_stream));
+		forked = true;
 	}
 	// the exchange step: K integers summed over the ranks, on the stream, before the decision
 	if (ds->comm &&
@@ -1334,12 +1336,9 @@ static int accept_enqueue(mdns_dataset *ds, Shard &s, const AcceptPlan &p, const
 	if ((rc = launch_select_first(s.d_counts, K, xp_candidate(ds, s) ? s.d_redo : nullptr, sel_final,
 	                              s.stream)) != MDNS_OK)
 		return rc;
-	if (s.n_act > 0 && p.want == WANT_DENSE && p.nchunk == 1) {
-		if ((rc = launch_gather_selected(s.d_out, s.n_act, 0, s.n_act, sel_final, s.d_pick, s.stream)) != MDNS_OK)
-			return rc;
-		MDNS_CUDA(cudaMemcpyAsync(p.Lout, s.d_pick, (size_t)s.n_act * sizeof(double),
-		                          cudaMemcpyDeviceToHost, s.stream));
-	} else if (s.n_act > 0 && p.want == WANT_SPARSE) {
+	// (dense: the rows of the accepted candidate are fetched by the host once it knows there is
+	// one -- accept_pass_single)
+	if (s.n_act > 0 && p.want == WANT_SPARSE) {
 		if ((rc = launch_selected_flags(s.d_out, s.n_act, s.n_act, sel_final, s.d_lmins, s.d_flags,
 		                                s.stream)) != MDNS_OK)
 			return rc;
@@ -1358,11 +1357,8 @@ static int accept_enqueue(mdns_dataset *ds, Shard &s, const AcceptPlan &p, const
 			                          cudaMemcpyDeviceToHost, s.stream));
 		}
 	}
-	// decision blocks -> pinned host memory; the chunk blocks were written on the copy stream,
-	// which then joins the main stream again
-	if (p.nchunk > 1 && used_chunks > 0) {
-		MDNS_CUDA(cudaMemcpyAsync(s.h_sel, s.d_sel, block * used_chunks * sizeof(int),
-		                          cudaMemcpyDeviceToHost, s.copy_stream));
+	// the chunk decisions went down on the copy stream, which joins the main stream again here
+	if (forked) {
 		MDNS_CUDA(cudaEventRecord(s.ev_pick[7], s.copy_stream));
 		MDNS_CUDA(cudaStreamWaitEvent(s.stream, s.ev_pick[7], 0));
 	}
@@ -1406,6 +1402,9 @@ static int accept_pass_single(mdns_dataset *ds, double noise, double scale, Acce
 		const char *e = getenv("MDNS_NO_GRAPH");
 		return !(e && *e && *e != '0');
 	}();
+	// chunk decisions not yet down: a value no decision block can hold
+	constexpr int NOT_YET = -2;
+	for (int c = 0; c + 1 < p.nchunk; ++c) ((volatile int *)s.h_sel)[block * c + SEL_COUNTS] = NOT_YET;
 	// (a by-value candidate is a kernel argument; a collective is not captured: NCCL may still be
 	// connecting its channels at the first call on a communicator, which a capture forbids)
 	if (!use_graph || inline_single(ds) || ds->comm) {
@@ -1475,6 +1474,35 @@ static int accept_pass_single(mdns_dataset *ds, double noise, double scale, Acce
 		hit->used = ++s.agraph_clock;
 		MDNS_CUDA(cudaGraphLaunch(hit->exec, s.stream));
 	}
+	// ---- dense: watch the chunk decisions come down; rows of a chunk whose (speculative)
+	// decision names a candidate start their way to the host while the next chunk is scored
+	int fetched[8];
+	for (int c = 0; c < 8; ++c) fetched[c] = -1;
+	bool copying = false;
+	auto fetch_rows = [&](int c, int k) -> int {
+		const int r0 = c * p.per;
+		const int nc = std::min(p.per, s.n_act - r0);
+		MDNS_CUDA(cudaMemcpyAsync(Lout + r0, s.d_out + (size_t)k * s.n_act + r0, (size_t)nc * sizeof(double),
+		                          cudaMemcpyDeviceToHost, s.copy_stream));
+		fetched[c] = k;
+		copying = true;
+		return MDNS_OK;
+	};
+	if (want == WANT_DENSE) {
+		for (int c = 0; c + 1 < p.nchunk; ++c) {
+			volatile int *snap = (volatile int *)s.h_sel + block * c + SEL_COUNTS;
+			int spins = 0;
+			while (snap[0] == NOT_YET) {
+				// (an error on the stream, or a pass that is over, ends the wait)
+				if ((++spins & 1023) == 0 && cudaStreamQuery(s.stream) != cudaErrorNotReady) break;
+			}
+			if (snap[0] == NOT_YET) break;
+			int spec = -1;
+			for (int k = 0; k < K && spec < 0; ++k)
+				if (snap[k] > 0) spec = k;
+			if (spec >= 0 && (rc = fetch_rows(c, spec)) != MDNS_OK) return rc;
+		}
+	}
 	MDNS_CUDA(cudaStreamSynchronize(s.stream));
 	ds->launched = 1;
 	const int *hf = s.h_sel + block * p.nchunk;
@@ -1483,22 +1511,14 @@ static int accept_pass_single(mdns_dataset *ds, double noise, double scale, Acce
 	if (accept_counts)
 		for (int k = 0; k < K; ++k) accept_counts[k] = hf[SEL_COUNTS + k];
 	if ((rc = xp_feedback_value(ds, s, hf[SEL_REDO])) != MDNS_OK) return rc;
-	if (first < 0 || s.n_act == 0) return MDNS_OK;
-	if (want == WANT_DENSE && p.nchunk > 1) {
-		// chunks whose speculative pick was a later candidate than the final decision: fetch again
-		bool again = false;
-		for (int r0 = 0, c = 0; r0 < s.n_act; r0 += p.per, ++c) {
-			if (s.h_sel[block * c + SEL_FIRST] == first) continue;
-			const int nc = std::min(p.per, s.n_act - r0);
-			int *sel_final = s.d_sel + block * p.nchunk;
-			if ((rc = launch_gather_selected(s.d_out, s.n_act, r0, nc, sel_final, s.d_pick, s.stream)) != MDNS_OK)
-				return rc;
-			MDNS_CUDA(cudaMemcpyAsync(Lout + r0, s.d_pick + r0, (size_t)nc * sizeof(double),
-			                          cudaMemcpyDeviceToHost, s.stream));
-			again = true;
-		}
-		if (again) MDNS_CUDA(cudaStreamSynchronize(s.stream));
+	if (want == WANT_DENSE && first >= 0 && s.n_act > 0) {
+		// the chunks not on their way yet (the last one always), and those whose speculative
+		// pick was a later candidate than the final decision
+		for (int c = 0; c * p.per < s.n_act; ++c)
+			if (fetched[c] != first && (rc = fetch_rows(c, first)) != MDNS_OK) return rc;
 	}
+	if (copying) MDNS_CUDA(cudaStreamSynchronize(s.copy_stream));
+	if (first < 0 || s.n_act == 0) return MDNS_OK;
 	if (want == WANT_SPARSE) {
 		// (under a communicator the candidate's count is the global one; hf[3] is this process's)
 		const int mine = hf[3];
