@@ -830,7 +830,8 @@ def bench_neighbors():
             cpu = time.perf_counter() - t0
             row[name] = {'ms': t, 'pair_tests_per_s': n * m / (t * 1e-3) if countmax == 0 else None,
                          'bit_exact': bool(numpy.array_equal(out, want)),
-                         'reference_ms': 1e3 * cpu, 'speedup': cpu / (t * 1e-3)}
+                         'reference_ms': 1e3 * cpu, 'speedup': cpu / (t * 1e-3),
+                         'kernel': lib.mdns_last_kernel().decode()}
         lib.mdns_region_timer_start(rg)
         _lib.check(lib.mdns_region_bootstrapped_maxdistance(rg, chosen.ctypes.data, 10, ctypes.byref(r)),
                    'mdns_region_bootstrapped_maxdistance')

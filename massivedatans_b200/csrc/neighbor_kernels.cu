@@ -118,10 +118,103 @@ __global__ void __launch_bounds__(NB_THREADS) count_within_generic_kernel(
 	if (lane == 0) counts[j] = cnt;
 }
 
+// Full counts of many candidates against many members (no early exit): lanes over CANDIDATES,
+// C of them per lane in registers, the members read once per warp with uniform (broadcast)
+// loads, four in flight.  Per pair test 8 FP64 instructions (the same separately rounded
+// sub/mul/add sequence) and nothing else on the FP64 pipe: `d < T` is decided on the bit
+// patterns -- d is a sum of squares, so it is +0, positive, +inf or NaN, and for T >= +0 the
+// unsigned order of the bits is the order of the values (NaN compares above everything, like
+// the floating-point test).  No ballot, no popcount: a predicated integer add per pair.
+// The warp-per-candidate kernel above spends a ninth FP64 slot on the compare and waits for
+// per-lane member loads (ncu, round 1: FP64 pipe 64 %, 25 % long-scoreboard stalls); it stays
+// for `any` / countmax queries, where its per-candidate early exit is the point.
+// ncu (profiles/r02_count_tile.md): FP64 pipe 73 %, issue slots 61 % busy, no memory stalls left.
+// An FP64 instruction holds the issue port of its sub-partition for two cycles, so the bound is
+// 2 x 8 + 3 (two ISETP + the add) + ~1.5 (loads, loop) = 20.5 issue cycles per pair test and
+// lane = 2.9 ms for 5e9 pairs; fusing the multiply-adds would break bit-exactness.
+// grid = (candidate tiles, member ranges): partial counts are added with integer atomics.
+constexpr int CT_THREADS = 128;
+
+template <int D, int C>
+__global__ void __launch_bounds__(CT_THREADS) count_tile_kernel(const double *__restrict__ xs, int n, int npad,
+                                                                 const double *__restrict__ yy, int m,
+                                                                 unsigned long long Tbits, int per_range,
+                                                                 int *__restrict__ counts)
+{
+	const long long j0 = ((long long)blockIdx.x * CT_THREADS + threadIdx.x) * C;
+	double y[C][D];
+	int cnt[C];
+#pragma unroll
+	for (int c = 0; c < C; ++c) {
+		const long long j = j0 + c < m ? j0 + c : (long long)m - 1;
+		cnt[c] = 0;
+#pragma unroll
+		for (int k = 0; k < D; ++k) y[c][k] = __ldg(yy + j * D + k);
+	}
+	const int i0 = blockIdx.y * per_range;
+	const int i1 = min(n, i0 + per_range);
+	int i = i0;
+	for (; i + 4 <= i1; i += 4) {
+		double x[4][D];
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+#pragma unroll
+			for (int k = 0; k < D; ++k) x[u][k] = __ldg(xs + (size_t)k * npad + i + u);
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+#pragma unroll
+			for (int c = 0; c < C; ++c) {
+				const double d = sqdist_reg<D>(x[u], y[c]);
+				cnt[c] += (unsigned long long)__double_as_longlong(d) < Tbits ? 1 : 0;
+			}
+	}
+	for (; i < i1; ++i) {
+		double x[D];
+#pragma unroll
+		for (int k = 0; k < D; ++k) x[k] = __ldg(xs + (size_t)k * npad + i);
+#pragma unroll
+		for (int c = 0; c < C; ++c) {
+			const double d = sqdist_reg<D>(x, y[c]);
+			cnt[c] += (unsigned long long)__double_as_longlong(d) < Tbits ? 1 : 0;
+		}
+	}
+#pragma unroll
+	for (int c = 0; c < C; ++c)
+		if (j0 + c < m && cnt[c]) atomicAdd(counts + j0 + c, cnt[c]);
+}
+
+// pair tests from which the tiled kernel is taken (below, the launch is latency either way)
+constexpr long long CT_MIN_PAIRS = 1LL << 24;
+
+template <int D>
+static int launch_count_tile(const double *xs, int n, int npad, const double *yy, int m, double T,
+                             int *counts, int sm_count, cudaStream_t st)
+{
+	constexpr int C = D <= 4 ? 4 : 2;
+	const int tiles = ceil_div(m, CT_THREADS * C);
+	// member ranges: ~64 CTAs per SM (nine are resident: the last, partial wave is then a few per
+	// cent of the run, not half of it -- 1372 CTAs on 1332 slots measured 3.39 ms), at least 256
+	// members each
+	int ranges = ceil_div((long long)sm_count * 64, tiles);
+	if (ranges > n / 256) ranges = n / 256;
+	if (ranges < 1) ranges = 1;
+	const int per_range = (int)round_up(ceil_div(n, ranges), 4);
+	ranges = ceil_div(n, per_range);
+	MDNS_CUDA(cudaMemsetAsync(counts, 0, (size_t)m * sizeof(int), st));
+	unsigned long long tb;
+	memcpy(&tb, &T, sizeof tb);
+	count_tile_kernel<D, C><<<dim3(tiles, ranges), CT_THREADS, 0, st>>>(xs, n, npad, yy, m, tb, per_range, counts);
+	MDNS_LAUNCHED("count_tile_kernel");
+	return MDNS_OK;
+}
+
 template <int D>
 static int launch_count_d(const double *xs, int n, int npad, const double *yy, int m, double T,
                           int stop_at, int *counts, int sm_count, cudaStream_t st)
 {
+	// full counts of a large problem: lanes over candidates (T >= +0 and not NaN: bit-pattern compare)
+	if (stop_at == 0 && (long long)n * m >= CT_MIN_PAIRS && T >= 0.0)
+		return launch_count_tile<D>(xs, n, npad, yy, m, T, counts, sm_count, st);
 	const long long warps_wanted = (long long)sm_count * 16;
 	if (m >= 4 * warps_wanted) {
 		const int warps = ceil_div(m, 4);

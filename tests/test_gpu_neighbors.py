@@ -71,6 +71,34 @@ def test_count_any_within_vs_oracle(oracle_port, n, m, ndim):
             oracle_port.is_within_distance_of(xx, r0, yy[j].copy())
 
 
+@pytest.mark.parametrize('n,m,ndim', [(4099, 4100, 1), (4099, 4100, 2), (4099, 4101, 3), (5001, 3400, 4),
+                                      (4099, 4100, 5), (4099, 4100, 6), (4099, 4100, 7), (4099, 4103, 8),
+                                      (257, 70001, 3)])
+def test_full_counts_of_large_problems_take_the_tiled_kernel(oracle_port, n, m, ndim):
+    # lanes over candidates, compare on the bit patterns (count_tile_kernel): same counts, bit for bit
+    xx, yy = synth.members_and_candidates(n, m, ndim, seed=n + m + ndim)
+    yy[::97] = xx[numpy.arange(0, m, 97) % n]           # candidates ON members: distance exactly 0
+    r0 = 0.5 * n ** (-1.0 / ndim)
+    for r in (r0, 2.5 * r0, 0.0, 10.0, numpy.nextafter(r0, 1)):
+        got = neighbors.count_within_distance_of(xx, r, yy)
+        assert _lib.load().mdns_last_kernel() == b'count_tile_kernel'
+        assert numpy.array_equal(got, oracle_port.count_within_distance_of(xx, r, yy)), r
+    # `any` queries keep the early-exit kernel
+    neighbors.any_within_distance_of(xx, r0, yy)
+    assert _lib.load().mdns_last_kernel() == b'count_within_kernel'
+
+
+def test_count_ties_exact_on_lattice_tiled(oracle_port):
+    g = numpy.arange(20, dtype=float)
+    xx = numpy.ascontiguousarray(numpy.array(numpy.meshgrid(g, g, g)).reshape(3, -1).T)      # 8000 members
+    yy = numpy.ascontiguousarray(numpy.tile(xx[::3], (1, 1)) + numpy.array([0.5, 0.0, 0.0]))  # 2667 candidates
+    assert len(xx) * len(yy) >= 1 << 24
+    for r in (0.5, 1.5, numpy.sqrt(2.25 + 1), 2.5, numpy.nextafter(2.5, 3)):
+        got = neighbors.count_within_distance_of(xx, r, yy)
+        assert _lib.load().mdns_last_kernel() == b'count_tile_kernel'
+        assert numpy.array_equal(got, oracle_port.count_within_distance_of(xx, r, yy))
+
+
 def test_count_ties_exact_on_lattice(oracle_port):
     # integer lattice: many distances coincide exactly with the radius -> strict '<'
     g = numpy.arange(12, dtype=float)
