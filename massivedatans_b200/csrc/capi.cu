@@ -60,6 +60,8 @@ struct Shard {
 	int sm_count = 148;
 	cudaStream_t stream = nullptr;
 	cudaStream_t copy_stream = nullptr;       // D2H of finished row chunks overlaps the next chunk
+	int *h_small = nullptr;                   // pinned block draw_small_kernel reports into
+	int small_seq = 0;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	cudaEvent_t ev_chunk[8] = {nullptr};
 	double *Y = nullptr, *W = nullptr, *x = nullptr;
@@ -246,6 +248,7 @@ static void shard_free(Shard &s)
 	for (auto &e : s.ev_chunk)
 		if (e) cudaEventDestroy(e);
 	if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
+	if (s.h_small) cudaFreeHost(s.h_small);
 	if (s.stream) cudaStreamDestroy(s.stream);
 	s = Shard();
 }
@@ -1631,6 +1634,12 @@ int mdns_clike_draw_pass(mdns_dataset *ds, const uint8_t *mask, const double *Lm
 	int rc = mdns_set_mask(ds, mask, &n_act);       // returns at once for a repeated mask
 	if (rc != MDNS_OK) return rc;
 	if (n_act_out) *n_act_out = n_act;
+	if (lout_capacity < n_act) {
+		// (checked before Lmins is read: it holds one entry per active data set, like Lout)
+		set_error("mdns_clike_draw_pass: %d active data sets, Lmins / Lout hold %lld", n_act,
+		          (long long)lout_capacity);
+		return MDNS_EINVAL;
+	}
 	*first_k = -1;
 	if (accept_counts)
 		for (int k = 0; k < K; ++k) accept_counts[k] = 0;
@@ -1641,6 +1650,61 @@ int mdns_clike_draw_pass(mdns_dataset *ds, const uint8_t *mask, const double *Lm
 	const bool same = ds->thresholds_staged && ds->host_lmins.size() == (size_t)n_act &&
 	                  memcmp(Lmins, ds->host_lmins.data(), (size_t)n_act * sizeof(double)) == 0;
 	if (!same && (rc = mdns_set_thresholds(ds, Lmins)) != MDNS_OK) return rc;
+	// a handful of active data sets (the focussed regime: one joint data set, long rejection
+	// chains): one launch, candidates by value, the answer written to pinned memory by the kernel
+	if (ds->shards.size() == 1 && !ds->comm && ds->has_x && !ds->has_var && n_act > 0 && lout_capacity >= n_act &&
+	    ds->tuning.lanes == 0 && ds->tuning.unroll == 0 && ds->tuning.ktile == 0 && ds->tuning.rows == 0) {
+		Shard &s = ds->shards[0];
+		LikeArgs a;
+		const int K_before = ds->K;
+		ds->K = K;
+		fill_args(ds, s, a);
+		ds->K = K_before;
+		a.noise2 = noise * noise;
+		a.scale = scale;
+		a.out_stride = s.n_act;
+		a.lmins = s.d_lmins;
+		if (draw_small_fits(a)) {
+			MDNS_CUDA(cudaSetDevice(s.device));
+			if ((rc = ensure_batch(ds, s, K)) != MDNS_OK) return rc;
+			a.out = s.d_out;
+			if (!s.h_small) {
+				MDNS_CUDA(cudaHostAlloc((void **)&s.h_small, draw_small_host_bytes(),
+				                        cudaHostAllocPortable | cudaHostAllocMapped));
+				memset(s.h_small, 0, draw_small_host_bytes());
+			}
+			const int seq = ++s.small_seq == 0 ? ++s.small_seq : s.small_seq;
+			if ((rc = launch_draw_small(a, params, seq, s.h_small, s.stream)) != MDNS_OK) return rc;
+			volatile int *flag = (volatile int *)s.h_small;
+			for (unsigned spins = 1; *flag != seq; ++spins) {
+				if ((spins & 0xfffu) == 0) {
+					const cudaError_t q = cudaStreamQuery(s.stream);
+					if (q == cudaErrorNotReady) continue;
+					if (q != cudaSuccess) {
+						set_error("draw_small_kernel failed: %s", cudaGetErrorString(q));
+						return MDNS_ECUDA;
+					}
+					if (*flag != seq) {
+						set_error("draw_small_kernel finished without reporting");
+						return MDNS_ECUDA;
+					}
+				}
+			}
+			std::atomic_thread_fence(std::memory_order_acquire);
+			const int first = s.h_small[1];
+			*first_k = first;
+			if (accept_counts)
+				for (int k = 0; k < K; ++k) accept_counts[k] = s.h_small[2 + k];
+			if (first >= 0)
+				memcpy(Lout, (const unsigned char *)s.h_small + 256, (size_t)n_act * sizeof(double));
+			// the logL matrix of the pass is on the device like after any other pass; the candidates
+			// themselves never were: a later launch needs them staged again
+			ds->K = K;
+			ds->staged = 0;
+			ds->launched = 1;
+			return MDNS_OK;
+		}
+	}
 	if ((rc = mdns_stage_params(ds, params, K)) != MDNS_OK) return rc;
 	return mdns_clike_first_accept(ds, noise, scale, nullptr, accept_counts, first_k, Lout,
 	                               lout_capacity);

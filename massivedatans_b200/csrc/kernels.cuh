@@ -102,6 +102,11 @@ struct Tuning {
 int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t st,
                  int *accept_fused = nullptr);
 int launch_muse(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t st);
+// one speculative pass over a handful of active data sets in ONE launch: candidates by value,
+// decision and the accepted vector written to pinned host memory (likelihood_kernels.cu)
+bool draw_small_fits(const LikeArgs &a);
+size_t draw_small_host_bytes();
+int launch_draw_small(const LikeArgs &a, const double *params, int seq, int *host_block, cudaStream_t st);
 // counts[k] = #{r : L[k*stride + r] > lmins[r]}  (hiermetriclearn.py:193 on the device)
 int launch_accept_count(const double *L, long long stride, int n, int K, const double *lmins,
                         int *counts, cudaStream_t st, bool zero = true);

@@ -389,6 +389,136 @@ __global__ void __launch_bounds__(LK_THREADS) clike_rows_kernel(const LikeArgs a
 	}
 }
 
+// ---- one speculative pass over a HANDFUL of active data sets, one launch, no copies ----------
+// The focussed regime of the constrained draw (hiermetriclearn.py:181-196 with a joint mask of one
+// or a few data sets, hundreds of rejected candidates per accepted one): the work is a few
+// microseconds, the cost was the choreography -- parameter upload, model kernel, likelihood
+// kernel, decision kernel, download, synchronisation (36 us of native time per pass).  Here the K
+// candidates come BY VALUE with the launch, one CTA builds their spectra in shared memory
+// (clike.c:65, un-fused like line_model_kernel), scores the rows exactly as
+// clike_rows_kernel<32, ...> does (same fragment order per lane, same butterfly: the logL are
+// bit-identical to what the general path returns for such masks), applies `L > Lmins`, picks the
+// first accepted candidate and writes {counts, first, its logL vector} straight into pinned host
+// memory, the sequence number last.  The host polls that word: no copy node, no stream wait.
+constexpr int DS_MAX_K = 32, DS_MAX_ROWS = 64, DS_KT = 8;
+struct DrawSmallParams {
+	double p[DS_MAX_K * 3];
+};
+// host block layout (ints): [0] sequence, [1] first, [2..2+DS_MAX_K) counts; doubles from byte 256
+constexpr int DS_HOST_VALUES_OFFSET = 256;
+
+__global__ void __launch_bounds__(LK_THREADS) draw_small_kernel(const LikeArgs a, const DrawSmallParams prm,
+                                                                const int seq, int *__restrict__ host_block)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	double *smd = reinterpret_cast<double *>(smem_raw);                  // [K][mpitch] spectra
+	const double2 *sm = reinterpret_cast<const double2 *>(smem_raw);
+	__shared__ double s_val[DS_MAX_K * DS_MAX_ROWS];
+	__shared__ int s_cnt[DS_MAX_K];
+	__shared__ int s_first;
+	const int K = a.K, n = a.n_rows;
+	const int mfp = a.mpitch >> 1;
+	const int nfrag = (a.nx + 1) >> 1;
+	for (int idx = threadIdx.x; idx < K * a.mpitch; idx += LK_THREADS) {
+		const int k = idx / a.mpitch, j = idx - k * a.mpitch;
+		double v = 0.0;
+		if (j < a.nx) {
+			const double t = __ddiv_rn(__dsub_rn(prm.p[3 * k + 1], a.x[j]), prm.p[3 * k + 2]);
+			v = __dmul_rn(prm.p[3 * k], exp(__dmul_rn(-0.5, __dmul_rn(t, t))));
+		}
+		smd[idx] = v;
+	}
+	if (threadIdx.x < DS_MAX_K) s_cnt[threadIdx.x] = 0;
+	__syncthreads();
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const double inv = a.scale / a.noise2;
+	for (int r = warp; r < n; r += LK_THREADS / 32) {
+		const long long row = a.active ? (long long)a.active[r] : r;
+		const double2 *p = reinterpret_cast<const double2 *>(a.Y + row * a.pitch);
+		const double lm = __ldg(a.lmins + r);
+		for (int k0 = 0; k0 < K; k0 += DS_KT) {
+			double acc0[DS_KT], acc1[DS_KT];
+#pragma unroll
+			for (int k = 0; k < DS_KT; ++k) acc0[k] = acc1[k] = 0.0;
+			for (int fi = lane; fi < nfrag; fi += 32) {
+				const double2 y = ldg_stream(p + fi);
+#pragma unroll
+				for (int k = 0; k < DS_KT; ++k) {
+					if (k0 + k < K) {
+						const double2 m = sm[(k0 + k) * mfp + fi];
+						const double d0 = m.x - y.x;
+						const double d1 = m.y - y.y;
+						acc0[k] = fma(d0, d0, acc0[k]);
+						acc1[k] = fma(d1, d1, acc1[k]);
+					}
+				}
+			}
+#pragma unroll
+			for (int k = 0; k < DS_KT; ++k) {
+				double sum = acc0[k] + acc1[k];
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) sum += shfl_xor_f64(sum, o);
+				if (lane == 0 && k0 + k < K) {
+					const double val = sum * inv;
+					s_val[(k0 + k) * DS_MAX_ROWS + r] = val;
+					if (a.out) a.out[(long long)(k0 + k) * a.out_stride + r] = val;
+					if (val > lm) atomicAdd(&s_cnt[k0 + k], 1);
+				}
+			}
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int first = -1;
+		for (int k = 0; k < K && first < 0; ++k)
+			if (s_cnt[k] > 0) first = k;
+		s_first = first;
+		host_block[1] = first;
+	}
+	if (threadIdx.x < K) host_block[2 + threadIdx.x] = s_cnt[threadIdx.x];
+	__syncthreads();
+	const int first = s_first;
+	if (first >= 0) {
+		double *hv = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(host_block) + DS_HOST_VALUES_OFFSET);
+		for (int r = threadIdx.x; r < n; r += LK_THREADS) hv[r] = s_val[first * DS_MAX_ROWS + r];
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		*reinterpret_cast<volatile int *>(host_block) = seq;
+	}
+}
+
+bool draw_small_fits(const LikeArgs &a)
+{
+	return a.K >= 1 && a.K <= DS_MAX_K && a.n_rows >= 1 && a.n_rows <= DS_MAX_ROWS && a.x && a.lmins &&
+	       !a.W && (size_t)a.K * a.mpitch * 8 <= 160 * 1024;
+}
+
+size_t draw_small_host_bytes() { return DS_HOST_VALUES_OFFSET + DS_MAX_ROWS * sizeof(double); }
+
+// params: K rows (A, mu, sig) on the HOST; host_block: pinned, mapped; seq: any value the block
+// does not hold yet
+int launch_draw_small(const LikeArgs &a, const double *params, int seq, int *host_block, cudaStream_t st)
+{
+	if (!draw_small_fits(a)) {
+		set_error("draw_small_kernel: at most %d candidates x %d active data sets", DS_MAX_K, DS_MAX_ROWS);
+		return MDNS_EINVAL;
+	}
+	DrawSmallParams prm;
+	memcpy(prm.p, params, (size_t)a.K * 3 * sizeof(double));
+	const size_t smem = (size_t)a.K * a.mpitch * 8;
+	static size_t smem_set = 0;
+	if (smem > smem_set) {
+		MDNS_CUDA(cudaFuncSetAttribute(draw_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                               (int)(160 * 1024)));
+		smem_set = 160 * 1024;
+	}
+	draw_small_kernel<<<1, LK_THREADS, smem, st>>>(a, prm, seq, host_block);
+	MDNS_LAUNCHED("draw_small_kernel");
+	return MDNS_OK;
+}
+
 // ---- register-blocked variant for candidate batches (K >= 4) -----------------
 // With KT candidates per pass the streaming kernel above becomes bound by shared-memory
 // bandwidth: every (element, candidate) pair needs 8 bytes of model from shared memory
