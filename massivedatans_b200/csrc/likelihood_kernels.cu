@@ -842,8 +842,11 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		d.allow_expanded = t.allow_expanded;
 		return launch_clike(a, d, sm_count, st, accept_fused);
 	}
+	// (from 8192 data sets: L2 flushed, 200 channels, tools/r2_small_n.py -- 1e4: K=16 0.027 ms
+	// against 0.038 for the lanes-across-channels kernel, K=8 equal; 3e4: 0.033 / 0.030 against
+	// 0.068 / 0.041; the threshold used to be 32768)
 	if (L == 0 && t.unroll == 0 && t.ktile == 0 && t.rows == 0 && !a.active && a.K >= XP_MIN_K &&
-	    a.n_rows >= 32768) {
+	    a.n_rows >= 8192) {
 		// automatic choice for all-active candidate batches: expanded form with the cross term
 		// on the FP64 tensor path when allowed (measured at N=1e6, C=200: K=8 0.277 ms, K=16
 		// 0.313 ms, K=32 0.46 ms; FMA form 0.29 / 0.35 / 0.69; direct form 0.30 / 0.56 / 1.1) ...

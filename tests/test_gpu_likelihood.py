@@ -64,8 +64,8 @@ def test_clike_vs_oracle_shapes(oracle_port, N, nx):
     for name, m in synth.masks(N, seed=N).items():
         got = ds.loglike_batch(pts, m, synth.NOISE_LEVEL, scale=1.0)
         assert got.shape == (3, int(m.sum()))
-        # all-active batches of >= 3 candidates over >= 32768 data sets take the expanded form
-        tol = TOL_XP if (m.all() and N >= 32768) else TOL
+        # all-active batches of >= 3 candidates over >= 8192 data sets take the expanded form
+        tol = TOL_XP if (m.all() and N >= 8192) else TOL
         for k, p in enumerate(pts):
             want = oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, m)
             assert rel_err(got[k], want) < tol, (name, k)
