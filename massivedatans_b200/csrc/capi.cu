@@ -941,7 +941,7 @@ static bool xp_candidate(const mdns_dataset *ds, const Shard &s)
 	if (!s.all_active) {
 		// masked batches: only the tensor path has a gather form
 		if (!s.has_gather) return false;
-		if (ds->tuning.lanes == 3) return true;
+		if (ds->tuning.lanes == 3 || ds->tuning.lanes == 6) return true;
 		return ds->tuning.lanes == 0 && ds->K >= XP_MIN_K_MASKED && ds->tuning.allow_expanded;
 	}
 	if (ds->tuning.lanes == 2 || ds->tuning.lanes == 3 || ds->tuning.lanes == 5 || ds->tuning.lanes == 6) return true;   // explicit request

@@ -790,7 +790,7 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		if (t.unroll == 1) return launch_clike_dmma(a, kt, stages, sm_count, st);
 		return launch_dmma_auto(a, kt, stages, sm_count, st, accept_fused);
 	}
-	if (L == 6 && !a.active) {
+	if (L == 6 && (!a.active || a.tmap_gather)) {
 		// expanded form, per-warp slabs with the batch resident in shared memory (short spectra)
 		const int kt = t.ktile == 8 ? 8 : 16;
 		const int nslot = t.rows == 2 ? 2 : 3;
@@ -833,7 +833,21 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		// 0.180), K=16 0.173 ms (0.358), K=32 0.43 ms (0.71); up to 4 candidates the block kernel
 		// wins (K=4 0.141 ms).
 		if (a.K >= 32 && dmma_fits(a, 32, 3)) return launch_dmma_auto(a, 32, 3, sm_count, st, accept_fused);
+		// per-warp slabs, every warp gathering its own listed rows (slab_dmma_kernel.cu); same box,
+		// 5e5 active of 1e6 x 200 (tools/sweep_masked.py): K=16 0.159 ms (0.84 of the roofline)
+		// against 0.181 (0.73) for the stream-K gather, K=8 0.150 (0.85) against 0.152 for round 1's
+		// whole-tile gather and 0.241 (0.53) for the stream-K 16-warp gather shape
+		const bool slabs_enough = (a.n_rows + 31) / 32 >= 2LL * 16 * sm_count;
+		if (a.K > 8 && slabs_enough && slab_dmma_fits(a, 16, 2)) {
+			if (accept_fused) *accept_fused = 1;
+			return launch_slab_dmma(a, 16, 2, sm_count, st);
+		}
 		if (a.K >= 16 && dmma_fits(a, 16, 13)) return launch_dmma_auto(a, 16, 13, sm_count, st, accept_fused);
+		if (slabs_enough && slab_dmma_fits(a, 8, 2)) {
+			if (accept_fused) *accept_fused = 1;
+			return launch_slab_dmma(a, 8, 2, sm_count, st);
+		}
+		if (dmma_fits(a, 8, 2)) return launch_clike_dmma(a, 8, 2, sm_count, st);
 		if (dmma_fits(a, 8, 13)) return launch_dmma_auto(a, 8, 13, sm_count, st, accept_fused);
 	}
 	if (L == 1 || L == 2 || L == 3 || L == 6) {

@@ -51,6 +51,16 @@ __device__ __forceinline__ void sl_tma_load_2d(void *smem_dst, const CUtensorMap
 	    : "memory");
 }
 
+__device__ __forceinline__ void sl_tma_gather4(void *smem_dst, const CUtensorMap *tmap, int c0, int r0, int r1,
+                                               int r2, int r3, uint64_t *bar)
+{
+	asm volatile(
+	    "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes "
+	    "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(smem_u32(smem_dst)),
+	    "l"(tmap), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+	    : "memory");
+}
+
 __device__ __forceinline__ void sl_dmma(double &c0, double &c1, double a, double b)
 {
 	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -90,7 +100,7 @@ __device__ __forceinline__ void sl_box(double (&acc)[4][NC][2], const unsigned c
 // Epilogue of one accumulator set: rows gr0 + mr * rstep.  Same arithmetic as
 // rd_epilogue_clike (rows_dmma_kernel.cu): chi = Syy - 2 S + Smm, guard, optional store, fused
 // accept test into packed 16-bit counters, fix-up list.
-template <int NC, bool COUNT, bool STORE>
+template <int NC, bool COUNT, bool STORE, bool GATHER>
 __device__ __forceinline__ void sl_epilogue(const double (&acc)[4][NC][2], const LikeArgs &a,
                                             const double *s_smm, long long gr0, int rstep, int t,
                                             int kp0, int kp1, int k0, int kt_valid, int pass, double inv,
@@ -101,7 +111,8 @@ __device__ __forceinline__ void sl_epilogue(const double (&acc)[4][NC][2], const
 	for (int mr = 0; mr < 4; ++mr) {
 		const long long gr = gr0 + mr * rstep;
 		const bool live = gr < a.n_rows;
-		syy[mr] = live ? __ldg(a.syy + a.row0 + gr) : 0.0;
+		// (masked batches: gr is the slot in the compacted order, Syy lives with the shard's rows)
+		syy[mr] = live ? __ldg(a.syy + (GATHER ? (long long)a.active[gr] : a.row0 + gr)) : 0.0;
 		lm[mr] = 0.0;
 		if (COUNT) lm[mr] = live ? __ldg(a.lmins + gr) : __longlong_as_double(0x7ff0000000000000LL);
 	}
@@ -144,7 +155,35 @@ __device__ __forceinline__ void sl_epilogue(const double (&acc)[4][NC][2], const
 	}
 }
 
-template <int NC, int P, int NSLOT>
+// one box of a slab on its way: plain rows (one tiled copy) or listed rows (masked batches: eight
+// gather4 copies of four listed rows each, issued by lanes 0..7 with the indices they hold)
+template <bool GATHER>
+__device__ __forceinline__ void sl_issue(unsigned char *slot, uint64_t *bar, const CUtensorMap *tmap, int box,
+                                         int slab, const int (&rows)[4], int lane)
+{
+	if (lane == 0) mbar_expect_tx(bar, SL_SLOT_BYTES);
+	if (GATHER) {
+		__syncwarp();
+		if (lane < 8) sl_tma_gather4(slot + lane * 512, tmap, box * 16, rows[0], rows[1], rows[2], rows[3], bar);
+	} else if (lane == 0) {
+		sl_tma_load_2d(slot, tmap, box * 16, slab * SL_ROWS, bar);
+	}
+}
+
+// the four listed rows lane l < 8 fetches for slab `slab` (clamped behind the end of the list:
+// the duplicates are never looked at)
+__device__ __forceinline__ void sl_rows_of(const LikeArgs &a, int slab, int nslabs, int lane, int (&rows)[4])
+{
+	if (lane < 8 && slab < nslabs) {
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const long long r = (long long)slab * SL_ROWS + lane * 4 + j;
+			rows[j] = a.active[r < a.n_rows ? r : a.n_rows - 1];
+		}
+	}
+}
+
+template <int NC, int P, int NSLOT, bool GATHER>
 __global__ void __launch_bounds__(SL_THREADS, 1) slab_dmma_kernel(
     const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const LikeArgs a,
     const int k0, const int kt_valid, const int pass)
@@ -197,12 +236,14 @@ __global__ void __launch_bounds__(SL_THREADS, 1) slab_dmma_kernel(
 	// the copy cursor runs NSLOT boxes ahead of the contraction: box `pb` of slab (ahead ? nxt : cur)
 	int pb = 0;
 	bool ahead = false;
+	int rows_cur[4] = {0, 0, 0, 0}, rows_nxt[4] = {0, 0, 0, 0};
+	if (GATHER) {
+		sl_rows_of(a, cur, nslabs, lane, rows_cur);
+		sl_rows_of(a, nxt, nslabs, lane, rows_nxt);
+	}
 	if (cur < nslabs) {
 		for (int s = 0; s < NSLOT; ++s) {
-			if (lane == 0) {
-				mbar_expect_tx(&bars[s], SL_SLOT_BYTES);
-				sl_tma_load_2d(ring + s * SL_SLOT_BYTES, &tmapA, pb * 16, cur * SL_ROWS, &bars[s]);
-			}
+			sl_issue<GATHER>(ring + s * SL_SLOT_BYTES, &bars[s], &tmapA, pb, cur, rows_cur, lane);
 			if (++pb == nbox) {
 				// (NSLOT <= nbox: only ever after the last slot)
 				pb = 0;
@@ -235,11 +276,12 @@ __global__ void __launch_bounds__(SL_THREADS, 1) slab_dmma_kernel(
 		body;                                                                               \
 		__syncwarp();                                                                       \
 		const int ps = ahead ? nxt : cur;                                                   \
-		if (lane == 0 && ps < nslabs) {                                                     \
+		if (ps < nslabs) {                                                                  \
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                \
-			mbar_expect_tx(&bars[slot], SL_SLOT_BYTES);                                 \
-			sl_tma_load_2d(ring + slot * SL_SLOT_BYTES, &tmapA, pb * 16, ps * SL_ROWS,  \
-			               &bars[slot]);                                                \
+			if (ahead)                                                                  \
+				sl_issue<GATHER>(ring + slot * SL_SLOT_BYTES, &bars[slot], &tmapA, pb, ps, rows_nxt, lane); \
+			else                                                                        \
+				sl_issue<GATHER>(ring + slot * SL_SLOT_BYTES, &bars[slot], &tmapA, pb, ps, rows_cur, lane); \
 		}                                                                                   \
 		if (++pb == nbox) {                                                                 \
 			pb = 0;                                                                     \
@@ -288,13 +330,13 @@ __global__ void __launch_bounds__(SL_THREADS, 1) slab_dmma_kernel(
 			const long long gr0 = ((long long)cur * SL_ROWS + pr) * P + p;
 			if (a.counts) {
 				if (a.out)
-					sl_epilogue<NC, true, true>(acc[p], a, s_smm, gr0, 8 * P, t, kp0, kp1, k0, kt_valid, pass,
+					sl_epilogue<NC, true, true, GATHER>(acc[p], a, s_smm, gr0, 8 * P, t, kp0, kp1, k0, kt_valid, pass,
 					                            inv, cntp);
 				else
-					sl_epilogue<NC, true, false>(acc[p], a, s_smm, gr0, 8 * P, t, kp0, kp1, k0, kt_valid, pass,
+					sl_epilogue<NC, true, false, GATHER>(acc[p], a, s_smm, gr0, 8 * P, t, kp0, kp1, k0, kt_valid, pass,
 					                             inv, cntp);
 			} else {
-				sl_epilogue<NC, false, true>(acc[p], a, s_smm, gr0, 8 * P, t, kp0, kp1, k0, kt_valid, pass, inv,
+				sl_epilogue<NC, false, true, GATHER>(acc[p], a, s_smm, gr0, 8 * P, t, kp0, kp1, k0, kt_valid, pass, inv,
 				                             cntp);
 			}
 		}
@@ -310,6 +352,11 @@ __global__ void __launch_bounds__(SL_THREADS, 1) slab_dmma_kernel(
 		cur = nxt;
 		nxt = __shfl_sync(0xffffffffu, grab, 0);
 		ahead = false;
+		if (GATHER) {
+#pragma unroll
+			for (int j = 0; j < 4; ++j) rows_cur[j] = rows_nxt[j];
+			sl_rows_of(a, nxt, nslabs, lane, rows_nxt);
+		}
 	}
 #undef SL_STEP
 	if (a.counts) {
@@ -332,6 +379,7 @@ int launch_xtile_fixup(const LikeArgs &a, int k0, int kv, int pass, int sm_count
 
 static int slab_pair_mode(const LikeArgs &a)
 {
+	if (a.active) return 1;      // listed rows: no pairs
 	// row pairs: pitch = 8 mod 16 doubles, and the launch starts on a line boundary
 	return (a.pitch % 16 == 8 && ((uintptr_t)a.Y & 127) == 0 && (a.row0 & 1) == 0) ? 2 : 1;
 }
@@ -355,7 +403,8 @@ int slab_counter_count() { return SL_MAX_PASSES; }
 bool slab_dmma_fits(const LikeArgs &a, int kt, int nslot)
 {
 	if ((kt != 8 && kt != 16) || (nslot != 2 && nslot != 3)) return false;
-	if (a.active || !a.Y || !a.syy || !a.smm || !a.xp_redo || !a.xp_list) return false;
+	if (!a.Y || !a.syy || !a.smm || !a.xp_redo || !a.xp_list) return false;
+	if (a.active && !a.tmap_gather) return false;
 	if (a.pitch % 2 || a.pitch < 16 * nslot || a.mpitch != a.pitch) return false;
 	const int npass = ceil_div(a.K, kt);
 	if (npass > SL_MAX_PASSES || npass + 1 > xtile_counter_capacity()) return false;
@@ -363,17 +412,21 @@ bool slab_dmma_fits(const LikeArgs &a, int kt, int nslot)
 	return slab_smem(a, kt, nslot) <= 225 * 1024;
 }
 
-template <int NC, int P, int NSLOT>
+template <int NC, int P, int NSLOT, bool GATHER>
 static int launch_slab_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 {
 	constexpr int KT = NC * 8;
 	const size_t smem = slab_smem(a, KT, NSLOT);
-	auto kern = slab_dmma_kernel<NC, P, NSLOT>;
+	auto kern = slab_dmma_kernel<NC, P, NSLOT, GATHER>;
 	MDNS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	CUtensorMap ta, tb;
 	// the rows of THIS launch as (super-)rows of P * pitch doubles, boxes of 32 x 16 channels
 	const long long nsup = ((long long)a.n_rows + P - 1) / P;
-	int rc = make_row_tensor_map_box(&ta, a.Y, nsup, (long long)P * a.pitch, SL_ROWS);
+	int rc = MDNS_OK;
+	if (GATHER)
+		memcpy(&ta, a.tmap_gather, sizeof ta);      // one-row boxes of the whole shard
+	else
+		rc = make_row_tensor_map_box(&ta, a.Y, nsup, (long long)P * a.pitch, SL_ROWS);
 	if (rc != MDNS_OK) return rc;
 	const long long kpad = (long long)round_up(a.K, KT_MAX);
 	rc = make_row_tensor_map_box(&tb, a.model, kpad, a.mpitch, KT);
@@ -388,7 +441,7 @@ static int launch_slab_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 	for (int k0 = 0, pass = 0; k0 < a.K; k0 += KT, ++pass) {
 		const int kv = a.K - k0 < KT ? a.K - k0 : KT;
 		kern<<<(unsigned)gx, SL_THREADS, smem, st>>>(ta, tb, a, k0, kv, pass);
-		MDNS_LAUNCHED("slab_dmma_kernel");
+		MDNS_LAUNCHED(GATHER ? "slab_dmma_kernel(gather)" : "slab_dmma_kernel");
 		// (the fix-up launch also hands the slab counter of this pass back at zero)
 		rc = launch_xtile_fixup(a, k0, kv, pass, sm_count, st);
 		if (rc != MDNS_OK) return rc;
@@ -400,13 +453,16 @@ int launch_slab_dmma(const LikeArgs &a, int kt, int nslot, int sm_count, cudaStr
 {
 	if (a.n_rows <= 0 || a.K <= 0) return MDNS_OK;
 	if (!slab_dmma_fits(a, kt, nslot)) {
-		set_error("slab_dmma_kernel: needs all rows active, the resident row sums and %zu bytes of shared memory",
+		set_error("slab_dmma_kernel: needs the resident row sums (and the gather map for listed rows) and %zu bytes of shared memory",
 		          slab_smem(a, kt, nslot));
 		return MDNS_EINVAL;
 	}
 	const int P = slab_pair_mode(a);
-#define MDNS_SL(KK, PP, SS)                                                   \
-	if (kt == KK && P == PP && nslot == SS) return launch_slab_inst<KK / 8, PP, SS>(a, sm_count, st);
+#define MDNS_SL(KK, PP, SS)                                                                      \
+	if (kt == KK && P == PP && nslot == SS) {                                                    \
+		if (PP == 1 && a.active) return launch_slab_inst<KK / 8, 1, SS, true>(a, sm_count, st);  \
+		return launch_slab_inst<KK / 8, PP, SS, false>(a, sm_count, st);                         \
+	}
 	MDNS_SL(16, 2, 3)
 	MDNS_SL(16, 1, 3)
 	MDNS_SL(16, 2, 2)

@@ -12,7 +12,7 @@ import pytest
 # the FP64 tensor-path kernels: stream-K (round 2) and whole-tile (round 1, kept for the shapes
 # only it is instantiated for)
 TENSOR = (b'rows_dmma_kernel', b'clike_dmma_kernel', b'slab_dmma_kernel')
-TENSOR_GATHER = (b'rows_dmma_kernel(gather)', b'clike_dmma_kernel(gather)')
+TENSOR_GATHER = (b'rows_dmma_kernel(gather)', b'clike_dmma_kernel(gather)', b'slab_dmma_kernel(gather)')
 
 from conftest import rel_err
 from massivedatans_b200 import _lib, synth
@@ -255,6 +255,43 @@ def test_clike_slab_tensor_kernel(oracle_port, ktile, nslot, N, nx, K):
         assert k == want_k and rel_err(Lk, L[want_k]) < 1e-13
     else:
         assert k == -1
+
+
+@pytest.mark.parametrize('ktile,nslot', [(16, 2), (16, 3), (8, 2)])
+@pytest.mark.parametrize('N,nx,K', [(700, 203, 9), (70001, 200, 16), (2049, 57, 20), (150000, 72, 16)])
+def test_clike_slab_kernel_masked_gather(oracle_port, ktile, nslot, N, nx, K):
+    # masked batches on the per-warp slab kernel: each warp fetches its listed rows itself with
+    # eight gather4 copies per box
+    x, y, _ = synth.horns(N, nx=nx, legacy=False, seed=N + 21)
+    ds = ResidentDataset(x, y)
+    pts = synth.parameter_points(K, seed=N + 22)
+    lib = _lib.load()
+    for name, m in synth.masks(N, seed=N).items():
+        if name == 'all' or not m.any():
+            continue
+        ds.set_tuning(6, 0, ktile, nslot)
+        got = numpy.array(ds.loglike_batch(pts, m, synth.NOISE_LEVEL, scale=1.0))
+        assert lib.mdns_last_kernel() == b'slab_dmma_kernel(gather)'
+        assert got.shape == (K, int(m.sum()))
+        again = numpy.array(ds.loglike_batch(pts, m, synth.NOISE_LEVEL, scale=1.0))
+        assert numpy.array_equal(got, again)
+        for k in sorted(set((0, 7, 8, K // 2, K - 1))):
+            p = pts[k]
+            want = oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, m)
+            assert rel_err(got[k], want) < TOL_XP, (name, k)
+        # fused accept test on the compacted rows
+        L = -0.5 * got
+        srt = numpy.sort(L, axis=0)
+        Lmins = srt[-1] + 1.0 + numpy.abs(srt[-1])
+        pick = numpy.arange(L.shape[1]) % 5 == 2
+        if pick.any():
+            Lmins[pick] = 0.5 * (srt[-1][pick] + srt[-2][pick])
+        k, Lk, counts = ds.first_accepted(pts, m, Lmins, synth.NOISE_LEVEL)
+        want_counts = (L > Lmins).sum(axis=1)
+        assert numpy.array_equal(counts, want_counts), name
+        if want_counts.any():
+            assert k == int(numpy.nonzero(want_counts)[0][0])
+    assert ds.expanded_stats() == (True, 0)
 
 
 @pytest.mark.parametrize('ktile,stages', [(8, 2), (8, 14), (16, 3), (16, 13), (32, 3), (32, 12)])

@@ -26,14 +26,16 @@ def main():
     masks = synth.masks(args.ndata)
     for K in (8, 16):
         ds.stage_params(synth.parameter_points(K, seed=7))
-        for mname in ('half',):
+        for mname in ('half', 'prefix'):
             n_act = ds.set_mask(masks[mname])
             for label, setup in (('auto', lambda: (ds.set_expanded(True), ds.set_tuning(0, 0, 0, 0))),
                                  ('direct', lambda: (ds.set_expanded(False), ds.set_tuning(0, 0, 0, 0))),
                                  ('gather 8w', lambda: (ds.set_expanded(True), ds.set_tuning(3, 0, min(K, 32) if K >= 8 else 8, 3))),
                                  ('gather 16w', lambda: (ds.set_expanded(True), ds.set_tuning(3, 0, min(K, 32) if K >= 8 else 8, 13))),
                                  ('gather 2st', lambda: (ds.set_expanded(True), ds.set_tuning(3, 0, min(K, 32) if K >= 8 else 8, 2))),
-                                 ('gather 16w2', lambda: (ds.set_expanded(True), ds.set_tuning(3, 0, min(K, 32) if K >= 8 else 8, 12)))):
+                                 ('gather 16w2', lambda: (ds.set_expanded(True), ds.set_tuning(3, 0, min(K, 32) if K >= 8 else 8, 12))),
+                                 ('slab 2', lambda: (ds.set_expanded(True), ds.set_tuning(6, 0, 16 if K > 8 else 8, 2))),
+                                 ('slab 3', lambda: (ds.set_expanded(True), ds.set_tuning(6, 0, 16 if K > 8 else 8, 3)))):
                 setup()
                 for _ in range(3):
                     ds.launch_clike(0.01, -0.5)
