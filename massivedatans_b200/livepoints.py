@@ -17,10 +17,7 @@ import weakref
 import numpy
 
 from . import _lib
-
-
-def _addr(a):
-    return a.ctypes.data if a is not None else None
+from .likelihood import _addr, _pool
 
 
 class LiveTable(object):
@@ -59,9 +56,11 @@ class LiveTable(object):
 
     def prepare(self):
         """(Lmins, Lmini, Lmax): min, argmin and max over the live points, per data set."""
-        lo = numpy.empty(self.ndata)
-        hi = numpy.empty(self.ndata)
-        at = numpy.empty(self.ndata, dtype=numpy.int64)
+        # pinned result vectors: three pageable downloads were most of the call (round 1: 1.24 ms
+        # for a 640 MB table whose reduction streams in 0.1-0.2 ms)
+        lo = _pool.empty(self.ndata)
+        hi = _pool.empty(self.ndata)
+        at = _pool.empty(self.ndata).view(numpy.int64)
         _lib.check(self._lib.mdns_livetable_colstats(self._h, _addr(lo), _addr(at), _addr(hi)),
                    'mdns_livetable_colstats')
         return lo, at, hi
