@@ -1432,7 +1432,8 @@ static int accept_pass_single(mdns_dataset *ds, double noise, double scale, Acce
 		key.xp_tol = ds->xp_tol;
 		key.comm = ds->comm;
 		const void *ptrs[] = {s.d_model, s.d_out, s.d_in, s.d_smm, s.d_counts, s.d_sel, s.d_snap, s.d_pick,
-		                      s.d_lmins, s.d_flags, s.d_acc_idx, s.d_acc_val, s.h_sel, Lout, idx_out, val_out};
+		                      s.d_lmins, s.d_flags, s.d_acc_idx, s.d_acc_val, s.h_sel,
+		                      nullptr /* Lout: fetched after the graph, not by it */, idx_out, val_out};
 		static_assert(sizeof ptrs == sizeof key.ptrs, "graph key");
 		memcpy(key.ptrs, ptrs, sizeof ptrs);
 		Shard::AcceptGraph *hit = nullptr, *victim = nullptr;
