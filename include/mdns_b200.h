@@ -169,9 +169,10 @@ int mdns_clike_launch_fetch(mdns_dataset *ds, double noise, double scale, double
  * the accept test on the device.  Lmins[n_act] is aligned with the compacted active order.
  * accept_counts[K] (may be NULL) = data sets with scale*chi2 > Lmins per candidate;
  * *first_k = first candidate with a non-zero count, or -1; its logL vector is copied to Lout
- * (contents unspecified when none accepts).  Only K ints and one vector cross PCIe.  The accept
- * test runs inside the likelihood kernels and the choice of first_k on the device; large vectors
- * are downloaded in row chunks overlapped with the scoring of the next chunk. */
+ * (contents unspecified when none accepts).  Only K ints and one vector cross PCIe -- and no
+ * vector at all when no candidate is accepted.  The accept test runs inside the likelihood
+ * kernels and the choice of first_k on the device; the accepted candidate's vector is then
+ * fetched from its row of the device-side logL matrix. */
 /* Thresholds may also be staged once per constrained draw (they are constant while candidates
  * are tried, hiermetriclearn.py:173-211): mdns_set_thresholds after mdns_set_mask, then
  * mdns_clike_first_accept with Lmins = NULL for every batch of candidates. */
@@ -181,8 +182,12 @@ int mdns_clike_first_accept(mdns_dataset *ds, double noise, double scale, const 
                             int64_t lout_capacity);
 /* One call per speculative pass of a constrained draw: mdns_set_mask (a repeated mask is
  * recognised), mdns_set_thresholds (skipped when a short Lmins equals the staged one),
- * mdns_stage_params and mdns_clike_first_accept.  *n_act_out = active data sets; Lout must hold
- * that many doubles. */
+ * mdns_stage_params and mdns_clike_first_accept.  *n_act_out = active data sets; Lmins and Lout
+ * must both hold lout_capacity >= n_act doubles (checked before either is touched).  With at most
+ * 64 active data sets and at most 32 candidates the pass is ONE kernel launch (candidates by
+ * value, decision and vector written to pinned memory; the logL are bit-identical to the general
+ * path's); after such a pass the candidates are not staged on the device: stage again before
+ * mdns_clike_launch / mdns_clike_first_accept. */
 int mdns_clike_draw_pass(mdns_dataset *ds, const uint8_t *mask, const double *Lmins,
                          const double *params, int K, double noise, double scale,
                          int *accept_counts, int *first_k, double *Lout, int64_t lout_capacity,
@@ -205,9 +210,10 @@ int mdns_clike_accept_counts(mdns_dataset *ds, double noise, double scale, const
 int mdns_fetch_candidate(mdns_dataset *ds, int k, double *Lout, int64_t lout_capacity);
 int mdns_fetch(mdns_dataset *ds, double *Lout, int64_t lout_capacity);
 int mdns_sync(mdns_dataset *ds);
-/* Experiment knob: the dense first-accept pass scores the active data sets in row chunks and
- * downloads the (speculatively) selected candidate's rows of a finished chunk while the next one
- * is scored; 0 = automatic, 1 = one chunk, up to 8. */
+/* Experiment knob: the dense first-accept pass can score the active data sets in row chunks; the
+ * accept counts so far go down after every chunk and the rows of a finished chunk start their
+ * way to the host as soon as the counts name a candidate.  0 = automatic (one launch: measured
+ * faster), 1 = one chunk, up to 7. */
 int mdns_set_draw_chunks(mdns_dataset *ds, int nchunks);
 
 /* ---- one process per GPU: the exchange step ---------- */
