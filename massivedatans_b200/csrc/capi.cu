@@ -2361,6 +2361,11 @@ struct mdns_region {
 	size_t counts_cap = 0;
 	int *h_counts = nullptr;          // pinned
 	size_t h_counts_cap = 0;
+	// small calls: candidates staged in pinned memory the kernel reads directly, a ticket on the
+	// device and a flag in pinned memory the host polls (count_done, neighbor_kernels.cu)
+	double *h_yy = nullptr;
+	int *h_flag = nullptr, *d_ticket = nullptr;
+	int small_seq = 0;
 	double *d_chosen = nullptr;
 	size_t chosen_cap = 0;
 	int *d_qidx = nullptr, *d_ridx = nullptr;
@@ -2426,6 +2431,9 @@ int mdns_region_destroy(mdns_region *rg)
 	cudaFree(rg->d_yy);
 	cudaFree(rg->d_counts);
 	if (rg->h_counts) cudaFreeHost(rg->h_counts);
+	if (rg->h_yy) cudaFreeHost(rg->h_yy);
+	if (rg->h_flag) cudaFreeHost(rg->h_flag);
+	cudaFree(rg->d_ticket);
 	cudaFree(rg->d_chosen);
 	cudaFree(rg->d_qidx);
 	cudaFree(rg->d_ridx);
@@ -2518,7 +2526,7 @@ int mdns_region_count_within(mdns_region *rg, double maxdistance, const double *
 		rg->h_counts = nullptr;
 		rg->h_counts_cap = 0;
 		const size_t cap = (size_t)m + m / 4;
-		MDNS_CUDA(cudaHostAlloc((void **)&rg->h_counts, cap * sizeof(int), cudaHostAllocPortable));
+		MDNS_CUDA(cudaHostAlloc((void **)&rg->h_counts, cap * sizeof(int), cudaHostAllocPortable | cudaHostAllocMapped));
 		rg->h_counts_cap = cap;
 	}
 	// The device may stop scanning a candidate once `countmax` hits are seen only if every
@@ -2526,15 +2534,44 @@ int mdns_region_count_within(mdns_region *rg, double maxdistance, const double *
 	bool zero_start = true;
 	for (int j = 0; j < m && zero_start; ++j) zero_start = out[j] == 0.0;
 	const int stop_at = (countmax > 0 && zero_start) ? countmax : 0;
-	MDNS_CUDA(cudaMemcpyAsync(rg->d_yy, yy, (size_t)m * rg->ndim * sizeof(double),
-	                          cudaMemcpyHostToDevice, rg->stream));
-	rc = launch_count_within(rg->d_xs, rg->n, rg->npad, rg->ndim, rg->d_yy, m,
-	                         sqrt_threshold(maxdistance), stop_at, rg->d_counts, rg->sm_count,
-	                         rg->stream);
-	if (rc != MDNS_OK) return rc;
-	MDNS_CUDA(cudaMemcpyAsync(rg->h_counts, rg->d_counts, (size_t)m * sizeof(int),
-	                          cudaMemcpyDeviceToHost, rg->stream));
-	MDNS_CUDA(cudaStreamSynchronize(rg->stream));
+	constexpr size_t SMALL_YY_BYTES = 128 * 1024;
+	const size_t yy_bytes = (size_t)m * rg->ndim * sizeof(double);
+	if (yy_bytes <= SMALL_YY_BYTES && (long long)rg->n * m <= (1LL << 22)) {
+		// latency path (the sampler's 400 x 1000 rounds): no copy calls, no stream wait
+		if (!rg->h_yy) {
+			MDNS_CUDA(cudaHostAlloc((void **)&rg->h_yy, SMALL_YY_BYTES, cudaHostAllocPortable | cudaHostAllocMapped));
+			MDNS_CUDA(cudaHostAlloc((void **)&rg->h_flag, sizeof(int), cudaHostAllocPortable | cudaHostAllocMapped));
+			*rg->h_flag = 0;
+			MDNS_CUDA(cudaMalloc((void **)&rg->d_ticket, sizeof(int)));
+			MDNS_CUDA(cudaMemsetAsync(rg->d_ticket, 0, sizeof(int), rg->stream));
+		}
+		memcpy(rg->h_yy, yy, yy_bytes);
+		const int seq = ++rg->small_seq == 0 ? ++rg->small_seq : rg->small_seq;
+		rc = launch_count_within(rg->d_xs, rg->n, rg->npad, rg->ndim, rg->h_yy, m, sqrt_threshold(maxdistance),
+		                         stop_at, rg->h_counts, rg->sm_count, rg->stream, rg->d_ticket, rg->h_flag, seq);
+		if (rc != MDNS_OK) return rc;
+		volatile int *flag = (volatile int *)rg->h_flag;
+		for (unsigned spins = 1; *flag != seq; ++spins) {
+			if ((spins & 0xfffu) == 0) {
+				const cudaError_t q = cudaStreamQuery(rg->stream);
+				if (q == cudaErrorNotReady) continue;
+				if (q != cudaSuccess || *flag != seq) {
+					set_error("neighbour count (latency path) failed: %s", cudaGetErrorString(q));
+					return MDNS_ECUDA;
+				}
+			}
+		}
+		std::atomic_thread_fence(std::memory_order_acquire);
+	} else {
+		MDNS_CUDA(cudaMemcpyAsync(rg->d_yy, yy, yy_bytes, cudaMemcpyHostToDevice, rg->stream));
+		rc = launch_count_within(rg->d_xs, rg->n, rg->npad, rg->ndim, rg->d_yy, m,
+		                         sqrt_threshold(maxdistance), stop_at, rg->d_counts, rg->sm_count,
+		                         rg->stream);
+		if (rc != MDNS_OK) return rc;
+		MDNS_CUDA(cudaMemcpyAsync(rg->h_counts, rg->d_counts, (size_t)m * sizeof(int),
+		                          cudaMemcpyDeviceToHost, rg->stream));
+		MDNS_CUDA(cudaStreamSynchronize(rg->stream));
+	}
 	// replay the reference's per-hit update of out[j] (cneighbors.c:110-114)
 	for (int j = 0; j < m; ++j) {
 		const int hits = rg->h_counts[j];

@@ -184,8 +184,12 @@ int tile_constant_capacity();
 
 // ------------------------------------------------------------ neighbours ---
 // members in SoA layout xs[k*npad + i]
+// ticket (device int, zero) / host_flag (pinned) / seq: the last CTA to finish writes seq to
+// *host_flag after every count is visible to the host (small calls polled by the host); nullptr:
+// an ordinary launch
 int launch_count_within(const double *xs, int n, int npad, int ndim, const double *yy, int m,
-                        double T, int stop_at, int *counts, int sm_count, cudaStream_t st);
+                        double T, int stop_at, int *counts, int sm_count, cudaStream_t st,
+                        int *ticket = nullptr, int *host_flag = nullptr, int seq = 0);
 // m ball draws of RadFriendsRegion.generate fused with the neighbour count: points[m][ndim],
 // keep[m] (accepted with probability 1/nnear), nnear[m]; Philox keyed by (seed, first + j)
 int launch_region_generate(const double *xs, int n, int npad, int ndim, double r, double T,

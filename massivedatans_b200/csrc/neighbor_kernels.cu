@@ -32,17 +32,46 @@ __device__ __forceinline__ double sqdist_reg(const double (&a)[D], const double 
 }
 
 // ------------------------------------------------------------------ count ---
+// Small calls (the sampler's 400 members x 1000 candidates, two per proposal round) are pure
+// latency: the candidates are read straight from pinned host memory, the counts written straight
+// into it, and the last CTA to finish (ticket) raises a flag the host polls -- no copy calls, no
+// stream wait.  `done` = {ticket on the device, flag in pinned memory}, null for ordinary launches.
+struct CountDone {
+	int *ticket;
+	int *host_flag;
+	int seq;
+};
+
+__device__ __forceinline__ void count_done(const CountDone &done)
+{
+	if (!done.ticket) return;
+	__threadfence_system();      // this thread's counts, for the host
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const int t = atomicAdd(done.ticket, 1);
+		if (t == (int)gridDim.x - 1) {
+			*done.ticket = 0;
+			__threadfence_system();
+			*reinterpret_cast<volatile int *>(done.host_flag) = done.seq;
+		}
+	}
+}
+
 template <int D, int CPW>
 __global__ void __launch_bounds__(NB_THREADS) count_within_kernel(const double *__restrict__ xs,
                                                                   int n, int npad,
                                                                   const double *__restrict__ yy,
                                                                   int m, double T, int stop_at,
-                                                                  int *__restrict__ counts)
+                                                                  int *__restrict__ counts,
+                                                                  const CountDone done)
 {
 	const int lane = threadIdx.x & 31;
 	const long long wid = ((long long)blockIdx.x * NB_THREADS + threadIdx.x) >> 5;
 	const long long j0 = wid * CPW;
-	if (j0 >= m) return;
+	if (j0 >= m) {
+		count_done(done);
+		return;
+	}
 	double y[CPW][D];
 	int cnt[CPW];
 #pragma unroll
@@ -88,16 +117,20 @@ __global__ void __launch_bounds__(NB_THREADS) count_within_kernel(const double *
 		for (int c = 0; c < CPW; ++c)
 			if (j0 + c < m) counts[j0 + c] = cnt[c];
 	}
+	count_done(done);
 }
 
 // any dimensionality: coordinates streamed per channel
 __global__ void __launch_bounds__(NB_THREADS) count_within_generic_kernel(
     const double *__restrict__ xs, int n, int npad, int ndim, const double *__restrict__ yy, int m,
-    double T, int stop_at, int *__restrict__ counts)
+    double T, int stop_at, int *__restrict__ counts, const CountDone done)
 {
 	const int lane = threadIdx.x & 31;
 	const long long j = ((long long)blockIdx.x * NB_THREADS + threadIdx.x) >> 5;
-	if (j >= m) return;
+	if (j >= m) {
+		count_done(done);
+		return;
+	}
 	const double *y = yy + j * ndim;
 	int cnt = 0;
 	for (int base = 0; base < n; base += 32) {
@@ -116,6 +149,7 @@ __global__ void __launch_bounds__(NB_THREADS) count_within_generic_kernel(
 		if (stop_at > 0 && cnt >= stop_at) break;
 	}
 	if (lane == 0) counts[j] = cnt;
+	count_done(done);
 }
 
 // Full counts of many candidates against many members (no early exit): lanes over CANDIDATES,
@@ -210,40 +244,43 @@ static int launch_count_tile(const double *xs, int n, int npad, const double *yy
 
 template <int D>
 static int launch_count_d(const double *xs, int n, int npad, const double *yy, int m, double T,
-                          int stop_at, int *counts, int sm_count, cudaStream_t st)
+                          int stop_at, int *counts, int sm_count, cudaStream_t st, const CountDone &done)
 {
 	// full counts of a large problem: lanes over candidates (T >= +0 and not NaN: bit-pattern compare)
-	if (stop_at == 0 && (long long)n * m >= CT_MIN_PAIRS && T >= 0.0)
+	if (!done.ticket && stop_at == 0 && (long long)n * m >= CT_MIN_PAIRS && T >= 0.0)
 		return launch_count_tile<D>(xs, n, npad, yy, m, T, counts, sm_count, st);
 	const long long warps_wanted = (long long)sm_count * 16;
 	if (m >= 4 * warps_wanted) {
 		const int warps = ceil_div(m, 4);
 		count_within_kernel<D, 4><<<ceil_div(warps, NB_THREADS / 32), NB_THREADS, 0, st>>>(
-		    xs, n, npad, yy, m, T, stop_at, counts);
+		    xs, n, npad, yy, m, T, stop_at, counts, done);
 	} else {
 		count_within_kernel<D, 1><<<ceil_div(m, NB_THREADS / 32), NB_THREADS, 0, st>>>(
-		    xs, n, npad, yy, m, T, stop_at, counts);
+		    xs, n, npad, yy, m, T, stop_at, counts, done);
 	}
 	MDNS_LAUNCHED("count_within_kernel");
 	return MDNS_OK;
 }
 
+// ticket / host_flag / seq: see CountDone (ticket == nullptr: an ordinary launch)
 int launch_count_within(const double *xs, int n, int npad, int ndim, const double *yy, int m,
-                        double T, int stop_at, int *counts, int sm_count, cudaStream_t st)
+                        double T, int stop_at, int *counts, int sm_count, cudaStream_t st, int *ticket,
+                        int *host_flag, int seq)
 {
 	if (m <= 0) return MDNS_OK;
+	const CountDone done = {ticket, host_flag, seq};
 	switch (ndim) {
-	case 1: return launch_count_d<1>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st);
-	case 2: return launch_count_d<2>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st);
-	case 3: return launch_count_d<3>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st);
-	case 4: return launch_count_d<4>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st);
-	case 5: return launch_count_d<5>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st);
-	case 6: return launch_count_d<6>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st);
-	case 7: return launch_count_d<7>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st);
-	case 8: return launch_count_d<8>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st);
+	case 1: return launch_count_d<1>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st, done);
+	case 2: return launch_count_d<2>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st, done);
+	case 3: return launch_count_d<3>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st, done);
+	case 4: return launch_count_d<4>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st, done);
+	case 5: return launch_count_d<5>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st, done);
+	case 6: return launch_count_d<6>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st, done);
+	case 7: return launch_count_d<7>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st, done);
+	case 8: return launch_count_d<8>(xs, n, npad, yy, m, T, stop_at, counts, sm_count, st, done);
 	default:
 		count_within_generic_kernel<<<ceil_div(m, NB_THREADS / 32), NB_THREADS, 0, st>>>(
-		    xs, n, npad, ndim, yy, m, T, stop_at, counts);
+		    xs, n, npad, ndim, yy, m, T, stop_at, counts, done);
 		MDNS_LAUNCHED("count_within_generic_kernel");
 		return MDNS_OK;
 	}
