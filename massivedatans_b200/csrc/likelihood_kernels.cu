@@ -837,7 +837,7 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		// 5e5 active of 1e6 x 200 (tools/sweep_masked.py): K=16 0.159 ms (0.84 of the roofline)
 		// against 0.181 (0.73) for the stream-K gather, K=8 0.150 (0.85) against 0.152 for round 1's
 		// whole-tile gather and 0.241 (0.53) for the stream-K 16-warp gather shape
-		const bool slabs_enough = (a.n_rows + 31) / 32 >= 2LL * 16 * sm_count;
+		const bool slabs_enough = (a.n_rows + 31) / 32 >= 4LL * sm_count;
 		if (a.K > 8 && slabs_enough && slab_dmma_fits(a, 16, 2)) {
 			if (accept_fused) *accept_fused = 1;
 			return launch_slab_dmma(a, 16, 2, sm_count, st);
@@ -876,11 +876,11 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 			// roofline) against 0.305-0.314 for the stream-K kernel; 192 channels 0.262 vs 0.282;
 			// K=24 (two passes of 16) 0.554 vs 0.596.  Two slots per warp beat three (0.288); up to
 			// 8 candidates the stream-K kernel stays ahead (0.258 vs 0.268 ms)
-			// Every warp runs its slabs one box at a time, two copies in flight: per-warp speed is
-			// latency-bound and the machine only saturates with every warp busy for several
-			// slabs.  Below ~2 slabs per warp the stream-K kernel wins (1e5 x 200: 0.057 ms
-			// against 0.082), which is also what the row chunks of the dense accept pass are
-			if (a.K > 8 && slab_dmma_fits(a, 16, 2) && slab_dmma_slabs(a) >= 2LL * 16 * sm_count) {
+			// Small launches: every warp starts with a fixed slab, interleaved over the SMs, so the
+			// kernel is at least level with the stream-K kernel from 1e4 data sets (L2 flushed,
+			// tools/r2_slab_flags.py: 1e4 0.027 / 0.027 ms, 1e5 0.050 / 0.057, 3e5 0.117 / 0.121,
+			// 1e6 0.285 / 0.322); taken from four slabs per SM
+			if (a.K > 8 && slab_dmma_fits(a, 16, 2) && slab_dmma_slabs(a) >= 4LL * sm_count) {
 				if (accept_fused) *accept_fused = 1;
 				return launch_slab_dmma(a, 16, 2, sm_count, st);
 			}

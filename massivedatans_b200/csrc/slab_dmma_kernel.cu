@@ -18,8 +18,9 @@
 //   * warp w owns NSLOT slots of 4 KB (32 rows x 16 channels).  Lane 0 issues the TMA copy of the
 //     box NSLOT units ahead the moment the warp has finished a slot: no producer warp, no empty
 //     barriers, a slot is out of flight only for the 32 DMMAs that read it;
-//   * slabs are handed out by an atomic counter (grabbed one slab ahead, so the round trip is
-//     never waited for); a warp's epilogue overlaps the other 15 warps' contraction;
+//   * every warp starts with a fixed slab (interleaved over the CTAs), further slabs are handed
+//     out by an atomic counter (grabbed one slab ahead, so the round trip is never waited for);
+//     a warp's epilogue overlaps the other 15 warps' contraction;
 //   * P = 2 ("row pairs") when pitch = 8 mod 16 doubles: the matrix is addressed as [N/2] rows
 //     of 2*pitch doubles, whose boxes ARE line-aligned.  Boxes 0..S-1 belong to the even row,
 //     box S holds the even row's last 8 channels and the odd row's first 8, boxes S+1..2S the
@@ -226,12 +227,12 @@ __global__ void __launch_bounds__(SL_THREADS, 1) slab_dmma_kernel(
 
 	// ---- this warp's slabs: `cur` is being contracted, `nxt` comes after it, `grab` is the one
 	// after that, asked for at the start of `cur` and looked at when `cur` is done
-	int cur = 0, nxt = 0, grab = 0;
-	if (lane == 0) {
-		cur = atomicAdd(ctr, 1);
-		nxt = atomicAdd(ctr, 1);
-	}
-	cur = __shfl_sync(0xffffffffu, cur, 0);
+	// The first slab of every warp is fixed -- warp w of CTA b starts with slab b + G w, so a
+	// launch with fewer slabs than warps still spreads over all the SMs -- the rest come from the
+	// counter (which therefore counts from G * 16).
+	const int first_dynamic = (int)gridDim.x * SL_WARPS;
+	int cur = (int)blockIdx.x + (int)gridDim.x * warp, nxt = 0, grab = 0;
+	if (lane == 0) nxt = first_dynamic + atomicAdd(ctr, 1);
 	nxt = __shfl_sync(0xffffffffu, nxt, 0);
 	// the copy cursor runs NSLOT boxes ahead of the contraction: box `pb` of slab (ahead ? nxt : cur)
 	int pb = 0;
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1) slab_dmma_kernel(
 	} while (0)
 
 	while (cur < nslabs) {
-		if (lane == 0) grab = atomicAdd(ctr, 1);
+		if (lane == 0) grab = first_dynamic + atomicAdd(ctr, 1);
 		double acc[P][4][NC][2];
 #pragma unroll
 		for (int p = 0; p < P; ++p)
@@ -432,8 +433,9 @@ static int launch_slab_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 	rc = make_row_tensor_map_box(&tb, a.model, kpad, a.mpitch, KT);
 	if (rc != MDNS_OK) return rc;
 	const long long nslabs = (nsup + SL_ROWS - 1) / SL_ROWS;
-	long long gx = (nslabs + SL_WARPS - 1) / SL_WARPS;
-	if (gx > sm_count) gx = sm_count;
+	// one CTA per SM even when the slabs would fit in fewer: 16 warps on one SM share its FP64
+	// tensor pipe, 16 warps on 16 SMs do not (1e5 x 200 on 98 CTAs: 0.075 ms)
+	long long gx = nslabs < sm_count ? nslabs : sm_count;
 	if (gx < 1) gx = 1;
 	const int npass = ceil_div(a.K, KT);
 	if (!a.xp_counters_clear)
