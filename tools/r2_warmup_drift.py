@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Stream-K kernel against the slab kernel at the bench shape, three rounds in one process: 300
 launches back to back and 40 launches with the L2 flushed before each -- how the two drift as the
-board warms up under its power cap.   python tools/r2_slab_flags.py"""
+board warms up under its power cap.   python tools/r2_warmup_drift.py"""
 import os
 import sys
 
