@@ -35,7 +35,7 @@ def main():
     for tuning, K in (((0, 0, 0, 0), 1), ((0, 0, 0, 0), 3), ((8, 2, 4, 4), 5), ((8, 4, 8, 2), 9),
                       ((1, 116, 8, 3), 9), ((1, 32, 16, 3), 17), ((2, 2, 8, 3), 9), ((2, 4, 16, 2), 17),
                       ((3, 0, 8, 4), 9), ((3, 0, 16, 3), 17), ((3, 0, 32, 2), 33), ((3, 0, 8, 14), 9),
-                      ((3, 0, 16, 13), 17)):
+                      ((3, 0, 16, 13), 17), ((6, 0, 16, 2), 17), ((6, 0, 16, 3), 9), ((6, 0, 8, 2), 9)):
         ds.set_tuning(*tuning)
         pts = synth.parameter_points(K, seed=K)
         for mname in ('all', 'half'):
@@ -46,6 +46,29 @@ def main():
                 want = port.clike(x, y, pts[k][0], pts[k][1], pts[k][2], synth.NOISE_LEVEL,
                                   allm if mname == 'all' else m)
                 assert rel(got[k], want) < 1e-10, (tuning, K, mname, k)
+    # the slab kernel in row-pair mode (pitch 200 = 8 mod 16, odd count) and on an aligned pitch
+    for Ns, nxs in ((4097, 200), (1500, 192)):
+        xs_, ys_, _ = synth.horns(Ns, nx=nxs, legacy=False, seed=2)
+        dss = ResidentDataset(xs_, ys_)
+        dss.set_tuning(6, 0, 16, 2)
+        ptss = synth.parameter_points(16, seed=3)
+        for mname in ('all', 'half'):
+            ms_ = synth.masks(Ns)[mname]
+            gots = dss.loglike_batch(ptss, None if mname == 'all' else ms_, synth.NOISE_LEVEL, scale=1.0)
+            seen.add(lib.mdns_last_kernel().decode())
+            want = port.clike(xs_, ys_, ptss[15][0], ptss[15][1], ptss[15][2], synth.NOISE_LEVEL, ms_)
+            assert rel(gots[15], want) < 1e-10, (Ns, nxs, mname)
+        # one launch per speculative pass over a handful of data sets
+        few = numpy.zeros(Ns, dtype=bool)
+        few[[3, 77, Ns - 1]] = True
+        dss.set_tuning(0, 0, 0, 0)
+        Lf = dss.loglike_batch(ptss, few, synth.NOISE_LEVEL).copy()
+        th = numpy.sort(Lf, axis=0)[12]                # three candidates per data set get through
+        kf, Lk, cf = dss.draw_pass(few, th, ptss, synth.NOISE_LEVEL)
+        seen.add(lib.mdns_last_kernel().decode())
+        wc = (Lf > th).sum(axis=1)
+        assert numpy.array_equal(cf, wc) and kf == int(numpy.nonzero(wc)[0][0]) and numpy.array_equal(Lk, Lf[kf])
+        dss.close()
     ds.set_tuning(0, 0, 0, 0)
     pts = synth.parameter_points(6, seed=2)
     Ls = numpy.array([-0.5 * port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, masks['half']) for p in pts])
@@ -69,6 +92,10 @@ def main():
     assert numpy.array_equal(neighbors.any_within_distance_of(xx, r, yy), port.any_within_distance_of(xx, r, yy))
     assert neighbors.most_distant_nearest_neighbor(xx) == port.most_distant_nearest_neighbor(xx)
     assert neighbors.is_within_distance_of(xx, r, yy[0]) == port.is_within_distance_of(xx, r, yy[0])
+    # full counts of a large problem: lanes over candidates, member ranges, atomics
+    xb, yb = synth.members_and_candidates(4099, 4101, 3)
+    assert numpy.array_equal(neighbors.count_within_distance_of(xb, 0.05, yb), port.count_within_distance_of(xb, 0.05, yb))
+    seen.add(lib.mdns_last_kernel().decode())
     # live table
     rs = numpy.random.RandomState(3)
     Lt = rs.normal(size=(23, N))
