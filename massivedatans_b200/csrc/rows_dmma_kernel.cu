@@ -552,6 +552,10 @@ static int launch_rd_inst(const LikeArgs &a, int nmat, int sm_count, cudaStream_
 	if (gx > resident) gx = resident;
 	if (gx > sm_count && T / gx < 64) gx = T / 64 > sm_count ? T / 64 : sm_count;
 	if (gx < 1) gx = 1;
+	if (const char *e = getenv("MDNS_RD_GX")) {      // experiment knob: CTAs of the launch
+		const long long v = atoll(e);
+		if (v >= 1 && v <= resident) gx = v;
+	}
 	const int npass = ceil_div(a.K, KT);
 	if (EPI == EPI_CLIKE) {
 		if (npass + 1 > xtile_counter_capacity()) {
