@@ -832,7 +832,6 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		// (two producer warps).  Measured, 5e5 active of 1e6 data sets: K=8 0.152 ms (block kernel
 		// 0.180), K=16 0.173 ms (0.358), K=32 0.43 ms (0.71); up to 4 candidates the block kernel
 		// wins (K=4 0.141 ms).
-		if (a.K >= 32 && dmma_fits(a, 32, 3)) return launch_dmma_auto(a, 32, 3, sm_count, st, accept_fused);
 		// per-warp slabs, every warp gathering its own listed rows (slab_dmma_kernel.cu); same box,
 		// 5e5 active of 1e6 x 200 (tools/sweep_masked.py): K=16 0.159 ms (0.84 of the roofline)
 		// against 0.181 (0.73) for the stream-K gather, K=8 0.150 (0.85) against 0.152 for round 1's
@@ -842,6 +841,8 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 			if (accept_fused) *accept_fused = 1;
 			return launch_slab_dmma(a, 16, 2, sm_count, st);
 		}
+		// (passes of 16 whatever K: 0.158 ms each against 0.43 ms for a gathered pass of 32)
+		if (a.K >= 32 && dmma_fits(a, 32, 3)) return launch_dmma_auto(a, 32, 3, sm_count, st, accept_fused);
 		if (a.K >= 16 && dmma_fits(a, 16, 13)) return launch_dmma_auto(a, 16, 13, sm_count, st, accept_fused);
 		if (slabs_enough && slab_dmma_fits(a, 8, 2)) {
 			if (accept_fused) *accept_fused = 1;
@@ -870,20 +871,26 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 			// 0.277).  Stage counts + 10 select the 16-warp shape.  From K = 3 on a pass of 8
 			// (padded) candidates on the tensor path beats the lanes-across-channels kernels
 			// (K=4: 0.266 ms vs 0.289 ms block kernel).
-			if (a.K >= 32 && dmma_fits(a, 32, 3)) return launch_dmma_auto(a, 32, 3, sm_count, st, accept_fused);
-			// 9..31 candidates on short spectra: per-warp slabs, batch resident in shared memory
+			// passes of 16 on the slab kernel (0.285 ms each at 1e6 x 200) against passes of 32 on
+			// the stream-K kernel (0.45-0.47 ms each, FP64-tensor-bound): K = 17..32 is one pass of
+			// 32 (0.45-0.52 ms; two slab passes 0.54-0.60), 33..48 three passes of 16
+			const int passes16 = (a.K + 15) / 16, passes32 = (a.K + 31) / 32;
+			const bool prefer16 = passes16 * 5 < passes32 * 8;
+			if (a.K > 16 && !prefer16 && dmma_fits(a, 32, 3)) return launch_dmma_auto(a, 32, 3, sm_count, st, accept_fused);
+			// 9..16 candidates on short spectra: per-warp slabs, batch resident in shared memory
 			// (slab_dmma_kernel.cu).  Same box, 1e6 x 200, K=16: 0.281-0.284 ms (0.93-0.94 of the
 			// roofline) against 0.305-0.314 for the stream-K kernel; 192 channels 0.262 vs 0.282;
 			// K=24 (two passes of 16) 0.554 vs 0.596.  Two slots per warp beat three (0.288); up to
 			// 8 candidates the stream-K kernel stays ahead (0.258 vs 0.268 ms)
 			// Small launches: every warp starts with a fixed slab, interleaved over the SMs, so the
 			// kernel is at least level with the stream-K kernel from 1e4 data sets (L2 flushed,
-			// tools/r2_slab_flags.py: 1e4 0.027 / 0.027 ms, 1e5 0.050 / 0.057, 3e5 0.117 / 0.121,
+			// tools/r2_warmup_drift.py and r2_small_n.py: 1e4 0.027 / 0.027 ms, 1e5 0.050 / 0.057, 3e5 0.117 / 0.121,
 			// 1e6 0.285 / 0.322); taken from four slabs per SM
 			if (a.K > 8 && slab_dmma_fits(a, 16, 2) && slab_dmma_slabs(a) >= 4LL * sm_count) {
 				if (accept_fused) *accept_fused = 1;
 				return launch_slab_dmma(a, 16, 2, sm_count, st);
 			}
+			if (a.K >= 32 && dmma_fits(a, 32, 3)) return launch_dmma_auto(a, 32, 3, sm_count, st, accept_fused);
 			if (a.K >= 16 && dmma_fits(a, 16, 13)) return launch_dmma_auto(a, 16, 13, sm_count, st, accept_fused);
 			if (dmma_fits(a, 8, 14)) return launch_dmma_auto(a, 8, 14, sm_count, st, accept_fused);
 			const int xkt = a.K >= 16 && xtile_fits(a, 16, 2) ? 16 : 8;
