@@ -252,7 +252,9 @@ int mdns_timer_stop(mdns_dataset *ds, float *elapsed_ms);
 int mdns_flush_l2(mdns_dataset *ds);
 /* Kernel-variant override for experiments: lanes per data set (0 = auto),
  * fragments in flight per lane (0 = auto), candidates per pass (0 = auto),
- * data sets per lane group (0 = auto; > 1 selects the register-blocked kernel). */
+ * data sets per lane group (0 = auto; > 1 selects the register-blocked kernel).
+ * lanes = 7: parameter-point batches of any size in ONE launch (every CTA builds the spectra,
+ * direct form) -- the automatic choice only up to a few 1e5 model x data-set evaluations. */
 int mdns_set_tuning(mdns_dataset *ds, int lanes, int unroll, int ktile, int rows);
 /* Expanded form of the candidate-batch kernel (K >= 3, all data sets active, >= 32768 of them):
  *     sum_j (m_j - y_j)^2 = Syy - 2*Sym + Smm ,  Syy resident per data set,

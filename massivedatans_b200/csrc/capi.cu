@@ -22,6 +22,15 @@ static thread_local std::string g_error;
 std::atomic<long long> g_launches{0};
 std::atomic<const char *> g_last_kernel{""};
 
+bool pdl_enabled()
+{
+	static const bool on = []() {
+		const char *e = getenv("MDNS_NO_PDL");
+		return !(e && *e && *e != '0');
+	}();
+	return on;
+}
+
 void set_error(const char *fmt, ...)
 {
 	char buf[1024];
@@ -657,6 +666,26 @@ int mdns_internal_threshold_buffer(mdns_dataset *ds, int shard, double **d_lmins
 	return MDNS_OK;
 }
 
+// a small batch of parameter points: one launch builds the spectra and scores the shard's active
+// rows in the direct form (clike_small_kernel) -- no model kernel, no row sums, no fix-up launch.
+// Automatic up to SMALL_AUTO_EVALS padded model x data-set evaluations per shard (the step of
+// the tensor path is ~20 us of launch latencies whatever the size; MDNS_SMALL_EVALS overrides
+// the limit); set_tuning(7, ...) asks for it at any size.
+constexpr long long SMALL_AUTO_EVALS = 400000;
+static bool inline_batch(const mdns_dataset *ds, const Shard &s)
+{
+	if (ds->staged != 1 || ds->K < 2 || ds->has_var || !clike_small_fits(ds->K, (int)ds->pitch)) return false;
+	if (ds->tuning.lanes == 7) return true;
+	if (ds->tuning.lanes != 0 || ds->tuning.unroll != 0 || ds->tuning.ktile != 0 || ds->tuning.rows != 0)
+		return false;
+	static const long long limit = []() {
+		const char *e = getenv("MDNS_SMALL_EVALS");
+		return e && *e ? atoll(e) : SMALL_AUTO_EVALS;
+	}();
+	const int kt = clike_small_ktile(ds->K);
+	return (long long)s.n_act * ceil_div(ds->K, kt) * kt <= limit;
+}
+
 static int ensure_batch(mdns_dataset *ds, Shard &s, int K);
 
 // internal (muse_model.cu): the model-spectrum buffer of shard `shard` sized for K spectra
@@ -922,6 +951,7 @@ static void fill_args(const mdns_dataset *ds, const Shard &s, LikeArgs &a)
 	a.line_A = ds->single[0];
 	a.line_mu = ds->single[1];
 	a.line_sig = ds->single[2];
+	a.params = inline_batch(ds, s) ? s.d_in : nullptr;
 	a.syy = s.syy;
 	a.smm = s.d_smm;
 	a.xp_redo = s.d_redo;
@@ -936,7 +966,7 @@ static void fill_args(const mdns_dataset *ds, const Shard &s, LikeArgs &a)
 // may this launch take the expanded form? (mirrors the automatic choice of launch_clike)
 static bool xp_candidate(const mdns_dataset *ds, const Shard &s)
 {
-	if (!s.syy) return false;
+	if (!s.syy || inline_batch(ds, s)) return false;
 	if (long_rows(ds) && ds->tuning.allow_expanded && (s.all_active || s.has_gather)) return true;
 	if (!s.all_active) {
 		// masked batches: only the tensor path has a gather form
@@ -964,7 +994,7 @@ static int clike_check(mdns_dataset *ds, const char *who)
 static int clike_model(mdns_dataset *ds, Shard &s)
 {
 	s.counters_clear = false;
-	if (inline_single(ds)) return MDNS_OK;    // built inside the likelihood kernel
+	if (inline_single(ds) || inline_batch(ds, s)) return MDNS_OK;    // built inside the likelihood kernel
 	const int Kpad = (int)round_up(ds->K, KT_MAX);
 	const bool xp = xp_candidate(ds, s);
 	const int npass = ceil_div(ds->K, 8);

@@ -69,6 +69,10 @@ __device__ __forceinline__ void xt_tma_load_2d(void *smem_dst, const CUtensorMap
 __global__ void __launch_bounds__(256) xtile_fixup_kernel(const LikeArgs a, const int k0,
                                                           const int kt_valid, const int pass)
 {
+	// launched as a programmatic dependent of the likelihood kernel: set up while that one is
+	// still running, and nothing is touched before it has completed
+	pdl_trigger();
+	pdl_wait();
 	// (slab_dmma_kernel hands out its slabs through a counter behind the list lengths: back to
 	// zero for the next launch of this pass)
 	if (blockIdx.x == 0 && threadIdx.x == 0 && pass < slab_counter_count_dev) a.xp_redo[slab_counter_base_dev + pass] = 0;
@@ -290,7 +294,7 @@ int launch_xtile_fixup(const LikeArgs &a, int k0, int kv, int pass, int sm_count
 {
 	int fix_blocks = ceil_div(a.n_rows, 8);
 	if (fix_blocks > 2 * sm_count) fix_blocks = 2 * sm_count;
-	xtile_fixup_kernel<<<fix_blocks, 256, 0, st>>>(a, k0, kv, pass);
+	launch_pdl(xtile_fixup_kernel, dim3(fix_blocks), dim3(256), 0, st, true, a, k0, kv, pass);
 	MDNS_LAUNCHED_HELPER("xtile_fixup_kernel");
 	return MDNS_OK;
 }

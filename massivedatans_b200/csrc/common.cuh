@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <string>
+#include <utility>
 
 #include "../../include/mdns_b200.h"
 
@@ -52,6 +53,33 @@ extern std::atomic<const char *> g_last_kernel;
 		}                                                                    \
 	} while (0)
 
+// Programmatic dependent launch (round 2): a kernel launched with `pdl` may start while the
+// kernel before it on the stream is still running, once every CTA of that kernel has executed
+// pdl_trigger() (or exited); whatever it reads of the earlier kernel's output comes after its
+// pdl_wait(), which returns when the earlier grid has completed and its writes are visible.
+// Only kernels that call pdl_wait() unconditionally on every thread are ever launched this way.
+// Inside a stream capture the dependency becomes a programmatic edge of the graph.
+// MDNS_NO_PDL=1 launches everything fully serialised.
+bool pdl_enabled();
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t st, bool pdl, Args &&...args)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid;
+	cfg.blockDim = block;
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = pdl && pdl_enabled() ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+#endif
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
@@ -68,6 +96,9 @@ __device__ __forceinline__ double2 ldg_stream(const double2 *p)
 	             : "l"(p));
 	return v;
 }
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {

@@ -63,6 +63,9 @@ struct LikeArgs {
 	int inline_model;
 	const double *x;      // wavelength grid
 	double line_A, line_mu, line_sig;
+	// small batches (clike_small_kernel): the staged parameter points (A, mu, sig) on the device;
+	// every CTA builds the spectra itself, no model kernel ran.  nullptr = spectra in `model`
+	const double *params = nullptr;
 	// expanded form (clike_xtile_kernel): Syy - 2 Sym + Smm
 	const double *syy;    // resident sum of squares of every row of the shard, or nullptr
 	const double *smm;    // [Kpad] sum of squares of every model spectrum
@@ -92,7 +95,8 @@ struct Tuning {
 	                 // stage 16/32, rows = ring stages 3/4/6, all-active only), 2 = expanded-form
 	                 // tile kernel (unroll = data sets per lane 2/4, rows = ring stages 2/3,
 	                 // all-active only), 3 = expanded form on the FP64 tensor path (DMMA;
-	                 // ktile 8/16/32, rows = ring stages 2/3/4); 0 = auto
+	                 // ktile 8/16/32, rows = ring stages 2/3/4); 6 = per-warp slabs on the tensor
+	                 // path; 7 = small batches in one launch (clike_small_kernel); 0 = auto
 	int unroll = 0;  // 128-bit fragments in flight per lane (0 = auto)
 	int ktile = 0;   // candidates per pass (0 = auto)
 	int rows = 0;    // data sets per lane group in the block kernel: 1, 2, 4 (0 = auto)
@@ -102,6 +106,9 @@ struct Tuning {
 int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t st,
                  int *accept_fused = nullptr);
 int launch_muse(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t st);
+// small batches in one launch (clike_small_kernel): candidates per slice, shared-memory fit
+int clike_small_ktile(int K);
+bool clike_small_fits(int K, int mpitch);
 // one speculative pass over a handful of active data sets in ONE launch: candidates by value,
 // decision and the accepted vector written to pinned host memory (likelihood_kernels.cu)
 bool draw_small_fits(const LikeArgs &a);

@@ -57,6 +57,9 @@ __global__ void __launch_bounds__(256) line_model_kernel(const double *__restric
                                                          int *__restrict__ counters, int ncounters)
 {
 	__shared__ double warp_sums[8];
+	// the likelihood kernel that follows may start its prologue and its first row copies now;
+	// it reads the spectra, Smm and the counters only after its pdl_wait()
+	pdl_trigger();
 	const int k = blockIdx.x;
 	double A = 0.0, mu = 0.0, sig = 1.0;
 	if (k < K) {
@@ -519,6 +522,151 @@ int launch_draw_small(const LikeArgs &a, const double *params, int seq, int *hos
 	return MDNS_OK;
 }
 
+// ---- small candidate batches in ONE launch ---------------------------------------------------
+// Up to a few 1e5 model x data-set evaluations (1e4 data sets x 16 candidates, the size of the
+// reference's own runs: BASELINE configs[0] / [1]) are a few microseconds of arithmetic; the
+// three-launch step of the tensor path (model kernel, contraction, fix-up) costs 20 us of launch
+// latencies there.  Here every CTA builds the KT spectra of its candidate slice in shared memory
+// from the staged parameter points (clike.c:65, un-fused like line_model_kernel: bit-identical
+// spectra) and scores its rows in the DIRECT form: 8 lanes per data set, the fragment order per
+// lane and the butterfly of clike_rows_kernel<8, ...> (so the two agree to the last bit), warps
+// strided over groups of four rows so that the FP64 work spreads evenly over the SMs.  No row
+// sums, no guard, no fix-up list; the accept test is fused in like everywhere else.
+template <int KT>
+__global__ void __launch_bounds__(LK_THREADS) clike_small_kernel(const LikeArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	double *smd = reinterpret_cast<double *>(smem_raw);                  // [KT][mpitch] spectra
+	const double2 *sm = reinterpret_cast<const double2 *>(smem_raw);
+	constexpr int L = 8, G = 32 / L, U = 4;
+	const int k0 = blockIdx.y * KT;
+	const int mfp = a.mpitch >> 1;
+	const int nfrag = (a.nx + 1) >> 1;
+	for (int idx = threadIdx.x; idx < KT * a.mpitch; idx += LK_THREADS) {
+		const int k = idx / a.mpitch, j = idx - k * a.mpitch;
+		double v = 0.0;
+		if (k0 + k < a.K && j < a.nx) {
+			const double *p = a.params + 3 * (k0 + k);
+			const double t = __ddiv_rn(__dsub_rn(p[1], a.x[j]), p[2]);
+			v = __dmul_rn(p[0], exp(__dmul_rn(-0.5, __dmul_rn(t, t))));
+		}
+		smd[idx] = v;
+	}
+	__syncthreads();
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int g = lane / L, gl = lane % L;
+	const double inv = a.scale / a.noise2;
+	int acnt[KT];
+#pragma unroll
+	for (int k = 0; k < KT; ++k) acnt[k] = 0;
+	const long long nquads = ((long long)a.n_rows + G - 1) / G;
+	const long long wstride = (long long)gridDim.x * (LK_THREADS / 32);
+	for (long long q = (long long)warp * gridDim.x + blockIdx.x; q < nquads; q += wstride) {
+		const long long r = q * G + g;
+		const bool valid = r < a.n_rows;
+		double acc0[KT], acc1[KT];
+#pragma unroll
+		for (int k = 0; k < KT; ++k) acc0[k] = acc1[k] = 0.0;
+		const double lm = (valid && a.lmins) ? __ldg(a.lmins + r) : 0.0;
+		if (valid) {
+			const long long row = a.active ? (long long)a.active[r] : r;
+			const double2 *p = reinterpret_cast<const double2 *>(a.Y + row * a.pitch);
+			for (int f = gl; f < nfrag; f += L * U) {
+				double2 y[U];
+#pragma unroll
+				for (int u = 0; u < U; ++u)
+					if (f + u * L < nfrag) y[u] = ldg_stream(p + f + u * L);
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					const int fi = f + u * L;
+					if (fi < nfrag) {
+#pragma unroll
+						for (int k = 0; k < KT; ++k) {
+							const double2 m = sm[k * mfp + fi];
+							const double d0 = m.x - y[u].x;
+							const double d1 = m.y - y[u].y;
+							acc0[k] = fma(d0, d0, acc0[k]);
+							acc1[k] = fma(d1, d1, acc1[k]);
+						}
+					}
+				}
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < KT; ++k) {
+			double s = acc0[k] + acc1[k];
+#pragma unroll
+			for (int o = L / 2; o > 0; o >>= 1) s += shfl_xor_f64(s, o);
+			const bool mine = valid && gl == 0 && k0 + k < a.K;
+			const double val = s * inv;
+			if (mine && a.out) a.out[(long long)(k0 + k) * a.out_stride + r] = val;
+			if (a.counts) acnt[k] += __popc(__ballot_sync(0xffffffffu, mine && val > lm));
+		}
+	}
+	if (a.counts && lane == 0) {
+#pragma unroll
+		for (int k = 0; k < KT; ++k)
+			if (acnt[k]) atomicAdd(a.counts + k0 + k, acnt[k]);
+	}
+}
+
+// candidates per slice: padded candidates + one per slice (every slice reads the rows again and
+// builds its own spectra) as small as possible, the larger slice on a tie
+int clike_small_ktile(int K)
+{
+	int best = 16;
+	long long best_cost = (long long)ceil_div(K, 16) * 17;
+	for (int kt : {8, 4, 2}) {
+		const long long cost = (long long)ceil_div(K, kt) * (kt + 1);
+		if (cost < best_cost) {
+			best = kt;
+			best_cost = cost;
+		}
+	}
+	return best;
+}
+
+bool clike_small_fits(int K, int mpitch)
+{
+	return K >= 1 && (size_t)clike_small_ktile(K) * mpitch * 8 <= 200 * 1024;
+}
+
+template <int KT>
+static int launch_clike_small_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
+{
+	const size_t smem = (size_t)KT * a.mpitch * 8;
+	auto kern = clike_small_kernel<KT>;
+	if (smem > 48 * 1024)
+		MDNS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int occ = 0;
+	MDNS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LK_THREADS, smem));
+	if (occ < 1) {
+		set_error("clike_small_kernel does not fit: %zu bytes of shared memory", smem);
+		return MDNS_EINVAL;
+	}
+	if (occ > 2) occ = 2;
+	// one group of four rows per warp at least; every CTA builds the spectra, so no more CTAs
+	// than there is row work for
+	long long gx = ceil_div(ceil_div(a.n_rows, 4), LK_THREADS / 32);
+	const long long resident = (long long)sm_count * occ;
+	if (gx > resident) gx = resident;
+	if (gx < 1) gx = 1;
+	kern<<<dim3((unsigned)gx, ceil_div(a.K, KT)), LK_THREADS, smem, st>>>(a);
+	MDNS_LAUNCHED("clike_small_kernel");
+	return MDNS_OK;
+}
+
+static int launch_clike_small(const LikeArgs &a, int sm_count, cudaStream_t st)
+{
+	switch (clike_small_ktile(a.K)) {
+	case 2: return launch_clike_small_inst<2>(a, sm_count, st);
+	case 4: return launch_clike_small_inst<4>(a, sm_count, st);
+	case 8: return launch_clike_small_inst<8>(a, sm_count, st);
+	default: return launch_clike_small_inst<16>(a, sm_count, st);
+	}
+}
+
 // ---- register-blocked variant for candidate batches (K >= 4) -----------------
 // With KT candidates per pass the streaming kernel above becomes bound by shared-memory
 // bandwidth: every (element, candidate) pair needs 8 bytes of model from shared memory
@@ -776,6 +924,12 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 {
 	if (accept_fused) *accept_fused = 0;
 	if (a.n_rows <= 0 || a.K <= 0) return MDNS_OK;
+	if (a.params) {
+		// small batch of parameter points: model, likelihood and accept test in one launch (the
+		// caller decided, and launched no model kernel: capi.cu inline_batch)
+		if (accept_fused) *accept_fused = 1;
+		return launch_clike_small(a, sm_count, st);
+	}
 	const int nfrag = (a.nx + 1) >> 1;
 	int L = t.lanes;
 	const bool tile_ok = a.tmap && !a.active && 4LL * a.mpitch <= tile_constant_capacity();

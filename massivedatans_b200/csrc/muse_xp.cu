@@ -73,6 +73,8 @@ __global__ void __launch_bounds__(256) muse_xp_finalize_kernel(const LikeArgs a,
                                                                const double *__restrict__ S2,
                                                                double guard, int *__restrict__ redo_total)
 {
+	// a programmatic dependent of the raw contraction: set up while it runs, S1 / S2 read after it
+	pdl_wait();
 	const int lane = threadIdx.x & 31;
 	const long long warps = (long long)gridDim.x * 8;
 	for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < a.n_rows; r += warps) {
@@ -131,7 +133,7 @@ int launch_muse_xp_finalize(const LikeArgs &a, const double *S1, const double *S
 	if (a.n_rows <= 0) return MDNS_OK;
 	int blocks = ceil_div(a.n_rows, 8);
 	if (blocks > 8 * sm_count) blocks = 8 * sm_count;
-	muse_xp_finalize_kernel<<<blocks, 256, 0, st>>>(a, S1, S2, guard, redo_total);
+	launch_pdl(muse_xp_finalize_kernel, dim3(blocks), dim3(256), 0, st, true, a, S1, S2, guard, redo_total);
 	MDNS_LAUNCHED_HELPER("muse_xp_finalize_kernel");
 	return MDNS_OK;
 }

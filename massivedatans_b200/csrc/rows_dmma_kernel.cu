@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(RD_ROWS / (8 * MR) * 32 + (GATHER ? 64 : 32), 
 	const int nch = ((int)a.pitch + RD_BOX_CH - 1) / RD_BOX_CH;
 	const int G = gridDim.x;
 
+	pdl_trigger();      // the fix-up / finalize launch behind this one waits for the whole grid itself
 	if (threadIdx.x == 0) {
 		const RdSched sc = rd_schedule(nmat, ntiles, nch, G);
 		RdMine m;
@@ -246,6 +247,8 @@ __global__ void __launch_bounds__(RD_ROWS / (8 * MR) * 32 + (GATHER ? 64 : 32), 
 		}
 		mbar_fence_init();
 	}
+	// (programmatic dependent launch: everything below reads the model kernel's output)
+	pdl_wait();
 	if (threadIdx.x < KT) {
 		s_counts[threadIdx.x] = 0;
 		s_smm[threadIdx.x] = EPI == EPI_CLIKE ? a.smm[k0 + threadIdx.x] : 0.0;
@@ -568,7 +571,8 @@ static int launch_rd_inst(const LikeArgs &a, int nmat, int sm_count, cudaStream_
 	}
 	for (int k0 = 0, pass = 0; k0 < a.K; k0 += KT, ++pass) {
 		const int kv = a.K - k0 < KT ? a.K - k0 : KT;
-		kern<<<(unsigned)gx, THREADS, smem, st>>>(ta0, ta1, tb0, tb1, a, k0, kv, pass, nmat);
+		launch_pdl(kern, dim3((unsigned)gx), dim3(THREADS), smem, st,
+		           EPI == EPI_CLIKE && (pass > 0 || a.xp_counters_clear), ta0, ta1, tb0, tb1, a, k0, kv, pass, nmat);
 		MDNS_LAUNCHED(EPI == EPI_RAW ? (GATHER ? "rows_dmma_kernel(raw,gather)" : "rows_dmma_kernel(raw)")
 		                             : (GATHER ? "rows_dmma_kernel(gather)" : "rows_dmma_kernel"));
 		if (EPI == EPI_CLIKE) {

@@ -209,27 +209,23 @@ __global__ void __launch_bounds__(SL_THREADS, 1) slab_dmma_kernel(
 	uint64_t *bars = full_bar + warp * NSLOT;
 	int *ctr = a.xp_redo + SL_COUNTER_BASE + pass;
 
+	// (programmatic dependent launch: the fix-up launch behind this one may be set up now; it
+	// does nothing before its own pdl_wait())
+	pdl_trigger();
 	if (threadIdx.x == 0) {
 		mbar_init(&batch_bar, 1);
 		for (int s = 0; s < SL_WARPS * NSLOT; ++s) mbar_init(&full_bar[s], 1);
 		mbar_fence_init();
 	}
-	if (threadIdx.x < KT) {
-		s_counts[threadIdx.x] = 0;
-		s_smm[threadIdx.x] = a.smm[k0 + threadIdx.x];
-	}
 	__syncthreads();
-	if (threadIdx.x == 0) {
-		mbar_expect_tx(&batch_bar, (uint32_t)(nchb * BBOX_BYTES));
-		for (int c = 0; c < nchb; ++c)
-			sl_tma_load_2d(batch + (size_t)c * BBOX_BYTES, &tmapB, c * 16, k0, &batch_bar);
-	}
 
 	// ---- this warp's slabs: `cur` is being contracted, `nxt` comes after it, `grab` is the one
 	// after that, asked for at the start of `cur` and looked at when `cur` is done
 	// The first slab of every warp is fixed -- warp w of CTA b starts with slab b + G w, so a
 	// launch with fewer slabs than warps still spreads over all the SMs -- the rest come from the
 	// counter (which therefore counts from G * 16).
+	// Nothing up to pdl_wait() depends on the model kernel this launch may be overlapping with:
+	// the rows are resident data, the slab counter was handed back by the previous fix-up launch.
 	const int first_dynamic = (int)gridDim.x * SL_WARPS;
 	int cur = (int)blockIdx.x + (int)gridDim.x * warp, nxt = 0, grab = 0;
 	if (lane == 0) nxt = first_dynamic + atomicAdd(ctr, 1);
@@ -252,6 +248,19 @@ __global__ void __launch_bounds__(SL_THREADS, 1) slab_dmma_kernel(
 			}
 		}
 	}
+
+	// ---- the candidate batch, its Smm and the list counters are the model kernel's output
+	pdl_wait();
+	if (threadIdx.x == 0) {
+		mbar_expect_tx(&batch_bar, (uint32_t)(nchb * BBOX_BYTES));
+		for (int c = 0; c < nchb; ++c)
+			sl_tma_load_2d(batch + (size_t)c * BBOX_BYTES, &tmapB, c * 16, k0, &batch_bar);
+	}
+	if (threadIdx.x < KT) {
+		s_counts[threadIdx.x] = 0;
+		s_smm[threadIdx.x] = a.smm[k0 + threadIdx.x];
+	}
+	__syncthreads();
 
 	const int g = lane >> 2, t = lane & 3;
 	const int pr = ((g & 3) << 1) | (g >> 2);      // physical row of logical row g (conflict-free loads)
@@ -442,7 +451,10 @@ static int launch_slab_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 		MDNS_CUDA(cudaMemsetAsync(a.xp_redo + 1, 0, (size_t)npass * sizeof(int), st));
 	for (int k0 = 0, pass = 0; k0 < a.K; k0 += KT, ++pass) {
 		const int kv = a.K - k0 < KT ? a.K - k0 : KT;
-		kern<<<(unsigned)gx, SL_THREADS, smem, st>>>(ta, tb, a, k0, kv, pass);
+		// behind the model kernel that also reset the counters (first pass) or behind the
+		// previous pass's fix-up launch: a programmatic dependent launch
+		launch_pdl(kern, dim3((unsigned)gx), dim3(SL_THREADS), smem, st, pass > 0 || a.xp_counters_clear, ta, tb, a,
+		           k0, kv, pass);
 		MDNS_LAUNCHED(GATHER ? "slab_dmma_kernel(gather)" : "slab_dmma_kernel");
 		// (the fix-up launch also hands the slab counter of this pass back at zero)
 		rc = launch_xtile_fixup(a, k0, kv, pass, sm_count, st);

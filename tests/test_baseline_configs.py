@@ -111,6 +111,33 @@ def test_config2_horns_100000_with_400_live_points(oracle_port):
     check_region(members, oracle_port)
 
 
+def test_bench_configuration_sampled_rows_vs_oracle(oracle_port):
+    # the configuration bench.py times by default, on the kernel it times: 1e6 horns data sets x
+    # 200 channels (bench.make_inputs: seed 1000), 16 candidates (seed 7), all active ->
+    # slab_dmma_kernel; every candidate compared with the oracle on 2000 sampled data sets
+    from massivedatans_b200 import _lib
+    from massivedatans_b200.likelihood import ResidentDataset
+    N, K = 1000000, 16
+    x, y, _ = synth.horns(N, nx=200, legacy=False, seed=1000)
+    pts = synth.parameter_points(K, seed=7)
+    ds = ResidentDataset(x, y)
+    ds.set_mask(None)
+    ds.stage_params(pts)
+    for _ in range(2):                       # the second launch replays the captured graph
+        ds.launch_clike(synth.NOISE_LEVEL, -0.5)
+    assert _lib.load().mdns_last_kernel() == b'slab_dmma_kernel'
+    got = numpy.empty((K, N))
+    ds.fetch(got)
+    sel = numpy.zeros(N, dtype=bool)
+    sel[numpy.random.RandomState(5).permutation(N)[:2000]] = True
+    sel[[0, 1, N - 2, N - 1]] = True
+    for k in range(K):
+        A, mu, sig = pts[k]
+        want = -0.5 * oracle_port.clike(x, y, A, mu, sig, synth.NOISE_LEVEL, sel)
+        assert rel(got[k][sel], want) < TOL, k
+    ds.close()
+
+
 def test_config3_realistic_shard_of_one_gpu(oracle_port):
     N, nx = 125000, 1000
     x, y, _ = synth.realistic(N, nx=nx)

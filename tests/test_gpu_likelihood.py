@@ -315,10 +315,59 @@ def test_clike_expanded_tensor_path_masked_gather(oracle_port, ktile, stages, N,
     assert ds.expanded_stats() == (True, 0)
 
 
+@pytest.mark.parametrize('N,nx,K', [(1, 200, 2), (33, 57, 3), (700, 203, 9), (10000, 200, 16),
+                                    (10000, 200, 5), (20000, 200, 17), (3000, 1000, 35), (40000, 31, 8)])
+def test_clike_small_batches_in_one_launch(oracle_port, N, nx, K):
+    # small batches of parameter points: spectra built by every CTA, direct form, one launch
+    # (clike_small_kernel) -- automatic up to a few 1e5 evaluations, lanes = 7 at any size
+    x, y, _ = synth.horns(N, nx=nx, legacy=False, seed=N + 31)
+    ds = ResidentDataset(x, y)
+    lib = _lib.load()
+    pts = synth.parameter_points(K, seed=N + 32)
+    for name, m in synth.masks(N, seed=N).items():
+        if not m.any():
+            continue
+        ds.set_tuning(7, 0, 0, 0)
+        got = numpy.array(ds.loglike_batch(pts, m, synth.NOISE_LEVEL, scale=1.0))
+        assert lib.mdns_last_kernel() == b'clike_small_kernel'
+        assert got.shape == (K, int(m.sum()))
+        for k in sorted({0, 1, K // 2, K - 1}):
+            p = pts[k]
+            want = oracle_port.clike(x, y, p[0], p[1], p[2], synth.NOISE_LEVEL, m)
+            assert rel_err(got[k], want) < TOL, (name, k)
+        # the same lanes, fragment order and butterfly as the lanes-across-channels kernel
+        ds.set_tuning(8, 0, 0, 1)
+        same = numpy.array(ds.loglike_batch(pts, m, synth.NOISE_LEVEL, scale=1.0))
+        assert lib.mdns_last_kernel() == b'clike_rows_kernel'
+        assert numpy.array_equal(got, same), name
+        # automatic choice + fused accept test
+        ds.set_tuning(0, 0, 0, 0)
+        auto = numpy.array(ds.loglike_batch(pts, m, synth.NOISE_LEVEL, scale=1.0))
+        if int(m.sum()) * K <= 200000:
+            assert lib.mdns_last_kernel() == b'clike_small_kernel'
+            assert numpy.array_equal(auto, got)
+        ds.set_tuning(7, 0, 0, 0)
+        L = -0.5 * got
+        srt = numpy.sort(L, axis=0)
+        Lmins = srt[-1] + 1.0 + numpy.abs(srt[-1])
+        pick = numpy.arange(L.shape[1]) % 7 == 3
+        if pick.any():
+            Lmins[pick] = 0.5 * (srt[-1][pick] + srt[-2][pick])
+        k, Lk, counts = ds.first_accepted(pts, m, Lmins, synth.NOISE_LEVEL)
+        want_counts = (L > Lmins).sum(axis=1)
+        assert numpy.array_equal(counts, want_counts)
+        if want_counts.any():
+            want_k = int(numpy.nonzero(want_counts)[0][0])
+            assert k == want_k and numpy.array_equal(Lk, L[want_k])
+        else:
+            assert k == -1
+    ds.close()
+
+
 def test_clike_masked_batches_automatic_choice(oracle_port):
     # masked batches: lanes-across-channels kernels up to 4 candidates, gather-fed tensor path
     # from 5 on
-    N = 80000
+    N = 160000
     x, y, _ = synth.horns(N, legacy=False, seed=8)
     ds = ResidentDataset(x, y)
     lib = _lib.load()
@@ -334,7 +383,7 @@ def test_clike_masked_batches_automatic_choice(oracle_port):
     assert lib.mdns_last_kernel() in TENSOR_GATHER
     assert rel_err(mid, got[:8]) < TOL_XP
     small = ds.loglike_batch(pts[:4], m, synth.NOISE_LEVEL)
-    assert lib.mdns_last_kernel() in (b'clike_block_kernel', b'clike_rows_kernel')
+    assert lib.mdns_last_kernel() in (b'clike_block_kernel', b'clike_rows_kernel', b'clike_small_kernel')
     assert rel_err(small, got[:4]) < TOL_XP
     # first-accept on a masked batch of 20 goes through the same kernel
     Ls = numpy.array(got)
