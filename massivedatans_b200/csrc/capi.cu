@@ -668,13 +668,14 @@ int mdns_internal_threshold_buffer(mdns_dataset *ds, int shard, double **d_lmins
 
 // a small batch of parameter points: one launch builds the spectra and scores the shard's active
 // rows in the direct form (clike_small_kernel) -- no model kernel, no row sums, no fix-up launch.
-// Automatic where it measured ahead of what ran there before (tools/r2_small_kernel.py,
-// profiles/r02_small_kernel.json): batches of 3 or more candidates over fewer active rows than
-// the tensor path takes (masked: < 32768, all active: < 8192), up to SMALL_AUTO_EVALS padded
-// model x data-set evaluations (MDNS_SMALL_EVALS overrides the limit, 0 = never); a handful of
-// rows stays with draw_small_kernel and the 32-lane kernel it agrees with bit for bit.
-// set_tuning(7, ...) asks for it at any size.
-constexpr long long SMALL_AUTO_EVALS = 600000;
+// Automatic where it measured ahead of what ran there before (tools/r2_small_arms.py,
+// profiles/r02_small_arms.json): 5 or more candidates, up to SMALL_AUTO_EVALS padded model x
+// data-set evaluations, masked or not (the three-launch step of the tensor path costs 16-20 us
+// whatever the size; this kernel 12-14 us up to there; up to 4 candidates the lanes-across-
+// channels kernel behind the model kernel is as fast).  MDNS_SMALL_EVALS overrides the limit
+// (0 = never); a handful of rows stays with draw_small_kernel and the 32-lane kernel it agrees
+// with bit for bit.  set_tuning(7, ...) asks for it at any size.
+constexpr long long SMALL_AUTO_EVALS = 100000;
 constexpr int SMALL_AUTO_MIN_ROWS = 65;      // DS_MAX_ROWS + 1
 static bool inline_batch(const mdns_dataset *ds, const Shard &s)
 {
@@ -686,7 +687,7 @@ static bool inline_batch(const mdns_dataset *ds, const Shard &s)
 		const char *e = getenv("MDNS_SMALL_EVALS");
 		return e && *e ? atoll(e) : SMALL_AUTO_EVALS;
 	}();
-	if (ds->K < 3 || s.n_act < SMALL_AUTO_MIN_ROWS || s.n_act >= (s.all_active ? 8192 : 32768)) return false;
+	if (ds->K < 5 || s.n_act < SMALL_AUTO_MIN_ROWS) return false;
 	const int kt = clike_small_ktile(ds->K);
 	return (long long)s.n_act * ceil_div(ds->K, kt) * kt <= limit;
 }

@@ -529,16 +529,19 @@ int launch_draw_small(const LikeArgs &a, const double *params, int seq, int *hos
 // latencies there.  Here every CTA builds the KT spectra of its candidate slice in shared memory
 // from the staged parameter points (clike.c:65, un-fused like line_model_kernel: bit-identical
 // spectra) and scores its rows in the DIRECT form: 8 lanes per data set, the fragment order per
-// lane and the butterfly of clike_rows_kernel<8, ...> (so the two agree to the last bit), warps
-// strided over groups of four rows so that the FP64 work spreads evenly over the SMs.  No row
-// sums, no guard, no fix-up list; the accept test is fused in like everywhere else.
-template <int KT>
-__global__ void __launch_bounds__(LK_THREADS) clike_small_kernel(const LikeArgs a)
+// lane and the butterfly of clike_rows_kernel<8, ...> (so the two agree to the last bit), every
+// lane group walking R data sets at once so that one 128-bit read of the model serves R of them
+// (the first version, R = 1 with 16 candidates per slice, ran at 30 % of the FP64 peak: four
+// shared-memory wavefronts per four FP64 instructions), warps strided over the groups of 4 R
+// rows so that the FP64 work spreads evenly over the SMs.  No row sums, no guard, no fix-up list;
+// the accept test is fused in like everywhere else.
+template <int KT, int R>
+__global__ void __launch_bounds__(LK_THREADS, (KT == 4 && R == 4) ? 1 : 2) clike_small_kernel(const LikeArgs a)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	double *smd = reinterpret_cast<double *>(smem_raw);                  // [KT][mpitch] spectra
 	const double2 *sm = reinterpret_cast<const double2 *>(smem_raw);
-	constexpr int L = 8, G = 32 / L, U = 4;
+	constexpr int L = 8, G = 32 / L, U = R >= 4 ? 1 : 2;
 	const int k0 = blockIdx.y * KT;
 	const int mfp = a.mpitch >> 1;
 	const int nfrag = (a.nx + 1) >> 1;
@@ -560,48 +563,62 @@ __global__ void __launch_bounds__(LK_THREADS) clike_small_kernel(const LikeArgs 
 	int acnt[KT];
 #pragma unroll
 	for (int k = 0; k < KT; ++k) acnt[k] = 0;
-	const long long nquads = ((long long)a.n_rows + G - 1) / G;
+	const long long ngroups = ((long long)a.n_rows + G * R - 1) / (G * R);
 	const long long wstride = (long long)gridDim.x * (LK_THREADS / 32);
-	for (long long q = (long long)warp * gridDim.x + blockIdx.x; q < nquads; q += wstride) {
-		const long long r = q * G + g;
-		const bool valid = r < a.n_rows;
-		double acc0[KT], acc1[KT];
+	for (long long q = (long long)warp * gridDim.x + blockIdx.x; q < ngroups; q += wstride) {
+		// rows (q R + j) G + g, j < R: every 128-bit load of the warp covers four consecutive rows.
+		// Rows behind the end are computed on the last row and dropped.
+		const double2 *p[R];
+		double acc0[R][KT], acc1[R][KT];
 #pragma unroll
-		for (int k = 0; k < KT; ++k) acc0[k] = acc1[k] = 0.0;
-		const double lm = (valid && a.lmins) ? __ldg(a.lmins + r) : 0.0;
-		if (valid) {
+		for (int j = 0; j < R; ++j) {
+			long long r = (q * R + j) * G + g;
+			if (r >= a.n_rows) r = a.n_rows - 1;
 			const long long row = a.active ? (long long)a.active[r] : r;
-			const double2 *p = reinterpret_cast<const double2 *>(a.Y + row * a.pitch);
-			for (int f = gl; f < nfrag; f += L * U) {
-				double2 y[U];
+			p[j] = reinterpret_cast<const double2 *>(a.Y + row * a.pitch);
+#pragma unroll
+			for (int k = 0; k < KT; ++k) acc0[j][k] = acc1[j][k] = 0.0;
+		}
+		for (int f = gl; f < nfrag; f += L * U) {
+			double2 y[R][U];
+#pragma unroll
+			for (int j = 0; j < R; ++j)
 #pragma unroll
 				for (int u = 0; u < U; ++u)
-					if (f + u * L < nfrag) y[u] = ldg_stream(p + f + u * L);
+					if (f + u * L < nfrag) y[j][u] = ldg_stream(p[j] + f + u * L);
 #pragma unroll
-				for (int u = 0; u < U; ++u) {
-					const int fi = f + u * L;
-					if (fi < nfrag) {
+			for (int u = 0; u < U; ++u) {
+				const int fi = f + u * L;
+				if (fi < nfrag) {
 #pragma unroll
-						for (int k = 0; k < KT; ++k) {
-							const double2 m = sm[k * mfp + fi];
-							const double d0 = m.x - y[u].x;
-							const double d1 = m.y - y[u].y;
-							acc0[k] = fma(d0, d0, acc0[k]);
-							acc1[k] = fma(d1, d1, acc1[k]);
+					for (int k = 0; k < KT; ++k) {
+						const double2 m = sm[k * mfp + fi];
+#pragma unroll
+						for (int j = 0; j < R; ++j) {
+							const double d0 = m.x - y[j][u].x;
+							const double d1 = m.y - y[j][u].y;
+							acc0[j][k] = fma(d0, d0, acc0[j][k]);
+							acc1[j][k] = fma(d1, d1, acc1[j][k]);
 						}
 					}
 				}
 			}
 		}
 #pragma unroll
-		for (int k = 0; k < KT; ++k) {
-			double s = acc0[k] + acc1[k];
+		for (int j = 0; j < R; ++j) {
+			const long long r = (q * R + j) * G + g;
+			const bool valid = r < a.n_rows;
+			const double lm = (valid && a.lmins) ? __ldg(a.lmins + r) : 0.0;
 #pragma unroll
-			for (int o = L / 2; o > 0; o >>= 1) s += shfl_xor_f64(s, o);
-			const bool mine = valid && gl == 0 && k0 + k < a.K;
-			const double val = s * inv;
-			if (mine && a.out) a.out[(long long)(k0 + k) * a.out_stride + r] = val;
-			if (a.counts) acnt[k] += __popc(__ballot_sync(0xffffffffu, mine && val > lm));
+			for (int k = 0; k < KT; ++k) {
+				double s = acc0[j][k] + acc1[j][k];
+#pragma unroll
+				for (int o = L / 2; o > 0; o >>= 1) s += shfl_xor_f64(s, o);
+				const bool mine = valid && gl == 0 && k0 + k < a.K;
+				const double val = s * inv;
+				if (mine && a.out) a.out[(long long)(k0 + k) * a.out_stride + r] = val;
+				if (a.counts) acnt[k] += __popc(__ballot_sync(0xffffffffu, mine && val > lm));
+			}
 		}
 	}
 	if (a.counts && lane == 0) {
@@ -611,32 +628,19 @@ __global__ void __launch_bounds__(LK_THREADS) clike_small_kernel(const LikeArgs 
 	}
 }
 
-// candidates per slice: padded candidates + one per slice (every slice reads the rows again and
-// builds its own spectra) as small as possible, the larger slice on a tie
-int clike_small_ktile(int K)
-{
-	int best = 16;
-	long long best_cost = (long long)ceil_div(K, 16) * 17;
-	for (int kt : {8, 4, 2}) {
-		const long long cost = (long long)ceil_div(K, kt) * (kt + 1);
-		if (cost < best_cost) {
-			best = kt;
-			best_cost = cost;
-		}
-	}
-	return best;
-}
+// candidates per slice (every slice reads the rows again and builds its own spectra)
+int clike_small_ktile(int K) { return K <= 2 ? 2 : K <= 4 ? 4 : 8; }
 
 bool clike_small_fits(int K, int mpitch)
 {
 	return K >= 1 && (size_t)clike_small_ktile(K) * mpitch * 8 <= 200 * 1024;
 }
 
-template <int KT>
+template <int KT, int R>
 static int launch_clike_small_inst(const LikeArgs &a, int sm_count, cudaStream_t st)
 {
 	const size_t smem = (size_t)KT * a.mpitch * 8;
-	auto kern = clike_small_kernel<KT>;
+	auto kern = clike_small_kernel<KT, R>;
 	if (smem > 48 * 1024)
 		MDNS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int occ = 0;
@@ -646,24 +650,38 @@ static int launch_clike_small_inst(const LikeArgs &a, int sm_count, cudaStream_t
 		return MDNS_EINVAL;
 	}
 	if (occ > 2) occ = 2;
-	// one group of four rows per warp at least; every CTA builds the spectra, so no more CTAs
-	// than there is row work for
-	long long gx = ceil_div(ceil_div(a.n_rows, 4), LK_THREADS / 32);
-	const long long resident = (long long)sm_count * occ;
+	// one group of 4 R rows per warp at least; every CTA builds the spectra, so no more CTAs
+	// than there is row work for -- and all candidate slices together in ONE wave (the first
+	// version let every slice fill the device: 15026 rows x 2 slices ran as 470 CTAs on 296 slots)
+	const int slices = ceil_div(a.K, KT);
+	long long gx = ceil_div(ceil_div(a.n_rows, 4 * R), LK_THREADS / 32);
+	long long resident = (long long)sm_count * occ / slices;
+	if (resident < 1) resident = 1;
 	if (gx > resident) gx = resident;
 	if (gx < 1) gx = 1;
-	kern<<<dim3((unsigned)gx, ceil_div(a.K, KT)), LK_THREADS, smem, st>>>(a);
+	kern<<<dim3((unsigned)gx, slices), LK_THREADS, smem, st>>>(a);
 	MDNS_LAUNCHED("clike_small_kernel");
 	return MDNS_OK;
 }
 
 static int launch_clike_small(const LikeArgs &a, int sm_count, cudaStream_t st)
 {
+	// rows per lane group: as many as still leave every warp of the device a group of its own
+	// (5000 rows in groups of 16 are 40 CTAs: R = 4 lost to the lanes-across-channels kernel there)
+	const long long warps = (long long)sm_count * (LK_THREADS / 32);
+	const int rmax = a.n_rows >= 16 * warps ? 4 : a.n_rows >= 8 * warps ? 2 : 1;
 	switch (clike_small_ktile(a.K)) {
-	case 2: return launch_clike_small_inst<2>(a, sm_count, st);
-	case 4: return launch_clike_small_inst<4>(a, sm_count, st);
-	case 8: return launch_clike_small_inst<8>(a, sm_count, st);
-	default: return launch_clike_small_inst<16>(a, sm_count, st);
+	case 2:
+		return rmax == 4   ? launch_clike_small_inst<2, 4>(a, sm_count, st)
+		       : rmax == 2 ? launch_clike_small_inst<2, 2>(a, sm_count, st)
+		                   : launch_clike_small_inst<2, 1>(a, sm_count, st);
+	case 4:
+		return rmax == 4   ? launch_clike_small_inst<4, 4>(a, sm_count, st)
+		       : rmax == 2 ? launch_clike_small_inst<4, 2>(a, sm_count, st)
+		                   : launch_clike_small_inst<4, 1>(a, sm_count, st);
+	default:
+		return rmax >= 2 ? launch_clike_small_inst<8, 2>(a, sm_count, st)
+		                 : launch_clike_small_inst<8, 1>(a, sm_count, st);
 	}
 }
 
@@ -920,6 +938,8 @@ static int launch_dmma_auto(const LikeArgs &a, int kt, int stages, int sm_count,
 	return launch_clike_dmma(a, kt, stages, sm_count, st);
 }
 
+constexpr int MASKED_TENSOR_MIN_ROWS = 4096;   // masked batches of >= 5 candidates: tensor path from here
+
 int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t st, int *accept_fused)
 {
 	if (accept_fused) *accept_fused = 0;
@@ -981,7 +1001,7 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		                         tile_rows, sm_count, st);
 	}
 	if (L == 0 && t.unroll == 0 && t.ktile == 0 && t.rows == 0 && a.active && a.tmap_gather &&
-	    t.allow_expanded && a.K >= XP_MIN_K_MASKED && a.n_rows >= 32768) {
+	    t.allow_expanded && a.K >= XP_MIN_K_MASKED && a.n_rows >= MASKED_TENSOR_MIN_ROWS) {
 		// masked candidate batches: the tensor path fed by gather4 copies of the listed rows
 		// (two producer warps).  Measured, 5e5 active of 1e6 data sets: K=8 0.152 ms (block kernel
 		// 0.180), K=16 0.173 ms (0.358), K=32 0.43 ms (0.71); up to 4 candidates the block kernel
@@ -990,15 +1010,19 @@ int launch_clike(const LikeArgs &a, const Tuning &t, int sm_count, cudaStream_t 
 		// 5e5 active of 1e6 x 200 (tools/sweep_masked.py): K=16 0.159 ms (0.84 of the roofline)
 		// against 0.181 (0.73) for the stream-K gather, K=8 0.150 (0.85) against 0.152 for round 1's
 		// whole-tile gather and 0.241 (0.53) for the stream-K 16-warp gather shape
-		const bool slabs_enough = (a.n_rows + 31) / 32 >= 4LL * sm_count;
-		if (a.K > 8 && slabs_enough && slab_dmma_fits(a, 16, 2)) {
+		// From 4096 active rows (it was 32768): the gathered slab kernel is a 16-18 us step at 16
+		// candidates whatever the size below 5e4 rows, the lanes-across-channels kernels that
+		// ran there took 22 / 35 / 48 / 56 us at 5053 / 10070 / 15026 / 24963 rows (K = 32: 37 ... 104
+		// against 31-33; tools/r2_small_arms.py, profiles/r02_small_arms.json); smaller batches
+		// go to clike_small_kernel before they get here (capi.cu inline_batch)
+		if (a.K > 8 && slab_dmma_fits(a, 16, 2)) {
 			if (accept_fused) *accept_fused = 1;
 			return launch_slab_dmma(a, 16, 2, sm_count, st);
 		}
 		// (passes of 16 whatever K: 0.158 ms each against 0.43 ms for a gathered pass of 32)
 		if (a.K >= 32 && dmma_fits(a, 32, 3)) return launch_dmma_auto(a, 32, 3, sm_count, st, accept_fused);
 		if (a.K >= 16 && dmma_fits(a, 16, 13)) return launch_dmma_auto(a, 16, 13, sm_count, st, accept_fused);
-		if (slabs_enough && slab_dmma_fits(a, 8, 2)) {
+		if (slab_dmma_fits(a, 8, 2)) {
 			if (accept_fused) *accept_fused = 1;
 			return launch_slab_dmma(a, 8, 2, sm_count, st);
 		}

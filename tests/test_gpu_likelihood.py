@@ -344,7 +344,7 @@ def test_clike_small_batches_in_one_launch(oracle_port, N, nx, K):
         ds.set_tuning(0, 0, 0, 0)
         auto = numpy.array(ds.loglike_batch(pts, m, synth.NOISE_LEVEL, scale=1.0))
         n_act = int(m.sum())
-        if K >= 3 and 64 < n_act < (8192 if m.all() else 32768) and n_act * K <= 300000:
+        if K >= 5 and n_act > 64 and n_act * ((K + 7) // 8 * 8) <= 100000:
             assert lib.mdns_last_kernel() == b'clike_small_kernel', name
             assert numpy.array_equal(auto, got)
         else:
@@ -398,14 +398,14 @@ def test_clike_masked_batches_automatic_choice(oracle_port):
 
 
 def test_clike_expanded_form_automatic_choice(oracle_port):
-    # all-active batches of >= 3 candidates take the expanded form on their own; masks and
-    # smaller batches stay on the direct kernels
+    # all-active batches of >= 3 candidates take the expanded form on their own, masked ones from
+    # 5 candidates over >= 4096 active rows; smaller batches stay on the direct kernels
     N = 50000
     x, y, _ = synth.horns(N, legacy=False, seed=21)
     ds = ResidentDataset(x, y)
     lib = _lib.load()
     pts = synth.parameter_points(35, seed=2)
-    got = ds.loglike_batch(pts, None, synth.NOISE_LEVEL)
+    got = numpy.array(ds.loglike_batch(pts, None, synth.NOISE_LEVEL))
     assert lib.mdns_last_kernel() in TENSOR
     allm = numpy.ones(N, dtype=bool)
     for k in (0, 7, 8, 31, 32, 34):
@@ -414,8 +414,11 @@ def test_clike_expanded_form_automatic_choice(oracle_port):
         assert rel_err(got[k], want) < TOL_XP
     ds.loglike_batch(pts[:2], None, synth.NOISE_LEVEL)
     assert lib.mdns_last_kernel() not in (b'clike_xtile_kernel',) + TENSOR
-    ds.loglike_batch(pts, synth.masks(N)['half'], synth.NOISE_LEVEL)
-    assert lib.mdns_last_kernel() not in (b'clike_xtile_kernel',) + TENSOR
+    # (masked batches of >= 5 candidates over >= 4096 active rows: the gathered tensor path)
+    half = synth.masks(N)['half']
+    gm = ds.loglike_batch(pts, half, synth.NOISE_LEVEL)
+    assert lib.mdns_last_kernel() in TENSOR_GATHER
+    assert rel_err(gm, got[:, half]) < TOL_XP
     ds.set_expanded(False)
     got = ds.loglike_batch(pts[:9], None, synth.NOISE_LEVEL)
     assert lib.mdns_last_kernel() == b'clike_tile_kernel'
