@@ -56,13 +56,16 @@ def worker():
 
 def main():
     rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-    res = {'pdl': [], 'serial': []}
+    # the switch of the 'serial' arm (default: MDNS_NO_PDL=1); e.g. MDNS_ONE_LAUNCH=0 compares the
+    # step with a model kernel against the one whose likelihood kernel builds the spectra itself
+    var, val = (sys.argv[2].split('=') + ['1'])[:2] if len(sys.argv) > 2 else ('MDNS_NO_PDL', '1')
+    res = {'pdl': [], 'serial': [], 'serial_arm': '%s=%s' % (var, val)}
     for r in range(rounds):
         for arm in ('serial', 'pdl'):
             env = dict(os.environ)
-            env.pop('MDNS_NO_PDL', None)
+            env.pop(var, None)
             if arm == 'serial':
-                env['MDNS_NO_PDL'] = '1'
+                env[var] = val
             p = subprocess.run([sys.executable, os.path.abspath(__file__), '--worker'], env=env,
                                capture_output=True, text=True, timeout=600)
             line = [ln for ln in p.stdout.splitlines() if ln.startswith('ROWS ')]
@@ -71,7 +74,7 @@ def main():
                 continue
             res[arm].append(json.loads(line[0][5:]))
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-    json.dump(res, open(os.path.join(ROOT, 'gpurun_out', 'r2_pdl_ab.json'), 'w'), indent=1)
+    json.dump(res, open(os.path.join(ROOT, 'gpurun_out', 'r2_pdl_ab.json' if var == 'MDNS_NO_PDL' else 'r2_ab_%s.json' % var.lower()), 'w'), indent=1)
     if res['pdl'] and res['serial']:
         for i, row in enumerate(res['pdl'][0]):
             def best(arm, key):
