@@ -254,9 +254,12 @@ int mdns_flush_l2(mdns_dataset *ds);
  * fragments in flight per lane (0 = auto), candidates per pass (0 = auto),
  * data sets per lane group (0 = auto; > 1 selects the register-blocked kernel).
  * lanes = 7: parameter-point batches of any size in ONE launch (every CTA builds the spectra,
- * direct form) -- the automatic choice only up to a few 1e5 model x data-set evaluations. */
+ * direct form) -- the automatic choice only from 5 candidates and up to 1e5 model x data-set
+ * evaluations. */
 int mdns_set_tuning(mdns_dataset *ds, int lanes, int unroll, int ktile, int rows);
-/* Expanded form of the candidate-batch kernel (K >= 3, all data sets active, >= 32768 of them):
+/* Expanded form of the candidate-batch kernels (automatic for K >= 3 over >= 8192 data sets when
+ * all are active, for K >= 5 over >= 4096 active data sets of a masked batch; batches of up to 1e5
+ * evaluations take the one-launch direct-form kernel instead):
  *     sum_j (m_j - y_j)^2 = Syy - 2*Sym + Smm ,  Syy resident per data set,
  * one FP64 FMA per (element, candidate) instead of two operations.  FP64 throughout; a
  * result is kept only when the rounding-error bound of the three sums is below rel_tol
